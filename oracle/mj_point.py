@@ -1,0 +1,218 @@
+"""CPU oracle, part 1: the MuJoCo 2.0 step for Safety Gym's ``xmls/point.xml``.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` may be imported by the
+product package; only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` use it.
+
+PARITY UNPINNED (physics).  The arithmetic restated here lives in third-party
+code that is *not* under /root/reference and cannot be installed in this image:
+
+* ``mujoco-py==2.0.2.9`` (reference ``requirements.txt:3``) wrapping the closed
+  MuJoCo 2.0 binary -- ``mj_step`` / ``mj_forward``;
+* ``safety-gym`` (un-pinned sibling checkout, reference ``README.md:36-37``,
+  ``main/setup.sh:2``) -- ``safety_gym/xmls/point.xml`` and ``World.build``.
+
+The reference's call sites into it are ``main/envs/zone_envs/ZoneEnvBase.py:94``
+(``data.get_body_xpos``), ``:145`` (``sim.forward``), ``:220-224``
+(``world.robot_pos / robot_vel``, ``get_body_xquat``, ``get_body_xvelr``) and
+``Engine.step`` (``sim.step()`` x frameskip) reached from
+``main/envs/TSP_env.py:49``.  What follows restates the published MuJoCo
+algorithm for this one model:
+
+model (point.xml): timestep 0.002; body ``robot`` at (x0, y0, 0.1) with quat
+(cos(rot/2),0,0,sin(rot/2)); joints in order slide-x (damping .01), slide-y
+(.01), hinge-z (.005); geoms sphere r=.1 and box half-size .05 at (.1,0,0),
+density 1; actuators ``motor gear=.3 site=robot`` and ``velocity gear=.3 kv=1``
+on the hinge, both ctrlrange +-1 and forcerange +-.05.
+
+mj_step = mj_forward (position, velocity, actuation, acceleration, constraint
+stages on the *current* state) followed by mj_Euler with implicit joint damping:
+solve (M + h diag(B)) a = qfrc_smooth + qfrc_constraint, v += h a, q += h v.
+The sphere/floor contact has signed distance exactly 0.0 == margin, which
+MuJoCo lists but excludes (``dist < includemargin`` is false), so
+``constraint_force`` returns zero; it is kept as an isolated hook.
+
+The mass matrix is assembled generically (composite rigid body of the two
+geoms) and the 3x3 system is solved with ``numpy.linalg.solve`` on purpose: the
+CUDA kernel uses an independently derived closed form, so agreement between the
+two is a real check and not the same formula typed twice.
+"""
+import math
+
+import numpy as np
+
+# ---- model constants derived from point.xml (density 1) -------------------
+TIMESTEP = 0.002
+SPHERE_R = 0.1
+BOX_HALF = 0.05
+BOX_X = 0.1
+M_SPHERE = 4.0 / 3.0 * math.pi * SPHERE_R ** 3
+M_BOX = 8.0 * BOX_HALF ** 3
+MASS = M_SPHERE + M_BOX
+# centre of mass offset along body-x and inertia about the hinge (body z) axis
+COM_X = M_BOX * BOX_X / MASS
+I_HINGE = (0.4 * M_SPHERE * SPHERE_R ** 2
+           + M_BOX / 3.0 * (BOX_HALF ** 2 + BOX_HALF ** 2)
+           + M_BOX * BOX_X ** 2)
+DAMPING = np.array([0.01, 0.01, 0.005])
+GEAR_MOTOR = 0.3
+GEAR_VELOCITY = 0.3
+KV = 1.0
+FORCE_LIMIT = 0.05
+CTRL_LIMIT = 1.0
+BODY_Z = 0.1
+
+
+def quat_rotate(quat, vec):
+    """v' = q v q*  (the two-product form MuJoCo's mju_rotVecQuat uses)."""
+    w, x, y, z = quat
+    t0 = -x * vec[0] - y * vec[1] - z * vec[2]
+    t1 = w * vec[0] + y * vec[2] - z * vec[1]
+    t2 = w * vec[1] + z * vec[0] - x * vec[2]
+    t3 = w * vec[2] + x * vec[1] - y * vec[0]
+    return np.array([
+        -t0 * x + t1 * w - t2 * z + t3 * y,
+        -t0 * y + t2 * w - t3 * x + t1 * z,
+        -t0 * z + t3 * w - t1 * y + t2 * x,
+    ])
+
+
+def quat_mul(a, b):
+    return np.array([
+        a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3],
+        a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+        a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1],
+        a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0],
+    ])
+
+
+def mass_matrix(theta):
+    """Joint-space inertia of the sphere+box body for q = (x, y, theta).
+
+    x, y are measured along the *initial* body axes (the slides precede the
+    hinge in the kinematic chain, so they do not rotate with theta).
+    """
+    s, c = math.sin(theta), math.cos(theta)
+    mc = MASS * COM_X
+    return np.array([[MASS, 0.0, -mc * s],
+                     [0.0, MASS, mc * c],
+                     [-mc * s, mc * c, I_HINGE]])
+
+
+def bias_force(theta, qvel):
+    """qfrc_bias: centrifugal term of the off-axis COM (gravity has no
+    generalized component: there is no z DOF and the hinge is vertical)."""
+    s, c = math.sin(theta), math.cos(theta)
+    mc = MASS * COM_X
+    w2 = qvel[2] * qvel[2]
+    return np.array([-mc * w2 * c, -mc * w2 * s, 0.0])
+
+
+def actuator_force(theta, qvel, ctrl):
+    """qfrc_actuator for the site motor and the hinge velocity servo."""
+    u0 = min(max(ctrl[0], -CTRL_LIMIT), CTRL_LIMIT)
+    u1 = min(max(ctrl[1], -CTRL_LIMIT), CTRL_LIMIT)
+    f_motor = min(max(u0, -FORCE_LIMIT), FORCE_LIMIT)
+    f_servo = KV * u1 - KV * (GEAR_VELOCITY * qvel[2])
+    f_servo = min(max(f_servo, -FORCE_LIMIT), FORCE_LIMIT)
+    s, c = math.sin(theta), math.cos(theta)
+    # site wrench: GEAR_MOTOR * f along body-x at the hinge axis (no yaw arm)
+    return np.array([GEAR_MOTOR * f_motor * c,
+                     GEAR_MOTOR * f_motor * s,
+                     GEAR_VELOCITY * f_servo])
+
+
+def constraint_force(qpos, qvel, qfrc_smooth):
+    """Sphere-on-plane contact: listed, excluded (dist == margin) -> no force."""
+    return np.zeros(3)
+
+
+def substep(qpos, qvel, ctrl, h=TIMESTEP):
+    """One mj_step.  Returns new (qpos, qvel); inputs are not modified."""
+    theta = qpos[2]
+    M = mass_matrix(theta)
+    passive = -DAMPING * qvel
+    smooth = passive - bias_force(theta, qvel) + actuator_force(theta, qvel, ctrl)
+    total = smooth + constraint_force(qpos, qvel, smooth)
+    qacc = np.linalg.solve(M + h * np.diag(DAMPING), total)
+    qvel_new = qvel + h * qacc
+    qpos_new = qpos + h * qvel_new
+    return qpos_new, qvel_new
+
+
+class _Model:
+    """The slice of ``sim.model`` the reference touches (geom ids, rgba)."""
+
+    def __init__(self, geom_names):
+        self._geom_ids = {n: i for i, n in enumerate(geom_names)}
+        self.geom_rgba = np.zeros((len(geom_names), 4))
+        self.actuator_ctrlrange = np.array([[-1.0, 1.0], [-1.0, 1.0]])
+        self.nu = 2
+
+    def geom_name2id(self, name):
+        return self._geom_ids[name]
+
+
+class _Data:
+    def __init__(self, sim):
+        self._sim = sim
+        self.qpos = np.zeros(3)
+        self.qvel = np.zeros(3)
+        self.ctrl = np.zeros(2)
+        self.time = 0.0
+
+    def get_body_xpos(self, name):
+        return self._sim._xpos[name]
+
+    def get_body_xquat(self, name):
+        return self._sim._xquat[name]
+
+    def get_body_xvelp(self, name):
+        return self._sim._xvelp[name]
+
+    def get_body_xvelr(self, name):
+        return self._sim._xvelr[name]
+
+
+class PointSim:
+    """Stand-in for the ``MjSim`` World.build makes: Point robot + static bodies.
+
+    ``static_bodies`` maps body name -> world position (3,), e.g. the zone
+    cylinders added by ``ZoneEnvBase.build_world_config`` (ZoneEnvBase.py:124-140;
+    contype = conaffinity = 0, so they never collide).
+    """
+
+    def __init__(self, robot_xy, robot_rot, static_bodies=None, geom_rgba=None):
+        self.robot_p0 = np.array([robot_xy[0], robot_xy[1], BODY_Z], dtype=np.float64)
+        q0 = np.array([math.cos(robot_rot / 2.0), 0.0, 0.0, math.sin(robot_rot / 2.0)])
+        self.robot_q0 = q0 / math.sqrt(float(q0 @ q0))
+        self.static = {k: np.asarray(v, dtype=np.float64) for k, v in (static_bodies or {}).items()}
+        names = ['floor', 'robot', 'pointarrow'] + list(self.static.keys())
+        self.model = _Model(names)
+        if geom_rgba:
+            for k, v in geom_rgba.items():
+                self.model.geom_rgba[self.model.geom_name2id(k)] = v
+        self.data = _Data(self)
+        self._xpos, self._xquat, self._xvelp, self._xvelr = {}, {}, {}, {}
+        self.forward()
+
+    def step(self):
+        self.data.qpos, self.data.qvel = substep(self.data.qpos, self.data.qvel, self.data.ctrl)
+        self.data.time += TIMESTEP
+
+    def forward(self):
+        """mj_kinematics + body velocities for the quantities the env reads."""
+        q, v = self.data.qpos, self.data.qvel
+        ax_x = quat_rotate(self.robot_q0, np.array([1.0, 0.0, 0.0]))
+        ax_y = quat_rotate(self.robot_q0, np.array([0.0, 1.0, 0.0]))
+        xpos = self.robot_p0 + ax_x * q[0] + ax_y * q[1]
+        qloc = np.array([math.cos(q[2] / 2.0), 0.0, 0.0, math.sin(q[2] / 2.0)])
+        xquat = quat_mul(self.robot_q0, qloc)
+        xquat = xquat / math.sqrt(float(xquat @ xquat))
+        self._xpos['robot'] = xpos
+        self._xquat['robot'] = xquat
+        # body origin lies on the hinge axis: no omega x r contribution
+        self._xvelp['robot'] = ax_x * v[0] + ax_y * v[1]
+        self._xvelr['robot'] = np.array([0.0, 0.0, v[2]])
+        for k, p in self.static.items():
+            self._xpos[k] = p

@@ -1,0 +1,299 @@
+"""CPU oracle, part 3: the task logic, observation build and vector-env
+protocol of PointTSP-v0 / PointTTSP-v0 / ColourMatch-v0, restated on flat
+arrays (one Python object per env, fp64 like the reference).
+
+TEST INFRASTRUCTURE ONLY (see oracle/mj_point.py header).
+
+PINNED by tests/golden/*.npz: tests/golden/gen_golden.py imports the REAL
+reference modules (``main/envs/{TSP,TTSP,colour_match}_env.py``,
+``zone_envs/ZoneEnvBase.py``, ``wrappers.py``, ``make_env.py``) over the stubbed
+upstream packages and records their outputs; tests/test_oracle_golden.py replays
+the same seeds and actions through this file and requires identical results.
+(The physics and layout sampler underneath both are oracle/mj_point.py and
+oracle/sg_engine.py -- parity unpinned, see their headers.)
+
+What each piece follows:
+  per-step order ............ Engine.step [upstream] + SURVEY.md Appendix B
+  visit event ............... TSP_env.py:54-69 (first unvisited zone, index
+                              order, fp64 sqrt(dx^2+dy^2) <= 0.2, PRE-physics pos)
+  TSP reward / bonus / goal . TSP_env.py:37-42, 71-72
+  TimedTSP timeouts ......... TTSP_env.py:19-27 (RandomState(_seed) BEFORE the
+                              Engine increments it), failure :62-71
+  ColourMatch ............... colour_match_env.py:26-36 (cycle B->G->R->B, cooldown
+                              150), :38-55 (Hamming), :57-68 (reset), :86-101
+  observation ............... ZoneEnvBase.py:143-235, obs_zones in the three task
+                              files, ZoneWrapper.split_zone_obs wrappers.py:136-142
+  per-episode seeding ....... FixedSeedsWrapper wrappers.py:10-23
+  auto-reset ................ penv.py:4-21, 52-66
+"""
+import math
+
+import numpy as np
+
+from . import mj_point
+
+TSP, TTSP, CM = 0, 1, 2
+TASK_OF_ENV_ID = {'PointTSP-v0': TSP, 'PointTTSP-v0': TTSP, 'ColourMatch-v0': CM}
+
+NUM_STEPS = 2000            # envs/__init__.py:13, :49
+NUM_ZONES = {TSP: 15, TTSP: 15, CM: 6}   # envs/__init__.py:9, :45
+ZONE_DIM = {TSP: 6, TTSP: 7, CM: 7}
+ZONE_SIZE = 0.2             # ZoneEnvBase.py:51
+ZONE_KEEPOUT = 0.55         # ZoneEnvBase.py:50
+ROBOT_KEEPOUT = 0.4         # Engine.DEFAULT [upstream]
+EXTENT = 3.0                # ZoneEnvBase.py:41,52
+FRAMESKIP = 10              # Engine.DEFAULT frameskip_binom_n, p = 1.0 [upstream]
+MAX_COOLDOWN = 150          # colour_match_env.py:16
+TIME_SAVED_REWARD = 0.01    # TSP_env.py:14
+BETA_A, BETA_B = 3, 1.5     # TTSP_env.py:13
+
+# colour codes: 0 Blue, 1 Green, 2 Red (the order of ``colours``,
+# colour_match_env.py:9); TSP zones: Cyan = unvisited, Yellow = visited.
+RGB_CM = np.array([[0., 0., 1.], [0., 1., 0.], [1., 0., 0.]])
+RGB_UNVISITED = np.array([0., 1., 1.])
+RGB_VISITED = np.array([1., 1., 0.])
+ALPHA = 0.25
+
+
+def hamming_to_goal(colours):
+    """colour_match_env.py:38-55."""
+    nb = int(np.sum(colours == 0))
+    ng = int(np.sum(colours == 1))
+    nr = int(np.sum(colours == 2))
+    return min(2 * ng + nr, 2 * nr + nb, 2 * nb + ng)
+
+
+def sample_layout(rs, num_zones):
+    """Engine.build_layout / sample_layout / build_world_config [upstream],
+    specialised to: robot (keepout .4) then ``num_zones`` zones (keepout .55),
+    extents +-3, no fixed locations.  Consumes ``rs`` exactly as upstream does
+    (x then y per candidate; robot_rot after the layout; one cosmetic
+    ``random_rot`` per zone, ZoneEnvBase.py:132).  Returns xy0, rot0, zone_xy."""
+    keepouts = [ROBOT_KEEPOUT] + [ZONE_KEEPOUT] * num_zones
+    for _ in range(10000):
+        placed = []
+        ok_layout = True
+        for k in keepouts:
+            lo, hi = -EXTENT + k, EXTENT - k
+            found = False
+            for _try in range(100):
+                xy = np.array([rs.uniform(lo, hi), rs.uniform(lo, hi)])
+                if all(np.sqrt(np.sum(np.square(xy - oxy))) >= ok + k for oxy, ok in placed):
+                    found = True
+                    break
+            if not found:
+                ok_layout = False
+                break
+            placed.append((xy, k))
+        if ok_layout:
+            break
+    else:
+        raise RuntimeError('layout sampling failed')
+    rot0 = rs.uniform(0, 2 * np.pi)
+    for _ in range(num_zones):
+        rs.uniform(0, 2 * np.pi)
+    return placed[0][0], rot0, np.array([p for p, _ in placed[1:]])
+
+
+class ZoneTaskEnv:
+    """One env, equivalent to ``ZoneWrapper(gym.make(env_id))``.
+
+    ``seed(s)`` / ``reset()`` / ``step(a)`` follow the reference; ``reset`` also
+    accepts an explicit ``layout`` dict (host-supplied-layout mode) with keys
+    xy0 (2,), rot0, zone_xy (N,2) and, per task, zone_max_steps (N,) / colours (N,).
+    """
+
+    def __init__(self, task, num_zones=None, num_steps=NUM_STEPS):
+        self.task = task
+        self.N = NUM_ZONES[task] if num_zones is None else num_zones
+        self.Z = ZONE_DIM[task]
+        self.num_steps = num_steps
+        self._seed = None
+        self.done = True
+        self.substep_trace = None   # set to a list to record (qpos, qvel) after each substep
+
+    # -- seeding and reset ---------------------------------------------------
+    def seed(self, seed):
+        self._seed = seed
+
+    def reset(self, layout=None):
+        N = self.N
+        if layout is None:
+            # task-level draws use the seed BEFORE Engine.reset increments it
+            if self.task == TTSP:
+                rs = np.random.RandomState(self._seed)
+                self.zone_max_steps = np.array([int(rs.beta(BETA_A, BETA_B) * self.num_steps) for _ in range(N)])
+            elif self.task == CM:
+                rs = np.random.RandomState(self._seed)
+                self.colours = np.array([int(rs.choice(3)) for _ in range(N)])
+            self._seed += 1
+            self.rs = np.random.RandomState(self._seed)
+            xy0, rot0, zone_xy = sample_layout(self.rs, N)
+        else:
+            xy0, rot0, zone_xy = layout['xy0'], layout['rot0'], layout['zone_xy']
+            if self.task == TTSP:
+                self.zone_max_steps = np.asarray(layout['zone_max_steps']).astype(np.int64)
+            elif self.task == CM:
+                self.colours = np.asarray(layout['colours']).astype(np.int64).copy()
+            self.rs = None
+        self.xy0 = np.asarray(xy0, dtype=np.float64)
+        self.rot0 = float(rot0)
+        self.zone_xy = np.asarray(zone_xy, dtype=np.float64).reshape(N, 2)
+        self.visited = np.zeros(N, dtype=bool)
+        if self.task == CM:
+            self.cooldown = np.zeros(N, dtype=np.int64)
+            self.goal_dist = hamming_to_goal(self.colours)
+        self.sim = mj_point.PointSim(self.xy0, self.rot0)
+        self.steps = 0
+        self.done = False
+        self.event = 0
+        return self._obs()
+
+    def set_state(self, qpos, qvel):
+        """Teacher forcing for parity tests: overwrite the physics state."""
+        self.sim.data.qpos = np.asarray(qpos, dtype=np.float64).copy()
+        self.sim.data.qvel = np.asarray(qvel, dtype=np.float64).copy()
+        self.sim.forward()
+
+    # -- one env step -----------------------------------
+    def step(self, action):
+        assert not self.done, 'Environment must be reset before stepping'
+        N = self.N
+        if self.task == CM:
+            self.cooldown[self.cooldown > 0] -= 1
+        ctrl = np.clip(np.asarray(action, dtype=np.float64), -1.0, 1.0)
+        self.sim.data.ctrl[:] = ctrl
+        if self.rs is not None:
+            self.rs.binomial(FRAMESKIP, 1.0)    # upstream draws the frameskip
+
+        # zone event on the pre-physics position
+        p = self.sim.data.get_body_xpos('robot')[:2]
+        fired = -1
+        for i in range(N):
+            eligible = (self.cooldown[i] == 0) if self.task == CM else (not self.visited[i])
+            if eligible and np.sqrt(np.sum(np.square(self.zone_xy[i] - p))) <= ZONE_SIZE:
+                fired = i
+                break
+        reward = 0
+        if fired >= 0:
+            if self.task == CM:
+                self.colours[fired] = (self.colours[fired] + 1) % 3
+                self.cooldown[fired] = MAX_COOLDOWN
+            else:
+                self.visited[fired] = True
+
+        for _ in range(FRAMESKIP):
+            self.sim.step()
+            if self.substep_trace is not None:
+                self.substep_trace.append((self.sim.data.qpos.copy(), self.sim.data.qvel.copy()))
+        self.sim.forward()
+
+        if self.task == CM:
+            if fired >= 0:
+                new_dist = hamming_to_goal(self.colours)
+                reward = self.goal_dist - new_dist
+                self.goal_dist = new_dist
+            goal = self.goal_dist == 0
+        else:
+            reward = 1 if fired >= 0 else 0
+            goal = bool(self.visited.all())
+        self.event = reward            # integer reward component
+        info = {'cost': 0}
+        if goal:
+            info['goal_met'] = True
+            reward = reward + (self.num_steps - self.steps) * TIME_SAVED_REWARD
+            self.done = True
+        self.steps += 1
+        if self.steps >= self.num_steps:
+            self.done = True
+        if self.task == TTSP and not self.done:
+            if (self._zone_times() <= 0).any():
+                self.done = True
+        return self._obs(), reward, self.done, info
+
+    # -- observation -----------------------------------------------------------
+    def _zone_times(self):
+        t = (self.zone_max_steps - self.steps) / self.num_steps
+        t[self.visited] = 1.0
+        return t
+
+    def _obs(self):
+        self.sim.forward()
+        d = self.sim.data
+        N, Z = self.N, self.Z
+        zone_obs = np.zeros((N, Z))
+        zone_obs[:, 0:2] = self.zone_xy / 3.0
+        if self.task == CM:
+            zone_obs[:, 2:5] = RGB_CM[self.colours]
+            zone_obs[:, 6] = (self.cooldown.astype(np.float32) / np.float32(MAX_COOLDOWN)).astype(np.float64)
+        else:
+            zone_obs[:, 2:5] = np.where(self.visited[:, None], RGB_VISITED, RGB_UNVISITED)
+            if self.task == TTSP:
+                zone_obs[:, 6] = self._zone_times()
+        zone_obs[:, 5] = ALPHA
+        quat = d.get_body_xquat('robot').astype(np.float32)
+        direction = np.array([quat[0] ** 2 - quat[3] ** 2, 2 * quat[0] * quat[3]])
+        obs = np.concatenate([
+            [1.0 - self.steps / self.num_steps],
+            d.get_body_xpos('robot')[:2] / 3.0,
+            direction,
+            d.get_body_xvelp('robot')[:2] / 1.5,
+            [d.get_body_xvelr('robot')[2] / 3.0],
+        ])
+        return {'zone_obs': zone_obs, 'obs': obs}
+
+    # -- state export (world frame), used by the CUDA parity tests -------------
+    def world_state(self):
+        d = self.sim.data
+        p = d.get_body_xpos('robot')
+        v = d.get_body_xvelp('robot')
+        return np.array([p[0], p[1], self.rot0 + d.qpos[2], v[0], v[1], d.qvel[2]])
+
+
+class FixedSeeds:
+    """FixedSeedsWrapper (wrappers.py:10-23) around a ZoneTaskEnv."""
+
+    def __init__(self, env, min_seed, max_seed, rng_seed=0):
+        self.env = env
+        self.min_seed, self.max_seed = min_seed, max_seed
+        self.rng = np.random.default_rng(seed=rng_seed)
+
+    def reset(self):
+        new_seed = self.rng.integers(low=self.min_seed, high=self.max_seed + 1, size=1)[0]
+        self.env.seed(new_seed)
+        return self.env.reset()
+
+    def step(self, action):
+        return self.env.step(action)
+
+
+class SerialVecEnv:
+    """ParallelEnv (penv.py:23-69) without the processes: same results."""
+
+    def __init__(self, envs):
+        self.envs = envs
+
+    def reset(self):
+        return [e.reset() for e in self.envs]
+
+    def step(self, actions):
+        out = []
+        for e, a in zip(self.envs, actions):
+            obs, reward, done, info = e.step(a)
+            if done:
+                obs = e.reset()
+            out.append((obs, reward, done, info))
+        return tuple(zip(*out))
+
+    def step_no_reset(self, actions):
+        return tuple(zip(*[e.step(a) for e, a in zip(self.envs, actions)]))
+
+
+def make_fixed_env(env_id, seed=1000, env_seed=0):
+    """make_env.make_fixed_env (make_env.py:37-51) for the three zone tasks."""
+    return FixedSeeds(ZoneTaskEnv(TASK_OF_ENV_ID[env_id]), env_seed, env_seed, rng_seed=seed)
+
+
+def make_train_env(env_id, num_training_tasks=100, rng_seed=0):
+    """make_env.make_train_env (make_env.py:3-18), hier=False."""
+    return FixedSeeds(ZoneTaskEnv(TASK_OF_ENV_ID[env_id]), 1, num_training_tasks, rng_seed=rng_seed)
