@@ -1,0 +1,4 @@
+"""B200-native batched simulator for the env.step() hot path of PointTSP / TimedTSP /
+ColourMatch (andrewli77/combinatorial-rl-tasks).  See DESIGN.md."""
+from .config import ENV_SPECS, TaskSpec  # noqa: F401
+from .vec_env import ZoneVecEnv, make_vec_env  # noqa: F401

@@ -1,0 +1,193 @@
+// crl_core.cuh -- per-env arithmetic of the fused step, shared by the sm_100a
+// kernels (crl_kernels.cu) and by a g++ build that tests/ uses to check the logic
+// without a GPU (tests/hostcheck).  Nothing here touches memory layout.
+//
+// What it computes and the reference lines it stands in for:
+//   substeps()      Engine.step's frameskip loop of sim.step() on xmls/point.xml
+//                   (MuJoCo 2.0 mj_step, implicit-damping Euler)
+//   inside_zone()   dist_xy(zone) <= zones_size, main/envs/TSP_env.py:59-60,
+//                   colour_match_env.py:111-112, evaluated exactly as numpy does
+//   hamming()       colour_match_env.py:38-55
+//   philox4x32()    counter-based RNG for layouts, timeouts, colours and actions
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define CRL_HD __host__ __device__ __forceinline__
+#else
+#define CRL_HD inline
+#endif
+
+namespace crl {
+
+// ---- point.xml, density 1 ---------------------------------
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kH = 0.002;
+constexpr double kMSphere = 4.0 / 3.0 * kPi * 0.1 * 0.1 * 0.1;
+constexpr double kMBox = 8.0 * 0.05 * 0.05 * 0.05;
+constexpr double kMass = kMSphere + kMBox;
+constexpr double kCom = kMBox * 0.1 / kMass;
+constexpr double kIHinge = 0.4 * kMSphere * 0.01 + kMBox / 3.0 * (0.0025 + 0.0025) + kMBox * 0.01;
+constexpr double kDampLin = 0.01;
+constexpr double kDampYaw = 0.005;
+constexpr double kGear = 0.3;
+constexpr double kForceLimit = 0.05;
+// closed form of (M + h B) a = tau for M = [[m,0,-ks],[0,m,kc],[-ks,kc,I]]:
+//   a_th = (tau_th - (k b / m')(s vx - c vy)) / D,  D = I' - k^2 / m'
+//   a_x  = (tau_x + k s a_th) / m',  a_y = (tau_y - k c a_th) / m'
+constexpr double kK = kMass * kCom;
+constexpr double kMp = kMass + kH * kDampLin;
+constexpr double kIp = kIHinge + kH * kDampYaw;
+constexpr double kD = kIp - kK * kK / kMp;
+
+struct Body {
+  float X, Y, phi;   // world position and heading
+  float vx, vy, w;   // world velocity and yaw rate
+};
+
+CRL_HD float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+// n MuJoCo substeps with constant ctrl.  (c, s) = (cos phi, sin phi) is carried in
+// registers and advanced by the exact rotation of h*w each substep (|h w| < 0.01, so
+// a 5th-order series is exact to fp32), instead of n full-range sincosf calls.
+// Returns the final (c, s), renormalised, for the observation.
+CRL_HD void substeps(Body& b, float a0, float a1, int n, float& c_out, float& s_out) {
+  const float h = (float)kH;
+  const float bl = (float)kDampLin, bt = (float)kDampYaw, g = (float)kGear;
+  const float k = (float)kK, inv_m = (float)(1.0 / kMp), inv_D = (float)(1.0 / kD);
+  const float kb_m = (float)(kK * kDampLin / kMp);
+  const float Fm = g * clampf(clampf(a0, -1.f, 1.f), -(float)kForceLimit, (float)kForceLimit);
+  const float u1 = clampf(a1, -1.f, 1.f);
+  float s, c;
+  sincosf(b.phi, &s, &c);
+  float X = b.X, Y = b.Y, phi = b.phi, vx = b.vx, vy = b.vy, w = b.w;
+#pragma unroll 1
+  for (int i = 0; i < n; ++i) {
+    const float servo = clampf(u1 - g * w, -(float)kForceLimit, (float)kForceLimit);
+    const float tau_th = g * servo - bt * w;
+    const float a_th = (tau_th - kb_m * (s * vx - c * vy)) * inv_D;
+    const float drive = k * w * w + Fm;           // centrifugal + motor, along heading
+    const float tau_x = drive * c - bl * vx;
+    const float tau_y = drive * s - bl * vy;
+    const float ka = k * a_th;
+    const float ax = (tau_x + ka * s) * inv_m;
+    const float ay = (tau_y - ka * c) * inv_m;
+    vx += h * ax;
+    vy += h * ay;
+    w += h * a_th;
+    X += h * vx;
+    Y += h * vy;
+    const float d = h * w;
+    phi += d;
+    const float d2 = d * d;
+    const float sd = d * (1.f + d2 * (-1.f / 6.f + d2 * (1.f / 120.f)));
+    const float cd = 1.f + d2 * (-0.5f + d2 * (1.f / 24.f));
+    const float cn = c * cd - s * sd;
+    s = s * cd + c * sd;
+    c = cn;
+  }
+  b.X = X; b.Y = Y; b.phi = phi; b.vx = vx; b.vy = vy; b.w = w;
+  const float r = 1.0f / sqrtf(c * c + s * s);
+  c_out = c * r;
+  s_out = s * r;
+}
+
+// heading kept in [-pi, pi]: one conditional suffices (|dphi| per env step << pi).
+CRL_HD float wrap_pi(float phi) {
+  const float two_pi_hi = 6.2831855f;             // fl32(2 pi)
+  const float two_pi_lo = -1.7484555e-07f;        // 2 pi - fl32(2 pi)
+  const float pi = 3.14159265f;
+  if (phi > pi) phi = (phi - two_pi_hi) - two_pi_lo;
+  else if (phi < -pi) phi = (phi + two_pi_hi) + two_pi_lo;
+  return phi;
+}
+
+// Largest double t with sqrt(t) <= r: then  sqrt(d2) <= r  <=>  d2 <= t  exactly,
+// because IEEE sqrt is correctly rounded and monotone.  Host only.
+inline double sqrt_threshold(double r) {
+  double t = r * r;
+  while (sqrt(nextafter(t, INFINITY)) <= r) t = nextafter(t, INFINITY);
+  while (sqrt(t) > r) t = nextafter(t, -INFINITY);
+  return t;
+}
+
+// numpy: sqrt(sum(square(zone - robot))) <= size.  fl(fl(dx*dx) + fl(dy*dy)) with no
+// fused multiply-add, compared against the pre-searched squared threshold.
+CRL_HD bool inside_zone(float X, float Y, float zx, float zy, double thresh2) {
+  const double dx = (double)zx - (double)X;
+  const double dy = (double)zy - (double)Y;
+#if defined(__CUDA_ARCH__)
+  const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+#else
+  volatile double xx = dx * dx;
+  volatile double yy = dy * dy;
+  const double d2 = xx + yy;
+#endif
+  return d2 <= thresh2;
+}
+
+// fp32 screen: true if the exact test could possibly pass (d2 within 1e-4 of r^2).
+CRL_HD bool near_zone(float X, float Y, float zx, float zy, float r2_guard) {
+  const float dx = zx - X, dy = zy - Y;
+  return dx * dx + dy * dy <= r2_guard;
+}
+
+// colour_match_env.py:38-55 on 2-bit colour codes packed from bit 0 (0 B, 1 G, 2 R).
+CRL_HD int hamming(uint32_t colours, int n) {
+  int nb = 0, ng = 0, nr = 0;
+  for (int i = 0; i < n; ++i) {
+    const uint32_t c = (colours >> (2 * i)) & 3u;
+    nb += (c == 0u);
+    ng += (c == 1u);
+    nr += (c == 2u);
+  }
+  const int to_b = 2 * ng + nr, to_g = 2 * nr + nb, to_r = 2 * nb + ng;
+  int m = to_b < to_g ? to_b : to_g;
+  return m < to_r ? m : to_r;
+}
+
+// ---- Philox4x32-10 (Salmon et al. 2011, the Random123 constants) -----------
+struct U4 { uint32_t x, y, z, w; };
+
+CRL_HD void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#if defined(__CUDA_ARCH__)
+  hi = __umulhi(a, b);
+  lo = a * b;
+#else
+  const uint64_t p = (uint64_t)a * (uint64_t)b;
+  hi = (uint32_t)(p >> 32);
+  lo = (uint32_t)p;
+#endif
+}
+
+CRL_HD U4 philox4x32(U4 ctr, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t h0, l0, h1, l1;
+    mulhilo(0xD2511F53u, ctr.x, h0, l0);
+    mulhilo(0xCD9E8D57u, ctr.z, h1, l1);
+    U4 n;
+    n.x = h1 ^ ctr.y ^ k0;
+    n.y = l1;
+    n.z = h0 ^ ctr.w ^ k1;
+    n.w = l0;
+    ctr = n;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return ctr;
+}
+
+// 24-bit uniform in [0, 1)
+CRL_HD float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+// 53-bit uniform in (0, 1]: safe under log()
+CRL_HD double u01d(uint32_t hi, uint32_t lo) {
+  const uint64_t v = ((uint64_t)(hi >> 5) << 26) | (uint64_t)(lo >> 6);
+  return ((double)v + 1.0) * (1.0 / 9007199254740992.0);
+}
+
+// counter word 3 tags: which draw family a Philox block belongs to
+enum : uint32_t { kTagLayout = 1, kTagRot = 2, kTagTask = 3, kTagSeed = 4, kTagAction = 5 };
+
+}  // namespace crl

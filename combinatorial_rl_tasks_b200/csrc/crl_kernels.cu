@@ -1,0 +1,821 @@
+// crl_kernels.cu -- sm_100a kernels and the C ABI (include/crl_b200.h) of the
+// batched Point-robot zone-task simulator.
+//
+// One thread per env.  Per env-step a thread
+//   1. loads its state planes (two float4), its action (float2) and its N zone
+//      centres (float2 each, plane-major so every load is a coalesced 256-B row),
+//   2. tests the zone event on the PRE-physics position (TSP_env.py:54-69,
+//      colour_match_env.py:106-120) -- fp32 screen, exact fp64 confirm,
+//   3. integrates all frameskip substeps in registers (crl_core.cuh),
+//   4. applies reward / goal / timeout / done (TSP_env.py:37-42,71-72,
+//      TTSP_env.py:62-71, colour_match_env.py:86-93,122-123, Engine.step),
+//   5. if the env finished and auto-reset is on, its warp builds the next
+//      episode's layout cooperatively (32 rejection-sampling candidates per round),
+//   6. writes state, CrlResult, obs, and stages its zone_obs row in shared memory,
+//      from where each warp's 32 rows (one contiguous span of B x N x Z) leave with a
+//      single cp.async.bulk shared->global copy.
+// Episode statistics go through warp ballots and one atomic per warp.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/crl_b200.h"
+#include "crl_core.cuh"
+
+namespace crl {
+
+constexpr int kThreads = 128;
+constexpr int kWarps = kThreads / 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+struct KParams {
+  // config
+  int B, num_steps, frameskip, max_cd, seed_mode, env_offset;
+  long long min_seed, max_seed;
+  double thresh2;        // sqrt_threshold(zone_size)
+  float r2_guard;        // fp32 screen radius^2
+  double bonus_per_step; // time_saved_reward
+  double beta_a, beta_b;
+  float robot_keepout, zone_keepout, extent;
+  unsigned flags;
+  unsigned long long action_seed, step_index;
+  // state
+  float4* pose;
+  float4* aux;
+  float2* zone_xy;
+  uint32_t* zone_tmax;
+  uint2* cooldown;
+  long long* seed;
+  uint32_t* episode;
+  float4* origin;
+  double* counters;
+  // io
+  const float2* actions;
+  float4* obs;
+  float* zone_obs;
+  unsigned long long* result;  // CrlResult as one 8-byte word
+  const uint8_t* mask;
+};
+
+template <int TASK>
+struct ZoneDim { static constexpr int Z = (TASK == CRL_TASK_TSP) ? 6 : 7; };
+
+// Registers describing one env between load and store.
+template <int N>
+struct Env {
+  Body b;
+  float ep_return;
+  int steps;
+  uint32_t hi;        // visited mask or colour codes
+  float2 zone[N];
+  uint32_t tmax[(N + 1) / 2];
+  uint2 cd;
+};
+
+__device__ __forceinline__ uint32_t cd_get(const uint2& cd, int i) {
+  const uint32_t w = i < 4 ? cd.x : cd.y;
+  return (w >> (8 * (i & 3))) & 0xffu;
+}
+__device__ __forceinline__ void cd_set(uint2& cd, int i, uint32_t v) {
+  uint32_t& w = i < 4 ? cd.x : cd.y;
+  const int sh = 8 * (i & 3);
+  w = (w & ~(0xffu << sh)) | (v << sh);
+}
+// every positive byte minus one (colour_match_env.py:98-100), SWAR on 4 bytes
+__device__ __forceinline__ uint32_t cd_dec4(uint32_t w) {
+  // nonzero-byte mask: 0x01 in each byte that is > 0
+  const uint32_t nz = (((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) >> 7 & 0x01010101u;
+  return w - nz;
+}
+
+// ---- reset: draws for one env, made by a whole warp ---------------------------
+// Result of a cooperative reset, valid in every lane (broadcast).
+struct Fresh {
+  float x0, y0, rot0;
+  long long seed_after;
+};
+
+// Philox key = the Engine seed in force for the draw (two 32-bit halves).
+__device__ __forceinline__ U4 draw(long long seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t tag) {
+  U4 ctr{c0, c1, c2, tag};
+  return philox4x32(ctr, (uint32_t)(unsigned long long)seed, (uint32_t)((unsigned long long)seed >> 32));
+}
+
+// Marsaglia-Tsang gamma(a), a >= 1, from a counter stream (fp64: reset is off the hot path)
+__device__ double gamma_mt(long long seed, double a, uint32_t zone, uint32_t which) {
+  const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+  for (uint32_t it = 0;; ++it) {
+    const U4 r0 = draw(seed, it, zone, which, kTagTask);
+    const U4 r1 = draw(seed, it, zone, which + 2u, kTagTask);
+    const double u1 = u01d(r0.x, r0.y), u2 = u01d(r0.z, r0.w), u3 = u01d(r1.x, r1.y);
+    const double x = sqrt(-2.0 * log(u1)) * cos(2.0 * kPi * u2);   // Box-Muller
+    double v = 1.0 + c * x;
+    if (v <= 0.0) continue;
+    v = v * v * v;
+    if (log(u3) < 0.5 * x * x + d - d * v + d * log(v) || it > 64u) return d * v;
+  }
+}
+
+// Rejection-sample robot + N zones exactly as Engine.sample_layout orders it (object by
+// object, <= 100 tries each, first valid try wins, 100 misses abandon the layout), but
+// 32 tries at a time across the warp.  Candidate j of object k in attempt L is a pure
+// function of (seed, j, k, L), so the outcome equals the sequential procedure's.
+// `placed` is warp-private shared scratch of N+1 float2.
+template <int N>
+__device__ void warp_layout(const KParams& p, long long seed, float2* placed, int lane) {
+  const float ext = p.extent;
+#pragma unroll 1
+  for (uint32_t attempt = 0; attempt < 10000u; ++attempt) {
+    bool ok_layout = true;
+#pragma unroll 1
+    for (int k = 0; k <= N && ok_layout; ++k) {
+      const float keep = k == 0 ? p.robot_keepout : p.zone_keepout;
+      const float lo = -ext + keep, span = (ext - keep) - lo;
+      bool found = false;
+#pragma unroll 1
+      for (int base = 0; base < 100 && !found; base += 32) {
+        const int j = base + lane;
+        const U4 r = draw(seed, (uint32_t)j, (uint32_t)k, attempt, kTagLayout);
+        const float x = __fadd_rn(lo, __fmul_rn(span, u01(r.x)));
+        const float y = __fadd_rn(lo, __fmul_rn(span, u01(r.y)));
+        bool valid = j < 100;
+        for (int q = 0; q < k; ++q) {
+          const float2 o = placed[q];
+          const float need = __fadd_rn(q == 0 ? p.robot_keepout : p.zone_keepout, keep);
+          const float dx = __fsub_rn(x, o.x), dy = __fsub_rn(y, o.y);
+          const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+          valid = valid && (d2 >= __fmul_rn(need, need));
+        }
+        const unsigned m = __ballot_sync(kFull, valid);
+        if (m) {
+          const int wlane = __ffs(m) - 1;
+          const float wx = __shfl_sync(kFull, x, wlane), wy = __shfl_sync(kFull, y, wlane);
+          if (lane == 0) placed[k] = make_float2(wx, wy);
+          found = true;
+        }
+        __syncwarp();
+      }
+      ok_layout = found;
+    }
+    if (ok_layout) return;
+  }
+}
+
+// Full Engine.reset for the env held by lane `src`: seed choice, task draws with the
+// pre-increment seed, layout with the incremented one.  Lane `src` takes the result
+// into its registers and writes the reset-only planes.
+template <int TASK, int N>
+__device__ void warp_reset_one(const KParams& p, int src, int lane, int e, float2* placed, Env<N>& env) {
+  long long seed = 0;
+  uint32_t episode = 0;
+  if (lane == src) {
+    seed = p.seed[e];
+    episode = p.episode[e];
+    if (p.seed_mode == CRL_SEED_FIXED_RANGE) {
+      // FixedSeedsWrapper.reset: uniform integer in [min_seed, max_seed]; the chooser's
+      // own stream is keyed by the env's global index, counter = episode number
+      const unsigned long long span = (unsigned long long)(p.max_seed - p.min_seed) + 1ull;
+      const U4 r = draw((long long)(p.env_offset + e), episode, 0u, 0u, kTagSeed);
+      const unsigned long long v = ((unsigned long long)r.x << 32) | r.y;
+      seed = p.min_seed + (long long)(span ? (v % span) : v);
+    }
+  }
+  seed = __shfl_sync(kFull, seed, src);
+  // task draws use the seed BEFORE Engine.reset increments it (TTSP_env.py:20, colour_match_env.py:60)
+  uint32_t my_tmax = 0, my_col = 0;
+  if (TASK == CRL_TASK_TTSP && lane < N) {
+    const double ga = gamma_mt(seed, p.beta_a, (uint32_t)lane, 0u);
+    const double gb = gamma_mt(seed, p.beta_b, (uint32_t)lane, 1u);
+    int t = (int)((ga / (ga + gb)) * (double)p.num_steps);
+    my_tmax = (uint32_t)min(max(t, 0), 65535);
+  }
+  if (TASK == CRL_TASK_CM && lane < N) {
+    // uniform over {0,1,2} by masked rejection on 2-bit fields
+    uint32_t c = 3u;
+    for (uint32_t it = 0; c == 3u && it < 64u; ++it) {
+      const U4 r = draw(seed, it, (uint32_t)lane, 0u, kTagTask);
+      uint32_t bits = r.x;
+      for (int q = 0; q < 16 && c == 3u; ++q, bits >>= 2) c = bits & 3u;
+    }
+    my_col = c == 3u ? 0u : c;
+  }
+  const long long seed_after = seed + 1;   // Engine.reset: self._seed += 1
+  warp_layout<N>(p, seed_after, placed, lane);
+  const U4 rr = draw(seed_after, 0u, 0u, 0u, kTagRot);
+  const float rot0 = __fmul_rn(6.2831855f, u01(rr.x));
+  __syncwarp();
+  // gather per-lane draws to lane src
+  uint32_t col_word = 0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const uint32_t t = __shfl_sync(kFull, my_tmax, i);
+    const uint32_t c = __shfl_sync(kFull, my_col, i);
+    if (lane == src) {
+      if (TASK == CRL_TASK_TTSP) {
+        if (i & 1) env.tmax[i >> 1] |= t << 16; else env.tmax[i >> 1] = t;
+      }
+      col_word |= c << (2 * i);
+    }
+  }
+  if (lane == src) {
+    const float2 r0 = placed[0];
+    env.b.X = r0.x; env.b.Y = r0.y; env.b.phi = wrap_pi(rot0);
+    env.b.vx = env.b.vy = env.b.w = 0.f;
+    env.ep_return = 0.f;
+    env.steps = 0;
+    env.hi = TASK == CRL_TASK_CM ? col_word : 0u;
+    env.cd = make_uint2(0u, 0u);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      env.zone[i] = placed[1 + i];
+      p.zone_xy[(size_t)i * p.B + e] = env.zone[i];
+    }
+    if (TASK == CRL_TASK_TTSP) {
+#pragma unroll
+      for (int j = 0; j < (N + 1) / 2; ++j) p.zone_tmax[(size_t)j * p.B + e] = env.tmax[j];
+    }
+    p.seed[e] = seed_after;
+    p.episode[e] = episode + 1u;
+    p.origin[e] = make_float4(r0.x, r0.y, rot0, 0.f);
+  }
+  __syncwarp();
+}
+
+// ---- observation and store: shared by step, reset and reset_from_layout -------
+template <int TASK, int N>
+__device__ __forceinline__ void zone_row(const KParams& p, const Env<N>& env, float* row) {
+  constexpr int Z = ZoneDim<TASK>::Z;
+  const float third = 1.0f / 3.0f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    float r, g, b;
+    if (TASK == CRL_TASK_CM) {
+      const uint32_t c = (env.hi >> (2 * i)) & 3u;   // 0 B, 1 G, 2 R (ZoneEnvBase.py:68-77)
+      r = c == 2u ? 1.f : 0.f; g = c == 1u ? 1.f : 0.f; b = c == 0u ? 1.f : 0.f;
+    } else {
+      const bool v = (env.hi >> i) & 1u;             // Yellow (1,1,0) / Cyan (0,1,1), TSP_env.py:9-10
+      r = v ? 1.f : 0.f; g = 1.f; b = v ? 0.f : 1.f;
+    }
+    float* z = row + i * Z;
+    if (Z == 6) {
+      reinterpret_cast<float2*>(z)[0] = make_float2(env.zone[i].x * third, env.zone[i].y * third);
+      reinterpret_cast<float2*>(z)[1] = make_float2(r, g);
+      reinterpret_cast<float2*>(z)[2] = make_float2(b, 0.25f);
+    } else {
+      z[0] = env.zone[i].x * third; z[1] = env.zone[i].y * third;
+      z[2] = r; z[3] = g; z[4] = b; z[5] = 0.25f;
+      if (TASK == CRL_TASK_TTSP) {
+        const bool v = (env.hi >> i) & 1u;
+        const int tm = (int)((env.tmax[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+        // TTSP_env.py:23-27: (zone_max_steps - steps) / max_steps in fp64, visited -> 1
+        z[6] = v ? 1.0f : (float)((double)(tm - env.steps) / (double)p.num_steps);
+      } else {
+        // colour_match_env.py:79: np.float32(cooldown) / 150 is a float32 division
+        z[6] = __fdiv_rn((float)cd_get(env.cd, i), (float)p.max_cd);
+      }
+    }
+  }
+}
+
+template <int TASK, int N>
+__device__ __forceinline__ void store_env(const KParams& p, const Env<N>& env, int e, bool valid,
+                                          float c, float s, float* stage, int lane, int warp_env0) {
+  constexpr int Z = ZoneDim<TASK>::Z;
+  constexpr int ROW = N * Z;
+  if (valid) {
+    p.pose[e] = make_float4(env.b.X, env.b.Y, env.b.phi, env.b.vx);
+    p.aux[e] = make_float4(env.b.vy, env.b.w, env.ep_return,
+                           __int_as_float((int)((uint32_t)env.steps | (env.hi << 16))));
+    if (TASK == CRL_TASK_CM) p.cooldown[e] = env.cd;
+    // ZoneEnvBase.py:190-192, 220-224; order fixed by wrappers.py:136-142
+    const float remaining = (float)(1.0 - (double)env.steps / (double)p.num_steps);
+    p.obs[2 * (size_t)e] = make_float4(remaining, env.b.X * (1.0f / 3.0f), env.b.Y * (1.0f / 3.0f), c);
+    p.obs[2 * (size_t)e + 1] = make_float4(s, env.b.vx * (1.0f / 1.5f), env.b.vy * (1.0f / 1.5f),
+                                           env.b.w * (1.0f / 3.0f));
+    zone_row<TASK, N>(p, env, stage + lane * ROW);
+  }
+  // the warp's rows are one contiguous span of zone_obs: one bulk copy moves them
+  const int n_valid = min(32, p.B - warp_env0);
+  const uint32_t bytes = (uint32_t)n_valid * ROW * 4u;
+  float* gdst = p.zone_obs + (size_t)warp_env0 * ROW;
+  if ((bytes & 15u) == 0u) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0 && n_valid > 0) {
+      const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(stage);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                   :: "l"(gdst), "r"(saddr), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+  } else {
+    __syncwarp();
+    for (int i = lane; i < n_valid * ROW; i += 32) gdst[i] = stage[i];
+  }
+}
+
+template <int TASK, int N>
+__device__ __forceinline__ void load_env(const KParams& p, int e, Env<N>& env) {
+  const float4 ps = p.pose[e];
+  const float4 ax = p.aux[e];
+#pragma unroll
+  for (int i = 0; i < N; ++i) env.zone[i] = p.zone_xy[(size_t)i * p.B + e];
+  if (TASK == CRL_TASK_TTSP) {
+#pragma unroll
+    for (int j = 0; j < (N + 1) / 2; ++j) env.tmax[j] = p.zone_tmax[(size_t)j * p.B + e];
+  }
+  if (TASK == CRL_TASK_CM) env.cd = p.cooldown[e];
+  env.b.X = ps.x; env.b.Y = ps.y; env.b.phi = ps.z; env.b.vx = ps.w;
+  env.b.vy = ax.x; env.b.w = ax.y; env.ep_return = ax.z;
+  const uint32_t bits = (uint32_t)__float_as_int(ax.w);
+  env.steps = (int)(bits & 0xffffu);
+  env.hi = bits >> 16;
+}
+
+// ---- the fused step ---------------------------------------------------------------
+template <int TASK, int N>
+__global__ void __launch_bounds__(kThreads) step_kernel(const KParams p) {
+  constexpr int Z = ZoneDim<TASK>::Z;
+  constexpr int ROW = N * Z;
+  extern __shared__ __align__(128) float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int e = blockIdx.x * kThreads + threadIdx.x;
+  const int warp_env0 = blockIdx.x * kThreads + warp * 32;
+  const bool valid = e < p.B;
+  float* stage = smem + warp * (32 * ROW);
+
+  Env<N> env;
+  float2 act = make_float2(0.f, 0.f);
+  if (valid) {
+    load_env<TASK, N>(p, e, env);
+    if (p.actions) {
+      act = p.actions[e];
+    } else {
+      const unsigned ge = (unsigned)(p.env_offset + e);
+      U4 ctr{ge, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32), kTagAction};
+      const U4 r = philox4x32(ctr, (uint32_t)p.action_seed, (uint32_t)(p.action_seed >> 32));
+      act = make_float2(2.f * u01(r.x) - 1.f, 2.f * u01(r.y) - 1.f);
+    }
+  } else {
+    env.b = Body{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    env.ep_return = 0.f; env.steps = 0; env.hi = 0u; env.cd = make_uint2(0u, 0u);
+#pragma unroll
+    for (int i = 0; i < N; ++i) env.zone[i] = make_float2(1e9f, 1e9f);
+#pragma unroll
+    for (int j = 0; j < (N + 1) / 2; ++j) env.tmax[j] = 0xffffffffu;
+  }
+
+  float c, s;
+  bool done = false, goal = false;
+  int event = 0;
+  float reward = 0.f;
+  if (p.flags & CRL_STEP_PHYSICS_ONLY) {
+    substeps(env.b, act.x, act.y, p.frameskip, c, s);
+    env.b.phi = wrap_pi(env.b.phi);
+  } else {
+    // (1) ColourMatch cooldowns tick before anything else (colour_match_env.py:98-100)
+    if (TASK == CRL_TASK_CM) { env.cd.x = cd_dec4(env.cd.x); env.cd.y = cd_dec4(env.cd.y); }
+    // (2) zone event on the pre-physics position: first eligible zone in index order
+    int fired = -1;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const bool eligible = TASK == CRL_TASK_CM ? (cd_get(env.cd, i) == 0u) : !((env.hi >> i) & 1u);
+      if (fired < 0 && eligible && near_zone(env.b.X, env.b.Y, env.zone[i].x, env.zone[i].y, p.r2_guard)) {
+        if (inside_zone(env.b.X, env.b.Y, env.zone[i].x, env.zone[i].y, p.thresh2)) fired = i;
+      }
+    }
+    int old_dist = 0;
+    if (TASK == CRL_TASK_CM) old_dist = hamming(env.hi, N);
+    if (fired >= 0) {
+      if (TASK == CRL_TASK_CM) {
+        const uint32_t col = (env.hi >> (2 * fired)) & 3u;
+        const uint32_t nxt = col == 2u ? 0u : col + 1u;         // Blue -> Green -> Red -> Blue
+        env.hi = (env.hi & ~(3u << (2 * fired))) | (nxt << (2 * fired));
+        cd_set(env.cd, fired, (uint32_t)p.max_cd);
+      } else {
+        env.hi |= 1u << fired;
+      }
+    }
+    // (3) physics
+    substeps(env.b, act.x, act.y, p.frameskip, c, s);
+    env.b.phi = wrap_pi(env.b.phi);
+    // (4) reward, goal, timeout
+    if (TASK == CRL_TASK_CM) {
+      const int new_dist = hamming(env.hi, N);
+      event = fired >= 0 ? old_dist - new_dist : 0;
+      goal = new_dist == 0;
+    } else {
+      event = fired >= 0 ? 1 : 0;
+      goal = env.hi == ((1u << N) - 1u);
+    }
+    double rew = (double)event;
+    if (goal) { rew += (double)(p.num_steps - env.steps) * p.bonus_per_step; done = true; }
+    reward = (float)rew;
+    env.steps += 1;
+    if (env.steps >= p.num_steps) done = true;
+    if (TASK == CRL_TASK_TTSP && !done) {
+      // TTSP_env.py:67: any unvisited zone with (zone_max_steps - steps) / max_steps <= 0
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const int tm = (int)((env.tmax[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+        if (!((env.hi >> i) & 1u) && env.steps >= tm) done = true;
+      }
+    }
+    env.ep_return += reward;
+    done = done && valid;
+    goal = goal && valid;
+    // (5) result word and episode statistics
+    if (valid) {
+      const unsigned long long word = (unsigned long long)__float_as_uint(reward) |
+          ((unsigned long long)(done ? 1u : 0u) << 32) | ((unsigned long long)(goal ? 1u : 0u) << 40) |
+          ((unsigned long long)(uint8_t)(int8_t)event << 48);
+      p.result[e] = word;
+    }
+    const unsigned dm = __ballot_sync(kFull, done);
+    if (dm) {
+      float ret = done ? env.ep_return : 0.f;
+      float len = done ? (float)env.steps : 0.f;
+      const unsigned gm = __ballot_sync(kFull, goal);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ret += __shfl_xor_sync(kFull, ret, o);
+        len += __shfl_xor_sync(kFull, len, o);
+      }
+      if (lane == 0) {
+        atomicAdd(p.counters + 0, (double)ret);
+        atomicAdd(p.counters + 1, (double)__popc(dm));
+        atomicAdd(p.counters + 2, (double)__popc(gm));
+        atomicAdd(p.counters + 3, (double)len);
+      }
+      // (6) auto-reset, penv.py:9-10: only the finished envs are rebuilt
+      if (p.flags & CRL_STEP_AUTO_RESET) {
+        float2* placed = reinterpret_cast<float2*>(stage);
+        unsigned m = dm;
+        while (m) {
+          const int src = __ffs(m) - 1;
+          m &= m - 1;
+          const int se = __shfl_sync(kFull, e, src);
+          warp_reset_one<TASK, N>(p, src, lane, se, placed, env);
+        }
+        if (done) { sincosf(env.b.phi, &s, &c); }
+      }
+    }
+  }
+  store_env<TASK, N>(p, env, e, valid, c, s, stage, lane, warp_env0);
+}
+
+// Engine.reset on the device for masked envs.
+template <int TASK, int N>
+__global__ void __launch_bounds__(kThreads) reset_kernel(const KParams p) {
+  constexpr int ROW = N * ZoneDim<TASK>::Z;
+  extern __shared__ __align__(128) float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int e = blockIdx.x * kThreads + threadIdx.x;
+  const int warp_env0 = blockIdx.x * kThreads + warp * 32;
+  const bool valid = e < p.B;
+  float* stage = smem + warp * (32 * ROW);
+  Env<N> env;
+  if (valid) load_env<TASK, N>(p, e, env);
+  const bool want = valid && (p.mask == nullptr || p.mask[e] != 0);
+  unsigned m = __ballot_sync(kFull, want);
+  float2* placed = reinterpret_cast<float2*>(stage);
+  while (m) {
+    const int src = __ffs(m) - 1;
+    m &= m - 1;
+    const int se = __shfl_sync(kFull, e, src);
+    warp_reset_one<TASK, N>(p, src, lane, se, placed, env);
+  }
+  float c = 1.f, s = 0.f;
+  if (valid) sincosf(env.b.phi, &s, &c);
+  // envs that were not reset are rewritten with the values just loaded (no change)
+  store_env<TASK, N>(p, env, e, valid, c, s, stage, lane, warp_env0);
+}
+
+// Host-supplied layouts: one thread per listed env.  Rows are written directly (this
+// path serves equivalence tests, not throughput).
+struct LayoutParams {
+  const double* xy0; const double* rot0; const double* zone_xy;
+  const int32_t* zone_max_steps; const int32_t* colours; const int32_t* env_ids; int n;
+};
+
+template <int TASK, int N>
+__global__ void reset_from_layout_kernel(const KParams p, const LayoutParams L) {
+  constexpr int ROW = N * ZoneDim<TASK>::Z;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L.n) return;
+  const int e = L.env_ids ? L.env_ids[i] : i;
+  if (e < 0 || e >= p.B) return;
+  Env<N> env;
+  const float rot0 = (float)L.rot0[i];
+  env.b = Body{(float)L.xy0[2 * i], (float)L.xy0[2 * i + 1], wrap_pi(rot0), 0.f, 0.f, 0.f};
+  env.ep_return = 0.f; env.steps = 0; env.hi = 0u; env.cd = make_uint2(0u, 0u);
+#pragma unroll
+  for (int j = 0; j < (N + 1) / 2; ++j) env.tmax[j] = 0u;
+#pragma unroll
+  for (int z = 0; z < N; ++z) {
+    env.zone[z] = make_float2((float)L.zone_xy[((size_t)i * N + z) * 2], (float)L.zone_xy[((size_t)i * N + z) * 2 + 1]);
+    p.zone_xy[(size_t)z * p.B + e] = env.zone[z];
+    if (TASK == CRL_TASK_TTSP) {
+      const uint32_t t = (uint32_t)min(max(L.zone_max_steps[(size_t)i * N + z], 0), 65535);
+      env.tmax[z >> 1] |= t << (16 * (z & 1));
+    }
+    if (TASK == CRL_TASK_CM) env.hi |= ((uint32_t)L.colours[(size_t)i * N + z] & 3u) << (2 * z);
+  }
+  if (TASK == CRL_TASK_TTSP) {
+#pragma unroll
+    for (int j = 0; j < (N + 1) / 2; ++j) p.zone_tmax[(size_t)j * p.B + e] = env.tmax[j];
+  }
+  p.episode[e] += 1u;
+  p.origin[e] = make_float4(env.b.X, env.b.Y, rot0, 0.f);
+  p.pose[e] = make_float4(env.b.X, env.b.Y, env.b.phi, 0.f);
+  p.aux[e] = make_float4(0.f, 0.f, 0.f, __int_as_float((int)(env.hi << 16)));
+  if (TASK == CRL_TASK_CM) p.cooldown[e] = env.cd;
+  float c, s;
+  sincosf(env.b.phi, &s, &c);
+  p.obs[2 * (size_t)e] = make_float4(1.0f, env.b.X * (1.0f / 3.0f), env.b.Y * (1.0f / 3.0f), c);
+  p.obs[2 * (size_t)e + 1] = make_float4(s, 0.f, 0.f, 0.f);
+  __align__(16) float row[ROW];
+  zone_row<TASK, N>(p, env, row);
+  float* g = p.zone_obs + (size_t)e * ROW;
+#pragma unroll
+  for (int k = 0; k < ROW; ++k) g[k] = row[k];
+}
+
+// qpos/qvel <-> world frame: world = xy0 + R(rot0) q_xy, heading = rot0 + q_theta.
+__global__ void set_qpos_qvel_kernel(const KParams p, const double* qpos, const double* qvel,
+                                     const int32_t* env_ids, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int e = env_ids ? env_ids[i] : i;
+  if (e < 0 || e >= p.B) return;
+  const float4 o = p.origin[e];
+  const double c0 = cos((double)o.z), s0 = sin((double)o.z);
+  const double x = qpos[3 * i], y = qpos[3 * i + 1], th = qpos[3 * i + 2];
+  const double vx = qvel[3 * i], vy = qvel[3 * i + 1];
+  double phi = fmod((double)o.z + th, 2.0 * kPi);
+  if (phi > kPi) phi -= 2.0 * kPi;
+  if (phi < -kPi) phi += 2.0 * kPi;
+  float4 ps = p.pose[e], ax = p.aux[e];
+  ps.x = (float)((double)o.x + c0 * x - s0 * y);
+  ps.y = (float)((double)o.y + s0 * x + c0 * y);
+  ps.z = (float)phi;
+  ps.w = (float)(c0 * vx - s0 * vy);
+  ax.x = (float)(s0 * vx + c0 * vy);
+  ax.y = (float)qvel[3 * i + 2];
+  p.pose[e] = ps;
+  p.aux[e] = ax;
+}
+
+__global__ void get_qpos_qvel_kernel(const KParams p, double* qpos, double* qvel,
+                                     const int32_t* env_ids, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int e = env_ids ? env_ids[i] : i;
+  if (e < 0 || e >= p.B) return;
+  const float4 o = p.origin[e];
+  const float4 ps = p.pose[e], ax = p.aux[e];
+  const double c0 = cos((double)o.z), s0 = sin((double)o.z);
+  const double dx = (double)ps.x - (double)o.x, dy = (double)ps.y - (double)o.y;
+  qpos[3 * i] = c0 * dx + s0 * dy;
+  qpos[3 * i + 1] = -s0 * dx + c0 * dy;
+  qpos[3 * i + 2] = (double)ps.z - (double)o.z;   // modulo 2 pi: the heading is kept wrapped
+  qvel[3 * i] = c0 * (double)ps.w + s0 * (double)ax.x;
+  qvel[3 * i + 1] = -s0 * (double)ps.w + c0 * (double)ax.x;
+  qvel[3 * i + 2] = (double)ax.y;
+}
+
+// ---- host side ---------------------------------------------------------------------
+static int zone_dim(int task) { return task == CRL_TASK_TSP ? 6 : 7; }
+
+static int check_config(const CrlConfig* c) {
+  if (!c) return CRL_ERR_NULL;
+  if (c->task < 0 || c->task > 2) return CRL_ERR_CONFIG;
+  if (c->num_envs <= 0 || c->num_zones <= 0 || c->num_zones > CRL_MAX_ZONES) return CRL_ERR_CONFIG;
+  if (c->task == CRL_TASK_CM && c->num_zones > 8) return CRL_ERR_CONFIG;
+  if (c->num_steps <= 0 || c->num_steps > 65535) return CRL_ERR_CONFIG;
+  if (c->frameskip < 0 || c->max_cooldown < 0 || c->max_cooldown > 255) return CRL_ERR_CONFIG;
+  if (c->seed_mode == CRL_SEED_FIXED_RANGE && c->max_seed < c->min_seed) return CRL_ERR_CONFIG;
+  if (!(c->zone_size > 0.0)) return CRL_ERR_CONFIG;
+  return CRL_OK;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int fill_params(const CrlConfig* c, const CrlState* st, const CrlOut* out, KParams& p) {
+  int rc = check_config(c);
+  if (rc) return rc;
+  if (!st || !st->pose || !st->aux || !st->zone_xy || !st->seed || !st->episode || !st->origin || !st->counters)
+    return CRL_ERR_NULL;
+  if (c->task == CRL_TASK_TTSP && !st->zone_tmax) return CRL_ERR_NULL;
+  if (c->task == CRL_TASK_CM && !st->cooldown) return CRL_ERR_NULL;
+  if (!aligned16(st->pose) || !aligned16(st->aux) || !aligned16(st->zone_xy) || !aligned16(st->origin))
+    return CRL_ERR_ALIGN;
+  memset(&p, 0, sizeof(p));
+  p.B = c->num_envs; p.num_steps = c->num_steps; p.frameskip = c->frameskip; p.max_cd = c->max_cooldown;
+  p.seed_mode = c->seed_mode; p.env_offset = c->env_offset; p.min_seed = c->min_seed; p.max_seed = c->max_seed;
+  p.thresh2 = sqrt_threshold(c->zone_size);
+  p.r2_guard = (float)(c->zone_size * c->zone_size * 1.001 + 1e-5);
+  p.bonus_per_step = c->time_saved_reward;
+  p.beta_a = c->beta_a; p.beta_b = c->beta_b;
+  p.robot_keepout = (float)c->robot_keepout; p.zone_keepout = (float)c->zone_keepout; p.extent = (float)c->extent;
+  p.pose = reinterpret_cast<float4*>(st->pose); p.aux = reinterpret_cast<float4*>(st->aux);
+  p.zone_xy = reinterpret_cast<float2*>(st->zone_xy); p.zone_tmax = st->zone_tmax;
+  p.cooldown = reinterpret_cast<uint2*>(st->cooldown);
+  p.seed = reinterpret_cast<long long*>(st->seed); p.episode = st->episode;
+  p.origin = reinterpret_cast<float4*>(st->origin); p.counters = st->counters;
+  if (out) {
+    if (!out->obs || !out->zone_obs || !out->result) return CRL_ERR_NULL;
+    if (!aligned16(out->obs) || !aligned16(out->zone_obs)) return CRL_ERR_ALIGN;
+    p.obs = reinterpret_cast<float4*>(out->obs); p.zone_obs = out->zone_obs;
+    p.result = reinterpret_cast<unsigned long long*>(out->result);
+  }
+  return CRL_OK;
+}
+
+static int launch_status() { return cudaGetLastError() == cudaSuccess ? CRL_OK : CRL_ERR_LAUNCH; }
+
+// (task, N) pairs with compiled kernels
+#define CRL_DISPATCH(task, n, CALL)                                              \
+  do {                                                                           \
+    if ((task) == CRL_TASK_TSP && (n) == 15) { CALL(CRL_TASK_TSP, 15); }         \
+    else if ((task) == CRL_TASK_TSP && (n) == 5) { CALL(CRL_TASK_TSP, 5); }      \
+    else if ((task) == CRL_TASK_TTSP && (n) == 15) { CALL(CRL_TASK_TTSP, 15); }  \
+    else if ((task) == CRL_TASK_TTSP && (n) == 5) { CALL(CRL_TASK_TTSP, 5); }    \
+    else if ((task) == CRL_TASK_CM && (n) == 6) { CALL(CRL_TASK_CM, 6); }        \
+    else return CRL_ERR_UNSUPPORTED;                                             \
+  } while (0)
+
+// opt in to > 48 KB dynamic shared memory once per kernel
+static int set_smem(void (*kernel)(const KParams), size_t bytes) {
+  static void (*done_for[32])(const KParams) = {nullptr};
+  if (bytes <= 48 * 1024) return CRL_OK;
+  for (int i = 0; i < 32; ++i) {
+    if (done_for[i] == kernel) return CRL_OK;
+    if (done_for[i] == nullptr) {
+      if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+        return CRL_ERR_DEVICE;
+      done_for[i] = kernel;
+      return CRL_OK;
+    }
+  }
+  return CRL_ERR_DEVICE;
+}
+
+}  // namespace crl
+
+using namespace crl;
+
+extern "C" {
+
+int crl_abi_version(void) { return CRL_ABI_VERSION; }
+
+const char* crl_strerror(int code) {
+  switch (code) {
+    case CRL_OK: return "ok";
+    case CRL_ERR_NULL: return "a required pointer is NULL";
+    case CRL_ERR_CONFIG: return "CrlConfig out of range";
+    case CRL_ERR_ALIGN: return "a float4 plane is not 16-byte aligned";
+    case CRL_ERR_UNSUPPORTED: return "no kernel compiled for this (task, num_zones)";
+    case CRL_ERR_LAUNCH: return "CUDA launch failed";
+    case CRL_ERR_DEVICE: return "CUDA device/runtime error";
+    default: return "unknown error";
+  }
+}
+
+int crl_plane_bytes(const CrlConfig* c, int64_t o[12]) {
+  int rc = check_config(c);
+  if (rc) return rc;
+  if (!o) return CRL_ERR_NULL;
+  const int64_t B = c->num_envs, N = c->num_zones, Z = zone_dim(c->task);
+  o[0] = 16 * B; o[1] = 16 * B; o[2] = 8 * N * B;
+  o[3] = c->task == CRL_TASK_TTSP ? 4 * ((N + 1) / 2) * B : 0;
+  o[4] = c->task == CRL_TASK_CM ? 8 * B : 0;
+  o[5] = 8 * B; o[6] = 4 * B; o[7] = 16 * B; o[8] = 4 * 8;
+  o[9] = 32 * B; o[10] = 4 * N * Z * B; o[11] = 8 * B;
+  return CRL_OK;
+}
+
+int crl_step_bytes(const CrlConfig* c, int64_t* rd, int64_t* wr) {
+  int rc = check_config(c);
+  if (rc) return rc;
+  if (!rd || !wr) return CRL_ERR_NULL;
+  const int64_t N = c->num_zones, Z = zone_dim(c->task);
+  int64_t r = 8 /*action*/ + 32 /*pose+aux*/ + 8 * N, w = 32 + 8 /*result*/ + 32 /*obs*/ + 4 * N * Z;
+  if (c->task == CRL_TASK_TTSP) r += 4 * ((N + 1) / 2);
+  if (c->task == CRL_TASK_CM) { r += 8; w += 8; }
+  *rd = r; *wr = w;
+  return CRL_OK;
+}
+
+int crl_step(const CrlConfig* c, const CrlState* st, const float* actions, const CrlOut* out,
+             uint32_t flags, uint64_t action_seed, uint64_t step_index, void* stream) {
+  KParams p;
+  if (!out) return CRL_ERR_NULL;
+  int rc = fill_params(c, st, out, p);
+  if (rc) return rc;
+  if (actions && (reinterpret_cast<uintptr_t>(actions) & 7u)) return CRL_ERR_ALIGN;
+  p.actions = reinterpret_cast<const float2*>(actions);
+  p.flags = flags; p.action_seed = action_seed; p.step_index = step_index;
+  const int blocks = (p.B + kThreads - 1) / kThreads;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define CRL_CALL_STEP(T, NN)                                                        \
+  {                                                                                 \
+    const size_t sm = (size_t)kThreads * NN * ZoneDim<T>::Z * 4;                    \
+    rc = set_smem(step_kernel<T, NN>, sm);                                          \
+    if (rc) return rc;                                                              \
+    step_kernel<T, NN><<<blocks, kThreads, sm, s>>>(p);                             \
+  }
+  CRL_DISPATCH(c->task, c->num_zones, CRL_CALL_STEP);
+  return launch_status();
+}
+
+int crl_reset(const CrlConfig* c, const CrlState* st, const CrlOut* out, const uint8_t* mask, void* stream) {
+  KParams p;
+  if (!out) return CRL_ERR_NULL;
+  int rc = fill_params(c, st, out, p);
+  if (rc) return rc;
+  p.mask = mask;
+  const int blocks = (p.B + kThreads - 1) / kThreads;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define CRL_CALL_RESET(T, NN)                                                       \
+  {                                                                                 \
+    const size_t sm = (size_t)kThreads * NN * ZoneDim<T>::Z * 4;                    \
+    rc = set_smem(reset_kernel<T, NN>, sm);                                         \
+    if (rc) return rc;                                                              \
+    reset_kernel<T, NN><<<blocks, kThreads, sm, s>>>(p);                            \
+  }
+  CRL_DISPATCH(c->task, c->num_zones, CRL_CALL_RESET);
+  return launch_status();
+}
+
+int crl_reset_from_layout(const CrlConfig* c, const CrlState* st, const CrlOut* out, const CrlLayoutIn* lay,
+                          const int32_t* env_ids, int32_t n, void* stream) {
+  KParams p;
+  if (!out || !lay || !lay->xy0 || !lay->rot0 || !lay->zone_xy) return CRL_ERR_NULL;
+  int rc = fill_params(c, st, out, p);
+  if (rc) return rc;
+  if (c->task == CRL_TASK_TTSP && !lay->zone_max_steps) return CRL_ERR_NULL;
+  if (c->task == CRL_TASK_CM && !lay->colours) return CRL_ERR_NULL;
+  if (n < 0 || n > c->num_envs) return CRL_ERR_CONFIG;
+  if (n == 0) return CRL_OK;
+  LayoutParams L{lay->xy0, lay->rot0, lay->zone_xy, lay->zone_max_steps, lay->colours, env_ids, n};
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define CRL_CALL_LAYOUT(T, NN) { reset_from_layout_kernel<T, NN><<<(n + 127) / 128, 128, 0, s>>>(p, L); }
+  CRL_DISPATCH(c->task, c->num_zones, CRL_CALL_LAYOUT);
+  return launch_status();
+}
+
+int crl_set_qpos_qvel(const CrlConfig* c, const CrlState* st, const double* qpos, const double* qvel,
+                      const int32_t* env_ids, int32_t n, void* stream) {
+  KParams p;
+  if (!qpos || !qvel) return CRL_ERR_NULL;
+  int rc = fill_params(c, st, nullptr, p);
+  if (rc) return rc;
+  if (n <= 0) return n == 0 ? CRL_OK : CRL_ERR_CONFIG;
+  set_qpos_qvel_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(p, qpos, qvel, env_ids, n);
+  return launch_status();
+}
+
+int crl_get_qpos_qvel(const CrlConfig* c, const CrlState* st, double* qpos, double* qvel,
+                      const int32_t* env_ids, int32_t n, void* stream) {
+  KParams p;
+  if (!qpos || !qvel) return CRL_ERR_NULL;
+  int rc = fill_params(c, st, nullptr, p);
+  if (rc) return rc;
+  if (n <= 0) return n == 0 ? CRL_OK : CRL_ERR_CONFIG;
+  get_qpos_qvel_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(p, qpos, qvel, env_ids, n);
+  return launch_status();
+}
+
+int crl_step_host(const CrlConfig* c, const CrlState* st, const float* actions_host, float* actions_dev,
+                  const CrlOut* out, const CrlOut* host_out, uint32_t flags, void* stream) {
+  if (!c || !actions_host || !actions_dev || !out || !host_out || !host_out->obs || !host_out->zone_obs ||
+      !host_out->result)
+    return CRL_ERR_NULL;
+  int rc = check_config(c);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t B = c->num_envs, N = c->num_zones, Z = zone_dim(c->task);
+  if (cudaMemcpyAsync(actions_dev, actions_host, B * 8, cudaMemcpyHostToDevice, s) != cudaSuccess) return CRL_ERR_DEVICE;
+  rc = crl_step(c, st, actions_dev, out, flags, 0, 0, stream);
+  if (rc) return rc;
+  if (cudaMemcpyAsync(host_out->obs, out->obs, B * 32, cudaMemcpyDeviceToHost, s) != cudaSuccess) return CRL_ERR_DEVICE;
+  if (cudaMemcpyAsync(host_out->zone_obs, out->zone_obs, B * N * Z * 4, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+    return CRL_ERR_DEVICE;
+  if (cudaMemcpyAsync(host_out->result, out->result, B * 8, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+    return CRL_ERR_DEVICE;
+  if (cudaStreamSynchronize(s) != cudaSuccess) return CRL_ERR_DEVICE;
+  return CRL_OK;
+}
+
+int crl_counters_read(const CrlState* st, double out[4], void* stream) {
+  if (!st || !st->counters || !out) return CRL_ERR_NULL;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (cudaMemcpyAsync(out, st->counters, 4 * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess)
+    return CRL_ERR_DEVICE;
+  if (cudaStreamSynchronize(s) != cudaSuccess) return CRL_ERR_DEVICE;
+  return CRL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,245 @@
+"""ZoneVecEnv: the reference's vector-env surface on one B200.
+
+Stands where ``ParallelEnv([make_train_env(...) for _ in range(B)])`` stands in the
+reference (main/src/torch_ac/torch_utils/penv.py:23-69 over main/envs/make_env.py:3-51):
+``reset() / step(actions) / step_no_reset(actions) / seed(...)``, attributes ``envs``,
+``observation_space``, ``action_space``.  Differences, all by design:
+
+* one object holds all B envs; every per-env Python list becomes a device tensor:
+  ``obs['obs']`` (B,8) f32, ``obs['zone_obs']`` (B,N,Z) f32 (the layout
+  main/src/utils/format.py:27-28 builds), ``reward`` (B,) f32, ``done`` (B,) bool,
+  ``info`` = dict of tensors {'goal_met' (B,) bool, 'cost' zeros, 'event' (B,) int8};
+* the returned tensors are persistent buffers owned by the env and overwritten by the
+  next call (clone what must outlive a step);
+* calls are asynchronous on the current CUDA stream.
+
+All arithmetic happens in libcrl_b200.so (include/crl_b200.h); torch only owns the
+memory.  There is no CPU path.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import ENV_SPECS
+from .spaces import Box, Dict
+
+
+class _EnvView:
+    """What ``penv.envs[i]`` must answer for the reference's callers."""
+
+    def __init__(self, vec, index):
+        self._vec, self.index = vec, index
+        self.observation_space = vec.observation_space
+        self.action_space = vec.action_space
+
+    @property
+    def unwrapped(self):
+        return self
+
+    @property
+    def num_cities(self):
+        return self._vec.spec.num_zones
+
+
+class ZoneVecEnv:
+    def __init__(self, env_id, num_envs, device='cuda:0', seed_mode='increment', min_seed=1, max_seed=100,
+                 env_offset=0, auto_reset=True):
+        if not torch.cuda.is_available():
+            raise RuntimeError('ZoneVecEnv needs a CUDA device (sm_100a); there is no CPU fallback')
+        self.lib = _lib.load()
+        self.env_id = env_id
+        self.spec = spec = ENV_SPECS[env_id]
+        self.num_envs = B = int(num_envs)
+        self.device = torch.device(device)
+        self.auto_reset = auto_reset
+        N, Z = spec.num_zones, spec.zone_dim
+        self.cfg = _lib.CrlConfig(
+            task=spec.task, num_envs=B, num_zones=N, num_steps=spec.num_steps, frameskip=spec.frameskip,
+            max_cooldown=spec.max_cooldown,
+            seed_mode=_lib.SEED_FIXED_RANGE if seed_mode == 'fixed_range' else _lib.SEED_INCREMENT,
+            env_offset=env_offset, min_seed=min_seed, max_seed=max_seed, zone_size=spec.zone_size,
+            time_saved_reward=spec.time_saved_reward, beta_a=spec.beta_a, beta_b=spec.beta_b,
+            robot_keepout=spec.robot_keepout, zone_keepout=spec.zone_keepout, extent=spec.extent)
+        dev = self.device
+        z = lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype, device=dev)
+        # state planes (layout documented in include/crl_b200.h)
+        self.pose = z(B, 4)
+        self.aux = z(B, 4)
+        self.zone_xy = z(N, B, 2)
+        self.zone_tmax = z((N + 1) // 2, B, dtype=torch.int32) if spec.task == _lib.TASK_TTSP else None
+        self.cooldown = z(B, 2, dtype=torch.int32) if spec.task == _lib.TASK_CM else None
+        self.seeds = z(B, dtype=torch.int64)
+        self.episode = z(B, dtype=torch.int32)
+        self.origin = z(B, 4)
+        self.counters_dev = z(4, dtype=torch.float64)
+        # outputs
+        self.obs = z(B, 8)
+        self.zone_obs = z(B, N, Z)
+        self.result = z(B, 8, dtype=torch.uint8)
+        self.reward = self.result.view(torch.float32)[:, 0]
+        self.done = self.result[:, 4].view(torch.bool)
+        self.goal_met = self.result[:, 5].view(torch.bool)
+        self.event = self.result[:, 6].view(torch.int8)
+        self._cost = z(B)
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        self.state = _lib.CrlState(pose=ptr(self.pose), aux=ptr(self.aux), zone_xy=ptr(self.zone_xy),
+                                   zone_tmax=ptr(self.zone_tmax), cooldown=ptr(self.cooldown),
+                                   seed=ptr(self.seeds), episode=ptr(self.episode), origin=ptr(self.origin),
+                                   counters=ptr(self.counters_dev))
+        self.out = _lib.CrlOut(obs=ptr(self.obs), zone_obs=ptr(self.zone_obs), result=ptr(self.result))
+        self._actions_dev = z(B, 2)
+        self._host = None
+        self._step_index = 0
+        self.gpu_launches = 0
+        # spaces: wrappers.py:144-153 (Box(-inf, inf)), Engine action space Box(-1, 1, (2,))
+        self.observation_space = Dict({'zone_obs': Box(-np.inf, np.inf, (N, Z)),
+                                       'obs': Box(-np.inf, np.inf, (8,))})
+        self.action_space = Box(-1.0, 1.0, (2,))
+        self.envs = [_EnvView(self, i) for i in range(min(B, 1))]
+        self.seed(torch.arange(B, dtype=torch.int64) + env_offset)
+
+    # -- plumbing ------------------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _obs_dict(self):
+        return {'zone_obs': self.zone_obs, 'obs': self.obs}
+
+    def _info(self):
+        return {'goal_met': self.goal_met, 'cost': self._cost, 'event': self.event}
+
+    def _as_dev(self, x, dtype):
+        return torch.as_tensor(x, dtype=dtype, device=self.device).contiguous()
+
+    # -- reference surface ---------------------------------------------------------
+    def seed(self, seeds):
+        """Engine.seed for every env: an int (env i gets seed + i) or a (B,) tensor."""
+        if isinstance(seeds, int):
+            seeds = torch.arange(self.num_envs, dtype=torch.int64) + seeds
+        self.seeds.copy_(self._as_dev(seeds, torch.int64))
+        self.episode.zero_()
+
+    def reset(self, layout=None, mask=None, env_ids=None):
+        """Engine.reset of all envs (or those in ``mask``).  ``layout`` switches to the
+        host-supplied-layout mode: dict with xy0 (n,2), rot0 (n,), zone_xy (n,N,2) and
+        zone_max_steps (n,N) / colours (n,N) per task, for envs ``env_ids`` (default 0..n)."""
+        with torch.cuda.device(self.device):
+            if layout is None:
+                m = None if mask is None else self._as_dev(mask, torch.uint8)
+                _lib.check(self.lib.crl_reset(self.cfg, self.state, self.out,
+                                              None if m is None else m.data_ptr(), self._stream()))
+            else:
+                xy0 = self._as_dev(layout['xy0'], torch.float64).reshape(-1, 2)
+                n = xy0.shape[0]
+                rot0 = self._as_dev(layout['rot0'], torch.float64).reshape(n)
+                zxy = self._as_dev(layout['zone_xy'], torch.float64).reshape(n, self.spec.num_zones, 2)
+                tm = self._as_dev(layout['zone_max_steps'], torch.int32) if 'zone_max_steps' in layout else None
+                col = self._as_dev(layout['colours'], torch.int32) if 'colours' in layout else None
+                ids = None if env_ids is None else self._as_dev(env_ids, torch.int32)
+                lay = _lib.CrlLayoutIn(xy0=xy0.data_ptr(), rot0=rot0.data_ptr(), zone_xy=zxy.data_ptr(),
+                                       zone_max_steps=None if tm is None else tm.data_ptr(),
+                                       colours=None if col is None else col.data_ptr())
+                _lib.check(self.lib.crl_reset_from_layout(self.cfg, self.state, self.out, lay,
+                                                          None if ids is None else ids.data_ptr(), n,
+                                                          self._stream()))
+            self.gpu_launches += 1
+        return self._obs_dict()
+
+    def _step(self, actions, flags, action_seed=0):
+        with torch.cuda.device(self.device):
+            if actions is None:
+                aptr = None
+            else:
+                if not (isinstance(actions, torch.Tensor) and actions.is_cuda and actions.dtype == torch.float32
+                        and actions.is_contiguous()):
+                    actions = self._as_dev(actions, torch.float32)
+                assert actions.shape == (self.num_envs, 2)
+                aptr = actions.data_ptr()
+            _lib.check(self.lib.crl_step(self.cfg, self.state, aptr, self.out, flags, action_seed,
+                                         self._step_index, self._stream()))
+        self._step_index += 1
+        self.gpu_launches += 1
+        return self._obs_dict(), self.reward, self.done, self._info()
+
+    def step(self, actions):
+        """ParallelEnv.step (penv.py:52-59): finished envs restart inside the call; their
+        returned observation is the new episode's first one, reward/done/info the old one's."""
+        return self._step(actions, _lib.STEP_AUTO_RESET if self.auto_reset else 0)
+
+    def step_no_reset(self, actions):
+        """ParallelEnv.step_no_reset (penv.py:61-66)."""
+        return self._step(actions, 0)
+
+    def step_random(self, action_seed=1, auto_reset=True):
+        """A step with U(-1,1)^2 actions drawn in-kernel (Philox): action_space.sample()."""
+        return self._step(None, _lib.STEP_AUTO_RESET if auto_reset else 0, action_seed)
+
+    def step_host(self, actions, auto_reset=True):
+        """The reference-facing call with HOST buffers: numpy actions in, numpy obs /
+        reward / done out (pinned staging; host<->device copies inside the call)."""
+        B, N, Z = self.num_envs, self.spec.num_zones, self.spec.zone_dim
+        if self._host is None:
+            pin = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype).pin_memory()
+            h = {'actions': pin(B, 2, dtype=torch.float32), 'obs': pin(B, 8, dtype=torch.float32),
+                 'zone_obs': pin(B, N, Z, dtype=torch.float32), 'result': pin(B, 8, dtype=torch.uint8)}
+            h['out'] = _lib.CrlOut(obs=h['obs'].data_ptr(), zone_obs=h['zone_obs'].data_ptr(),
+                                   result=h['result'].data_ptr())
+            h['np'] = {k: h[k].numpy() for k in ('actions', 'obs', 'zone_obs', 'result')}
+            self._host = h
+        h = self._host
+        np.copyto(h['np']['actions'], np.asarray(actions, dtype=np.float32).reshape(B, 2))
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.crl_step_host(self.cfg, self.state, h['actions'].data_ptr(),
+                                              self._actions_dev.data_ptr(), self.out, h['out'],
+                                              _lib.STEP_AUTO_RESET if auto_reset else 0, self._stream()))
+        self._step_index += 1
+        self.gpu_launches += 1
+        res = h['np']['result']
+        return ({'zone_obs': h['np']['zone_obs'], 'obs': h['np']['obs']}, res.view(np.float32)[:, 0],
+                res[:, 4].view(np.bool_), {'goal_met': res[:, 5].view(np.bool_), 'event': res[:, 6].view(np.int8)})
+
+    # -- extras ----------------------------------------------------------------------
+    @property
+    def steps(self):
+        return self.aux[:, 3].view(torch.int32) & 0xffff
+
+    def counters(self):
+        """Episode statistics accumulated in-kernel since construction."""
+        out = (ctypes.c_double * 4)()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.crl_counters_read(self.state, out, self._stream()))
+        return {'return_sum': out[0], 'episodes': out[1], 'successes': out[2], 'length_sum': out[3]}
+
+    def set_qpos_qvel(self, qpos, qvel, env_ids=None):
+        """Overwrite sim.data.qpos / qvel (fp64, reference coordinates) of some envs."""
+        qp, qv = self._as_dev(qpos, torch.float64).reshape(-1, 3), self._as_dev(qvel, torch.float64).reshape(-1, 3)
+        ids = None if env_ids is None else self._as_dev(env_ids, torch.int32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.crl_set_qpos_qvel(self.cfg, self.state, qp.data_ptr(), qv.data_ptr(),
+                                                  None if ids is None else ids.data_ptr(), qp.shape[0],
+                                                  self._stream()))
+
+    def get_qpos_qvel(self, env_ids=None):
+        n = self.num_envs if env_ids is None else len(env_ids)
+        qp = torch.empty(n, 3, dtype=torch.float64, device=self.device)
+        qv = torch.empty_like(qp)
+        ids = None if env_ids is None else self._as_dev(env_ids, torch.int32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.crl_get_qpos_qvel(self.cfg, self.state, qp.data_ptr(), qv.data_ptr(),
+                                                  None if ids is None else ids.data_ptr(), n, self._stream()))
+        return qp, qv
+
+    def physics_substeps(self, actions, n):
+        """Debug/parity: integrate n MuJoCo substeps with no task logic."""
+        old = self.cfg.frameskip
+        self.cfg.frameskip = n
+        try:
+            return self._step(actions, _lib.STEP_PHYSICS_ONLY)
+        finally:
+            self.cfg.frameskip = old
+
+
+def make_vec_env(env_id, num_envs, **kw):
+    return ZoneVecEnv(env_id, num_envs, **kw)

@@ -1,0 +1,193 @@
+/*
+ * crl_b200.h -- C ABI of the B200 batched simulator for the env.step() hot path
+ * of PointTSP-v0 / PointTTSP-v0 / ColourMatch-v0.
+ *
+ * This is the drop-in boundary.  It replaces what sits
+ * under the reference's vector env,
+ *     main/src/torch_ac/torch_utils/penv.py:4-21   worker(): step / reset on done
+ *     main/src/torch_ac/torch_utils/penv.py:46-66  ParallelEnv.reset/step/step_no_reset
+ * i.e. N x { ZoneWrapper(FixedSeedsWrapper(TSPEnv|TimedTSPEnv|ColourMatchEnv)) }
+ * (main/envs/make_env.py:3-51) each driving mujoco-py, by one call per batch.
+ *
+ * Rules of the boundary
+ *  - plain C: pointers, sizes, PODs.  No C++ types, no torch types, no exceptions.
+ *  - every pointer inside CrlState / CrlOut / CrlLayoutIn is DEVICE memory that the
+ *    caller owns (torch allocates it); the library borrows it for the stream work
+ *    it enqueues and allocates nothing itself.
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*) and
+ *    does not synchronise, except crl_counters_read and crl_step_host, which say so.
+ *  - return value 0 = OK; negative = CrlError.  Argument errors are detected on the
+ *    host before anything is launched.  crl_strerror() names a code.
+ *  - not re-entrant on the same CrlState; distinct states/devices may be driven
+ *    from distinct host threads.
+ *
+ * Device layout (B = num_envs, N = num_zones, Z = zone_dim: 6 for TSP, 7 otherwise)
+ *  state, structure-of-arrays, one 16-byte vector per env and plane:
+ *    pose      float4[B]   (X, Y, phi, Vx)      world-frame position, heading in
+ *                                                [-pi, pi], world-frame velocity
+ *    aux       float4[B]   (Vy, omega, episode_return, bits)
+ *                          bits (int32 reinterpret): steps in bits 0-15; bits 16-31 =
+ *                          visited mask (TSP/TTSP) or 2-bit colour codes (ColourMatch:
+ *                          0 Blue, 1 Green, 2 Red)
+ *    zone_xy   float2[N][B]                      zone centres, plane-major
+ *    zone_tmax uint32[ceil(N/2)][B]              TimedTSP only: zone_max_steps, two
+ *                                                uint16 per word (zone 2j low half)
+ *    cooldown  uint2[B]                          ColourMatch only: one byte per zone
+ *    seed      int64[B]    Engine._seed of each env (incremented by every reset)
+ *    episode   uint32[B]   resets performed so far
+ *    origin    float4[B]   (x0, y0, rot0, 0): the MuJoCo body frame of the episode,
+ *                          kept only to convert to/from qpos/qvel
+ *    counters  double[4]   sum of episode returns, episodes finished, successes
+ *                          (goal_met), sum of episode lengths
+ *  outputs, the layout the reference's consumer builds (main/src/utils/format.py:27-28):
+ *    obs       float[B][8]      remaining, pos/3 (2), dir (2), vel/1.5 (2), yaw rate/3
+ *    zone_obs  float[B][N][Z]   x/3, y/3, r, g, b, 0.25 [, time left | cooldown/150]
+ *    result    CrlResult[B]     reward, done, goal_met, integer reward component
+ */
+#ifndef CRL_B200_H_
+#define CRL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRL_ABI_VERSION 1
+#define CRL_MAX_ZONES 16
+
+/* task ids; reference classes: main/envs/TSP_env.py:11, TTSP_env.py:12, colour_match_env.py:11 */
+enum CrlTask { CRL_TASK_TSP = 0, CRL_TASK_TTSP = 1, CRL_TASK_CM = 2 };
+
+enum CrlError {
+  CRL_OK = 0,
+  CRL_ERR_NULL = -1,        /* a required pointer is NULL */
+  CRL_ERR_CONFIG = -2,      /* task / sizes out of range */
+  CRL_ERR_ALIGN = -3,       /* a vector plane is not 16-byte aligned */
+  CRL_ERR_UNSUPPORTED = -4, /* (task, num_zones) has no compiled kernel */
+  CRL_ERR_LAUNCH = -5,      /* CUDA reported an error at launch */
+  CRL_ERR_DEVICE = -6       /* no sm_100 device / CUDA runtime failure */
+};
+
+/* flags for crl_step */
+#define CRL_STEP_AUTO_RESET 1u   /* penv.py:9-10: finished envs restart inside the call */
+#define CRL_STEP_PHYSICS_ONLY 2u /* debug/parity: integrate `frameskip` substeps, no task logic */
+
+/* how a reset chooses the episode's seed; wrappers.py:10-23 and Engine.seed/reset */
+enum CrlSeedMode {
+  CRL_SEED_INCREMENT = 0, /* make_test_env: seed once, every reset does _seed += 1 */
+  CRL_SEED_FIXED_RANGE = 1 /* FixedSeedsWrapper: each reset re-seeds uniformly in [min_seed, max_seed] */
+};
+
+typedef struct CrlConfig {
+  int32_t task;          /* CrlTask */
+  int32_t num_envs;      /* B */
+  int32_t num_zones;     /* N: 15 / 15 / 6 (main/envs/__init__.py:9,45) */
+  int32_t num_steps;     /* 2000 (main/envs/__init__.py:13) */
+  int32_t frameskip;     /* 10 (Engine frameskip_binom_n, p = 1) */
+  int32_t max_cooldown;  /* 150 (colour_match_env.py:16) */
+  int32_t seed_mode;     /* CrlSeedMode */
+  int32_t env_offset;    /* global index of env 0 of this shard (multi-GPU: rank * B) */
+  int64_t min_seed;      /* CRL_SEED_FIXED_RANGE bounds, inclusive */
+  int64_t max_seed;
+  double zone_size;      /* 0.2 (ZoneEnvBase.py:51) */
+  double time_saved_reward; /* 0.01 (TSP_env.py:14) */
+  double beta_a;         /* 3.0 (TTSP_env.py:13) */
+  double beta_b;         /* 1.5 */
+  double robot_keepout;  /* 0.4 (Engine default) */
+  double zone_keepout;   /* 0.55 (ZoneEnvBase.py:50) */
+  double extent;         /* 3.0 (ZoneEnvBase.py:41) */
+} CrlConfig;
+
+typedef struct CrlState {
+  float* pose;          /* float4[B] */
+  float* aux;           /* float4[B] */
+  float* zone_xy;       /* float2[N][B] */
+  uint32_t* zone_tmax;  /* uint32[ceil(N/2)][B]; TTSP only */
+  uint32_t* cooldown;   /* uint2[B]; ColourMatch only */
+  int64_t* seed;        /* int64[B] */
+  uint32_t* episode;    /* uint32[B] */
+  float* origin;        /* float4[B] */
+  double* counters;     /* double[4] */
+} CrlState;
+
+typedef struct CrlResult {
+  float reward;     /* float reward of the step (dense + time bonus) */
+  uint8_t done;
+  uint8_t goal_met; /* info['goal_met'] */
+  int8_t event;     /* integer reward component: new_city in {0,1} or Hamming delta in {-2..1} */
+  uint8_t reserved;
+} CrlResult;
+
+typedef struct CrlOut {
+  float* obs;        /* float[B][8] */
+  float* zone_obs;   /* float[B][N][Z] */
+  CrlResult* result; /* [B] */
+} CrlOut;
+
+/* Host-supplied-layout mode (equivalence testing): n layouts in the reference's own
+ * units and frame, array-of-structures, fp64 like the reference. */
+typedef struct CrlLayoutIn {
+  const double* xy0;             /* [n][2]  layout['robot'] */
+  const double* rot0;            /* [n]     world_config['robot_rot'] */
+  const double* zone_xy;         /* [n][N][2] layout['zone{i}'] */
+  const int32_t* zone_max_steps; /* [n][N]  TTSP (TTSP_env.py:19-21), else NULL */
+  const int32_t* colours;        /* [n][N]  ColourMatch codes 0/1/2 (colour_match_env.py:57-68), else NULL */
+} CrlLayoutIn;
+
+int crl_abi_version(void);
+const char* crl_strerror(int code);
+
+/* Bytes the caller must allocate for each plane of CrlState / CrlOut, in the order
+ * pose, aux, zone_xy, zone_tmax, cooldown, seed, episode, origin, counters,
+ * obs, zone_obs, result (12 entries; 0 = plane unused by this task). */
+int crl_plane_bytes(const CrlConfig* cfg, int64_t out_bytes[12]);
+
+/* Algorithmic HBM bytes one env-step moves in this layout: read, written. */
+int crl_step_bytes(const CrlConfig* cfg, int64_t* bytes_read, int64_t* bytes_written);
+
+/* Engine.reset() for the envs with mask[e] != 0 (all envs if mask == NULL): choose the
+ * seed per cfg->seed_mode, draw timeouts / colours and the layout on the device with
+ * Philox4x32-10, zero the physics state, write the first observation.
+ * Replaces Engine.reset -> build_layout/sample_layout -> World.rebuild, and
+ * TTSP_env.py:73-76 / colour_match_env.py:125-127. */
+int crl_reset(const CrlConfig* cfg, const CrlState* st, const CrlOut* out,
+              const uint8_t* mask, void* stream);
+
+/* The same reset with the layout handed in (device arrays, see CrlLayoutIn) for
+ * envs env_ids[0..n) (env_ids == NULL: envs 0..n). */
+int crl_reset_from_layout(const CrlConfig* cfg, const CrlState* st, const CrlOut* out,
+                          const CrlLayoutIn* layout, const int32_t* env_ids, int32_t n,
+                          void* stream);
+
+/* One env.step() of every env: TSPEnv.step / TimedTSPEnv.step / ColourMatchEnv.step
+ * over Engine.step (TSP_env.py:45-49, TTSP_env.py:62-71, colour_match_env.py:95-101).
+ * actions: float[B][2] device, or NULL to draw U(-1,1)^2 in-kernel from
+ * Philox(key = action_seed, counter = (global env, step_index)). */
+int crl_step(const CrlConfig* cfg, const CrlState* st, const float* actions,
+             const CrlOut* out, uint32_t flags, uint64_t action_seed,
+             uint64_t step_index, void* stream);
+
+/* crl_step with HOST buffers (pinned or pageable): copies actions host->device into
+ * `actions_dev`, steps, copies obs / zone_obs / result device->host into `host_out`,
+ * then synchronises the stream.  The reference-facing call ParallelEnv.step makes. */
+int crl_step_host(const CrlConfig* cfg, const CrlState* st, const float* actions_host,
+                  float* actions_dev, const CrlOut* out, const CrlOut* host_out,
+                  uint32_t flags, void* stream);
+
+/* Physics state in the reference's own coordinates (sim.data.qpos / qvel, fp64, device
+ * arrays [n][3]) for envs env_ids[0..n) (NULL: 0..n).  set: teacher forcing for the
+ * per-substep parity tests; get: export. */
+int crl_set_qpos_qvel(const CrlConfig* cfg, const CrlState* st, const double* qpos,
+                      const double* qvel, const int32_t* env_ids, int32_t n, void* stream);
+int crl_get_qpos_qvel(const CrlConfig* cfg, const CrlState* st, double* qpos, double* qvel,
+                      const int32_t* env_ids, int32_t n, void* stream);
+
+/* Copies counters to the host (synchronises `stream`): sum of returns, episodes,
+ * successes, sum of lengths.  These four doubles are what ranks all-reduce. */
+int crl_counters_read(const CrlState* st, double out[4], void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRL_B200_H_ */
