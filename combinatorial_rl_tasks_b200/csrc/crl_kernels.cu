@@ -26,7 +26,6 @@
 namespace crl {
 
 constexpr int kThreads = 128;
-constexpr int kWarps = kThreads / 32;
 constexpr unsigned kFull = 0xffffffffu;
 
 struct KParams {
@@ -90,11 +89,6 @@ __device__ __forceinline__ uint32_t cd_dec4(uint32_t w) {
 }
 
 // ---- reset: draws for one env, made by a whole warp ---------------------------
-// Result of a cooperative reset, valid in every lane (broadcast).
-struct Fresh {
-  float x0, y0, rot0;
-  long long seed_after;
-};
 
 // Philox key = the Engine seed in force for the draw (two 32-bit halves).
 __device__ __forceinline__ U4 draw(long long seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t tag) {
@@ -268,8 +262,10 @@ __device__ __forceinline__ void zone_row(const KParams& p, const Env<N>& env, fl
       if (TASK == CRL_TASK_TTSP) {
         const bool v = (env.hi >> i) & 1u;
         const int tm = (int)((env.tmax[i >> 1] >> (16 * (i & 1))) & 0xffffu);
-        // TTSP_env.py:23-27: (zone_max_steps - steps) / max_steps in fp64, visited -> 1
-        z[6] = v ? 1.0f : (float)((double)(tm - env.steps) / (double)p.num_steps);
+        // TTSP_env.py:23-27: (zone_max_steps - steps) / max_steps in fp64, visited -> 1; its
+        // float32 cast equals the correctly rounded float32 quotient (double rounding of a
+        // quotient of two small integers is innocuous: 53 >= 2*24 + 2)
+        z[6] = v ? 1.0f : __fdiv_rn((float)(tm - env.steps), (float)p.num_steps);
       } else {
         // colour_match_env.py:79: np.float32(cooldown) / 150 is a float32 division
         z[6] = __fdiv_rn((float)cd_get(env.cd, i), (float)p.max_cd);
@@ -278,24 +274,16 @@ __device__ __forceinline__ void zone_row(const KParams& p, const Env<N>& env, fl
   }
 }
 
+// Stage this warp's 32 zone_obs rows in shared memory and send them: the rows are one
+// contiguous span of zone_obs, so a single cp.async.bulk moves them.  Everything a row
+// holds (zone centres, colours, time left, cooldowns) is known BEFORE the physics, so
+// the copy is issued early and drains while the warp integrates; zone_obs_wait() must
+// run before the CTA exits (the copy reads shared memory asynchronously).
 template <int TASK, int N>
-__device__ __forceinline__ void store_env(const KParams& p, const Env<N>& env, int e, bool valid,
-                                          float c, float s, float* stage, int lane, int warp_env0) {
-  constexpr int Z = ZoneDim<TASK>::Z;
-  constexpr int ROW = N * Z;
-  if (valid) {
-    p.pose[e] = make_float4(env.b.X, env.b.Y, env.b.phi, env.b.vx);
-    p.aux[e] = make_float4(env.b.vy, env.b.w, env.ep_return,
-                           __int_as_float((int)((uint32_t)env.steps | (env.hi << 16))));
-    if (TASK == CRL_TASK_CM) p.cooldown[e] = env.cd;
-    // ZoneEnvBase.py:190-192, 220-224; order fixed by wrappers.py:136-142
-    const float remaining = (float)(1.0 - (double)env.steps / (double)p.num_steps);
-    p.obs[2 * (size_t)e] = make_float4(remaining, env.b.X * (1.0f / 3.0f), env.b.Y * (1.0f / 3.0f), c);
-    p.obs[2 * (size_t)e + 1] = make_float4(s, env.b.vx * (1.0f / 1.5f), env.b.vy * (1.0f / 1.5f),
-                                           env.b.w * (1.0f / 3.0f));
-    zone_row<TASK, N>(p, env, stage + lane * ROW);
-  }
-  // the warp's rows are one contiguous span of zone_obs: one bulk copy moves them
+__device__ __forceinline__ void zone_obs_send(const KParams& p, const Env<N>& env, bool valid,
+                                              float* stage, int lane, int warp_env0) {
+  constexpr int ROW = N * ZoneDim<TASK>::Z;
+  if (valid) zone_row<TASK, N>(p, env, stage + lane * ROW);
   const int n_valid = min(32, p.B - warp_env0);
   const uint32_t bytes = (uint32_t)n_valid * ROW * 4u;
   float* gdst = p.zone_obs + (size_t)warp_env0 * ROW;
@@ -307,12 +295,32 @@ __device__ __forceinline__ void store_env(const KParams& p, const Env<N>& env, i
       asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                    :: "l"(gdst), "r"(saddr), "r"(bytes) : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
-  } else {
+  } else {   // ragged tail whose byte count is not a multiple of 16: plain coalesced stores
     __syncwarp();
     for (int i = lane; i < n_valid * ROW; i += 32) gdst[i] = stage[i];
   }
+}
+
+__device__ __forceinline__ void zone_obs_wait(int lane) {
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// State planes and the 8-float obs row (ZoneEnvBase.py:190-192, 220-224; order fixed by
+// wrappers.py:136-142).  remaining = 1 - steps/num_steps: the reference's fp64 value cast
+// to float32 equals the correctly rounded float32 quotient (num_steps - steps)/num_steps
+// (the exact value is k/num_steps, never within 2^-53 of a float32 rounding boundary
+// unless it is one), so one IEEE float division reproduces it bit for bit.
+template <int TASK, int N>
+__device__ __forceinline__ void store_state_obs(const KParams& p, const Env<N>& env, int e, float c, float s) {
+  p.pose[e] = make_float4(env.b.X, env.b.Y, env.b.phi, env.b.vx);
+  p.aux[e] = make_float4(env.b.vy, env.b.w, env.ep_return,
+                         __int_as_float((int)((uint32_t)env.steps | (env.hi << 16))));
+  if (TASK == CRL_TASK_CM) p.cooldown[e] = env.cd;
+  const float remaining = __fdiv_rn((float)(p.num_steps - env.steps), (float)p.num_steps);
+  p.obs[2 * (size_t)e] = make_float4(remaining, env.b.X * (1.0f / 3.0f), env.b.Y * (1.0f / 3.0f), c);
+  p.obs[2 * (size_t)e + 1] = make_float4(s, env.b.vx * (1.0f / 1.5f), env.b.vy * (1.0f / 1.5f),
+                                         env.b.w * (1.0f / 3.0f));
 }
 
 template <int TASK, int N>
@@ -334,10 +342,14 @@ __device__ __forceinline__ void load_env(const KParams& p, int e, Env<N>& env) {
 }
 
 // ---- the fused step ---------------------------------------------------------------
+// Order inside the kernel.  Everything the reference decides in a step except the
+// physics state itself depends only on the PRE-physics position and the counters
+// (SURVEY.md Appendix B), so the task logic, the result word, the auto-reset and the
+// whole zone_obs row come first and the bulk copy of zone_obs is in flight while the
+// frameskip substeps run; state and the 8-float obs row are written last.
 template <int TASK, int N>
 __global__ void __launch_bounds__(kThreads) step_kernel(const KParams p) {
-  constexpr int Z = ZoneDim<TASK>::Z;
-  constexpr int ROW = N * Z;
+  constexpr int ROW = N * ZoneDim<TASK>::Z;
   extern __shared__ __align__(128) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int e = blockIdx.x * kThreads + threadIdx.x;
@@ -366,14 +378,8 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const KParams p) {
     for (int j = 0; j < (N + 1) / 2; ++j) env.tmax[j] = 0xffffffffu;
   }
 
-  float c, s;
-  bool done = false, goal = false;
-  int event = 0;
-  float reward = 0.f;
-  if (p.flags & CRL_STEP_PHYSICS_ONLY) {
-    substeps(env.b, act.x, act.y, p.frameskip, c, s);
-    env.b.phi = wrap_pi(env.b.phi);
-  } else {
+  bool fresh = false;   // true: this env was rebuilt by the auto-reset, no physics this call
+  if (!(p.flags & CRL_STEP_PHYSICS_ONLY)) {
     // (1) ColourMatch cooldowns tick before anything else (colour_match_env.py:98-100)
     if (TASK == CRL_TASK_CM) { env.cd.x = cd_dec4(env.cd.x); env.cd.y = cd_dec4(env.cd.y); }
     // (2) zone event on the pre-physics position: first eligible zone in index order
@@ -385,7 +391,8 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const KParams p) {
         if (inside_zone(env.b.X, env.b.Y, env.zone[i].x, env.zone[i].y, p.thresh2)) fired = i;
       }
     }
-    int old_dist = 0;
+    int event, old_dist = 0;
+    bool goal;
     if (TASK == CRL_TASK_CM) old_dist = hamming(env.hi, N);
     if (fired >= 0) {
       if (TASK == CRL_TASK_CM) {
@@ -397,10 +404,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const KParams p) {
         env.hi |= 1u << fired;
       }
     }
-    // (3) physics
-    substeps(env.b, act.x, act.y, p.frameskip, c, s);
-    env.b.phi = wrap_pi(env.b.phi);
-    // (4) reward, goal, timeout
+    // (3) reward, goal, timeout: none of it reads the post-physics state
     if (TASK == CRL_TASK_CM) {
       const int new_dist = hamming(env.hi, N);
       event = fired >= 0 ? old_dist - new_dist : 0;
@@ -409,9 +413,10 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const KParams p) {
       event = fired >= 0 ? 1 : 0;
       goal = env.hi == ((1u << N) - 1u);
     }
+    bool done = false;
     double rew = (double)event;
     if (goal) { rew += (double)(p.num_steps - env.steps) * p.bonus_per_step; done = true; }
-    reward = (float)rew;
+    const float reward = (float)rew;
     env.steps += 1;
     if (env.steps >= p.num_steps) done = true;
     if (TASK == CRL_TASK_TTSP && !done) {
@@ -425,7 +430,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const KParams p) {
     env.ep_return += reward;
     done = done && valid;
     goal = goal && valid;
-    // (5) result word and episode statistics
+    // (4) result word and episode statistics
     if (valid) {
       const unsigned long long word = (unsigned long long)__float_as_uint(reward) |
           ((unsigned long long)(done ? 1u : 0u) << 32) | ((unsigned long long)(goal ? 1u : 0u) << 40) |
@@ -448,7 +453,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const KParams p) {
         atomicAdd(p.counters + 2, (double)__popc(gm));
         atomicAdd(p.counters + 3, (double)len);
       }
-      // (6) auto-reset, penv.py:9-10: only the finished envs are rebuilt
+      // (5) auto-reset, penv.py:9-10: only the finished envs are rebuilt
       if (p.flags & CRL_STEP_AUTO_RESET) {
         float2* placed = reinterpret_cast<float2*>(stage);
         unsigned m = dm;
@@ -458,11 +463,22 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const KParams p) {
           const int se = __shfl_sync(kFull, e, src);
           warp_reset_one<TASK, N>(p, src, lane, se, placed, env);
         }
-        if (done) { sincosf(env.b.phi, &s, &c); }
+        fresh = done;
       }
     }
   }
-  store_env<TASK, N>(p, env, e, valid, c, s, stage, lane, warp_env0);
+  // (6) zone_obs leaves now and drains under the physics
+  zone_obs_send<TASK, N>(p, env, valid, stage, lane, warp_env0);
+  // (7) physics: all frameskip substeps in registers
+  float c, s;
+  if (fresh) {
+    sincosf(env.b.phi, &s, &c);
+  } else {
+    substeps(env.b, act.x, act.y, p.frameskip, c, s);
+    env.b.phi = wrap_pi(env.b.phi);
+  }
+  if (valid) store_state_obs<TASK, N>(p, env, e, c, s);
+  zone_obs_wait(lane);
 }
 
 // Engine.reset on the device for masked envs.
@@ -489,7 +505,9 @@ __global__ void __launch_bounds__(kThreads) reset_kernel(const KParams p) {
   float c = 1.f, s = 0.f;
   if (valid) sincosf(env.b.phi, &s, &c);
   // envs that were not reset are rewritten with the values just loaded (no change)
-  store_env<TASK, N>(p, env, e, valid, c, s, stage, lane, warp_env0);
+  zone_obs_send<TASK, N>(p, env, valid, stage, lane, warp_env0);
+  if (valid) store_state_obs<TASK, N>(p, env, e, c, s);
+  zone_obs_wait(lane);
 }
 
 // Host-supplied layouts: one thread per listed env.  Rows are written directly (this

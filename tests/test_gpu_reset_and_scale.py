@@ -1,0 +1,254 @@
+"""Device reset (Philox), auto-reset, ragged batches, sharding independence and
+size-independent properties at the BASELINE.json sizes.  All through the C ABI."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip('torch')
+pytestmark = pytest.mark.gpu
+
+from oracle import c_oracle as co  # noqa: E402
+
+TASKS = ['PointTSP-v0', 'PointTTSP-v0', 'ColourMatch-v0']
+
+
+@pytest.fixture(scope='module')
+def crl():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    import combinatorial_rl_tasks_b200 as m
+    return m
+
+
+def bits_of(env):
+    return env.aux[:, 3].view(torch.int32).cpu().numpy().astype(np.int64) & 0xffffffff
+
+
+def tmax_of(env):
+    w = env.zone_tmax.cpu().numpy().astype(np.int64) & 0xffffffff          # (ceil(N/2), B)
+    N = env.spec.num_zones
+    return np.stack([w & 0xffff, w >> 16], 1).reshape(-1, w.shape[1])[:N].T  # (B, N)
+
+
+def cooldown_of(env):
+    return env.cooldown.cpu().numpy().view(np.uint8).reshape(env.num_envs, 8)[:, :env.spec.num_zones]
+
+
+def snapshot(env):
+    keys = ['pose', 'aux', 'zone_xy', 'zone_tmax', 'cooldown', 'seeds', 'episode', 'origin', 'obs', 'zone_obs', 'result']
+    return {k: getattr(env, k).clone() for k in keys if getattr(env, k) is not None}
+
+
+@pytest.mark.parametrize('env_id', TASKS)
+def test_device_reset_matches_design_twin(crl, env_id):
+    """crl_reset (Philox on the device, one warp per env) against the sequential twin in
+    oracle/crl_oracle.c: layouts, headings, colours bit-exact; timeouts (fp64 log/cos on
+    both sides) equal."""
+    B = 500                                      # ragged: last warp holds 20 envs
+    env = crl.ZoneVecEnv(env_id, B)
+    env.seed(1000)
+    obs = env.reset()
+    torch.cuda.synchronize()
+    origin, zxy = env.origin.cpu().numpy(), env.zone_xy.cpu().numpy()
+    bits = bits_of(env)
+    assert np.all(env.seeds.cpu().numpy() == 1001 + np.arange(B)) and np.all(env.episode.cpu().numpy() == 1)
+    mism = 0
+    for i in list(range(0, 64)) + list(range(B - 40, B)):
+        tw = co.philox_reset(env_id, 1000 + i)
+        assert np.array_equal(origin[i, :2], tw['xy0']) and origin[i, 2] == np.float32(tw['rot0']), i
+        assert np.array_equal(zxy[:, i, :], tw['zone_xy']), i
+        if env_id == 'PointTTSP-v0':
+            mism += int(np.sum(tmax_of(env)[i] != tw['zone_max_steps']))
+        if env_id == 'ColourMatch-v0':
+            col = [(bits[i] >> 16 >> (2 * k)) & 3 for k in range(6)]
+            assert col == list(tw['colours']), i
+    assert mism == 0
+    o = obs['obs'].cpu().numpy()
+    assert np.all(o[:, 0] == 1.0) and np.all(o[:, 5:] == 0.0)
+    assert np.allclose(o[:, 1:3] * 3, origin[:, :2], atol=1e-6)
+    assert np.allclose(o[:, 3], np.cos(origin[:, 2]), atol=1e-6) and np.allclose(o[:, 4], np.sin(origin[:, 2]), atol=1e-6)
+
+
+def test_fixed_range_seed_mode(crl):
+    """FixedSeedsWrapper semantics: every reset re-seeds uniformly in [min_seed, max_seed];
+    the same seed always builds the same map."""
+    B = 256
+    env = crl.ZoneVecEnv('PointTSP-v0', B, seed_mode='fixed_range', min_seed=1, max_seed=5, env_offset=4096)
+    env.reset()
+    torch.cuda.synchronize()
+    seeds = env.seeds.cpu().numpy() - 1                     # Engine.reset left seed + 1 behind
+    assert set(seeds) <= {1, 2, 3, 4, 5} and len(set(seeds)) == 5
+    zxy, origin = env.zone_xy.cpu().numpy(), env.origin.cpu().numpy()
+    for s in range(1, 6):
+        idx = np.where(seeds == s)[0]
+        tw = co.philox_reset('PointTSP-v0', 0, seed_mode=1, min_seed=s, max_seed=s)
+        for i in idx[:5]:
+            assert np.array_equal(zxy[:, i, :], tw['zone_xy']) and np.array_equal(origin[i, :2], tw['xy0'])
+    # the chooser is keyed by the GLOBAL env index and the episode number
+    tw = co.philox_reset('PointTSP-v0', 0, seed_mode=1, min_seed=1, max_seed=5, global_env=4096 + 17, episode=0)
+    assert tw['seed_after'] - 1 == seeds[17]
+
+
+@pytest.mark.parametrize('env_id', TASKS)
+def test_auto_reset_semantics(crl, env_id):
+    """penv.py:9-10: a finished env restarts inside step(); the returned obs is the new
+    episode's first observation, reward/done/goal_met are the finished step's."""
+    B = 2048
+    env = crl.ZoneVecEnv(env_id, B)
+    env.seed(50000)
+    env.reset()
+    # make episodes end soon: put every env a few steps before the step limit
+    bits = env.aux[:, 3].view(torch.int32)
+    start = torch.randint(1960, 1999, (B,), device='cuda', dtype=torch.int32)
+    bits.copy_((bits & ~0xffff) | start)
+    n_done = 0
+    seen_done = torch.zeros(B, dtype=torch.bool, device='cuda')
+    for t in range(45):
+        seeds_before, ep_before = env.seeds.clone(), env.episode.clone()
+        obs, reward, done, info = env.step_random(action_seed=9)
+        d = done.clone()
+        n_done += int(d.sum())
+        seen_done |= d
+        if d.any():
+            idx = torch.where(d)[0]
+            o = obs['obs'][idx].cpu().numpy()
+            assert np.all(o[:, 0] == 1.0) and np.all(o[:, 5:] == 0.0)             # fresh episode
+            assert torch.all(env.steps[idx] == 0)
+            assert torch.all(env.seeds[idx] == seeds_before[idx] + 1)               # Engine: _seed += 1
+            assert torch.all(env.episode[idx] == ep_before[idx] + 1)
+            i = int(idx[0])
+            tw = co.philox_reset(env_id, int(seeds_before[i]))
+            assert np.array_equal(env.zone_xy[:, i, :].cpu().numpy(), tw['zone_xy'])
+            assert np.array_equal(obs['zone_obs'][i, :, 0:2].cpu().numpy(),
+                                  (tw['zone_xy'] * np.float32(1.0 / 3.0)).astype(np.float32))
+        nd = torch.where(~d)[0]
+        assert torch.all(env.seeds[nd] == seeds_before[nd])                       # untouched envs
+    assert bool(seen_done.all())
+    c = env.counters()
+    assert c['episodes'] == n_done and c['length_sum'] >= 2000 * n_done * 0.3
+    # step_no_reset leaves finished envs alone
+    env2 = crl.ZoneVecEnv(env_id, 64)
+    env2.reset()
+    b2 = env2.aux[:, 3].view(torch.int32)
+    b2.copy_((b2 & ~0xffff) | 1999)
+    z_before = env2.zone_xy.clone()
+    obs, reward, done, info = env2.step_no_reset(torch.zeros(64, 2, device='cuda'))
+    assert bool(done.all()) and torch.equal(env2.zone_xy, z_before) and torch.all(env2.steps == 2000)
+    assert torch.all(obs['obs'][:, 0] == 0.0)
+
+
+@pytest.mark.parametrize('env_id', TASKS)
+def test_ragged_batch_equals_prefix_of_full_batch(crl, env_id):
+    """B not a multiple of 32 (and of 4: the bulk copy falls back to plain stores)."""
+    full = crl.ZoneVecEnv(env_id, 128)
+    full.seed(7); full.reset()
+    acts = torch.rand(40, 128, 2, device='cuda') * 2 - 1
+    for B in (1, 33, 99, 100):
+        env = crl.ZoneVecEnv(env_id, B)
+        env.seed(7); env.reset()
+        ref = crl.ZoneVecEnv(env_id, 128)
+        ref.seed(7); ref.reset()
+        for t in range(40):
+            env.step(acts[t, :B].contiguous())
+            ref.step(acts[t])
+        a, b = snapshot(env), snapshot(ref)
+        for k in a:
+            if k == 'zone_xy' or k == 'zone_tmax':
+                assert torch.equal(a[k], b[k][:, :B]), (B, k)
+            else:
+                assert torch.equal(a[k], b[k][:B]), (B, k)
+
+
+def test_sharding_independence(crl):
+    """Two shards with env_offset 0 / 1024 == one batch of 2048: Philox counters use the
+    global env index, so results do not depend on the GPU count."""
+    env_id = 'PointTTSP-v0'
+    whole = crl.ZoneVecEnv(env_id, 2048, seed_mode='fixed_range', min_seed=1, max_seed=100)
+    parts = [crl.ZoneVecEnv(env_id, 1024, seed_mode='fixed_range', min_seed=1, max_seed=100, env_offset=o)
+             for o in (0, 1024)]
+    for e in [whole] + parts:
+        e.reset()
+    for t in range(60):
+        whole.step_random(action_seed=4)
+        for e in parts:
+            e._step_index = whole._step_index - 1
+            e.step_random(action_seed=4)
+    for k in ('pose', 'aux', 'obs', 'zone_obs', 'result', 'seeds'):
+        assert torch.equal(getattr(whole, k), torch.cat([getattr(e, k) for e in parts])), k
+    assert torch.equal(whole.zone_xy, torch.cat([e.zone_xy for e in parts], dim=1))
+
+
+def test_step_host_equals_device_step(crl):
+    env_a = crl.ZoneVecEnv('ColourMatch-v0', 300); env_a.seed(3); env_a.reset()
+    env_b = crl.ZoneVecEnv('ColourMatch-v0', 300); env_b.seed(3); env_b.reset()
+    rs = np.random.RandomState(0)
+    for t in range(25):
+        a = rs.uniform(-1, 1, (300, 2)).astype(np.float32)
+        obs_h, rew_h, done_h, info_h = env_a.step_host(a)
+        obs_d, rew_d, done_d, info_d = env_b.step(torch.from_numpy(a).cuda())
+        assert np.array_equal(obs_h['obs'], obs_d['obs'].cpu().numpy())
+        assert np.array_equal(obs_h['zone_obs'], obs_d['zone_obs'].cpu().numpy())
+        assert np.array_equal(rew_h, rew_d.cpu().numpy()) and np.array_equal(done_h, done_d.cpu().numpy())
+
+
+@pytest.mark.parametrize('env_id,B', [('PointTSP-v0', 65536), ('PointTTSP-v0', 262144), ('ColourMatch-v0', 262144)])
+def test_full_size_properties(crl, env_id, B):
+    """BASELINE.json configs 2-4 at full size: invariants that hold at any size."""
+    env = crl.ZoneVecEnv(env_id, B)
+    env.seed(123)
+    env.reset()
+    N, Z = env.spec.num_zones, env.spec.zone_dim
+    n_done, ret_sum = 0, 0.0
+    ep_ret = torch.zeros(B, device='cuda')
+    hamming0 = None
+    if env_id == 'ColourMatch-v0':
+        col = (torch.from_numpy(bits_of(env)).cuda() >> 16).unsqueeze(1) >> (2 * torch.arange(N, device='cuda')) & 3
+        nb, ng, nr = [(col == c).sum(1) for c in range(3)]
+        hamming0 = torch.minimum(torch.minimum(2 * ng + nr, 2 * nr + nb), 2 * nb + ng)
+    # shorten episodes so that auto-resets happen within the test
+    bits = env.aux[:, 3].view(torch.int32)
+    bits.copy_((bits & ~0xffff) | torch.randint(1700, 1990, (B,), device='cuda', dtype=torch.int32))
+    for t in range(320):
+        obs, reward, done, info = env.step_random(action_seed=77)
+        ep_ret += reward
+        n_done += int(done.sum())
+        ret_sum += float(ep_ret[done].double().sum())
+        ep_ret[done] = 0
+    torch.cuda.synchronize()
+    c = env.counters()
+    assert c['episodes'] == n_done and n_done >= B
+    assert abs(c['return_sum'] - ret_sum) <= 1e-3 * max(1.0, abs(ret_sum))
+    bits_np = bits_of(env)
+    steps, hi = bits_np & 0xffff, bits_np >> 16
+    o, z = env.obs.cpu().numpy(), env.zone_obs.cpu().numpy()
+    assert np.array_equal(o[:, 0], (1.0 - steps / 2000.0).astype(np.float32))
+    assert np.allclose(np.hypot(o[:, 3], o[:, 4]), 1.0, atol=1e-6)
+    zxy = env.zone_xy.cpu().numpy().transpose(1, 0, 2)                               # (B, N, 2)
+    assert np.allclose(z[:, :, 0:2], zxy / 3.0, atol=1e-6) and np.all(z[:, :, 5] == 0.25)
+    pose, aux = env.pose.cpu().numpy(), env.aux.cpu().numpy()
+    assert np.all(np.abs(pose[:, 2]) <= np.pi + 1e-5) and np.all(np.isfinite(pose)) and np.all(np.isfinite(aux[:, :3]))
+    assert np.all(np.hypot(pose[:, 3], aux[:, 0]) <= 1.5 + 1e-3)                      # terminal speed
+    # layouts valid: keepouts and extents
+    pts = np.concatenate([env.origin.cpu().numpy()[:, None, :2], zxy], 1).astype(np.float64)[:4096]
+    keep = np.array([0.4] + [0.55] * N)
+    assert np.all(np.abs(pts) <= (3.0 - keep)[None, :, None] + 1e-5)
+    d = np.linalg.norm(pts[:, :, None] - pts[:, None], axis=3)
+    iu = np.triu_indices(N + 1, 1)
+    assert np.all(d[:, iu[0], iu[1]] >= (keep[:, None] + keep[None])[iu] - 1e-5)
+    if env_id == 'ColourMatch-v0':
+        colz = (hi[:, None] >> (2 * np.arange(N))) & 3
+        assert np.all(colz < 3)
+        rgb = np.stack([colz == 2, colz == 1, colz == 0], 2).astype(np.float32)
+        assert np.array_equal(z[:, :, 2:5], rgb)
+        cd = cooldown_of(env)
+        assert cd.max() <= 150 and np.array_equal(z[:, :, 6], cd.astype(np.float32) / np.float32(150))
+    else:
+        vis = ((hi[:, None] >> np.arange(N)) & 1).astype(bool)
+        assert np.array_equal(z[:, :, 2], vis.astype(np.float32)) and np.array_equal(z[:, :, 4], (~vis).astype(np.float32))
+        assert np.all(z[:, :, 3] == 1.0)
+        # dense TSP reward: the running return of an unfinished episode is its visit count
+        assert np.array_equal(aux[:, 2], vis.sum(1).astype(np.float32))
+        if env_id == 'PointTTSP-v0':
+            tm = tmax_of(env)
+            assert np.all((steps[:, None] < tm) | vis)                               # else it would have ended
+            want = np.where(vis, np.float32(1.0), ((tm - steps[:, None]) / 2000.0).astype(np.float32))
+            assert np.array_equal(z[:, :, 6], want)

@@ -1,0 +1,175 @@
+"""CPU-side checks of the product's host logic and of the kernel's per-env arithmetic
+compiled for the host (tests/hostcheck): no GPU needed."""
+import ctypes
+import itertools
+import math
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as co
+from oracle import mj_point as mj
+from oracle import zone_env as ze
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HC = os.path.join(ROOT, 'tests', 'hostcheck')
+
+
+@pytest.fixture(scope='module')
+def hc():
+    so = os.path.join(HC, 'libhostcheck.so')
+    src = os.path.join(HC, 'hostcheck.cpp')
+    core = os.path.join(ROOT, 'combinatorial_rl_tasks_b200', 'csrc', 'crl_core.cuh')
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core)):
+        subprocess.run(['g++', '-O2', '-x', 'c++', '-shared', '-fPIC', '-o', so, src], check=True)
+    L = ctypes.CDLL(so)
+    fp = ctypes.POINTER(ctypes.c_float)
+    L.hc_substeps.argtypes = [fp, ctypes.c_float, ctypes.c_float, ctypes.c_int, fp]
+    L.hc_wrap_pi.restype = ctypes.c_float
+    L.hc_wrap_pi.argtypes = [ctypes.c_float]
+    L.hc_sqrt_threshold.restype = ctypes.c_double
+    L.hc_sqrt_threshold.argtypes = [ctypes.c_double]
+    L.hc_inside_zone.argtypes = [ctypes.c_float] * 4 + [ctypes.c_double]
+    L.hc_hamming.argtypes = [ctypes.c_uint32, ctypes.c_int]
+    L.hc_philox.argtypes = [ctypes.c_void_p] * 3
+    return L
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads without a GPU and exports all of include/crl_b200.h."""
+    from combinatorial_rl_tasks_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'crl_b200.h')).read()
+    declared = set(re.findall(r'\b(crl_[a-z_0-9]+)\s*\(', hdr))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = _lib.load()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.crl_abi_version() == 1
+    assert b'NULL' in lib.crl_strerror(-1)
+
+
+def test_argument_errors_are_detected_on_the_host():
+    from combinatorial_rl_tasks_b200 import _lib
+    lib = _lib.load()
+    cfg = _lib.CrlConfig(task=0, num_envs=64, num_zones=15, num_steps=2000, frameskip=10, max_cooldown=150,
+                         zone_size=0.2)
+    sizes = (ctypes.c_int64 * 12)()
+    assert lib.crl_plane_bytes(cfg, sizes) == 0
+    assert list(sizes) == [1024, 1024, 7680, 0, 0, 512, 256, 1024, 32, 2048, 64 * 90 * 4, 512]
+    rd, wr = ctypes.c_int64(), ctypes.c_int64()
+    assert lib.crl_step_bytes(cfg, ctypes.byref(rd), ctypes.byref(wr)) == 0 and (rd.value, wr.value) == (160, 432)
+    bad = _lib.CrlConfig(task=7, num_envs=64, num_zones=15, num_steps=2000, zone_size=0.2)
+    assert lib.crl_plane_bytes(bad, sizes) == -2
+    st, out = _lib.CrlState(), _lib.CrlOut()
+    assert lib.crl_step(cfg, st, None, out, 0, 0, 0, None) == -1          # NULL planes
+    cfg2 = _lib.CrlConfig(task=0, num_envs=64, num_zones=9, num_steps=2000, frameskip=10, zone_size=0.2)
+    buf = (ctypes.c_char * 4096)()
+    a = ctypes.addressof(buf)
+    a16 = (a + 15) & ~15
+    st = _lib.CrlState(pose=a16, aux=a16, zone_xy=a16, seed=a16, episode=a16, origin=a16, counters=a16)
+    out = _lib.CrlOut(obs=a16, zone_obs=a16, result=a16)
+    assert lib.crl_step(cfg2, st, None, out, 0, 0, 0, None) == -4         # no kernel for N = 9
+    st.pose = a16 + 4
+    assert lib.crl_step(cfg, st, None, out, 0, 0, 0, None) == -3          # misaligned plane
+
+
+def test_vec_env_fails_loudly_without_cuda():
+    torch = pytest.importorskip('torch')
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    import combinatorial_rl_tasks_b200 as crl
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        crl.ZoneVecEnv('PointTSP-v0', 8)
+
+
+def test_philox_known_answers(hc):
+    """Random123 kat_vectors, philox4x32-10."""
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        c, k, o = np.array(ctr, np.uint32), np.array(key, np.uint32), np.zeros(4, np.uint32)
+        hc.hc_philox(c.ctypes.data, k.ctypes.data, o.ctypes.data)
+        assert tuple(o) == want
+        co.lib().ph_philox(c.ctypes.data, k.ctypes.data, o.ctypes.data)     # the oracle's twin agrees
+        assert tuple(o) == want
+
+
+def test_zone_predicate_is_numpy_exact(hc):
+    t2 = hc.hc_sqrt_threshold(0.2)
+    assert math.sqrt(t2) <= 0.2 < math.sqrt(np.nextafter(t2, 1.0))
+    rs = np.random.RandomState(0)
+    n_in = 0
+    for k in range(200000):
+        z = rs.uniform(-2.5, 2.5, 2).astype(np.float32)
+        ang, r = rs.uniform(0, 2 * np.pi), 0.2 + rs.choice([0.0, 1e-9, -1e-9, 3e-8, -3e-8, 1e-6, -1e-6, 0.05, -0.05])
+        p = (z.astype(np.float64) + r * np.array([math.cos(ang), math.sin(ang)])).astype(np.float32)
+        ref = bool(np.sqrt(np.sum(np.square(z.astype(np.float64) - p.astype(np.float64)))) <= 0.2)
+        got = bool(hc.hc_inside_zone(float(p[0]), float(p[1]), float(z[0]), float(z[1]), t2))
+        assert got == ref, (k, z, p)
+        n_in += ref
+    assert 20000 < n_in < 180000
+
+
+def test_hamming_exhaustive(hc):
+    for cols in itertools.product(range(3), repeat=6):
+        word = sum(c << (2 * i) for i, c in enumerate(cols))
+        assert hc.hc_hamming(word, 6) == ze.hamming_to_goal(np.array(cols))
+
+
+def test_closed_form_substep_vs_oracle(hc):
+    """The kernel's closed-form (M + hB)^-1 solve, compiled for the host, against the
+    oracle's generic 3x3 solve: 1e-5 relative per substep from identical inputs."""
+    rs = np.random.RandomState(0)
+    fp = ctypes.POINTER(ctypes.c_float)
+    cs = (ctypes.c_float * 2)()
+    worst = 0.0
+    for trial in range(2000):
+        st = np.array([rs.uniform(-2.5, 2.5), rs.uniform(-2.5, 2.5), rs.uniform(-np.pi, np.pi),
+                       rs.uniform(-1.5, 1.5), rs.uniform(-1.5, 1.5), rs.uniform(-4.5, 4.5)], dtype=np.float32)
+        a = rs.uniform(-1.3, 1.3, 2).astype(np.float32)
+        if trial % 3 == 0:
+            a[0] *= 0.04
+        if trial % 5 == 0:
+            a[1] = np.float32(0.3 * st[5] + rs.uniform(-0.04, 0.04))
+        w = st.astype(np.float64)
+        q_ref, v_ref = mj.substep(w[:3], w[3:], a.astype(np.float64))     # rot0 = 0: world == qpos frame
+        out = st.copy()
+        hc.hc_substeps(out.ctypes.data_as(fp), float(a[0]), float(a[1]), 1, cs)
+        ref = np.concatenate([q_ref, v_ref])
+        err = np.abs(out - ref) / np.maximum(1.0, np.abs(ref))
+        worst = max(worst, err.max())
+        assert abs(cs[0] - math.cos(q_ref[2])) < 2e-6 and abs(cs[1] - math.sin(q_ref[2])) < 2e-6
+    assert worst <= 1e-5, worst
+
+
+def test_wrap_pi(hc):
+    for x in np.linspace(-3.3, 3.3, 1001):
+        y = hc.hc_wrap_pi(float(x))
+        assert -math.pi - 1e-6 <= y <= math.pi + 1e-6
+        assert abs(math.remainder(y - x, 2 * math.pi)) < 5e-7
+
+
+def test_philox_reset_twin_layouts_are_valid():
+    """The design twin of the device reset: keepouts, extents, Beta(3,1.5) timeouts."""
+    tm_all = []
+    for seed in range(200):
+        r = co.philox_reset('PointTTSP-v0', seed)
+        pts = np.vstack([r['xy0'][None], r['zone_xy']]).astype(np.float64)
+        keep = np.array([0.4] + [0.55] * 15)
+        assert np.all(np.abs(pts) <= 3.0 - keep[:, None] + 1e-6)
+        d = np.linalg.norm(pts[:, None] - pts[None], axis=2)
+        need = keep[:, None] + keep[None]
+        iu = np.triu_indices(16, 1)
+        assert np.all(d[iu] >= need[iu] - 1e-6)
+        assert 0.0 <= r['rot0'] < 2 * np.pi + 1e-6 and r['seed_after'] == seed + 1
+        tm_all.append(r['zone_max_steps'])
+    tm = np.concatenate(tm_all) / 2000.0
+    # Beta(3, 1.5): mean 2/3, variance ab/((a+b)^2 (a+b+1)) = 0.0404
+    assert abs(tm.mean() - 2 / 3) < 0.015 and abs(tm.var() - 0.0404) < 0.004
+    cols = np.concatenate([co.philox_reset('ColourMatch-v0', s)['colours'] for s in range(2000)])
+    assert np.all(np.abs(np.bincount(cols, minlength=3) / len(cols) - 1 / 3) < 0.02)
