@@ -104,7 +104,7 @@ def test_zone_predicate_is_numpy_exact(hc):
     assert math.sqrt(t2) <= 0.2 < math.sqrt(np.nextafter(t2, 1.0))
     rs = np.random.RandomState(0)
     n_in = 0
-    for k in range(200000):
+    for k in range(60000):
         z = rs.uniform(-2.5, 2.5, 2).astype(np.float32)
         ang, r = rs.uniform(0, 2 * np.pi), 0.2 + rs.choice([0.0, 1e-9, -1e-9, 3e-8, -3e-8, 1e-6, -1e-6, 0.05, -0.05])
         p = (z.astype(np.float64) + r * np.array([math.cos(ang), math.sin(ang)])).astype(np.float32)
@@ -112,7 +112,7 @@ def test_zone_predicate_is_numpy_exact(hc):
         got = bool(hc.hc_inside_zone(float(p[0]), float(p[1]), float(z[0]), float(z[1]), t2))
         assert got == ref, (k, z, p)
         n_in += ref
-    assert 20000 < n_in < 180000
+    assert 6000 < n_in < 54000
 
 
 def test_hamming_exhaustive(hc):
