@@ -48,7 +48,11 @@ class ClockSampler:
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.first = index, [], None, 0
+
+    def mark(self):
+        """Samples taken before this call (warm-up) are dropped."""
+        self.first = len(self.rows)
 
     def start(self):
         try:
@@ -69,6 +73,7 @@ class ClockSampler:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         self.proc.terminate()
         self.t.join(timeout=2)
+        self.rows = self.rows[max(0, self.first - 1):]
         sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit())
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k] == 'Active' for r in self.rows)]
@@ -167,12 +172,14 @@ def run_ours(args):
         if n_steps % R:
             tails[n_steps % R].replay()
 
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.5)                                                # nvidia-smi start-up
     run(W)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.mark()
     reps = []
     n_rep = args.repeats
     for _ in range(n_rep):
@@ -232,6 +239,11 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     peak, peak_src = measured_peaks()
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(f'{args.env}:{B}')
     achieved = step_bytes * B / (ms_per_step * 1e-3) / 1e9
     canon = {'PointTSP-v0': 614, 'PointTTSP-v0': 734, 'ColourMatch-v0': 374}.get(args.env)
     out = {
@@ -244,7 +256,7 @@ def run_ours(args):
                          f'cycle) > 2x the 126 MB L2, so every launch reads HBM',
                    'launch': 'CUDA graph of one ring cycle, replayed', 'repeats': n_rep, 'timing': 'best of repeats'},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': None, 'peak_source': peak_src, 'kernel': 'step_kernel',
+                     'traffic': traffic, 'algorithmic_bytes_per_launch': step_bytes * B, 'peak_source': peak_src, 'kernel': 'step_kernel',
                      'bytes_per_env_step': step_bytes,
                      'canonical_bytes_per_env_step': canon,
                      'achieved_canonical': canon * B / (ms_per_step * 1e-3) / 1e9 if canon else None,

@@ -134,12 +134,14 @@ __device__ void warp_layout(const KParams& p, long long seed, float2* placed, in
         const float x = __fadd_rn(lo, __fmul_rn(span, u01(r.x)));
         const float y = __fadd_rn(lo, __fmul_rn(span, u01(r.y)));
         bool valid = j < 100;
-        for (int q = 0; q < k; ++q) {
+        // fixed trip count so the shared-memory reads are issued together; slots >= k are ignored
+#pragma unroll
+        for (int q = 0; q < N; ++q) {
           const float2 o = placed[q];
           const float need = __fadd_rn(q == 0 ? p.robot_keepout : p.zone_keepout, keep);
           const float dx = __fsub_rn(x, o.x), dy = __fsub_rn(y, o.y);
           const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-          valid = valid && (d2 >= __fmul_rn(need, need));
+          valid = valid && (q >= k || d2 >= __fmul_rn(need, need));
         }
         const unsigned m = __ballot_sync(kFull, valid);
         if (m) {
@@ -356,6 +358,11 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const KParams p) {
   const int warp_env0 = blockIdx.x * kThreads + warp * 32;
   const bool valid = e < p.B;
   float* stage = smem + warp * (32 * ROW);
+  // Programmatic dependent launch: this grid may be scheduled while the previous kernel
+  // of the stream is still draining; let the next one do the same, then wait here until
+  // everything the previous kernel wrote (state, actions) is visible.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   Env<N> env;
   float2 act = make_float2(0.f, 0.f);
@@ -382,14 +389,23 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const KParams p) {
   if (!(p.flags & CRL_STEP_PHYSICS_ONLY)) {
     // (1) ColourMatch cooldowns tick before anything else (colour_match_env.py:98-100)
     if (TASK == CRL_TASK_CM) { env.cd.x = cd_dec4(env.cd.x); env.cd.y = cd_dec4(env.cd.y); }
-    // (2) zone event on the pre-physics position: first eligible zone in index order
-    int fired = -1;
+    // (2) zone event on the pre-physics position: first eligible zone in index order.
+    // fp32 screen of all N zones without branches; the (rare) candidates are confirmed
+    // with the exact fp64 predicate, lowest index first.
+    uint32_t cand = 0u;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       const bool eligible = TASK == CRL_TASK_CM ? (cd_get(env.cd, i) == 0u) : !((env.hi >> i) & 1u);
-      if (fired < 0 && eligible && near_zone(env.b.X, env.b.Y, env.zone[i].x, env.zone[i].y, p.r2_guard)) {
-        if (inside_zone(env.b.X, env.b.Y, env.zone[i].x, env.zone[i].y, p.thresh2)) fired = i;
-      }
+      cand |= (eligible && near_zone(env.b.X, env.b.Y, env.zone[i].x, env.zone[i].y, p.r2_guard)) ? (1u << i) : 0u;
+    }
+    int fired = -1;
+    while (cand) {
+      const int i = __ffs(cand) - 1;
+      cand &= cand - 1u;
+      float zx = 0.f, zy = 0.f;
+#pragma unroll
+      for (int j = 0; j < N; ++j) if (j == i) { zx = env.zone[j].x; zy = env.zone[j].y; }
+      if (inside_zone(env.b.X, env.b.Y, zx, zy, p.thresh2)) { fired = i; break; }
     }
     int event, old_dist = 0;
     bool goal;
@@ -742,7 +758,17 @@ int crl_step(const CrlConfig* c, const CrlState* st, const float* actions, const
     const size_t sm = (size_t)kThreads * NN * ZoneDim<T>::Z * 4;                    \
     rc = set_smem(step_kernel<T, NN>, sm);                                          \
     if (rc) return rc;                                                              \
-    step_kernel<T, NN><<<blocks, kThreads, sm, s>>>(p);                             \
+    cudaLaunchConfig_t lc = {};                                                     \
+    lc.gridDim = dim3(blocks); lc.blockDim = dim3(kThreads);                        \
+    lc.dynamicSmemBytes = sm; lc.stream = s;                                        \
+    cudaLaunchAttribute at[1];                                                      \
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                  \
+    at[0].val.programmaticStreamSerializationAllowed = 1;                           \
+    lc.attrs = at; lc.numAttrs = 1;                                                 \
+    if (cudaLaunchKernelEx(&lc, step_kernel<T, NN>, p) != cudaSuccess) {            \
+      (void)cudaGetLastError();                                                     \
+      return CRL_ERR_LAUNCH;                                                        \
+    }                                                                               \
   }
   CRL_DISPATCH(c->task, c->num_zones, CRL_CALL_STEP);
   return launch_status();
