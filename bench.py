@@ -166,9 +166,17 @@ def run_ours(args):
         with torch.cuda.graph(tails[n]):
             cycle(n)
 
+    launches = {'prefetch': 0}
+
     def run(n_steps):
-        for _ in range(n_steps // R):
+        # one graph replay = one step of every ring replica; every 8th cycle the next-layout
+        # slots are topped up on each replica's side stream (concurrent with the steps)
+        for i in range(n_steps // R):
             graph.replay()
+            if i % 8 == 7:
+                for e in envs:
+                    e.prefetch()
+                launches['prefetch'] += R
         if n_steps % R:
             tails[n_steps % R].replay()
 
@@ -177,6 +185,7 @@ def run_ours(args):
     time.sleep(0.5)                                                # nvidia-smi start-up
     run(W)
     torch.cuda.synchronize()
+    launches['prefetch'] = 0
     if world > 1:
         dist.barrier()
     sampler.mark()
@@ -202,7 +211,7 @@ def run_ours(args):
     ms_per_step = ms / K
 
     # episode statistics: the path's only collective
-    c = torch.zeros(4, dtype=torch.float64, device=dev)
+    c = torch.zeros(8, dtype=torch.float64, device=dev)
     for e in envs:
         c += e.counters_dev
     if world > 1:
@@ -261,8 +270,10 @@ def run_ours(args):
                      'canonical_bytes_per_env_step': canon,
                      'achieved_canonical': canon * B / (ms_per_step * 1e-3) / 1e9 if canon else None,
                      'frac_of_nominal_8TBs': achieved / 8000.0},
-        'clocks': clocks, 'e2e': e2e, 'gpu_launches': K,
+        'clocks': clocks, 'e2e': e2e, 'gpu_launches': K + launches['prefetch'],
+        'gpu_launches_detail': {'step_kernel': K, 'prefetch_kernel (side stream)': launches['prefetch']},
         'episode_stats': {'return_sum': c[0], 'episodes': c[1], 'successes': c[2], 'length_sum': c[3],
+                          'resets_prefetched': c[4], 'resets_inline': c[5],
                           'reduction': 'nccl all_reduce(sum)' if world > 1 else 'single rank'},
         'all_reps_ms': reps,
     }

@@ -12,11 +12,11 @@ c_void_p, c_int32, c_int64, c_uint32, c_uint64, c_double = (
 TASK_TSP, TASK_TTSP, TASK_CM = 0, 1, 2
 SEED_INCREMENT, SEED_FIXED_RANGE = 0, 1
 STEP_AUTO_RESET, STEP_PHYSICS_ONLY = 1, 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # every symbol include/crl_b200.h declares
 SYMBOLS = ['crl_abi_version', 'crl_strerror', 'crl_plane_bytes', 'crl_step_bytes', 'crl_reset',
-           'crl_reset_from_layout', 'crl_step', 'crl_step_host', 'crl_set_qpos_qvel',
+           'crl_prefetch_layouts', 'crl_reset_from_layout', 'crl_step', 'crl_step_host', 'crl_set_qpos_qvel',
            'crl_get_qpos_qvel', 'crl_counters_read']
 
 
@@ -31,7 +31,8 @@ class CrlConfig(ctypes.Structure):
 
 class CrlState(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in ('pose', 'aux', 'zone_xy', 'zone_tmax', 'cooldown', 'seed',
-                                        'episode', 'origin', 'counters')]
+                                        'episode', 'origin', 'counters', 'next_zone_xy', 'next_task',
+                                        'next_origin', 'next_seed', 'next_ready')]
 
 
 class CrlOut(ctypes.Structure):
@@ -61,6 +62,7 @@ def load():
     lib.crl_plane_bytes.argtypes = [P(CrlConfig), P(c_int64)]
     lib.crl_step_bytes.argtypes = [P(CrlConfig), P(c_int64), P(c_int64)]
     lib.crl_reset.argtypes = [P(CrlConfig), P(CrlState), P(CrlOut), c_void_p, c_void_p]
+    lib.crl_prefetch_layouts.argtypes = [P(CrlConfig), P(CrlState), c_void_p]
     lib.crl_reset_from_layout.argtypes = [P(CrlConfig), P(CrlState), P(CrlOut), P(CrlLayoutIn), c_void_p,
                                           c_int32, c_void_p]
     lib.crl_step.argtypes = [P(CrlConfig), P(CrlState), c_void_p, P(CrlOut), c_uint32, c_uint64, c_uint64,

@@ -49,6 +49,11 @@ struct KParams {
   uint32_t* episode;
   float4* origin;
   double* counters;
+  float2* next_zone_xy;
+  uint32_t* next_task;
+  float4* next_origin;
+  long long* next_seed;
+  uint32_t* next_ready;
   // io
   const float2* actions;
   float4* obs;
@@ -115,10 +120,11 @@ __device__ double gamma_mt(long long seed, double a, uint32_t zone, uint32_t whi
 // object, <= 100 tries each, first valid try wins, 100 misses abandon the layout), but
 // 32 tries at a time across the warp.  Candidate j of object k in attempt L is a pure
 // function of (seed, j, k, L), so the outcome equals the sequential procedure's.
-// `placed` is warp-private shared scratch of N+1 float2.
+// `placed` is warp-private shared scratch of N+1 float2 (16-byte aligned).
 template <int N>
 __device__ void warp_layout(const KParams& p, long long seed, float2* placed, int lane) {
   const float ext = p.extent;
+  constexpr int NP = (N + 2) / 2;                 // float4 pairs covering placed[0..N]
 #pragma unroll 1
   for (uint32_t attempt = 0; attempt < 10000u; ++attempt) {
     bool ok_layout = true;
@@ -126,6 +132,10 @@ __device__ void warp_layout(const KParams& p, long long seed, float2* placed, in
     for (int k = 0; k <= N && ok_layout; ++k) {
       const float keep = k == 0 ? p.robot_keepout : p.zone_keepout;
       const float lo = -ext + keep, span = (ext - keep) - lo;
+      // everything placed so far, read once per object with independent 16-byte loads
+      float4 pl[NP];
+#pragma unroll
+      for (int q2 = 0; q2 < NP; ++q2) pl[q2] = reinterpret_cast<const float4*>(placed)[q2];
       bool found = false;
 #pragma unroll 1
       for (int base = 0; base < 100 && !found; base += 32) {
@@ -134,12 +144,12 @@ __device__ void warp_layout(const KParams& p, long long seed, float2* placed, in
         const float x = __fadd_rn(lo, __fmul_rn(span, u01(r.x)));
         const float y = __fadd_rn(lo, __fmul_rn(span, u01(r.y)));
         bool valid = j < 100;
-        // fixed trip count so the shared-memory reads are issued together; slots >= k are ignored
 #pragma unroll
-        for (int q = 0; q < N; ++q) {
-          const float2 o = placed[q];
+        for (int q = 0; q < N; ++q) {             // slots >= k hold stale values and are ignored
+          const float ox = (q & 1) ? pl[q >> 1].z : pl[q >> 1].x;
+          const float oy = (q & 1) ? pl[q >> 1].w : pl[q >> 1].y;
           const float need = __fadd_rn(q == 0 ? p.robot_keepout : p.zone_keepout, keep);
-          const float dx = __fsub_rn(x, o.x), dy = __fsub_rn(y, o.y);
+          const float dx = __fsub_rn(x, ox), dy = __fsub_rn(y, oy);
           const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
           valid = valid && (q >= k || d2 >= __fmul_rn(need, need));
         }
@@ -150,92 +160,194 @@ __device__ void warp_layout(const KParams& p, long long seed, float2* placed, in
           if (lane == 0) placed[k] = make_float2(wx, wy);
           found = true;
         }
-        __syncwarp();
       }
+      __syncwarp();
       ok_layout = found;
     }
     if (ok_layout) return;
   }
 }
 
-// Full Engine.reset for the env held by lane `src`: seed choice, task draws with the
-// pre-increment seed, layout with the incremented one.  Lane `src` takes the result
-// into its registers and writes the reset-only planes.
+// The seed Engine.reset will run with for env e (lane-local).  CRL_SEED_INCREMENT: the
+// env's current seed.  CRL_SEED_FIXED_RANGE: FixedSeedsWrapper.reset, a uniform integer in
+// [min_seed, max_seed] from the chooser's own stream (key = GLOBAL env index, counter =
+// episode number).
+__device__ __forceinline__ long long choose_seed(const KParams& p, int e, uint32_t episode) {
+  if (p.seed_mode != CRL_SEED_FIXED_RANGE) return p.seed[e];
+  const unsigned long long span = (unsigned long long)(p.max_seed - p.min_seed) + 1ull;
+  const U4 r = draw((long long)(p.env_offset + e), episode, 0u, 0u, kTagSeed);
+  const unsigned long long v = ((unsigned long long)r.x << 32) | r.y;
+  return p.min_seed + (long long)(span ? (v % span) : v);
+}
+
+// All draws of one Engine.reset run with seed `chosen`, made by a whole warp: task draws
+// with the seed BEFORE the increment (TTSP_env.py:20, colour_match_env.py:60), layout and
+// heading with chosen + 1 (Engine.reset: self._seed += 1).  On return placed[0] = robot,
+// placed[1..N] = zones (shared memory), lane i < N holds zone i's timeout / colour in
+// `my_draw`, every lane holds rot0.
 template <int TASK, int N>
-__device__ void warp_reset_one(const KParams& p, int src, int lane, int e, float2* placed, Env<N>& env) {
-  long long seed = 0;
-  uint32_t episode = 0;
-  if (lane == src) {
-    seed = p.seed[e];
-    episode = p.episode[e];
-    if (p.seed_mode == CRL_SEED_FIXED_RANGE) {
-      // FixedSeedsWrapper.reset: uniform integer in [min_seed, max_seed]; the chooser's
-      // own stream is keyed by the env's global index, counter = episode number
-      const unsigned long long span = (unsigned long long)(p.max_seed - p.min_seed) + 1ull;
-      const U4 r = draw((long long)(p.env_offset + e), episode, 0u, 0u, kTagSeed);
-      const unsigned long long v = ((unsigned long long)r.x << 32) | r.y;
-      seed = p.min_seed + (long long)(span ? (v % span) : v);
-    }
-  }
-  seed = __shfl_sync(kFull, seed, src);
-  // task draws use the seed BEFORE Engine.reset increments it (TTSP_env.py:20, colour_match_env.py:60)
-  uint32_t my_tmax = 0, my_col = 0;
+__device__ void warp_generate(const KParams& p, long long chosen, float2* placed, int lane,
+                              uint32_t& my_draw, float& rot0) {
+  my_draw = 0u;
   if (TASK == CRL_TASK_TTSP && lane < N) {
-    const double ga = gamma_mt(seed, p.beta_a, (uint32_t)lane, 0u);
-    const double gb = gamma_mt(seed, p.beta_b, (uint32_t)lane, 1u);
-    int t = (int)((ga / (ga + gb)) * (double)p.num_steps);
-    my_tmax = (uint32_t)min(max(t, 0), 65535);
+    const double ga = gamma_mt(chosen, p.beta_a, (uint32_t)lane, 0u);
+    const double gb = gamma_mt(chosen, p.beta_b, (uint32_t)lane, 1u);
+    const int t = (int)((ga / (ga + gb)) * (double)p.num_steps);
+    my_draw = (uint32_t)min(max(t, 0), 65535);
   }
   if (TASK == CRL_TASK_CM && lane < N) {
-    // uniform over {0,1,2} by masked rejection on 2-bit fields
-    uint32_t c = 3u;
+    uint32_t c = 3u;                              // uniform over {0,1,2}: masked rejection on 2-bit fields
     for (uint32_t it = 0; c == 3u && it < 64u; ++it) {
-      const U4 r = draw(seed, it, (uint32_t)lane, 0u, kTagTask);
+      const U4 r = draw(chosen, it, (uint32_t)lane, 0u, kTagTask);
       uint32_t bits = r.x;
       for (int q = 0; q < 16 && c == 3u; ++q, bits >>= 2) c = bits & 3u;
     }
-    my_col = c == 3u ? 0u : c;
+    my_draw = c == 3u ? 0u : c;
   }
-  const long long seed_after = seed + 1;   // Engine.reset: self._seed += 1
-  warp_layout<N>(p, seed_after, placed, lane);
-  const U4 rr = draw(seed_after, 0u, 0u, 0u, kTagRot);
-  const float rot0 = __fmul_rn(6.2831855f, u01(rr.x));
+  warp_layout<N>(p, chosen + 1, placed, lane);
+  const U4 rr = draw(chosen + 1, 0u, 0u, 0u, kTagRot);
+  rot0 = __fmul_rn(6.2831855f, u01(rr.x));
   __syncwarp();
-  // gather per-lane draws to lane src
-  uint32_t col_word = 0;
+}
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// Engine.reset for the lanes in `dm` (each lane = one env).  A lane whose next layout
+// was prefetched (next_ready set for exactly the seed this reset runs with) only copies
+// it: no sampling latency on the step's critical path.  The others are rebuilt one at a
+// time by the whole warp.  Both ways produce the same layout: it is a pure function of
+// the seed.
+template <int TASK, int N>
+__device__ void warp_reset(const KParams& p, unsigned dm, int lane, int e, float2* placed, Env<N>& env) {
+  const bool mine = (dm >> lane) & 1u;
+  long long chosen = 0;
+  uint32_t episode = 0;
+  bool fast = false;
+  float x0 = 0.f, y0 = 0.f, rot0 = 0.f;
+  uint32_t col_word = 0u;
+  if (mine) {
+    episode = p.episode[e];
+    chosen = choose_seed(p, e, episode);
+    if (p.next_ready && ld_acquire_u32(p.next_ready + e) != 0u && p.next_seed[e] == chosen) {
+      fast = true;
+      const float4 o = p.next_origin[e];
+      x0 = o.x; y0 = o.y; rot0 = o.z;
 #pragma unroll
-  for (int i = 0; i < N; ++i) {
-    const uint32_t t = __shfl_sync(kFull, my_tmax, i);
-    const uint32_t c = __shfl_sync(kFull, my_col, i);
-    if (lane == src) {
+      for (int i = 0; i < N; ++i) env.zone[i] = p.next_zone_xy[(size_t)i * p.B + e];
       if (TASK == CRL_TASK_TTSP) {
-        if (i & 1) env.tmax[i >> 1] |= t << 16; else env.tmax[i >> 1] = t;
+#pragma unroll
+        for (int j = 0; j < (N + 1) / 2; ++j) env.tmax[j] = p.next_task[(size_t)j * p.B + e];
       }
-      col_word |= c << (2 * i);
+      if (TASK == CRL_TASK_CM) col_word = p.next_task[e];
     }
   }
-  if (lane == src) {
-    const float2 r0 = placed[0];
-    env.b.X = r0.x; env.b.Y = r0.y; env.b.phi = wrap_pi(rot0);
+  unsigned slow = __ballot_sync(kFull, mine && !fast);
+  while (slow) {
+    const int src = __ffs(slow) - 1;
+    slow &= slow - 1;
+    const long long ch = __shfl_sync(kFull, chosen, src);
+    uint32_t my_draw;
+    float r0;
+    warp_generate<TASK, N>(p, ch, placed, lane, my_draw, r0);
+    uint32_t cw = 0u;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const uint32_t d = __shfl_sync(kFull, my_draw, i);
+      if (lane == src) {
+        if (TASK == CRL_TASK_TTSP) {
+          if (i & 1) env.tmax[i >> 1] |= d << 16; else env.tmax[i >> 1] = d;
+        }
+        cw |= d << (2 * i);
+      }
+    }
+    if (lane == src) {
+      const float2 rb = placed[0];
+      x0 = rb.x; y0 = rb.y; rot0 = r0; col_word = cw;
+#pragma unroll
+      for (int i = 0; i < N; ++i) env.zone[i] = placed[1 + i];
+    }
+    __syncwarp();
+  }
+  if (mine) {
+    env.b.X = x0; env.b.Y = y0; env.b.phi = wrap_pi(rot0);
     env.b.vx = env.b.vy = env.b.w = 0.f;
     env.ep_return = 0.f;
     env.steps = 0;
     env.hi = TASK == CRL_TASK_CM ? col_word : 0u;
     env.cd = make_uint2(0u, 0u);
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      env.zone[i] = placed[1 + i];
-      p.zone_xy[(size_t)i * p.B + e] = env.zone[i];
-    }
+    for (int i = 0; i < N; ++i) p.zone_xy[(size_t)i * p.B + e] = env.zone[i];
     if (TASK == CRL_TASK_TTSP) {
 #pragma unroll
       for (int j = 0; j < (N + 1) / 2; ++j) p.zone_tmax[(size_t)j * p.B + e] = env.tmax[j];
     }
-    p.seed[e] = seed_after;
+    p.seed[e] = chosen + 1;                       // Engine.reset: self._seed += 1
     p.episode[e] = episode + 1u;
-    p.origin[e] = make_float4(r0.x, r0.y, rot0, 0.f);
+    p.origin[e] = make_float4(x0, y0, rot0, 0.f);
+    // hand the slot back to the prefetcher (release: our reads of it are done)
+    if (p.next_ready) st_release_u32(p.next_ready + e, 0u);
+  }
+  const unsigned fm = __ballot_sync(kFull, mine && fast);
+  if (lane == 0) {
+    if (fm) atomicAdd(p.counters + 4, (double)__popc(fm));
+    if (dm & ~fm) atomicAdd(p.counters + 5, (double)__popc(dm & ~fm));
   }
   __syncwarp();
+}
+
+// Background prefetch: for every env whose next-layout slot is empty, run the draws of
+// its NEXT Engine.reset (seed known in advance in both seed modes) and park the result in
+// the next_* planes.  One warp per 32-env chunk, grid-stride.  Launched off the step's
+// stream; the step kernel never waits for it (an env that finishes before its slot is
+// filled samples inline instead).
+template <int TASK, int N>
+__global__ void __launch_bounds__(256) prefetch_kernel(const KParams p) {
+  __shared__ __align__(16) float2 scratch[8][2 * ((N + 2) / 2)];   // rows stay 16-byte aligned
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float2* placed = scratch[warp];
+  const int n_chunks = (p.B + 31) / 32;
+  for (int chunk = blockIdx.x * 8 + warp; chunk < n_chunks; chunk += gridDim.x * 8) {
+    const int e = chunk * 32 + lane;
+    const bool need = e < p.B && ld_acquire_u32(p.next_ready + e) == 0u;
+    unsigned m = __ballot_sync(kFull, need);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const int se = chunk * 32 + src;
+      long long chosen = 0;
+      if (lane == src) chosen = choose_seed(p, se, p.episode[se]);
+      chosen = __shfl_sync(kFull, chosen, src);
+      uint32_t my_draw;
+      float rot0;
+      warp_generate<TASK, N>(p, chosen, placed, lane, my_draw, rot0);
+      if (lane < N) p.next_zone_xy[(size_t)lane * p.B + se] = placed[1 + lane];
+      if (TASK == CRL_TASK_TTSP) {
+        const uint32_t hi = __shfl_down_sync(kFull, my_draw, 1);
+        if (lane < N && !(lane & 1)) p.next_task[(size_t)(lane >> 1) * p.B + se] = my_draw | (lane + 1 < N ? hi << 16 : 0u);
+      }
+      if (TASK == CRL_TASK_CM) {
+        uint32_t cw = 0u;
+#pragma unroll
+        for (int i = 0; i < N; ++i) cw |= __shfl_sync(kFull, my_draw, i) << (2 * i);
+        if (lane == 0) p.next_task[se] = cw;
+      }
+      if (lane == 0) {
+        const float2 rb = placed[0];
+        p.next_origin[se] = make_float4(rb.x, rb.y, rot0, 0.f);
+        p.next_seed[se] = chosen;
+      }
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) st_release_u32(p.next_ready + se, 1u);
+    }
+  }
 }
 
 // ---- observation and store: shared by step, reset and reset_from_layout -------
@@ -471,14 +583,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const KParams p) {
       }
       // (5) auto-reset, penv.py:9-10: only the finished envs are rebuilt
       if (p.flags & CRL_STEP_AUTO_RESET) {
-        float2* placed = reinterpret_cast<float2*>(stage);
-        unsigned m = dm;
-        while (m) {
-          const int src = __ffs(m) - 1;
-          m &= m - 1;
-          const int se = __shfl_sync(kFull, e, src);
-          warp_reset_one<TASK, N>(p, src, lane, se, placed, env);
-        }
+        warp_reset<TASK, N>(p, dm, lane, e, reinterpret_cast<float2*>(stage), env);
         fresh = done;
       }
     }
@@ -510,14 +615,8 @@ __global__ void __launch_bounds__(kThreads) reset_kernel(const KParams p) {
   Env<N> env;
   if (valid) load_env<TASK, N>(p, e, env);
   const bool want = valid && (p.mask == nullptr || p.mask[e] != 0);
-  unsigned m = __ballot_sync(kFull, want);
-  float2* placed = reinterpret_cast<float2*>(stage);
-  while (m) {
-    const int src = __ffs(m) - 1;
-    m &= m - 1;
-    const int se = __shfl_sync(kFull, e, src);
-    warp_reset_one<TASK, N>(p, src, lane, se, placed, env);
-  }
+  const unsigned m = __ballot_sync(kFull, want);
+  if (m) warp_reset<TASK, N>(p, m, lane, e, reinterpret_cast<float2*>(stage), env);
   float c = 1.f, s = 0.f;
   if (valid) sincosf(env.b.phi, &s, &c);
   // envs that were not reset are rewritten with the values just loaded (no change)
@@ -658,6 +757,15 @@ static int fill_params(const CrlConfig* c, const CrlState* st, const CrlOut* out
   p.cooldown = reinterpret_cast<uint2*>(st->cooldown);
   p.seed = reinterpret_cast<long long*>(st->seed); p.episode = st->episode;
   p.origin = reinterpret_cast<float4*>(st->origin); p.counters = st->counters;
+  // optional prefetch planes: all present or none
+  if (st->next_ready) {
+    if (!st->next_zone_xy || !st->next_origin || !st->next_seed || (c->task != CRL_TASK_TSP && !st->next_task))
+      return CRL_ERR_NULL;
+    if (!aligned16(st->next_origin) || !aligned16(st->next_zone_xy)) return CRL_ERR_ALIGN;
+    p.next_zone_xy = reinterpret_cast<float2*>(st->next_zone_xy); p.next_task = st->next_task;
+    p.next_origin = reinterpret_cast<float4*>(st->next_origin);
+    p.next_seed = reinterpret_cast<long long*>(st->next_seed); p.next_ready = st->next_ready;
+  }
   if (out) {
     if (!out->obs || !out->zone_obs || !out->result) return CRL_ERR_NULL;
     if (!aligned16(out->obs) || !aligned16(out->zone_obs)) return CRL_ERR_ALIGN;
@@ -717,7 +825,7 @@ const char* crl_strerror(int code) {
   }
 }
 
-int crl_plane_bytes(const CrlConfig* c, int64_t o[12]) {
+int crl_plane_bytes(const CrlConfig* c, int64_t o[17]) {
   int rc = check_config(c);
   if (rc) return rc;
   if (!o) return CRL_ERR_NULL;
@@ -725,8 +833,11 @@ int crl_plane_bytes(const CrlConfig* c, int64_t o[12]) {
   o[0] = 16 * B; o[1] = 16 * B; o[2] = 8 * N * B;
   o[3] = c->task == CRL_TASK_TTSP ? 4 * ((N + 1) / 2) * B : 0;
   o[4] = c->task == CRL_TASK_CM ? 8 * B : 0;
-  o[5] = 8 * B; o[6] = 4 * B; o[7] = 16 * B; o[8] = 4 * 8;
-  o[9] = 32 * B; o[10] = 4 * N * Z * B; o[11] = 8 * B;
+  o[5] = 8 * B; o[6] = 4 * B; o[7] = 16 * B; o[8] = 8 * 8;
+  o[9] = 8 * N * B;
+  o[10] = c->task == CRL_TASK_TTSP ? 4 * ((N + 1) / 2) * B : (c->task == CRL_TASK_CM ? 4 * B : 0);
+  o[11] = 16 * B; o[12] = 8 * B; o[13] = 4 * B;
+  o[14] = 32 * B; o[15] = 4 * N * Z * B; o[16] = 8 * B;
   return CRL_OK;
 }
 
@@ -810,6 +921,19 @@ int crl_reset_from_layout(const CrlConfig* c, const CrlState* st, const CrlOut* 
   return launch_status();
 }
 
+int crl_prefetch_layouts(const CrlConfig* c, const CrlState* st, void* stream) {
+  KParams p;
+  int rc = fill_params(c, st, nullptr, p);
+  if (rc) return rc;
+  if (!p.next_ready) return CRL_ERR_NULL;
+  const int n_chunks = (p.B + 31) / 32;
+  const int blocks = min((n_chunks + 7) / 8, 148 * 8);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define CRL_CALL_PREFETCH(T, NN) { prefetch_kernel<T, NN><<<blocks, 256, 0, s>>>(p); }
+  CRL_DISPATCH(c->task, c->num_zones, CRL_CALL_PREFETCH);
+  return launch_status();
+}
+
 int crl_set_qpos_qvel(const CrlConfig* c, const CrlState* st, const double* qpos, const double* qvel,
                       const int32_t* env_ids, int32_t n, void* stream) {
   KParams p;
@@ -853,10 +977,10 @@ int crl_step_host(const CrlConfig* c, const CrlState* st, const float* actions_h
   return CRL_OK;
 }
 
-int crl_counters_read(const CrlState* st, double out[4], void* stream) {
+int crl_counters_read(const CrlState* st, double out[8], void* stream) {
   if (!st || !st->counters || !out) return CRL_ERR_NULL;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (cudaMemcpyAsync(out, st->counters, 4 * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess)
+  if (cudaMemcpyAsync(out, st->counters, 8 * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess)
     return CRL_ERR_DEVICE;
   if (cudaStreamSynchronize(s) != cudaSuccess) return CRL_ERR_DEVICE;
   return CRL_OK;

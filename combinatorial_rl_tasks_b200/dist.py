@@ -17,9 +17,9 @@ def shard(num_envs_per_gpu, rank=None):
 
 
 def reduce_counters(counters):
-    """all-reduce(sum) of the (4,) float64 counter tensor; returns a dict of floats plus
+    """all-reduce(sum) of the float64 counter tensor (first four entries); returns a dict of floats plus
     the derived mean return / success rate / mean length."""
-    c = counters.detach().clone()
+    c = counters.detach().clone()[:4]
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
     ret, n, succ, length = (float(x) for x in c.cpu())

@@ -45,7 +45,7 @@ class _EnvView:
 
 class ZoneVecEnv:
     def __init__(self, env_id, num_envs, device='cuda:0', seed_mode='increment', min_seed=1, max_seed=100,
-                 env_offset=0, auto_reset=True):
+                 env_offset=0, auto_reset=True, prefetch_every=8):
         if not torch.cuda.is_available():
             raise RuntimeError('ZoneVecEnv needs a CUDA device (sm_100a); there is no CPU fallback')
         self.lib = _lib.load()
@@ -54,6 +54,7 @@ class ZoneVecEnv:
         self.num_envs = B = int(num_envs)
         self.device = torch.device(device)
         self.auto_reset = auto_reset
+        self.prefetch_every = prefetch_every      # 0: never park next layouts (resets sample inline)
         N, Z = spec.num_zones, spec.zone_dim
         self.cfg = _lib.CrlConfig(
             task=spec.task, num_envs=B, num_zones=N, num_steps=spec.num_steps, frameskip=spec.frameskip,
@@ -73,7 +74,19 @@ class ZoneVecEnv:
         self.seeds = z(B, dtype=torch.int64)
         self.episode = z(B, dtype=torch.int32)
         self.origin = z(B, 4)
-        self.counters_dev = z(4, dtype=torch.float64)
+        self.counters_dev = z(8, dtype=torch.float64)
+        # next-layout slots, filled in the background by crl_prefetch_layouts
+        self.next_zone_xy = z(N, B, 2)
+        if spec.task == _lib.TASK_TTSP:
+            self.next_task = z((N + 1) // 2, B, dtype=torch.int32)
+        elif spec.task == _lib.TASK_CM:
+            self.next_task = z(B, dtype=torch.int32)
+        else:
+            self.next_task = None
+        self.next_origin = z(B, 4)
+        self.next_seed = z(B, dtype=torch.int64)
+        self.next_ready = z(B, dtype=torch.int32)
+        self._side = torch.cuda.Stream(device=dev)
         # outputs
         self.obs = z(B, 8)
         self.zone_obs = z(B, N, Z)
@@ -87,7 +100,9 @@ class ZoneVecEnv:
         self.state = _lib.CrlState(pose=ptr(self.pose), aux=ptr(self.aux), zone_xy=ptr(self.zone_xy),
                                    zone_tmax=ptr(self.zone_tmax), cooldown=ptr(self.cooldown),
                                    seed=ptr(self.seeds), episode=ptr(self.episode), origin=ptr(self.origin),
-                                   counters=ptr(self.counters_dev))
+                                   counters=ptr(self.counters_dev), next_zone_xy=ptr(self.next_zone_xy),
+                                   next_task=ptr(self.next_task), next_origin=ptr(self.next_origin),
+                                   next_seed=ptr(self.next_seed), next_ready=ptr(self.next_ready))
         self.out = _lib.CrlOut(obs=ptr(self.obs), zone_obs=ptr(self.zone_obs), result=ptr(self.result))
         self._actions_dev = z(B, 2)
         self._host = None
@@ -120,6 +135,22 @@ class ZoneVecEnv:
             seeds = torch.arange(self.num_envs, dtype=torch.int64) + seeds
         self.seeds.copy_(self._as_dev(seeds, torch.int64))
         self.episode.zero_()
+        self.next_ready.zero_()          # parked layouts were drawn for the old seeds
+
+    def prefetch(self, stream=None):
+        """Fill the empty next-layout slots in the background (crl_prefetch_layouts) on a
+        side stream.  Needs no ordering with step(): slots change hands through
+        acquire/release flags and an env that finishes before its slot is filled is
+        sampled inline with the identical result."""
+        if stream is None:
+            # not earlier than the work already queued on the stepping stream (the host may
+            # run far ahead of the device), but never blocking it
+            stream = self._side
+            stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.crl_prefetch_layouts(self.cfg, self.state,
+                                                     ctypes.c_void_p(stream.cuda_stream)))
+        self.gpu_launches += 1
 
     def reset(self, layout=None, mask=None, env_ids=None):
         """Engine.reset of all envs (or those in ``mask``).  ``layout`` switches to the
@@ -145,6 +176,9 @@ class ZoneVecEnv:
                                                           None if ids is None else ids.data_ptr(), n,
                                                           self._stream()))
             self.gpu_launches += 1
+            if self.prefetch_every and not torch.cuda.is_current_stream_capturing():
+                # the reset above must be visible to the prefetcher: same-stream launch
+                self.prefetch(torch.cuda.current_stream(self.device))
         return self._obs_dict()
 
     def _step(self, actions, flags, action_seed=0):
@@ -161,6 +195,9 @@ class ZoneVecEnv:
                                          self._step_index, self._stream()))
         self._step_index += 1
         self.gpu_launches += 1
+        if (self.prefetch_every and self._step_index % self.prefetch_every == 0
+                and not torch.cuda.is_current_stream_capturing()):
+            self.prefetch()
         return self._obs_dict(), self.reward, self.done, self._info()
 
     def step(self, actions):
@@ -207,10 +244,11 @@ class ZoneVecEnv:
 
     def counters(self):
         """Episode statistics accumulated in-kernel since construction."""
-        out = (ctypes.c_double * 4)()
+        out = (ctypes.c_double * 8)()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.crl_counters_read(self.state, out, self._stream()))
-        return {'return_sum': out[0], 'episodes': out[1], 'successes': out[2], 'length_sum': out[3]}
+        return {'return_sum': out[0], 'episodes': out[1], 'successes': out[2], 'length_sum': out[3],
+                'resets_prefetched': out[4], 'resets_inline': out[5]}
 
     def set_qpos_qvel(self, qpos, qvel, env_ids=None):
         """Overwrite sim.data.qpos / qvel (fp64, reference coordinates) of some envs."""

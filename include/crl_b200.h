@@ -37,8 +37,15 @@
  *    episode   uint32[B]   resets performed so far
  *    origin    float4[B]   (x0, y0, rot0, 0): the MuJoCo body frame of the episode,
  *                          kept only to convert to/from qpos/qvel
- *    counters  double[4]   sum of episode returns, episodes finished, successes
- *                          (goal_met), sum of episode lengths
+ *    counters  double[8]   sum of episode returns, episodes finished, successes
+ *                          (goal_met), sum of episode lengths, resets served from a
+ *                          prefetched layout, resets sampled inline, 2 reserved
+ *  optional next-layout planes (all NULL = no prefetch): the draws of each env's NEXT
+ *  Engine.reset, made in the background by crl_prefetch_layouts so that an auto-reset
+ *  inside crl_step is a copy instead of a rejection-sampling loop
+ *    next_zone_xy float2[N][B], next_task uint32[ceil(N/2)][B] (TimedTSP timeouts) or
+ *    uint32[B] (ColourMatch colour codes), next_origin float4[B], next_seed int64[B]
+ *    (the seed the parked layout was drawn for), next_ready uint32[B] (0 = slot empty)
  *  outputs, the layout the reference's consumer builds (main/src/utils/format.py:27-28):
  *    obs       float[B][8]      remaining, pos/3 (2), dir (2), vel/1.5 (2), yaw rate/3
  *    zone_obs  float[B][N][Z]   x/3, y/3, r, g, b, 0.25 [, time left | cooldown/150]
@@ -53,7 +60,7 @@
 extern "C" {
 #endif
 
-#define CRL_ABI_VERSION 1
+#define CRL_ABI_VERSION 2
 #define CRL_MAX_ZONES 16
 
 /* task ids; reference classes: main/envs/TSP_env.py:11, TTSP_env.py:12, colour_match_env.py:11 */
@@ -108,7 +115,12 @@ typedef struct CrlState {
   int64_t* seed;        /* int64[B] */
   uint32_t* episode;    /* uint32[B] */
   float* origin;        /* float4[B] */
-  double* counters;     /* double[4] */
+  double* counters;     /* double[8] */
+  float* next_zone_xy;  /* float2[N][B]; optional (prefetch) */
+  uint32_t* next_task;  /* TTSP: uint32[ceil(N/2)][B]; ColourMatch: uint32[B]; optional */
+  float* next_origin;   /* float4[B]; optional */
+  int64_t* next_seed;   /* int64[B]; optional */
+  uint32_t* next_ready; /* uint32[B]; optional.  Zero it whenever CrlState.seed is rewritten */
 } CrlState;
 
 typedef struct CrlResult {
@@ -139,9 +151,10 @@ int crl_abi_version(void);
 const char* crl_strerror(int code);
 
 /* Bytes the caller must allocate for each plane of CrlState / CrlOut, in the order
- * pose, aux, zone_xy, zone_tmax, cooldown, seed, episode, origin, counters,
- * obs, zone_obs, result (12 entries; 0 = plane unused by this task). */
-int crl_plane_bytes(const CrlConfig* cfg, int64_t out_bytes[12]);
+ * pose, aux, zone_xy, zone_tmax, cooldown, seed, episode, origin, counters, next_zone_xy,
+ * next_task, next_origin, next_seed, next_ready, obs, zone_obs, result
+ * (17 entries; 0 = plane unused by this task). */
+int crl_plane_bytes(const CrlConfig* cfg, int64_t out_bytes[17]);
 
 /* Algorithmic HBM bytes one env-step moves in this layout: read, written. */
 int crl_step_bytes(const CrlConfig* cfg, int64_t* bytes_read, int64_t* bytes_written);
@@ -153,6 +166,14 @@ int crl_step_bytes(const CrlConfig* cfg, int64_t* bytes_read, int64_t* bytes_wri
  * TTSP_env.py:73-76 / colour_match_env.py:125-127. */
 int crl_reset(const CrlConfig* cfg, const CrlState* st, const CrlOut* out,
               const uint8_t* mask, void* stream);
+
+/* Fill the empty next-layout slots (see CrlState.next_*): for each env whose slot is
+ * empty, draw its NEXT reset now.  Meant to be launched every few steps on a stream other
+ * than the stepping one; it needs no ordering with crl_step (slots are handed over with
+ * acquire/release flags, and an env that finishes before its slot is filled is sampled
+ * inline by crl_step with the identical result).  Hides Engine.build_layout's rejection
+ * sampling, which the reference runs inside reset() (penv.py:9-10). */
+int crl_prefetch_layouts(const CrlConfig* cfg, const CrlState* st, void* stream);
 
 /* The same reset with the layout handed in (device arrays, see CrlLayoutIn) for
  * envs env_ids[0..n) (env_ids == NULL: envs 0..n). */
@@ -183,9 +204,9 @@ int crl_set_qpos_qvel(const CrlConfig* cfg, const CrlState* st, const double* qp
 int crl_get_qpos_qvel(const CrlConfig* cfg, const CrlState* st, double* qpos, double* qvel,
                       const int32_t* env_ids, int32_t n, void* stream);
 
-/* Copies counters to the host (synchronises `stream`): sum of returns, episodes,
- * successes, sum of lengths.  These four doubles are what ranks all-reduce. */
-int crl_counters_read(const CrlState* st, double out[4], void* stream);
+/* Copies the eight counters to the host (synchronises `stream`).  The first four (sum of
+ * returns, episodes, successes, sum of lengths) are what ranks all-reduce. */
+int crl_counters_read(const CrlState* st, double out[8], void* stream);
 
 #ifdef __cplusplus
 }

@@ -252,3 +252,87 @@ def test_full_size_properties(crl, env_id, B):
             assert np.all((steps[:, None] < tm) | vis)                               # else it would have ended
             want = np.where(vis, np.float32(1.0), ((tm - steps[:, None]) / 2000.0).astype(np.float32))
             assert np.array_equal(z[:, :, 6], want)
+
+
+@pytest.mark.parametrize('env_id', ['PointTTSP-v0', 'ColourMatch-v0'])
+def test_device_sampler_is_distribution_equivalent_to_reference_sampler(crl, env_id):
+    """The Philox reset on the device vs Engine.sample_layout / beta / choice on numpy's
+    legacy stream (the oracle's C twin): two-sample Kolmogorov-Smirnov / chi-square tests
+    on the statistics a layout is made of.  Different streams, same distribution."""
+    from scipy import stats
+    n = 6000
+    env = crl.ZoneVecEnv(env_id, n)
+    env.seed(424242)
+    env.reset()
+    torch.cuda.synchronize()
+    N = env.spec.num_zones
+    g_xy0 = env.origin[:, :2].cpu().numpy().astype(np.float64)
+    g_rot = env.origin[:, 2].cpu().numpy().astype(np.float64)
+    g_z = env.zone_xy.cpu().numpy().transpose(1, 0, 2).astype(np.float64)
+    r_xy0, r_rot, r_z, r_tm, r_col = [], [], [], [], []
+    c = co.CEnv(env_id)
+    for s in range(n):
+        c.seed(7000000 + s)
+        c.reset()
+        lay = c.layout()
+        r_xy0.append(lay['xy0']); r_rot.append(lay['rot0']); r_z.append(lay['zone_xy'])
+        r_tm.append(lay.get('zone_max_steps', np.zeros(N))); r_col.append(lay.get('colours', np.zeros(N)))
+    r_xy0, r_rot, r_z = np.array(r_xy0), np.array(r_rot), np.array(r_z)
+
+    def ks(a, b, what):
+        p = stats.ks_2samp(np.ravel(a), np.ravel(b)).pvalue
+        assert p > 1e-4, (what, p)
+
+    ks(g_xy0[:, 0], r_xy0[:, 0], 'robot x'); ks(g_xy0[:, 1], r_xy0[:, 1], 'robot y'); ks(g_rot, r_rot, 'robot rot')
+    for k in (0, N // 2, N - 1):                 # early, middle and last-placed zone differ in distribution
+        ks(g_z[:, k, 0], r_z[:, k, 0], f'zone {k} x'); ks(g_z[:, k, 1], r_z[:, k, 1], f'zone {k} y')
+        ks(np.linalg.norm(g_z[:, k] - g_xy0, axis=1), np.linalg.norm(r_z[:, k] - r_xy0, axis=1), f'zone {k} - robot')
+
+    def nearest(z):
+        d = np.linalg.norm(z[:, :, None] - z[:, None], axis=3) + np.eye(z.shape[1]) * 1e9
+        return d.min(2)
+    ks(nearest(g_z), nearest(r_z), 'nearest-neighbour distance')
+    ks(np.abs(g_z).max(2), np.abs(r_z).max(2), 'distance to the arena edge')
+    if env_id == 'PointTTSP-v0':
+        ks(tmax_of(env), np.array(r_tm), 'zone_max_steps ~ int(Beta(3,1.5)*2000)')
+    else:
+        bits = bits_of(env) >> 16
+        g_col = (bits[:, None] >> (2 * np.arange(N))) & 3
+        obs_counts = np.array([np.bincount(g_col.ravel(), minlength=3), np.bincount(np.array(r_col).astype(int).ravel(), minlength=3)])
+        assert stats.chi2_contingency(obs_counts)[1] > 1e-4
+
+
+@pytest.mark.parametrize('env_id', TASKS)
+def test_prefetched_resets_equal_inline_resets(crl, env_id):
+    """A reset served from a parked (prefetched) layout and a reset sampled inline give
+    bit-identical state: the layout is a pure function of the seed.  Also checks that the
+    parked path is the one taken when slots are full, and that re-seeding invalidates it."""
+    B = 1000
+    a = crl.ZoneVecEnv(env_id, B, prefetch_every=4)
+    b = crl.ZoneVecEnv(env_id, B, prefetch_every=0)
+    for e in (a, b):
+        e.seed(31337); e.reset()
+    torch.cuda.synchronize()
+    assert bool((a.next_ready == 1).all()) and bool((b.next_ready == 0).all())
+    gen = torch.Generator(device='cuda'); gen.manual_seed(0)
+    for rnd in range(3):
+        for e in (a, b):                      # everyone finishes within the next 30 steps
+            bits = e.aux[:, 3].view(torch.int32)
+            bits.copy_((bits & ~0xffff) | (e.spec.num_steps - 1 - (torch.arange(B, device='cuda', dtype=torch.int32) % 30)))
+        for t in range(40):
+            act = torch.rand(B, 2, device='cuda', generator=gen) * 2 - 1
+            a.step(act); b.step(act)
+            torch.cuda.synchronize()          # let the side-stream prefetch land before the next wave
+    sa, sb = snapshot(a), snapshot(b)
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    ca, cb = a.counters(), b.counters()
+    assert cb['resets_prefetched'] == 0 and cb['resets_inline'] == cb['episodes'] + B
+    assert ca['resets_prefetched'] >= 3 * B and ca['resets_prefetched'] + ca['resets_inline'] == ca['episodes'] + B
+    # re-seeding drops the parked layouts: the next reset must not use them
+    a.seed(99)
+    assert bool((a.next_ready == 0).all())
+    a.prefetch_every = 0
+    a.reset()
+    tw = co.philox_reset(env_id, 99 + 5)
+    assert np.array_equal(a.zone_xy[:, 5, :].cpu().numpy(), tw['zone_xy'])
