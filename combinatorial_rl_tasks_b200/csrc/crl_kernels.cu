@@ -308,12 +308,13 @@ __device__ void warp_reset(const KParams& p, unsigned dm, int lane, int e, float
 // stream; the step kernel never waits for it (an env that finishes before its slot is
 // filled samples inline instead).
 template <int TASK, int N>
-__global__ void __launch_bounds__(256) prefetch_kernel(const KParams p) {
-  __shared__ __align__(16) float2 scratch[8][2 * ((N + 2) / 2)];   // rows stay 16-byte aligned
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float2* placed = scratch[warp];
+__global__ void __launch_bounds__(32) prefetch_kernel(const KParams p) {
+  // One warp per block and a small persistent grid: the kernel shares the SMs with the
+  // step kernels of the main stream and must not crowd them out of registers or slots.
+  __shared__ __align__(16) float2 placed[2 * ((N + 2) / 2)];
+  const int lane = threadIdx.x;
   const int n_chunks = (p.B + 31) / 32;
-  for (int chunk = blockIdx.x * 8 + warp; chunk < n_chunks; chunk += gridDim.x * 8) {
+  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
     const int e = chunk * 32 + lane;
     const bool need = e < p.B && ld_acquire_u32(p.next_ready + e) == 0u;
     unsigned m = __ballot_sync(kFull, need);
@@ -927,9 +928,9 @@ int crl_prefetch_layouts(const CrlConfig* c, const CrlState* st, void* stream) {
   if (rc) return rc;
   if (!p.next_ready) return CRL_ERR_NULL;
   const int n_chunks = (p.B + 31) / 32;
-  const int blocks = min((n_chunks + 7) / 8, 148 * 8);
+  const int blocks = min(n_chunks, 148 * 4);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-#define CRL_CALL_PREFETCH(T, NN) { prefetch_kernel<T, NN><<<blocks, 256, 0, s>>>(p); }
+#define CRL_CALL_PREFETCH(T, NN) { prefetch_kernel<T, NN><<<blocks, 32, 0, s>>>(p); }
   CRL_DISPATCH(c->task, c->num_zones, CRL_CALL_PREFETCH);
   return launch_status();
 }
