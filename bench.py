@@ -142,14 +142,15 @@ def run_ours(args):
     W = max(3, args.warmup)
     envs = []
     for r in range(R):
-        e = crl.ZoneVecEnv(args.env, B, device=dev, env_offset=(rank * R + r) * B)
+        e = crl.ZoneVecEnv(args.env, B, device=dev, env_offset=(rank * R + r) * B,
+                           prefetch_every=args.prefetch_every)
         e.seed(1 + (rank * R + r) * B)
         e.reset()
         envs.append(e)
     g = torch.Generator(device=dev)
     g.manual_seed(1234 + rank)
     actions = [torch.rand(B, 2, device=dev, generator=g) * 2 - 1 for _ in range(R)]
-    flags = _lib.STEP_AUTO_RESET
+    flags = 0 if args.no_auto_reset else _lib.STEP_AUTO_RESET
 
     def cycle(n=R):
         for e, a in list(zip(envs, actions))[:n]:
@@ -173,7 +174,7 @@ def run_ours(args):
         # slots are topped up on each replica's side stream (concurrent with the steps)
         for i in range(n_steps // R):
             graph.replay()
-            if i % 8 == 7:
+            if args.prefetch_every and i % args.prefetch_every == args.prefetch_every - 1:
                 for e in envs:
                     e.prefetch()
                 launches['prefetch'] += R
@@ -259,7 +260,8 @@ def run_ours(args):
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'{args.env}, {B} batched envs per launch, random actions, auto-reset on',
+        'config': {'workload': f'{args.env}, {B} batched envs per launch, random actions, auto-reset {"off" if args.no_auto_reset else "on"}',
+                   'prefetch_every': args.prefetch_every,
                    'envs_per_gpu_per_launch': B, 'ring_replicas': R,
                    'l2': f'ring of {R} independent {B}-env replicas ({R * B * step_bytes / 1e6:.0f} MB touched per '
                          f'cycle) > 2x the 126 MB L2, so every launch reads HBM',
@@ -299,6 +301,9 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=50)
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-auto-reset', action='store_true', help='diagnostic: finished envs keep stepping')
+    ap.add_argument('--prefetch-every', type=int, default=8,
+                    help='top up the next-layout slots every N ring cycles (0: resets sample inline)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

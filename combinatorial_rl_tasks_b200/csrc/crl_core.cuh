@@ -88,7 +88,8 @@ CRL_HD void substeps(Body& b, float a0, float a1, int n, float& c_out, float& s_
     c = cn;
   }
   b.X = X; b.Y = Y; b.phi = phi; b.vx = vx; b.vy = vy; b.w = w;
-  const float r = 1.0f / sqrtf(c * c + s * s);
+  // c^2 + s^2 = 1 + e with |e| ~ 1e-6 after n rotations: 1/sqrt(1+e) = 1.5 - 0.5(1+e) + O(e^2)
+  const float r = 1.5f - 0.5f * (c * c + s * s);
   c_out = c * r;
   s_out = s * r;
 }
@@ -110,6 +111,37 @@ inline double sqrt_threshold(double r) {
   while (sqrt(nextafter(t, INFINITY)) <= r) t = nextafter(t, INFINITY);
   while (sqrt(t) > r) t = nextafter(t, -INFINITY);
   return t;
+}
+
+// n / d correctly rounded (== IEEE float division) for integer-valued n and the two
+// divisors the observation uses (num_steps, max_cooldown): q0 = RN(n y), y = RN(1/d),
+// one exact-remainder correction (Markstein).  div_const_ok() proves it on the host, for
+// the divisor in force, over every numerator the kernels can form; a divisor that failed
+// the proof would be divided with __fdiv_rn instead (DivConst::exact == 0).
+struct DivConst { float d, y; int exact; };
+
+CRL_HD float div_const(float n, const DivConst& k) {
+#if defined(__CUDA_ARCH__)
+  if (!k.exact) return __fdiv_rn(n, k.d);
+  const float q0 = __fmul_rn(n, k.y);
+  return __fmaf_rn(__fmaf_rn(-q0, k.d, n), k.y, q0);
+#else
+  if (!k.exact) return n / k.d;
+  const float q0 = n * k.y;
+  return fmaf(fmaf(-q0, k.d, n), k.y, q0);
+#endif
+}
+
+inline DivConst make_div_const(int d, int n_lo, int n_hi) {
+  DivConst k{(float)d, 1.0f / (float)d, 1};
+  for (int n = n_lo; n <= n_hi && k.exact; ++n) {
+    volatile float fn = (float)n, fd = (float)d;
+    const float want = fn / fd;                    // IEEE division
+    const float q0 = (float)n * k.y;
+    const float got = fmaf(fmaf(-q0, k.d, (float)n), k.y, q0);
+    if (!(got == want)) k.exact = 0;
+  }
+  return k;
 }
 
 // numpy: sqrt(sum(square(zone - robot))) <= size.  fl(fl(dx*dx) + fl(dy*dy)) with no
@@ -134,14 +166,19 @@ CRL_HD bool near_zone(float X, float Y, float zx, float zy, float r2_guard) {
 }
 
 // colour_match_env.py:38-55 on 2-bit colour codes packed from bit 0 (0 B, 1 G, 2 R).
+CRL_HD int popcount32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __popc(x);
+#else
+  return __builtin_popcount(x);
+#endif
+}
+
 CRL_HD int hamming(uint32_t colours, int n) {
-  int nb = 0, ng = 0, nr = 0;
-  for (int i = 0; i < n; ++i) {
-    const uint32_t c = (colours >> (2 * i)) & 3u;
-    nb += (c == 0u);
-    ng += (c == 1u);
-    nr += (c == 2u);
-  }
+  const uint32_t field = n >= 16 ? 0x55555555u : ((1u << (2 * n)) - 1u) & 0x55555555u;
+  const uint32_t lo = colours & field, hi = (colours >> 1) & field;
+  const int ng = popcount32(lo & ~hi), nr = popcount32(hi & ~lo);
+  const int nb = popcount32(field & ~(lo | hi));
   const int to_b = 2 * ng + nr, to_g = 2 * nr + nb, to_r = 2 * nb + ng;
   int m = to_b < to_g ? to_b : to_g;
   return m < to_r ? m : to_r;

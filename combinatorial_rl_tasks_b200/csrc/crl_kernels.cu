@@ -38,6 +38,7 @@ struct KParams {
   double beta_a, beta_b;
   float robot_keepout, zone_keepout, extent;
   unsigned flags;
+  DivConst div_steps, div_cd;   // x / num_steps, x / max_cooldown (crl_core.cuh)
   unsigned long long action_seed, step_index;
   // state
   float4* pose;
@@ -380,10 +381,10 @@ __device__ __forceinline__ void zone_row(const KParams& p, const Env<N>& env, fl
         // TTSP_env.py:23-27: (zone_max_steps - steps) / max_steps in fp64, visited -> 1; its
         // float32 cast equals the correctly rounded float32 quotient (double rounding of a
         // quotient of two small integers is innocuous: 53 >= 2*24 + 2)
-        z[6] = v ? 1.0f : __fdiv_rn((float)(tm - env.steps), (float)p.num_steps);
+        z[6] = v ? 1.0f : div_const((float)(tm - env.steps), p.div_steps);
       } else {
         // colour_match_env.py:79: np.float32(cooldown) / 150 is a float32 division
-        z[6] = __fdiv_rn((float)cd_get(env.cd, i), (float)p.max_cd);
+        z[6] = div_const((float)cd_get(env.cd, i), p.div_cd);
       }
     }
   }
@@ -432,7 +433,7 @@ __device__ __forceinline__ void store_state_obs(const KParams& p, const Env<N>& 
   p.aux[e] = make_float4(env.b.vy, env.b.w, env.ep_return,
                          __int_as_float((int)((uint32_t)env.steps | (env.hi << 16))));
   if (TASK == CRL_TASK_CM) p.cooldown[e] = env.cd;
-  const float remaining = __fdiv_rn((float)(p.num_steps - env.steps), (float)p.num_steps);
+  const float remaining = div_const((float)(p.num_steps - env.steps), p.div_steps);
   p.obs[2 * (size_t)e] = make_float4(remaining, env.b.X * (1.0f / 3.0f), env.b.Y * (1.0f / 3.0f), c);
   p.obs[2 * (size_t)e + 1] = make_float4(s, env.b.vx * (1.0f / 1.5f), env.b.vy * (1.0f / 1.5f),
                                          env.b.w * (1.0f / 3.0f));
@@ -507,9 +508,15 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const KParams p) {
     // with the exact fp64 predicate, lowest index first.
     uint32_t cand = 0u;
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      const bool eligible = TASK == CRL_TASK_CM ? (cd_get(env.cd, i) == 0u) : !((env.hi >> i) & 1u);
-      cand |= (eligible && near_zone(env.b.X, env.b.Y, env.zone[i].x, env.zone[i].y, p.r2_guard)) ? (1u << i) : 0u;
+    for (int i = 0; i < N; ++i)
+      if (near_zone(env.b.X, env.b.Y, env.zone[i].x, env.zone[i].y, p.r2_guard)) cand |= 1u << i;
+    if (TASK == CRL_TASK_CM) {
+      if (cand) {                                  // rare: keep only zones whose cooldown is 0
+#pragma unroll
+        for (int i = 0; i < N; ++i) if (cd_get(env.cd, i) != 0u) cand &= ~(1u << i);
+      }
+    } else {
+      cand &= ~env.hi;                             // not yet visited (TSP_env.py:58)
     }
     int fired = -1;
     while (cand) {
@@ -520,32 +527,35 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const KParams p) {
       for (int j = 0; j < N; ++j) if (j == i) { zx = env.zone[j].x; zy = env.zone[j].y; }
       if (inside_zone(env.b.X, env.b.Y, zx, zy, p.thresh2)) { fired = i; break; }
     }
-    int event, old_dist = 0;
-    bool goal;
-    if (TASK == CRL_TASK_CM) old_dist = hamming(env.hi, N);
+    // (3) reward, goal, timeout: none of it reads the post-physics state
+    int event = 0;
     if (fired >= 0) {
       if (TASK == CRL_TASK_CM) {
+        const int old_dist = hamming(env.hi, N);
         const uint32_t col = (env.hi >> (2 * fired)) & 3u;
         const uint32_t nxt = col == 2u ? 0u : col + 1u;         // Blue -> Green -> Red -> Blue
         env.hi = (env.hi & ~(3u << (2 * fired))) | (nxt << (2 * fired));
         cd_set(env.cd, fired, (uint32_t)p.max_cd);
+        event = old_dist - hamming(env.hi, N);                  // colour_match_env.py:86-93
       } else {
         env.hi |= 1u << fired;
+        event = 1;
       }
     }
-    // (3) reward, goal, timeout: none of it reads the post-physics state
+    bool goal;
     if (TASK == CRL_TASK_CM) {
-      const int new_dist = hamming(env.hi, N);
-      event = fired >= 0 ? old_dist - new_dist : 0;
-      goal = new_dist == 0;
+      // goal_dist == 0 (colour_match_env.py:122-123)  <=>  all N zones share one colour
+      constexpr uint32_t kOnes = ((1u << (2 * N)) - 1u) & 0x55555555u;
+      goal = env.hi == 0u || env.hi == kOnes || env.hi == 2u * kOnes;
     } else {
-      event = fired >= 0 ? 1 : 0;
       goal = env.hi == ((1u << N) - 1u);
     }
     bool done = false;
-    double rew = (double)event;
-    if (goal) { rew += (double)(p.num_steps - env.steps) * p.bonus_per_step; done = true; }
-    const float reward = (float)rew;
+    float reward = (float)event;
+    if (goal) {                                    // reward_goal, fp64 as the reference (TSP_env.py:37-39)
+      reward = (float)((double)event + (double)(p.num_steps - env.steps) * p.bonus_per_step);
+      done = true;
+    }
     env.steps += 1;
     if (env.steps >= p.num_steps) done = true;
     if (TASK == CRL_TASK_TTSP && !done) {
@@ -736,6 +746,18 @@ static int check_config(const CrlConfig* c) {
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// DivConst for a divisor, proven once per distinct (divisor, numerator range) and cached.
+static DivConst cached_div_const(int d, int n_lo, int n_hi) {
+  struct Slot { int d, lo, hi; DivConst k; };
+  static Slot slots[8];
+  static int used = 0;
+  for (int i = 0; i < used; ++i)
+    if (slots[i].d == d && slots[i].lo == n_lo && slots[i].hi == n_hi) return slots[i].k;
+  const DivConst k = make_div_const(d, n_lo, n_hi);
+  if (used < 8) slots[used++] = Slot{d, n_lo, n_hi, k};
+  return k;
+}
+
 static int fill_params(const CrlConfig* c, const CrlState* st, const CrlOut* out, KParams& p) {
   int rc = check_config(c);
   if (rc) return rc;
@@ -752,6 +774,9 @@ static int fill_params(const CrlConfig* c, const CrlState* st, const CrlOut* out
   p.r2_guard = (float)(c->zone_size * c->zone_size * 1.001 + 1e-5);
   p.bonus_per_step = c->time_saved_reward;
   p.beta_a = c->beta_a; p.beta_b = c->beta_b;
+  // numerators: num_steps - steps and zone_max_steps - steps, both within +-65535
+  p.div_steps = cached_div_const(c->num_steps, -65535, 65535);
+  p.div_cd = cached_div_const(c->max_cooldown > 0 ? c->max_cooldown : 1, 0, 255);
   p.robot_keepout = (float)c->robot_keepout; p.zone_keepout = (float)c->zone_keepout; p.extent = (float)c->extent;
   p.pose = reinterpret_cast<float4*>(st->pose); p.aux = reinterpret_cast<float4*>(st->aux);
   p.zone_xy = reinterpret_cast<float2*>(st->zone_xy); p.zone_tmax = st->zone_tmax;

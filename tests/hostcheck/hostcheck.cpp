@@ -15,6 +15,12 @@ float hc_wrap_pi(float phi) { return crl::wrap_pi(phi); }
 double hc_sqrt_threshold(double r) { return crl::sqrt_threshold(r); }
 int hc_inside_zone(float X, float Y, float zx, float zy, double t2) { return crl::inside_zone(X, Y, zx, zy, t2); }
 int hc_hamming(uint32_t colours, int n) { return crl::hamming(colours, n); }
+// div_const over [n_lo, n_hi]: returns the host proof's verdict; out[i] = n / d as the kernel forms it
+int hc_div_const(int d, int n_lo, int n_hi, float* out) {
+  const crl::DivConst k = crl::make_div_const(d, n_lo, n_hi);
+  for (int n = n_lo; n <= n_hi; ++n) out[n - n_lo] = crl::div_const((float)n, k);
+  return k.exact;
+}
 void hc_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
   crl::U4 r = crl::philox4x32(crl::U4{ctr[0], ctr[1], ctr[2], ctr[3]}, key[0], key[1]);
   out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;

@@ -35,6 +35,7 @@ def hc():
     L.hc_inside_zone.argtypes = [ctypes.c_float] * 4 + [ctypes.c_double]
     L.hc_hamming.argtypes = [ctypes.c_uint32, ctypes.c_int]
     L.hc_philox.argtypes = [ctypes.c_void_p] * 3
+    L.hc_div_const.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p]
     return L
 
 
@@ -120,6 +121,28 @@ def test_hamming_exhaustive(hc):
     for cols in itertools.product(range(3), repeat=6):
         word = sum(c << (2 * i) for i, c in enumerate(cols))
         assert hc.hc_hamming(word, 6) == ze.hamming_to_goal(np.array(cols))
+
+
+def test_constant_division_equals_the_reference_values(hc):
+    """The kernel divides small integers by num_steps / max_cooldown with a reciprocal multiply and
+    one exact-remainder correction.  It must equal what the reference computes in fp64 and the
+    consumer casts to float32 (format.py:27-28): zone time (zone_max_steps - steps) / max_steps
+    (TTSP_env.py:25), remaining 1 - steps / num_steps (ZoneEnvBase.py:190-192), and
+    np.float32(cooldown) / 150 (colour_match_env.py:79)."""
+    for d in (2000, 1000, 300, 150, 7, 1999, 65535):
+        lo, hi = -65535, 65535
+        out = np.zeros(hi - lo + 1, dtype=np.float32)
+        assert hc.hc_div_const(d, lo, hi, out.ctypes.data) == 1, d
+        n = np.arange(lo, hi + 1, dtype=np.float64)
+        assert np.array_equal(out, (n / d).astype(np.float32)), d
+        assert np.array_equal(out, np.arange(lo, hi + 1).astype(np.float32) / np.float32(d)), d
+    steps = np.arange(0, 2001, dtype=np.float64)
+    out = np.zeros(2001, dtype=np.float32)
+    hc.hc_div_const(2000, 0, 2000, out.ctypes.data)
+    assert np.array_equal(out[::-1], (1.0 - steps / 2000).astype(np.float32))
+    out = np.zeros(256, dtype=np.float32)
+    hc.hc_div_const(150, 0, 255, out.ctypes.data)
+    assert np.array_equal(out, (np.arange(256).astype(np.float32) / 150).astype(np.float64).astype(np.float32))
 
 
 def test_closed_form_substep_vs_oracle(hc):
