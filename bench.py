@@ -151,10 +151,12 @@ def run_ours(args):
     g.manual_seed(1234 + rank)
     actions = [torch.rand(B, 2, device=dev, generator=g) * 2 - 1 for _ in range(R)]
     flags = 0 if args.no_auto_reset else _lib.STEP_AUTO_RESET
+    if args.chained < 0:
+        args.chained = 1 if B <= 131072 else 0
 
     def cycle(n=R):
         for e, a in list(zip(envs, actions))[:n]:
-            e._step(a, flags)
+            e._step(a, flags, chained=args.chained)
 
     cycle()                                                        # eager: smem opt-in, first touch
     torch.cuda.synchronize()
@@ -177,7 +179,7 @@ def run_ours(args):
             if args.prefetch_every and i % args.prefetch_every == args.prefetch_every - 1:
                 for e in envs:
                     e.prefetch()
-                launches['prefetch'] += R
+                launches['prefetch'] += R * (1 if envs[0].spec.task == _lib.TASK_TSP else 2)
         if n_steps % R:
             tails[n_steps % R].replay()
 
@@ -261,7 +263,7 @@ def run_ours(args):
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': f'{args.env}, {B} batched envs per launch, random actions, auto-reset {"off" if args.no_auto_reset else "on"}',
-                   'prefetch_every': args.prefetch_every,
+                   'prefetch_every': args.prefetch_every, 'chained_steps': bool(args.chained),
                    'envs_per_gpu_per_launch': B, 'ring_replicas': R,
                    'l2': f'ring of {R} independent {B}-env replicas ({R * B * step_bytes / 1e6:.0f} MB touched per '
                          f'cycle) > 2x the 126 MB L2, so every launch reads HBM',
@@ -273,9 +275,9 @@ def run_ours(args):
                      'achieved_canonical': canon * B / (ms_per_step * 1e-3) / 1e9 if canon else None,
                      'frac_of_nominal_8TBs': achieved / 8000.0},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': K + launches['prefetch'],
-        'gpu_launches_detail': {'step_kernel': K, 'prefetch_kernel (side stream)': launches['prefetch']},
+        'gpu_launches_detail': {'step_kernel': K, 'prefetch_layout_kernel + prefetch_task_kernel (side stream)': launches['prefetch']},
         'episode_stats': {'return_sum': c[0], 'episodes': c[1], 'successes': c[2], 'length_sum': c[3],
-                          'resets_prefetched': c[4], 'resets_inline': c[5],
+                          'resets_prefetched': c[4], 'resets_inline': c[5], 'chain_wait_timeouts': c[7],
                           'reduction': 'nccl all_reduce(sum)' if world > 1 else 'single rank'},
         'all_reps_ms': reps,
     }
@@ -302,6 +304,9 @@ def main():
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-auto-reset', action='store_true', help='diagnostic: finished envs keep stepping')
+    ap.add_argument('--chained', type=int, default=-1,
+                    help='1: back-to-back steps order themselves warp by warp (CRL_STEP_CHAINED); 0: whole-grid '
+                         'wait; -1: chained when a launch is at most a wave or two (<= 131072 envs)')
     ap.add_argument('--prefetch-every', type=int, default=8,
                     help='top up the next-layout slots every N ring cycles (0: resets sample inline)')
     args = ap.parse_args()

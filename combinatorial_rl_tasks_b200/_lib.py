@@ -4,15 +4,16 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libcrl_b200.so')
+# CRL_B200_LIB: a tuning variant built by build.py (another CUDA build of the same source), never a fallback
+LIB_PATH = os.environ.get('CRL_B200_LIB') or os.path.join(HERE, 'libcrl_b200.so')
 
 c_void_p, c_int32, c_int64, c_uint32, c_uint64, c_double = (
     ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_double)
 
 TASK_TSP, TASK_TTSP, TASK_CM = 0, 1, 2
 SEED_INCREMENT, SEED_FIXED_RANGE = 0, 1
-STEP_AUTO_RESET, STEP_PHYSICS_ONLY = 1, 2
-ABI_VERSION = 2
+STEP_AUTO_RESET, STEP_PHYSICS_ONLY, STEP_CHAINED, STEP_CHAIN_START = 1, 2, 4, 8
+ABI_VERSION = 3
 
 # every symbol include/crl_b200.h declares
 SYMBOLS = ['crl_abi_version', 'crl_strerror', 'crl_plane_bytes', 'crl_step_bytes', 'crl_reset',
@@ -32,7 +33,8 @@ class CrlConfig(ctypes.Structure):
 class CrlState(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in ('pose', 'aux', 'zone_xy', 'zone_tmax', 'cooldown', 'seed',
                                         'episode', 'origin', 'counters', 'next_zone_xy', 'next_task',
-                                        'next_origin', 'next_seed', 'next_ready')]
+                                        'next_origin', 'next_seed', 'next_ready', 'stamp',
+                                        'prefetch_cursor')]
 
 
 class CrlOut(ctypes.Structure):
@@ -62,7 +64,7 @@ def load():
     lib.crl_plane_bytes.argtypes = [P(CrlConfig), P(c_int64)]
     lib.crl_step_bytes.argtypes = [P(CrlConfig), P(c_int64), P(c_int64)]
     lib.crl_reset.argtypes = [P(CrlConfig), P(CrlState), P(CrlOut), c_void_p, c_void_p]
-    lib.crl_prefetch_layouts.argtypes = [P(CrlConfig), P(CrlState), c_void_p]
+    lib.crl_prefetch_layouts.argtypes = [P(CrlConfig), P(CrlState), c_int32, c_void_p]
     lib.crl_reset_from_layout.argtypes = [P(CrlConfig), P(CrlState), P(CrlOut), P(CrlLayoutIn), c_void_p,
                                           c_int32, c_void_p]
     lib.crl_step.argtypes = [P(CrlConfig), P(CrlState), c_void_p, P(CrlOut), c_uint32, c_uint64, c_uint64,

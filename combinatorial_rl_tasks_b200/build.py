@@ -19,14 +19,27 @@ def stale():
     return any(os.path.getmtime(d) > t for d in DEPS)
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, defines=None, out=None):
+    """defines/out: tuning variants (e.g. {'CRL_THREADS': 64} -> another .so, selected at run time
+    with CRL_B200_LIB=<path>); the product is the default build."""
+    out = out or LIB
+    if out == LIB and not force and not stale():
         return LIB
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB, SRC]
+    dflags = [f'-D{k}={v}' for k, v in (defines or {}).items()]
+    cmd = [nvcc] + NVCC_FLAGS + dflags + (['-Xptxas', '-v'] if verbose else []) + ['-o', out, SRC]
     subprocess.run(cmd, check=True)
-    return LIB
+    return out
 
 
 if __name__ == '__main__':
-    print(build(force=True, verbose=True))
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == 'variants':       # python build.py variants 64 32
+        for t in sys.argv[2:]:                                  # 64 -> CRL_THREADS=64; NAME=VAL -> -DNAME=VAL
+            if '=' in t:
+                k, v = t.split('=')
+                print(build(force=True, defines={k: v}, out=os.path.join(HERE, f'libcrl_b200_{k.lower()}.so')))
+            else:
+                print(build(force=True, defines={'CRL_THREADS': int(t)}, out=os.path.join(HERE, f'libcrl_b200_t{t}.so')))
+    else:
+        print(build(force=True, verbose=True))

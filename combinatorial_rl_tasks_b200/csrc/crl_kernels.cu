@@ -16,6 +16,8 @@
 //      single cp.async.bulk shared->global copy.
 // Episode statistics go through warp ballots and one atomic per warp.
 #include <cuda_runtime.h>
+
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -25,7 +27,10 @@
 
 namespace crl {
 
-constexpr int kThreads = 128;
+#ifndef CRL_THREADS
+#define CRL_THREADS 128
+#endif
+constexpr int kThreads = CRL_THREADS;
 constexpr unsigned kFull = 0xffffffffu;
 
 struct KParams {
@@ -55,6 +60,7 @@ struct KParams {
   float4* next_origin;
   long long* next_seed;
   uint32_t* next_ready;
+  uint32_t* stamp;
   // io
   const float2* actions;
   float4* obs;
@@ -65,6 +71,14 @@ struct KParams {
 
 template <int TASK>
 struct ZoneDim { static constexpr int Z = (TASK == CRL_TASK_TSP) ? 6 : 7; };
+
+// Resident warps per SM the step kernel is compiled for (register cap = 64 K / 32 / this):
+// the zone_obs stage (32 rows per warp in shared memory) allows 16-19 warps at 15 zones
+// and 42 at 6, so registers are capped to match rather than left to ptxas.
+template <int N>
+struct Occupancy { static constexpr int kWarps = N > 8 ? 16 : 28; };
+template <int N>
+constexpr int min_blocks() { return Occupancy<N>::kWarps * 32 / kThreads; }
 
 // Registers describing one env between load and store.
 template <int N>
@@ -102,7 +116,8 @@ __device__ __forceinline__ U4 draw(long long seed, uint32_t c0, uint32_t c1, uin
   return philox4x32(ctr, (uint32_t)(unsigned long long)seed, (uint32_t)((unsigned long long)seed >> 32));
 }
 
-// Marsaglia-Tsang gamma(a), a >= 1, from a counter stream (fp64: reset is off the hot path)
+// Marsaglia-Tsang gamma(a), a >= 1, from a counter stream (fp64: reset is off the hot path).
+// General-shape fallback; the reference's shapes take gamma_half_integer below.
 __device__ double gamma_mt(long long seed, double a, uint32_t zone, uint32_t which) {
   const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
   for (uint32_t it = 0;; ++it) {
@@ -115,6 +130,53 @@ __device__ double gamma_mt(long long seed, double a, uint32_t zone, uint32_t whi
     v = v * v * v;
     if (log(u3) < 0.5 * x * x + d - d * v + d * log(v) || it > 64u) return d * v;
   }
+}
+
+// gamma(k/2) for a small integer k, exactly and without rejection: the sum of floor(k/2)
+// unit exponentials, -log(u_0 ... u_{m-1}), plus, for odd k, half the square of a standard
+// normal, -log(U) cos^2(2 pi V) (Box-Muller squared).  TTSP_env.py:20 draws beta(3, 1.5):
+// k = 6 and k = 3, i.e. three logs and one cosine per zone and no data-dependent loop.
+// Uniform j of the stream is half j&1 of Philox block j>>1 (counter = (block, zone, which)).
+__device__ double gamma_half_integer(long long seed, int k, uint32_t zone, uint32_t which) {
+  const int m = k >> 1;
+  double prod = 1.0, U = 1.0, V = 0.0;
+  const int n_u = m + ((k & 1) ? 2 : 0);
+  for (int j = 0; j < n_u; j += 2) {
+    const U4 r = draw(seed, (uint32_t)(j >> 1), zone, which, kTagTask);
+    const double ua = u01d(r.x, r.y), ub = u01d(r.z, r.w);
+    if (j < m) prod *= ua; else if (j == m) U = ua; else V = ua;
+    if (j + 1 < m) prod *= ub; else if (j + 1 == m) U = ub; else if (j + 1 < n_u) V = ub;
+  }
+  double g = -log(prod);
+  if (k & 1) {
+    const double c = cos(2.0 * kPi * V);
+    g += -log(U) * (c * c);
+  }
+  return g;
+}
+
+// 2a if gamma_half_integer applies to shape a (2a a whole number in [1, 16]), else 0
+CRL_HD int half_integer_shape(double a) {
+  const double t = 2.0 * a;
+  const int k = (int)t;
+  return ((double)k == t && k >= 1 && k <= 16) ? k : 0;
+}
+
+__device__ double gamma_draw(long long seed, double a, uint32_t zone, uint32_t which) {
+  const int k = half_integer_shape(a);
+  return k ? gamma_half_integer(seed, k, zone, which) : gamma_mt(seed, a, zone, which);
+}
+
+// ColourMatch colour of one zone (colour_match_env.py:60-61, rs.choice of three): uniform
+// over {0,1,2} by masked rejection on the 2-bit fields of a Philox word.
+__device__ uint32_t colour_draw(long long seed, uint32_t zone) {
+  uint32_t c = 3u;
+  for (uint32_t it = 0; c == 3u && it < 64u; ++it) {
+    const U4 r = draw(seed, it, zone, 0u, kTagTask);
+    uint32_t bits = r.x;
+    for (int q = 0; q < 16 && c == 3u; ++q, bits >>= 2) c = bits & 3u;
+  }
+  return c == 3u ? 0u : c;
 }
 
 // Rejection-sample robot + N zones exactly as Engine.sample_layout orders it (object by
@@ -191,20 +253,12 @@ __device__ void warp_generate(const KParams& p, long long chosen, float2* placed
                               uint32_t& my_draw, float& rot0) {
   my_draw = 0u;
   if (TASK == CRL_TASK_TTSP && lane < N) {
-    const double ga = gamma_mt(chosen, p.beta_a, (uint32_t)lane, 0u);
-    const double gb = gamma_mt(chosen, p.beta_b, (uint32_t)lane, 1u);
+    const double ga = gamma_draw(chosen, p.beta_a, (uint32_t)lane, 0u);
+    const double gb = gamma_draw(chosen, p.beta_b, (uint32_t)lane, 1u);
     const int t = (int)((ga / (ga + gb)) * (double)p.num_steps);
     my_draw = (uint32_t)min(max(t, 0), 65535);
   }
-  if (TASK == CRL_TASK_CM && lane < N) {
-    uint32_t c = 3u;                              // uniform over {0,1,2}: masked rejection on 2-bit fields
-    for (uint32_t it = 0; c == 3u && it < 64u; ++it) {
-      const U4 r = draw(chosen, it, (uint32_t)lane, 0u, kTagTask);
-      uint32_t bits = r.x;
-      for (int q = 0; q < 16 && c == 3u; ++q, bits >>= 2) c = bits & 3u;
-    }
-    my_draw = c == 3u ? 0u : c;
-  }
+  if (TASK == CRL_TASK_CM && lane < N) my_draw = colour_draw(chosen, (uint32_t)lane);
   warp_layout<N>(p, chosen + 1, placed, lane);
   const U4 rr = draw(chosen + 1, 0u, 0u, 0u, kTagRot);
   rot0 = __fmul_rn(6.2831855f, u01(rr.x));
@@ -225,8 +279,13 @@ __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
 // it: no sampling latency on the step's critical path.  The others are rebuilt one at a
 // time by the whole warp.  Both ways produce the same layout: it is a pure function of
 // the seed.
+#ifdef CRL_INLINE_RESET
+#define CRL_RESET_INLINING __forceinline__
+#else
+#define CRL_RESET_INLINING __noinline__
+#endif
 template <int TASK, int N>
-__device__ void warp_reset(const KParams& p, unsigned dm, int lane, int e, float2* placed, Env<N>& env) {
+__device__ CRL_RESET_INLINING void warp_reset(const KParams& p, unsigned dm, int lane, int e, float2* placed, Env<N>& env) {
   const bool mine = (dm >> lane) & 1u;
   long long chosen = 0;
   uint32_t episode = 0;
@@ -236,7 +295,7 @@ __device__ void warp_reset(const KParams& p, unsigned dm, int lane, int e, float
   if (mine) {
     episode = p.episode[e];
     chosen = choose_seed(p, e, episode);
-    if (p.next_ready && ld_acquire_u32(p.next_ready + e) != 0u && p.next_seed[e] == chosen) {
+    if (p.next_ready && ld_acquire_u32(p.next_ready + e) == 1u /* kSlotReady */ && p.next_seed[e] == chosen) {
       fast = true;
       const float4 o = p.next_origin[e];
       x0 = o.x; y0 = o.y; rot0 = o.z;
@@ -303,51 +362,136 @@ __device__ void warp_reset(const KParams& p, unsigned dm, int lane, int e, float
   __syncwarp();
 }
 
-// Background prefetch: for every env whose next-layout slot is empty, run the draws of
-// its NEXT Engine.reset (seed known in advance in both seed modes) and park the result in
-// the next_* planes.  One warp per 32-env chunk, grid-stride.  Launched off the step's
-// stream; the step kernel never waits for it (an env that finishes before its slot is
-// filled samples inline instead).
-template <int TASK, int N>
-__global__ void __launch_bounds__(32) prefetch_kernel(const KParams p) {
-  // One warp per block and a small persistent grid: the kernel shares the SMs with the
-  // step kernels of the main stream and must not crowd them out of registers or slots.
-  __shared__ __align__(16) float2 placed[2 * ((N + 2) / 2)];
+// ---- background prefetch of next layouts -------------------------------------------
+// For every env whose next-layout slot is empty (next_ready == 0), run the draws of its NEXT
+// Engine.reset (the seed is known in advance in both seed modes) and park the result in the
+// next_* planes.  Launched off the step's stream; the step kernel never waits for it (an env
+// that finishes before its slot is filled samples inline instead, with the identical result).
+//
+// Two kernels.  (A) prefetch_layout_kernel: the rejection sampler with ONE LANE PER ENV.
+// The warp-cooperative sampler above spends a 32-candidate round on an object whose first
+// candidate is usually valid (about 44 rounds per 15-zone layout, of ~300 instructions each);
+// here each lane runs the sequential procedure itself, one candidate per iteration, on its own
+// env, so all 32 lanes do useful work (about 435 candidates per layout, i.e. ~14 warp-rounds
+// per env).  Lanes are persistent: a lane that finishes an env takes the next empty slot from
+// a device-wide cursor, so the long tail of the sampler (p99 is 4x the mean) never idles a
+// warp.  Candidate j of object k in attempt L is Philox(seed, (j, k, L)) in both samplers, so
+// they produce the same layout bit for bit.  (B) prefetch_task_kernel: TimedTSP timeouts /
+// ColourMatch colours, one lane per (env, zone), two envs per warp iteration.
+// Slot states: 0 empty, 2 layout parked (task draws pending), 1 ready.
+constexpr uint32_t kSlotEmpty = 0u, kSlotReady = 1u, kSlotLayoutDone = 2u;
+
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <int N>
+__global__ void __launch_bounds__(32) prefetch_layout_kernel(const __grid_constant__ KParams p,
+                                                             unsigned int* cursor, uint32_t done_state) {
+  __shared__ float2 placed[N + 1][32];            // [object][lane]: conflict-free for a common object index
   const int lane = threadIdx.x;
+  bool have = false, exhausted = false;
+  uint32_t pending = 0u;                          // empty slots of this lane's current 32-env chunk
+  int base = 0, e = -1, k = 0, j = 0;
+  uint32_t attempt = 0u;
+  long long chosen = 0;
+  for (;;) {
+    if (!have && !exhausted) {
+      while (pending == 0u) {
+        base = (int)atomicAdd(cursor, 32u);
+        if (base >= p.B) { exhausted = true; break; }
+        const int n = min(32, p.B - base);
+        for (int i = 0; i < n; ++i)
+          if (ld_relaxed_u32(p.next_ready + base + i) == kSlotEmpty) pending |= 1u << i;
+      }
+      if (pending) {
+        e = base + __ffs(pending) - 1;
+        pending &= pending - 1u;
+        chosen = choose_seed(p, e, p.episode[e]);
+        have = true; k = 0; j = 0; attempt = 0u;
+      }
+    }
+    if (__all_sync(kFull, !have)) break;
+    if (have) {
+      // one candidate of Engine.sample_layout's sequential procedure (layout seed = chosen + 1)
+      const float keep = k == 0 ? p.robot_keepout : p.zone_keepout;
+      const float lo = -p.extent + keep, span = (p.extent - keep) - lo;
+      const U4 r = draw(chosen + 1, (uint32_t)j, (uint32_t)k, attempt, kTagLayout);
+      const float x = __fadd_rn(lo, __fmul_rn(span, u01(r.x)));
+      const float y = __fadd_rn(lo, __fmul_rn(span, u01(r.y)));
+      bool valid = true;
+#pragma unroll
+      for (int q = 0; q < N; ++q) {               // objects >= k hold stale values and are ignored
+        const float2 o = placed[q][lane];
+        const float need = __fadd_rn(q == 0 ? p.robot_keepout : p.zone_keepout, keep);
+        const float dx = __fsub_rn(x, o.x), dy = __fsub_rn(y, o.y);
+        const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        valid = valid && (q >= k || d2 >= __fmul_rn(need, need));
+      }
+      if (valid) {
+        placed[k][lane] = make_float2(x, y);
+        ++k; j = 0;
+      } else if (++j >= 100) {                    // 100 misses abandon the layout
+        j = 0; k = 0;
+        if (++attempt >= 10000u) k = N + 1;       // as the twin: give up with what there is
+      }
+      if (k > N) {
+        const U4 rr = draw(chosen + 1, 0u, 0u, 0u, kTagRot);
+        const float2 rb = placed[0][lane];
+#pragma unroll
+        for (int i = 0; i < N; ++i) p.next_zone_xy[(size_t)i * p.B + e] = placed[1 + i][lane];
+        p.next_origin[e] = make_float4(rb.x, rb.y, __fmul_rn(6.2831855f, u01(rr.x)), 0.f);
+        p.next_seed[e] = chosen;
+        __threadfence();
+        st_release_u32(p.next_ready + e, done_state);
+        have = false;
+      }
+    }
+  }
+}
+
+template <int TASK, int N>
+__global__ void __launch_bounds__(128) prefetch_task_kernel(const __grid_constant__ KParams p) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
   const int n_chunks = (p.B + 31) / 32;
-  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-    const int e = chunk * 32 + lane;
-    const bool need = e < p.B && ld_acquire_u32(p.next_ready + e) == 0u;
-    unsigned m = __ballot_sync(kFull, need);
+  const int half = lane >> 4, zone = lane & 15;
+  for (int chunk = warp; chunk < n_chunks; chunk += n_warps) {
+    const int ce = chunk * 32 + lane;
+    unsigned m = __ballot_sync(kFull, ce < p.B && ld_acquire_u32(p.next_ready + ce) == kSlotLayoutDone);
     while (m) {
-      const int src = __ffs(m) - 1;
+      const int e0 = chunk * 32 + __ffs(m) - 1;
       m &= m - 1;
-      const int se = chunk * 32 + src;
-      long long chosen = 0;
-      if (lane == src) chosen = choose_seed(p, se, p.episode[se]);
-      chosen = __shfl_sync(kFull, chosen, src);
-      uint32_t my_draw;
-      float rot0;
-      warp_generate<TASK, N>(p, chosen, placed, lane, my_draw, rot0);
-      if (lane < N) p.next_zone_xy[(size_t)lane * p.B + se] = placed[1 + lane];
+      int e1 = -1;
+      if (m) { e1 = chunk * 32 + __ffs(m) - 1; m &= m - 1; }
+      const int e = half ? e1 : e0;
+      uint32_t my_draw = 0u;
+      if (e >= 0 && zone < N) {
+        const long long chosen = p.next_seed[e];  // task draws use the seed BEFORE the increment
+        if (TASK == CRL_TASK_TTSP) {
+          const double ga = gamma_draw(chosen, p.beta_a, (uint32_t)zone, 0u);
+          const double gb = gamma_draw(chosen, p.beta_b, (uint32_t)zone, 1u);
+          const int t = (int)((ga / (ga + gb)) * (double)p.num_steps);
+          my_draw = (uint32_t)min(max(t, 0), 65535);
+        } else {
+          my_draw = colour_draw(chosen, (uint32_t)zone);
+        }
+      }
       if (TASK == CRL_TASK_TTSP) {
         const uint32_t hi = __shfl_down_sync(kFull, my_draw, 1);
-        if (lane < N && !(lane & 1)) p.next_task[(size_t)(lane >> 1) * p.B + se] = my_draw | (lane + 1 < N ? hi << 16 : 0u);
-      }
-      if (TASK == CRL_TASK_CM) {
-        uint32_t cw = 0u;
+        if (e >= 0 && zone < N && !(zone & 1))
+          p.next_task[(size_t)(zone >> 1) * p.B + e] = my_draw | (zone + 1 < N ? hi << 16 : 0u);
+      } else {
+        uint32_t cw = zone < N ? my_draw << (2 * zone) : 0u;
 #pragma unroll
-        for (int i = 0; i < N; ++i) cw |= __shfl_sync(kFull, my_draw, i) << (2 * i);
-        if (lane == 0) p.next_task[se] = cw;
-      }
-      if (lane == 0) {
-        const float2 rb = placed[0];
-        p.next_origin[se] = make_float4(rb.x, rb.y, rot0, 0.f);
-        p.next_seed[se] = chosen;
+        for (int o = 8; o > 0; o >>= 1) cw |= __shfl_xor_sync(kFull, cw, o);   // within the half-warp
+        if (e >= 0 && zone == 0) p.next_task[e] = cw;
       }
       __threadfence();
       __syncwarp();
-      if (lane == 0) st_release_u32(p.next_ready + se, 1u);
+      if (e >= 0 && zone == 0) st_release_u32(p.next_ready + e, kSlotReady);
     }
   }
 }
@@ -457,6 +601,44 @@ __device__ __forceinline__ void load_env(const KParams& p, int e, Env<N>& env) {
   env.hi = bits >> 16;
 }
 
+// ---- chained steps (CRL_STEP_CHAINED) ------------------------------------------------
+// stamp[0][w] = steps started, stamp[1][w] = steps finished for envs [32 w, 32 w + 32).
+// Every step takes a ticket t = started++ BEFORE it lets dependents launch, so tickets
+// follow launch order; a chained step's warp then spins until finished == t, i.e. until
+// its own previous step is done, instead of waiting for the whole preceding grid.  All
+// CTAs of the preceding grid are resident before this grid may start (the trigger is
+// their first instruction), so the wait cannot deadlock; the spin is bounded anyway.
+__device__ __forceinline__ uint32_t chain_ticket(const KParams& p, int w, int lane) {
+  uint32_t t = 0u;
+  if (lane == 0 && w < (p.B + 31) / 32) t = atomicAdd(p.stamp + w, 1u);
+  return t;
+}
+
+__device__ __forceinline__ void chain_wait(const KParams& p, int w, int lane, uint32_t ticket) {
+  if (lane == 0 && w < (p.B + 31) / 32) {
+    const uint32_t* fin = p.stamp + (p.B + 31) / 32 + w;
+    uint32_t polls = 0;
+    while (ld_acquire_u32(fin) != ticket) {
+      __nanosleep(64);
+      if (++polls > (1u << 22)) { atomicAdd(p.counters + 7, 1.0); break; }
+    }
+  }
+  __syncwarp();
+}
+
+// Publish this warp's step: every lane's stores are ordered before lane 0 by the warp
+// barrier, the bulk copy is waited for to completion, then one release store.
+__device__ __forceinline__ void chain_release(const KParams& p, int w, int lane, uint32_t ticket) {
+  __syncwarp();
+  if (lane == 0) {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (w < (p.B + 31) / 32) {
+      __threadfence();
+      st_release_u32(p.stamp + (p.B + 31) / 32 + w, ticket + 1u);
+    }
+  }
+}
+
 // ---- the fused step ---------------------------------------------------------------
 // Order inside the kernel.  Everything the reference decides in a step except the
 // physics state itself depends only on the PRE-physics position and the counters
@@ -464,7 +646,7 @@ __device__ __forceinline__ void load_env(const KParams& p, int e, Env<N>& env) {
 // whole zone_obs row come first and the bulk copy of zone_obs is in flight while the
 // frameskip substeps run; state and the 8-float obs row are written last.
 template <int TASK, int N>
-__global__ void __launch_bounds__(kThreads) step_kernel(const KParams p) {
+__global__ void __launch_bounds__(kThreads, min_blocks<N>()) step_kernel(const __grid_constant__ KParams p) {
   constexpr int ROW = N * ZoneDim<TASK>::Z;
   extern __shared__ __align__(128) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -475,8 +657,23 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const KParams p) {
   // Programmatic dependent launch: this grid may be scheduled while the previous kernel
   // of the stream is still draining; let the next one do the same, then wait here until
   // everything the previous kernel wrote (state, actions) is visible.
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  uint32_t ticket = 0u;
+  const bool ticketed = (p.flags & (CRL_STEP_CHAINED | CRL_STEP_CHAIN_START)) != 0u;
+  if (ticketed) {
+    // the ticket must be taken before dependents may launch: the operand makes the
+    // trigger wait for the atomic's return
+    ticket = chain_ticket(p, warp_env0 >> 5, lane);
+    asm volatile("griddepcontrol.launch_dependents;" :: "r"(ticket) : "memory");
+  } else {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
+  if (p.flags & CRL_STEP_CHAINED) {
+    // back-to-back steps: wait only for THIS warp's own previous step, not for the whole
+    // preceding grid; the tail of one launch overlaps the head of the next
+    chain_wait(p, warp_env0 >> 5, lane, ticket);
+  } else {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
 
   Env<N> env;
   float2 act = make_float2(0.f, 0.f);
@@ -594,7 +791,10 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const KParams p) {
       }
       // (5) auto-reset, penv.py:9-10: only the finished envs are rebuilt
       if (p.flags & CRL_STEP_AUTO_RESET) {
-        warp_reset<TASK, N>(p, dm, lane, e, reinterpret_cast<float2*>(stage), env);
+        // a copy crosses the (cold, out-of-line) call so that `env` itself stays in registers
+        Env<N> next = env;
+        warp_reset<TASK, N>(p, dm, lane, e, reinterpret_cast<float2*>(stage), next);
+        env = next;
         fresh = done;
       }
     }
@@ -610,12 +810,16 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const KParams p) {
     env.b.phi = wrap_pi(env.b.phi);
   }
   if (valid) store_state_obs<TASK, N>(p, env, e, c, s);
-  zone_obs_wait(lane);
+  if (ticketed) {
+    chain_release(p, warp_env0 >> 5, lane, ticket);
+  } else {
+    zone_obs_wait(lane);
+  }
 }
 
 // Engine.reset on the device for masked envs.
 template <int TASK, int N>
-__global__ void __launch_bounds__(kThreads) reset_kernel(const KParams p) {
+__global__ void __launch_bounds__(kThreads) reset_kernel(const __grid_constant__ KParams p) {
   constexpr int ROW = N * ZoneDim<TASK>::Z;
   extern __shared__ __align__(128) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -792,6 +996,7 @@ static int fill_params(const CrlConfig* c, const CrlState* st, const CrlOut* out
     p.next_origin = reinterpret_cast<float4*>(st->next_origin);
     p.next_seed = reinterpret_cast<long long*>(st->next_seed); p.next_ready = st->next_ready;
   }
+  p.stamp = st->stamp;
   if (out) {
     if (!out->obs || !out->zone_obs || !out->result) return CRL_ERR_NULL;
     if (!aligned16(out->obs) || !aligned16(out->zone_obs)) return CRL_ERR_ALIGN;
@@ -851,7 +1056,7 @@ const char* crl_strerror(int code) {
   }
 }
 
-int crl_plane_bytes(const CrlConfig* c, int64_t o[17]) {
+int crl_plane_bytes(const CrlConfig* c, int64_t o[19]) {
   int rc = check_config(c);
   if (rc) return rc;
   if (!o) return CRL_ERR_NULL;
@@ -864,6 +1069,8 @@ int crl_plane_bytes(const CrlConfig* c, int64_t o[17]) {
   o[10] = c->task == CRL_TASK_TTSP ? 4 * ((N + 1) / 2) * B : (c->task == CRL_TASK_CM ? 4 * B : 0);
   o[11] = 16 * B; o[12] = 8 * B; o[13] = 4 * B;
   o[14] = 32 * B; o[15] = 4 * N * Z * B; o[16] = 8 * B;
+  o[17] = 2 * 4 * ((B + 31) / 32);
+  o[18] = 16;
   return CRL_OK;
 }
 
@@ -888,6 +1095,17 @@ int crl_step(const CrlConfig* c, const CrlState* st, const float* actions, const
   if (actions && (reinterpret_cast<uintptr_t>(actions) & 7u)) return CRL_ERR_ALIGN;
   p.actions = reinterpret_cast<const float2*>(actions);
   p.flags = flags; p.action_seed = action_seed; p.step_index = step_index;
+  const bool ticketed = (flags & (CRL_STEP_CHAINED | CRL_STEP_CHAIN_START)) != 0u;
+  if (ticketed && !p.stamp) return CRL_ERR_NULL;
+  // Programmatic launch (this grid may start while its predecessor drains) is safe when the
+  // kernel then waits for the whole predecessor (plain, chain start) or for its own previous
+  // step (chained).  After a CHAINED launch, though, "the predecessor is complete" no longer
+  // implies that everything before it is: a step that is not itself chained is then launched
+  // without the attribute, i.e. with full stream ordering.
+  static std::atomic<void*> last_chained_stream{reinterpret_cast<void*>(-1)};
+  const bool after_chained = last_chained_stream.load(std::memory_order_relaxed) == stream;
+  const bool programmatic = (flags & CRL_STEP_CHAINED) || !after_chained;
+  last_chained_stream.store((flags & CRL_STEP_CHAINED) ? stream : reinterpret_cast<void*>(-1), std::memory_order_relaxed);
   const int blocks = (p.B + kThreads - 1) / kThreads;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 #define CRL_CALL_STEP(T, NN)                                                        \
@@ -901,7 +1119,7 @@ int crl_step(const CrlConfig* c, const CrlState* st, const float* actions, const
     cudaLaunchAttribute at[1];                                                      \
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                  \
     at[0].val.programmaticStreamSerializationAllowed = 1;                           \
-    lc.attrs = at; lc.numAttrs = 1;                                                 \
+    lc.attrs = at; lc.numAttrs = programmatic ? 1 : 0;                              \
     if (cudaLaunchKernelEx(&lc, step_kernel<T, NN>, p) != cudaSuccess) {            \
       (void)cudaGetLastError();                                                     \
       return CRL_ERR_LAUNCH;                                                        \
@@ -947,16 +1165,27 @@ int crl_reset_from_layout(const CrlConfig* c, const CrlState* st, const CrlOut* 
   return launch_status();
 }
 
-int crl_prefetch_layouts(const CrlConfig* c, const CrlState* st, void* stream) {
+int crl_prefetch_layouts(const CrlConfig* c, const CrlState* st, int32_t warps_per_sm, void* stream) {
   KParams p;
   int rc = fill_params(c, st, nullptr, p);
   if (rc) return rc;
-  if (!p.next_ready) return CRL_ERR_NULL;
+  if (!p.next_ready || !st->prefetch_cursor) return CRL_ERR_NULL;
+  if (warps_per_sm <= 0) warps_per_sm = 2;
+  if (warps_per_sm > 32) warps_per_sm = 32;
   const int n_chunks = (p.B + 31) / 32;
-  const int blocks = min(n_chunks, 148 * 4);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-#define CRL_CALL_PREFETCH(T, NN) { prefetch_kernel<T, NN><<<blocks, 32, 0, s>>>(p); }
-  CRL_DISPATCH(c->task, c->num_zones, CRL_CALL_PREFETCH);
+  if (cudaMemsetAsync(st->prefetch_cursor, 0, 16, s) != cudaSuccess) return CRL_ERR_DEVICE;
+  // (A) layouts: persistent lanes, one env each; a few warps per SM share it with the steps
+  const int blocks_a = min(n_chunks, 148 * warps_per_sm);
+  const uint32_t done_state = c->task == CRL_TASK_TSP ? kSlotReady : kSlotLayoutDone;
+#define CRL_CALL_PREFETCH_A(T, NN) { prefetch_layout_kernel<NN><<<blocks_a, 32, 0, s>>>(p, st->prefetch_cursor, done_state); }
+  CRL_DISPATCH(c->task, c->num_zones, CRL_CALL_PREFETCH_A);
+  rc = launch_status();
+  if (rc || c->task == CRL_TASK_TSP) return rc;
+  // (B) task draws for the slots (A) just filled
+  const int blocks_b = min((n_chunks + 3) / 4, 148 * 2);
+#define CRL_CALL_PREFETCH_B(T, NN) { prefetch_task_kernel<T, NN><<<blocks_b, 128, 0, s>>>(p); }
+  CRL_DISPATCH(c->task, c->num_zones, CRL_CALL_PREFETCH_B);
   return launch_status();
 }
 

@@ -86,7 +86,11 @@ class ZoneVecEnv:
         self.next_origin = z(B, 4)
         self.next_seed = z(B, dtype=torch.int64)
         self.next_ready = z(B, dtype=torch.int32)
+        self._prefetch_cursor = z(4, dtype=torch.int32)
         self._side = torch.cuda.Stream(device=dev)
+        # per-warp completion stamps of crl_step (CRL_STEP_CHAINED)
+        self.stamp = z(2, (B + 31) // 32, dtype=torch.int32)
+        self._chain_ok = False                    # True: the last kernel enqueued for this state was a ticketed step
         # outputs
         self.obs = z(B, 8)
         self.zone_obs = z(B, N, Z)
@@ -102,7 +106,8 @@ class ZoneVecEnv:
                                    seed=ptr(self.seeds), episode=ptr(self.episode), origin=ptr(self.origin),
                                    counters=ptr(self.counters_dev), next_zone_xy=ptr(self.next_zone_xy),
                                    next_task=ptr(self.next_task), next_origin=ptr(self.next_origin),
-                                   next_seed=ptr(self.next_seed), next_ready=ptr(self.next_ready))
+                                   next_seed=ptr(self.next_seed), next_ready=ptr(self.next_ready),
+                                   stamp=ptr(self.stamp), prefetch_cursor=ptr(self._prefetch_cursor))
         self.out = _lib.CrlOut(obs=ptr(self.obs), zone_obs=ptr(self.zone_obs), result=ptr(self.result))
         self._actions_dev = z(B, 2)
         self._host = None
@@ -136,8 +141,9 @@ class ZoneVecEnv:
         self.seeds.copy_(self._as_dev(seeds, torch.int64))
         self.episode.zero_()
         self.next_ready.zero_()          # parked layouts were drawn for the old seeds
+        self._chain_ok = False
 
-    def prefetch(self, stream=None):
+    def prefetch(self, stream=None, warps_per_sm=0):
         """Fill the empty next-layout slots in the background (crl_prefetch_layouts) on a
         side stream.  Needs no ordering with step(): slots change hands through
         acquire/release flags and an env that finishes before its slot is filled is
@@ -148,9 +154,9 @@ class ZoneVecEnv:
             stream = self._side
             stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.crl_prefetch_layouts(self.cfg, self.state,
+            _lib.check(self.lib.crl_prefetch_layouts(self.cfg, self.state, warps_per_sm,
                                                      ctypes.c_void_p(stream.cuda_stream)))
-        self.gpu_launches += 1
+        self.gpu_launches += 1 if self.spec.task == _lib.TASK_TSP else 2
 
     def reset(self, layout=None, mask=None, env_ids=None):
         """Engine.reset of all envs (or those in ``mask``).  ``layout`` switches to the
@@ -159,6 +165,10 @@ class ZoneVecEnv:
         with torch.cuda.device(self.device):
             if layout is None:
                 m = None if mask is None else self._as_dev(mask, torch.uint8)
+                if mask is None and not torch.cuda.is_current_stream_capturing():
+                    # a full reset: sample every layout with the one-lane-per-env sampler first
+                    # (all SMs, nothing else is running), then crl_reset only copies
+                    self.prefetch(torch.cuda.current_stream(self.device), warps_per_sm=16)
                 _lib.check(self.lib.crl_reset(self.cfg, self.state, self.out,
                                               None if m is None else m.data_ptr(), self._stream()))
             else:
@@ -176,12 +186,18 @@ class ZoneVecEnv:
                                                           None if ids is None else ids.data_ptr(), n,
                                                           self._stream()))
             self.gpu_launches += 1
+            self._chain_ok = False
             if self.prefetch_every and not torch.cuda.is_current_stream_capturing():
                 # the reset above must be visible to the prefetcher: same-stream launch
                 self.prefetch(torch.cuda.current_stream(self.device))
         return self._obs_dict()
 
-    def _step(self, actions, flags, action_seed=0):
+    def _step(self, actions, flags, action_seed=0, chained=False):
+        """``chained=True``: the caller asserts that the kernel enqueued just before this call on the
+        current stream is a step (of this env or another ZoneVecEnv) that did not write ``actions``
+        (CRL_STEP_CHAINED: back-to-back rollout steps overlap across the launch boundary)."""
+        if chained:
+            flags |= _lib.STEP_CHAINED if self._chain_ok else _lib.STEP_CHAIN_START
         with torch.cuda.device(self.device):
             if actions is None:
                 aptr = None
@@ -195,6 +211,7 @@ class ZoneVecEnv:
                                          self._step_index, self._stream()))
         self._step_index += 1
         self.gpu_launches += 1
+        self._chain_ok = bool(chained)
         if (self.prefetch_every and self._step_index % self.prefetch_every == 0
                 and not torch.cuda.is_current_stream_capturing()):
             self.prefetch()
@@ -209,9 +226,10 @@ class ZoneVecEnv:
         """ParallelEnv.step_no_reset (penv.py:61-66)."""
         return self._step(actions, 0)
 
-    def step_random(self, action_seed=1, auto_reset=True):
-        """A step with U(-1,1)^2 actions drawn in-kernel (Philox): action_space.sample()."""
-        return self._step(None, _lib.STEP_AUTO_RESET if auto_reset else 0, action_seed)
+    def step_random(self, action_seed=1, auto_reset=True, chained=False):
+        """A step with U(-1,1)^2 actions drawn in-kernel (Philox): action_space.sample().
+        ``chained=True`` for back-to-back rollout steps with nothing else enqueued in between."""
+        return self._step(None, _lib.STEP_AUTO_RESET if auto_reset else 0, action_seed, chained=chained)
 
     def step_host(self, actions, auto_reset=True):
         """The reference-facing call with HOST buffers: numpy actions in, numpy obs /
@@ -233,6 +251,7 @@ class ZoneVecEnv:
                                               _lib.STEP_AUTO_RESET if auto_reset else 0, self._stream()))
         self._step_index += 1
         self.gpu_launches += 1
+        self._chain_ok = False                    # memcpys follow the step kernel on the stream
         res = h['np']['result']
         return ({'zone_obs': h['np']['zone_obs'], 'obs': h['np']['obs']}, res.view(np.float32)[:, 0],
                 res[:, 4].view(np.bool_), {'goal_met': res[:, 5].view(np.bool_), 'event': res[:, 6].view(np.int8)})
@@ -248,7 +267,7 @@ class ZoneVecEnv:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.crl_counters_read(self.state, out, self._stream()))
         return {'return_sum': out[0], 'episodes': out[1], 'successes': out[2], 'length_sum': out[3],
-                'resets_prefetched': out[4], 'resets_inline': out[5]}
+                'resets_prefetched': out[4], 'resets_inline': out[5], 'chain_wait_timeouts': out[7]}
 
     def set_qpos_qvel(self, qpos, qvel, env_ids=None):
         """Overwrite sim.data.qpos / qvel (fp64, reference coordinates) of some envs."""
@@ -258,6 +277,7 @@ class ZoneVecEnv:
             _lib.check(self.lib.crl_set_qpos_qvel(self.cfg, self.state, qp.data_ptr(), qv.data_ptr(),
                                                   None if ids is None else ids.data_ptr(), qp.shape[0],
                                                   self._stream()))
+        self._chain_ok = False
 
     def get_qpos_qvel(self, env_ids=None):
         n = self.num_envs if env_ids is None else len(env_ids)
@@ -267,6 +287,7 @@ class ZoneVecEnv:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.crl_get_qpos_qvel(self.cfg, self.state, qp.data_ptr(), qv.data_ptr(),
                                                   None if ids is None else ids.data_ptr(), n, self._stream()))
+        self._chain_ok = False
         return qp, qv
 
     def physics_substeps(self, actions, n):

@@ -39,13 +39,17 @@
  *                          kept only to convert to/from qpos/qvel
  *    counters  double[8]   sum of episode returns, episodes finished, successes
  *                          (goal_met), sum of episode lengths, resets served from a
- *                          prefetched layout, resets sampled inline, 2 reserved
+ *                          prefetched layout, resets sampled inline, 1 reserved, chained-step
+ *                          waits that gave up (must stay 0)
  *  optional next-layout planes (all NULL = no prefetch): the draws of each env's NEXT
  *  Engine.reset, made in the background by crl_prefetch_layouts so that an auto-reset
  *  inside crl_step is a copy instead of a rejection-sampling loop
  *    next_zone_xy float2[N][B], next_task uint32[ceil(N/2)][B] (TimedTSP timeouts) or
  *    uint32[B] (ColourMatch colour codes), next_origin float4[B], next_seed int64[B]
- *    (the seed the parked layout was drawn for), next_ready uint32[B] (0 = slot empty)
+ *    (the seed the parked layout was drawn for), next_ready uint32[B] (0 = slot empty, 1 =
+ *    ready, 2 = layout parked and task draws pending)
+ *  optional stamp uint32[2][ceil(B/32)]: steps started / finished per group of 32 envs,
+ *  see CRL_STEP_CHAINED
  *  outputs, the layout the reference's consumer builds (main/src/utils/format.py:27-28):
  *    obs       float[B][8]      remaining, pos/3 (2), dir (2), vel/1.5 (2), yaw rate/3
  *    zone_obs  float[B][N][Z]   x/3, y/3, r, g, b, 0.25 [, time left | cooldown/150]
@@ -60,7 +64,7 @@
 extern "C" {
 #endif
 
-#define CRL_ABI_VERSION 2
+#define CRL_ABI_VERSION 3
 #define CRL_MAX_ZONES 16
 
 /* task ids; reference classes: main/envs/TSP_env.py:11, TTSP_env.py:12, colour_match_env.py:11 */
@@ -79,6 +83,19 @@ enum CrlError {
 /* flags for crl_step */
 #define CRL_STEP_AUTO_RESET 1u   /* penv.py:9-10: finished envs restart inside the call */
 #define CRL_STEP_PHYSICS_ONLY 2u /* debug/parity: integrate `frameskip` substeps, no task logic */
+/* Back-to-back rollout steps.  CRL_STEP_CHAINED: the caller asserts that the kernel enqueued
+ * immediately before this call on `stream` is a crl_step (of this or of another CrlState) that
+ * did not produce this call's `actions`, and that the previous crl_step of THIS CrlState was
+ * made with CRL_STEP_CHAINED or CRL_STEP_CHAIN_START and nothing else touched the state since.
+ * The step then orders itself after the previous step of the same CrlState warp by warp
+ * (CrlState.stamp: steps started / finished per group of 32 envs, release/acquire) instead of
+ * waiting for the whole preceding grid, so the tail of one launch overlaps the head of the
+ * next.  CRL_STEP_CHAIN_START: first step of such a run (ordinary whole-grid wait, but it
+ * takes part in the stamp protocol).  Both need CrlState.stamp.  Safe inside CUDA graphs: the
+ * counts live on the device, nothing per-launch comes from the host.  Steps without either
+ * flag never touch the stamps. */
+#define CRL_STEP_CHAINED 4u
+#define CRL_STEP_CHAIN_START 8u
 
 /* how a reset chooses the episode's seed; wrappers.py:10-23 and Engine.seed/reset */
 enum CrlSeedMode {
@@ -121,6 +138,9 @@ typedef struct CrlState {
   float* next_origin;   /* float4[B]; optional */
   int64_t* next_seed;   /* int64[B]; optional */
   uint32_t* next_ready; /* uint32[B]; optional.  Zero it whenever CrlState.seed is rewritten */
+  uint32_t* stamp;      /* uint32[2][ceil(B/32)]; optional, zero-initialised.  Steps started and
+                           steps finished for each group of 32 envs (CRL_STEP_CHAINED) */
+  uint32_t* prefetch_cursor; /* uint32[4]; workspace of crl_prefetch_layouts (needed with next_*) */
 } CrlState;
 
 typedef struct CrlResult {
@@ -152,9 +172,9 @@ const char* crl_strerror(int code);
 
 /* Bytes the caller must allocate for each plane of CrlState / CrlOut, in the order
  * pose, aux, zone_xy, zone_tmax, cooldown, seed, episode, origin, counters, next_zone_xy,
- * next_task, next_origin, next_seed, next_ready, obs, zone_obs, result
- * (17 entries; 0 = plane unused by this task). */
-int crl_plane_bytes(const CrlConfig* cfg, int64_t out_bytes[17]);
+ * next_task, next_origin, next_seed, next_ready, obs, zone_obs, result, stamp,
+ * prefetch_cursor (19 entries; 0 = plane unused by this task). */
+int crl_plane_bytes(const CrlConfig* cfg, int64_t out_bytes[19]);
 
 /* Algorithmic HBM bytes one env-step moves in this layout: read, written. */
 int crl_step_bytes(const CrlConfig* cfg, int64_t* bytes_read, int64_t* bytes_written);
@@ -172,8 +192,11 @@ int crl_reset(const CrlConfig* cfg, const CrlState* st, const CrlOut* out,
  * than the stepping one; it needs no ordering with crl_step (slots are handed over with
  * acquire/release flags, and an env that finishes before its slot is filled is sampled
  * inline by crl_step with the identical result).  Hides Engine.build_layout's rejection
- * sampling, which the reference runs inside reset() (penv.py:9-10). */
-int crl_prefetch_layouts(const CrlConfig* cfg, const CrlState* st, void* stream);
+ * sampling, which the reference runs inside reset() (penv.py:9-10).  The sampler runs one
+ * lane per env on `warps_per_sm` persistent warps per SM (0 = default 2: a background job
+ * beside the steps; up to 32 before a full crl_reset, where nothing else is running). */
+int crl_prefetch_layouts(const CrlConfig* cfg, const CrlState* st, int32_t warps_per_sm,
+                         void* stream);
 
 /* The same reset with the layout handed in (device arrays, see CrlLayoutIn) for
  * envs env_ids[0..n) (env_ids == NULL: envs 0..n). */

@@ -46,6 +46,8 @@ def lib():
                                + [ctypes.c_void_p] * 6)
         L.ph_action.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_void_p]
         L.ph_philox.argtypes = [ctypes.c_void_p] * 3
+        L.ph_gamma_sample.restype = ctypes.c_double
+        L.ph_gamma_sample.argtypes = [ctypes.c_int64, ctypes.c_double, ctypes.c_uint32, ctypes.c_uint32]
         _lib = L
     return _lib
 
@@ -167,3 +169,8 @@ def philox_action(action_seed, global_env, step_index):
     a = np.zeros(2, np.float32)
     lib().ph_action(action_seed, global_env, step_index, a.ctypes.data)
     return a
+
+
+def philox_gamma(seed, shape, zone=0, which=0):
+    """One gamma(shape) draw of the device's task stream (design twin)."""
+    return lib().ph_gamma_sample(seed, shape, zone, which)

@@ -547,6 +547,34 @@ static double ph_gamma(int64_t seed, double a, uint32_t zone, uint32_t which) {
   }
 }
 
+/* gamma(k/2), k a small integer: -log of the product of floor(k/2) uniforms, plus for odd
+ * k the Box-Muller half-square -log(U) cos^2(2 pi V).  Uniform j = half j&1 of block j>>1. */
+static double ph_gamma_half_integer(int64_t seed, int k, uint32_t zone, uint32_t which) {
+  const int m = k >> 1, n_u = m + ((k & 1) ? 2 : 0);
+  double prod = 1.0, U = 1.0, V = 0.0;
+  for (int j = 0; j < n_u; j += 2) {
+    uint32_t r[4];
+    ph_draw(seed, (uint32_t)(j >> 1), zone, which, TAG_TASK, r);
+    const double ua = ph_u01d(r[0], r[1]), ub = ph_u01d(r[2], r[3]);
+    if (j < m) prod *= ua; else if (j == m) U = ua; else V = ua;
+    if (j + 1 < m) prod *= ub; else if (j + 1 == m) U = ub; else if (j + 1 < n_u) V = ub;
+  }
+  double g = -log(prod);
+  if (k & 1) {
+    const double c = cos(2.0 * PI * V);
+    g += -log(U) * (c * c);
+  }
+  return g;
+}
+static double ph_gamma_draw(int64_t seed, double a, uint32_t zone, uint32_t which) {
+  const double t = 2.0 * a;
+  const int k = (int)t;
+  if ((double)k == t && k >= 1 && k <= 16) return ph_gamma_half_integer(seed, k, zone, which);
+  return ph_gamma(seed, a, zone, which);
+}
+/* one gamma draw of the device stream, for distribution tests */
+double ph_gamma_sample(int64_t seed, double a, uint32_t zone, uint32_t which) { return ph_gamma_draw(seed, a, zone, which); }
+
 /* The product's reset for one env, sequentially.  seed_in = CrlState.seed[e] before the
  * reset (seed_mode 0) ; for seed_mode 1 the seed is first re-drawn in [min_seed, max_seed]
  * from Philox(key = global env index, counter = episode). */
@@ -565,7 +593,7 @@ void ph_reset(int task, int N, int num_steps, int seed_mode, int64_t min_seed, i
   for (int i = 0; i < N; ++i) {
     tmax[i] = 0; colours[i] = 0;
     if (task == T_TTSP) {
-      const double ga = ph_gamma(seed, beta_a, (uint32_t)i, 0u), gb = ph_gamma(seed, beta_b, (uint32_t)i, 1u);
+      const double ga = ph_gamma_draw(seed, beta_a, (uint32_t)i, 0u), gb = ph_gamma_draw(seed, beta_b, (uint32_t)i, 1u);
       int t = (int)((ga / (ga + gb)) * (double)num_steps);
       tmax[i] = t < 0 ? 0 : (t > 65535 ? 65535 : t);
     }

@@ -88,3 +88,19 @@ def test_c_oracle_matches_reference_fixture(path):
 def test_timed_rollout_runs():
     rate, steps, wall = co.timed_rollout('PointTSP-v0', threads=2, seconds=0.3)
     assert steps > 1000 and rate > 1e4
+
+
+def test_device_gamma_and_beta_streams_have_the_reference_distribution():
+    """The device draws TimedTSP's beta(3, 1.5) (TTSP_env.py:20) as Ga / (Ga + Gb) with
+    gamma(k/2) built exactly from exponentials and a squared normal (design twin here, the
+    kernel is compared with the twin bit for bit on the GPU).  Kolmogorov-Smirnov against
+    scipy's gamma / beta CDFs, and against the Marsaglia-Tsang fallback for other shapes."""
+    from scipy import stats
+    n = 20000
+    for shape in (3.0, 1.5, 0.5, 1.0, 2.2):
+        g = np.array([co.philox_gamma(1000 + s, shape, s % 15, 0) for s in range(n)])
+        assert stats.kstest(g, stats.gamma(shape).cdf).pvalue > 1e-3, shape
+    tm = np.concatenate([co.philox_reset('PointTTSP-v0', 5000 + s)['zone_max_steps'] for s in range(1500)])
+    ref = (np.random.RandomState(3).beta(3, 1.5, size=tm.size) * 2000).astype(np.int64)
+    assert stats.ks_2samp(tm, ref).pvalue > 1e-3
+    assert tm.min() >= 0 and tm.max() < 2000

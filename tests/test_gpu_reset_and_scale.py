@@ -327,7 +327,7 @@ def test_prefetched_resets_equal_inline_resets(crl, env_id):
     for k in sa:
         assert torch.equal(sa[k], sb[k]), k
     ca, cb = a.counters(), b.counters()
-    assert cb['resets_prefetched'] == 0 and cb['resets_inline'] == cb['episodes'] + B
+    assert cb['resets_prefetched'] == B and cb['resets_inline'] == cb['episodes']   # a full reset() samples through the slots
     assert ca['resets_prefetched'] >= 3 * B and ca['resets_prefetched'] + ca['resets_inline'] == ca['episodes'] + B
     # re-seeding drops the parked layouts: the next reset must not use them
     a.seed(99)
@@ -336,3 +336,61 @@ def test_prefetched_resets_equal_inline_resets(crl, env_id):
     a.reset()
     tw = co.philox_reset(env_id, 99 + 5)
     assert np.array_equal(a.zone_xy[:, 5, :].cpu().numpy(), tw['zone_xy'])
+
+
+@pytest.mark.parametrize('env_id', TASKS)
+def test_chained_steps_equal_plain_steps(crl, env_id):
+    """CRL_STEP_CHAINED (a step waits for its own previous step warp by warp instead of for the
+    whole preceding grid) must not change a single bit: two envs from the same seeds, one stepped
+    with plain launches, one with chained launches -- eagerly, interleaved with a second chained
+    env on the same stream, and replayed from a CUDA graph -- end in identical state and output."""
+    B = 40000                                    # ragged; several waves of warps
+    plain = crl.ZoneVecEnv(env_id, B, prefetch_every=0)
+    chain = crl.ZoneVecEnv(env_id, B, prefetch_every=0)
+    other = crl.ZoneVecEnv(env_id, 3000, prefetch_every=0, env_offset=B)
+    for e in (plain, chain, other):
+        e.seed(777); e.reset()
+    for e in (plain, chain):                     # make episodes end (and auto-reset) during the run
+        bits = e.aux[:, 3].view(torch.int32)
+        bits.copy_((bits & ~0xffff) | (e.spec.num_steps - 1 - (torch.arange(B, device='cuda', dtype=torch.int32) % 50)))
+    n_eager, n_graph = 25, 30
+    for t in range(n_eager + n_graph):
+        plain.step_random(action_seed=5)
+    for t in range(n_eager):
+        chain.step_random(action_seed=5, chained=True)
+        other.step_random(action_seed=6, chained=True)
+    torch.cuda.synchronize()
+    # graph part: explicit (fixed) actions, because a captured step_index is frozen and in-kernel
+    # actions would repeat; every replay is then a well-defined step
+    g = torch.cuda.CUDAGraph()
+    act = torch.rand(B, 2, device='cuda') * 2 - 1
+    act_o = torch.rand(3000, 2, device='cuda') * 2 - 1
+    plain2 = crl.ZoneVecEnv(env_id, B, prefetch_every=0)
+    chain2 = crl.ZoneVecEnv(env_id, B, prefetch_every=0)
+    for e in (plain2, chain2):
+        e.seed(778); e.reset()
+        bits = e.aux[:, 3].view(torch.int32)
+        bits.copy_((bits & ~0xffff) | (e.spec.num_steps - 1 - (torch.arange(B, device='cuda', dtype=torch.int32) % 50)))
+    for t in range(2 * n_graph + 2):
+        plain2.step(act)
+    chain2._step(act, 1, chained=True); other._step(act_o, 1, chained=True)      # eager first: chain established
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        chain2._step(act, 1, chained=True); other._step(act_o, 1, chained=True)
+        chain2._step(act, 1, chained=True); other._step(act_o, 1, chained=True)
+    chain2._step(act, 1, chained=True)
+    for t in range(n_graph):
+        g.replay()
+    torch.cuda.synchronize()
+    # the eager chained run only covered n_eager steps: finish it plainly, then compare
+    for t in range(n_graph):
+        chain.step_random(action_seed=5)
+    torch.cuda.synchronize()
+    for x, y in ((plain, chain), (plain2, chain2)):
+        sx, sy = snapshot(x), snapshot(y)
+        for k in sx:
+            assert torch.equal(sx[k], sy[k]), k
+        assert y.counters()['chain_wait_timeouts'] == 0
+    assert chain.counters()['episodes'] > B // 2     # resets did happen under chaining
+    st = chain2.stamp.cpu().numpy()
+    assert np.all(st[0] == st[1]) and np.all(st[0] == 2 * n_graph + 2)

@@ -48,7 +48,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.crl_abi_version() == 2
+    assert lib.crl_abi_version() == 3
     assert b'NULL' in lib.crl_strerror(-1)
 
 
@@ -57,10 +57,10 @@ def test_argument_errors_are_detected_on_the_host():
     lib = _lib.load()
     cfg = _lib.CrlConfig(task=0, num_envs=64, num_zones=15, num_steps=2000, frameskip=10, max_cooldown=150,
                          zone_size=0.2)
-    sizes = (ctypes.c_int64 * 17)()
+    sizes = (ctypes.c_int64 * 18)()
     assert lib.crl_plane_bytes(cfg, sizes) == 0
     assert list(sizes) == [1024, 1024, 7680, 0, 0, 512, 256, 1024, 64, 7680, 0, 1024, 512, 256,
-                           2048, 64 * 90 * 4, 512]
+                           2048, 64 * 90 * 4, 512, 16]
     rd, wr = ctypes.c_int64(), ctypes.c_int64()
     assert lib.crl_step_bytes(cfg, ctypes.byref(rd), ctypes.byref(wr)) == 0 and (rd.value, wr.value) == (160, 432)
     bad = _lib.CrlConfig(task=7, num_envs=64, num_zones=15, num_steps=2000, zone_size=0.2)
@@ -74,6 +74,7 @@ def test_argument_errors_are_detected_on_the_host():
     st = _lib.CrlState(pose=a16, aux=a16, zone_xy=a16, seed=a16, episode=a16, origin=a16, counters=a16)
     out = _lib.CrlOut(obs=a16, zone_obs=a16, result=a16)
     assert lib.crl_step(cfg2, st, None, out, 0, 0, 0, None) == -4         # no kernel for N = 9
+    assert lib.crl_step(cfg, st, None, out, _lib.STEP_CHAINED, 0, 0, None) == -1   # chained needs CrlState.stamp
     st.pose = a16 + 4
     assert lib.crl_step(cfg, st, None, out, 0, 0, 0, None) == -3          # misaligned plane
 
