@@ -179,7 +179,7 @@ def run_ours(args):
             if args.prefetch_every and i % args.prefetch_every == args.prefetch_every - 1:
                 for e in envs:
                     e.prefetch()
-                launches['prefetch'] += R * (1 if envs[0].spec.task == _lib.TASK_TSP else 2)
+                launches['prefetch'] += R * (2 if envs[0].spec.task == _lib.TASK_TSP else 3)
         if n_steps % R:
             tails[n_steps % R].replay()
 
@@ -275,7 +275,7 @@ def run_ours(args):
                      'achieved_canonical': canon * B / (ms_per_step * 1e-3) / 1e9 if canon else None,
                      'frac_of_nominal_8TBs': achieved / 8000.0},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': K + launches['prefetch'],
-        'gpu_launches_detail': {'step_kernel': K, 'prefetch_layout_kernel + prefetch_task_kernel (side stream)': launches['prefetch']},
+        'gpu_launches_detail': {'step_kernel': K, 'prefetch_scan/layout/task kernels (side stream)': launches['prefetch']},
         'episode_stats': {'return_sum': c[0], 'episodes': c[1], 'successes': c[2], 'length_sum': c[3],
                           'resets_prefetched': c[4], 'resets_inline': c[5], 'chain_wait_timeouts': c[7],
                           'reduction': 'nccl all_reduce(sum)' if world > 1 else 'single rank'},

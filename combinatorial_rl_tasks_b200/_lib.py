@@ -34,7 +34,7 @@ class CrlState(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in ('pose', 'aux', 'zone_xy', 'zone_tmax', 'cooldown', 'seed',
                                         'episode', 'origin', 'counters', 'next_zone_xy', 'next_task',
                                         'next_origin', 'next_seed', 'next_ready', 'stamp',
-                                        'prefetch_cursor')]
+                                        'prefetch_work')]
 
 
 class CrlOut(ctypes.Structure):

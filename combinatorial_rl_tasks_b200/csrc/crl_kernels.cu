@@ -76,9 +76,14 @@ struct ZoneDim { static constexpr int Z = (TASK == CRL_TASK_TSP) ? 6 : 7; };
 // the zone_obs stage (32 rows per warp in shared memory) allows 16-19 warps at 15 zones
 // and 42 at 6, so registers are capped to match rather than left to ptxas.
 template <int N>
-struct Occupancy { static constexpr int kWarps = N > 8 ? 16 : 28; };
+struct Occupancy { static constexpr int kWarps = N > 8 ? 16 : 24; };
+#ifdef CRL_NO_MINBLOCKS
+template <int N>
+constexpr int min_blocks() { return 1; }
+#else
 template <int N>
 constexpr int min_blocks() { return Occupancy<N>::kWarps * 32 / kThreads; }
+#endif
 
 // Registers describing one env between load and store.
 template <int N>
@@ -182,7 +187,8 @@ __device__ uint32_t colour_draw(long long seed, uint32_t zone) {
 // Rejection-sample robot + N zones exactly as Engine.sample_layout orders it (object by
 // object, <= 100 tries each, first valid try wins, 100 misses abandon the layout), but
 // 32 tries at a time across the warp.  Candidate j of object k in attempt L is a pure
-// function of (seed, j, k, L), so the outcome equals the sequential procedure's.
+// function of (seed, j, k, L) -- half (j & 1) of Philox block (j >> 1, k, L) -- so the
+// outcome equals the sequential procedure's.
 // `placed` is warp-private shared scratch of N+1 float2 (16-byte aligned).
 template <int N>
 __device__ void warp_layout(const KParams& p, long long seed, float2* placed, int lane) {
@@ -203,9 +209,10 @@ __device__ void warp_layout(const KParams& p, long long seed, float2* placed, in
 #pragma unroll 1
       for (int base = 0; base < 100 && !found; base += 32) {
         const int j = base + lane;
-        const U4 r = draw(seed, (uint32_t)j, (uint32_t)k, attempt, kTagLayout);
-        const float x = __fadd_rn(lo, __fmul_rn(span, u01(r.x)));
-        const float y = __fadd_rn(lo, __fmul_rn(span, u01(r.y)));
+        // try j = half (j & 1) of Philox block (j >> 1): one block serves two tries
+        const U4 r = draw(seed, (uint32_t)(j >> 1), (uint32_t)k, attempt, kTagLayout);
+        const float x = __fadd_rn(lo, __fmul_rn(span, u01((j & 1) ? r.z : r.x)));
+        const float y = __fadd_rn(lo, __fmul_rn(span, u01((j & 1) ? r.w : r.y)));
         bool valid = j < 100;
 #pragma unroll
         for (int q = 0; q < N; ++q) {             // slots >= k hold stale values and are ignored
@@ -231,14 +238,15 @@ __device__ void warp_layout(const KParams& p, long long seed, float2* placed, in
   }
 }
 
-// The seed Engine.reset will run with for env e (lane-local).  CRL_SEED_INCREMENT: the
-// env's current seed.  CRL_SEED_FIXED_RANGE: FixedSeedsWrapper.reset, a uniform integer in
-// [min_seed, max_seed] from the chooser's own stream (key = GLOBAL env index, counter =
-// episode number).
-__device__ __forceinline__ long long choose_seed(const KParams& p, int e, uint32_t episode) {
-  if (p.seed_mode != CRL_SEED_FIXED_RANGE) return p.seed[e];
+// The seed the reset number (episode + ahead) of env e will run with (lane-local), ahead = 0
+// for the next reset.  CRL_SEED_INCREMENT: the env's current seed, +1 per further reset
+// (Engine.reset: self._seed += 1).  CRL_SEED_FIXED_RANGE: FixedSeedsWrapper.reset, a uniform
+// integer in [min_seed, max_seed] from the chooser's own stream (key = GLOBAL env index,
+// counter = episode number).
+__device__ __forceinline__ long long choose_seed(const KParams& p, int e, uint32_t episode, uint32_t ahead = 0u) {
+  if (p.seed_mode != CRL_SEED_FIXED_RANGE) return p.seed[e] + (long long)ahead;
   const unsigned long long span = (unsigned long long)(p.max_seed - p.min_seed) + 1ull;
-  const U4 r = draw((long long)(p.env_offset + e), episode, 0u, 0u, kTagSeed);
+  const U4 r = draw((long long)(p.env_offset + e), episode + ahead, 0u, 0u, kTagSeed);
   const unsigned long long v = ((unsigned long long)r.x << 32) | r.y;
   return p.min_seed + (long long)(span ? (v % span) : v);
 }
@@ -265,9 +273,17 @@ __device__ void warp_generate(const KParams& p, long long chosen, float2* placed
   __syncwarp();
 }
 
+// next-layout slot states (CrlState.next_ready)
+constexpr uint32_t kSlotEmpty = 0u, kSlotReady = 1u, kSlotLayoutDone = 2u, kSlotClaimed = 3u;
+
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
@@ -292,20 +308,43 @@ __device__ CRL_RESET_INLINING void warp_reset(const KParams& p, unsigned dm, int
   bool fast = false;
   float x0 = 0.f, y0 = 0.f, rot0 = 0.f;
   uint32_t col_word = 0u;
+  const int B = p.B;
+  uint32_t* slot_flag = nullptr;
   if (mine) {
     episode = p.episode[e];
     chosen = choose_seed(p, e, episode);
-    if (p.next_ready && ld_acquire_u32(p.next_ready + e) == 1u /* kSlotReady */ && p.next_seed[e] == chosen) {
-      fast = true;
-      const float4 o = p.next_origin[e];
-      x0 = o.x; y0 = o.y; rot0 = o.z;
+    if (p.next_ready) {
+      // reset number n takes slot n & 1.  Everything is loaded into registers first, in one
+      // batch of independent loads, and only then written into `env` (which lives in local
+      // memory across this out-of-line call).
+      const size_t sb = (size_t)(episode & 1u) * (size_t)B;
+      slot_flag = p.next_ready + sb + e;
+      if (ld_acquire_u32(slot_flag) == kSlotReady) {
+        const float2* nz = p.next_zone_xy + sb * N + e;
+        const uint32_t* nt = p.next_task ? p.next_task + sb * (TASK == CRL_TASK_TTSP ? (N + 1) / 2 : 1) + e : nullptr;
+        const long long parked_for = p.next_seed[sb + e];
+        const float4 o = p.next_origin[sb + e];
+        float2 z[N];
+        uint32_t t[(N + 1) / 2];
 #pragma unroll
-      for (int i = 0; i < N; ++i) env.zone[i] = p.next_zone_xy[(size_t)i * p.B + e];
-      if (TASK == CRL_TASK_TTSP) {
+        for (int i = 0; i < N; ++i) z[i] = nz[(size_t)i * B];
+        if (TASK == CRL_TASK_TTSP) {
 #pragma unroll
-        for (int j = 0; j < (N + 1) / 2; ++j) env.tmax[j] = p.next_task[(size_t)j * p.B + e];
+          for (int j = 0; j < (N + 1) / 2; ++j) t[j] = nt[(size_t)j * B];
+        }
+        if (TASK == CRL_TASK_CM) t[0] = nt[0];
+        if (parked_for == chosen) {
+          fast = true;
+          x0 = o.x; y0 = o.y; rot0 = o.z;
+#pragma unroll
+          for (int i = 0; i < N; ++i) env.zone[i] = z[i];
+          if (TASK == CRL_TASK_TTSP) {
+#pragma unroll
+            for (int j = 0; j < (N + 1) / 2; ++j) env.tmax[j] = t[j];
+          }
+          if (TASK == CRL_TASK_CM) col_word = t[0];
+        }
       }
-      if (TASK == CRL_TASK_CM) col_word = p.next_task[e];
     }
   }
   unsigned slow = __ballot_sync(kFull, mine && !fast);
@@ -342,17 +381,19 @@ __device__ CRL_RESET_INLINING void warp_reset(const KParams& p, unsigned dm, int
     env.steps = 0;
     env.hi = TASK == CRL_TASK_CM ? col_word : 0u;
     env.cd = make_uint2(0u, 0u);
+    float2* zp = p.zone_xy + e;
+    uint32_t* tp = p.zone_tmax + e;
 #pragma unroll
-    for (int i = 0; i < N; ++i) p.zone_xy[(size_t)i * p.B + e] = env.zone[i];
+    for (int i = 0; i < N; ++i) zp[(size_t)i * B] = env.zone[i];
     if (TASK == CRL_TASK_TTSP) {
 #pragma unroll
-      for (int j = 0; j < (N + 1) / 2; ++j) p.zone_tmax[(size_t)j * p.B + e] = env.tmax[j];
+      for (int j = 0; j < (N + 1) / 2; ++j) tp[(size_t)j * B] = env.tmax[j];
     }
     p.seed[e] = chosen + 1;                       // Engine.reset: self._seed += 1
     p.episode[e] = episode + 1u;
     p.origin[e] = make_float4(x0, y0, rot0, 0.f);
     // hand the slot back to the prefetcher (release: our reads of it are done)
-    if (p.next_ready) st_release_u32(p.next_ready + e, 0u);
+    if (slot_flag) st_release_u32(slot_flag, kSlotEmpty);
   }
   const unsigned fm = __ballot_sync(kFull, mine && fast);
   if (lane == 0) {
@@ -363,74 +404,105 @@ __device__ CRL_RESET_INLINING void warp_reset(const KParams& p, unsigned dm, int
 }
 
 // ---- background prefetch of next layouts -------------------------------------------
-// For every env whose next-layout slot is empty (next_ready == 0), run the draws of its NEXT
-// Engine.reset (the seed is known in advance in both seed modes) and park the result in the
-// next_* planes.  Launched off the step's stream; the step kernel never waits for it (an env
-// that finishes before its slot is filled samples inline instead, with the identical result).
+// Every env has TWO next-layout slots: reset number n takes slot n & 1, so the layouts of
+// its next two resets can be parked at once and an env that finishes again before the
+// prefetcher has come round still finds its layout (with one slot, about one launch in two
+// at 262,144 TimedTSP envs met an empty slot and stalled on the inline sampler).  The seeds
+// of both resets are known in advance in both seed modes.  The prefetcher runs off the
+// step's stream and the step never waits for it: slots change hands through acquire /
+// release flags, and an env whose slot is empty samples inline with the identical result.
 //
-// Two kernels.  (A) prefetch_layout_kernel: the rejection sampler with ONE LANE PER ENV.
-// The warp-cooperative sampler above spends a 32-candidate round on an object whose first
-// candidate is usually valid (about 44 rounds per 15-zone layout, of ~300 instructions each);
-// here each lane runs the sequential procedure itself, one candidate per iteration, on its own
-// env, so all 32 lanes do useful work (about 435 candidates per layout, i.e. ~14 warp-rounds
-// per env).  Lanes are persistent: a lane that finishes an env takes the next empty slot from
-// a device-wide cursor, so the long tail of the sampler (p99 is 4x the mean) never idles a
-// warp.  Candidate j of object k in attempt L is Philox(seed, (j, k, L)) in both samplers, so
-// they produce the same layout bit for bit.  (B) prefetch_task_kernel: TimedTSP timeouts /
-// ColourMatch colours, one lane per (env, zone), two envs per warp iteration.
-// Slot states: 0 empty, 2 layout parked (task draws pending), 1 ready.
-constexpr uint32_t kSlotEmpty = 0u, kSlotReady = 1u, kSlotLayoutDone = 2u;
+// Three kernels.  (0) prefetch_scan_kernel compacts the empty slots into a dense work list
+// (env, slot, seed).  (A) prefetch_layout_kernel: the rejection sampler with ONE LANE PER
+// LAYOUT.  The warp-cooperative sampler above spends a 32-candidate round on an object whose
+// first candidate is usually valid (about 44 rounds of ~300 instructions per 15-zone layout);
+// here each lane runs the sequential procedure itself, one candidate per iteration, so all
+// 32 lanes do useful work (about 435 candidates per layout = 14 warp-rounds per layout).
+// Lanes are persistent: a lane that finishes takes the next work item, so the long tail of
+// the sampler (p99 is 4x the mean) does not idle a warp.  Candidate j of object k in attempt
+// L is the same function of (seed, j, k, L) in both samplers: same layout bit for bit.
+// (B) prefetch_task_kernel: TimedTSP timeouts / ColourMatch colours, one lane per (item,
+// zone), two items per warp iteration.
+// Slot states: empty -> claimed (in the work list) -> [layout parked, task draws pending] -> ready.
+struct WorkItem { int e; uint32_t slot; long long seed; };   // 16 bytes; item 0 of the plane is the header
+struct WorkHeader { uint32_t count, cursor, pad0, pad1; };
 
-__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
+template <int N>
+__global__ void __launch_bounds__(256) prefetch_scan_kernel(const __grid_constant__ KParams p, WorkItem* work) {
+  WorkHeader* hdr = reinterpret_cast<WorkHeader*>(work);
+  const int lane = threadIdx.x & 31;
+  const int n_round = (p.B + 31) & ~31;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_round; e += gridDim.x * blockDim.x) {
+    const bool in = e < p.B;
+    const uint32_t episode = in ? p.episode[e] : 0u;
+#pragma unroll
+    for (uint32_t ahead = 0; ahead < 2u; ++ahead) {
+      const uint32_t slot = (episode + ahead) & 1u;
+      uint32_t* flag = p.next_ready + (size_t)slot * p.B + e;
+      const bool want = in && ld_relaxed_u32(flag) == kSlotEmpty;
+      const unsigned m = __ballot_sync(kFull, want);
+      if (m) {
+        uint32_t base = 0u;
+        if (lane == 0) base = atomicAdd(&hdr->count, (uint32_t)__popc(m));
+        base = __shfl_sync(kFull, base, 0);
+        if (want) {
+          WorkItem it;
+          it.e = e; it.slot = slot; it.seed = choose_seed(p, e, episode, ahead);
+          work[1u + base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = it;
+          *flag = kSlotClaimed;                 // not empty: a later scan must not list it again
+        }
+      }
+    }
+  }
 }
 
 template <int N>
-__global__ void __launch_bounds__(32) prefetch_layout_kernel(const __grid_constant__ KParams p,
-                                                             unsigned int* cursor, uint32_t done_state) {
+__global__ void __launch_bounds__(32) prefetch_layout_kernel(const __grid_constant__ KParams p, WorkItem* work,
+                                                             uint32_t done_state) {
   __shared__ float2 placed[N + 1][32];            // [object][lane]: conflict-free for a common object index
+  WorkHeader* hdr = reinterpret_cast<WorkHeader*>(work);
   const int lane = threadIdx.x;
-  bool have = false, exhausted = false;
-  uint32_t pending = 0u;                          // empty slots of this lane's current 32-env chunk
-  int base = 0, e = -1, k = 0, j = 0;
-  uint32_t attempt = 0u;
-  long long chosen = 0;
+  const uint32_t count = hdr->count;              // final: the scan kernel precedes this one on the stream
+  const float rk = p.robot_keepout, zk = p.zone_keepout, ext = p.extent;
+  bool have = false, drained = false;
+  int e = -1, k = 0, j = 0;
+  uint32_t attempt = 0u, slot = 0u;
+  long long layout_seed = 0;
+  U4 r{0u, 0u, 0u, 0u};
   for (;;) {
-    if (!have && !exhausted) {
-      while (pending == 0u) {
-        base = (int)atomicAdd(cursor, 32u);
-        if (base >= p.B) { exhausted = true; break; }
-        const int n = min(32, p.B - base);
-        for (int i = 0; i < n; ++i)
-          if (ld_relaxed_u32(p.next_ready + base + i) == kSlotEmpty) pending |= 1u << i;
-      }
-      if (pending) {
-        e = base + __ffs(pending) - 1;
-        pending &= pending - 1u;
-        chosen = choose_seed(p, e, p.episode[e]);
+    const unsigned idle = __ballot_sync(kFull, !have);
+    if (idle && !drained) {                       // one atomic refills every idle lane of the warp
+      uint32_t base = 0u;
+      if (lane == 0) base = atomicAdd(&hdr->cursor, (uint32_t)__popc(idle));
+      base = __shfl_sync(kFull, base, 0);
+      drained = base + (uint32_t)__popc(idle) >= count;
+      const uint32_t idx = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+      if (!have && idx < count) {
+        const WorkItem it = work[1u + idx];
+        e = it.e; slot = it.slot; layout_seed = it.seed + 1;   // Engine.reset: _seed += 1 before the layout
         have = true; k = 0; j = 0; attempt = 0u;
       }
     }
-    if (__all_sync(kFull, !have)) break;
+    if (__ballot_sync(kFull, have) == 0u) break;
     if (have) {
-      // one candidate of Engine.sample_layout's sequential procedure (layout seed = chosen + 1)
-      const float keep = k == 0 ? p.robot_keepout : p.zone_keepout;
-      const float lo = -p.extent + keep, span = (p.extent - keep) - lo;
-      const U4 r = draw(chosen + 1, (uint32_t)j, (uint32_t)k, attempt, kTagLayout);
-      const float x = __fadd_rn(lo, __fmul_rn(span, u01(r.x)));
-      const float y = __fadd_rn(lo, __fmul_rn(span, u01(r.y)));
-      bool valid = true;
+      // one try of Engine.sample_layout's sequential procedure
+      const float keep = k == 0 ? rk : zk;
+      const float lo = -ext + keep, span = (ext - keep) - lo;
+      if (!(j & 1)) r = draw(layout_seed, (uint32_t)(j >> 1), (uint32_t)k, attempt, kTagLayout);
+      const float x = __fadd_rn(lo, __fmul_rn(span, u01((j & 1) ? r.z : r.x)));
+      const float y = __fadd_rn(lo, __fmul_rn(span, u01((j & 1) ? r.w : r.y)));
+      const float need_r = __fadd_rn(rk, keep), need_z = __fadd_rn(zk, keep);
+      const float need_r2 = __fmul_rn(need_r, need_r), need_z2 = __fmul_rn(need_z, need_z);
+      uint32_t bad = 0u;                          // bit q: too close to object q (no branches)
 #pragma unroll
-      for (int q = 0; q < N; ++q) {               // objects >= k hold stale values and are ignored
+      for (int q = 0; q < N; ++q) {
         const float2 o = placed[q][lane];
-        const float need = __fadd_rn(q == 0 ? p.robot_keepout : p.zone_keepout, keep);
         const float dx = __fsub_rn(x, o.x), dy = __fsub_rn(y, o.y);
         const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-        valid = valid && (q >= k || d2 >= __fmul_rn(need, need));
+        bad |= (d2 >= (q == 0 ? need_r2 : need_z2)) ? 0u : (1u << q);
       }
-      if (valid) {
+      bad &= (1u << k) - 1u;                      // objects >= k hold stale values
+      if (bad == 0u) {
         placed[k][lane] = make_float2(x, y);
         ++k; j = 0;
       } else if (++j >= 100) {                    // 100 misses abandon the layout
@@ -438,14 +510,16 @@ __global__ void __launch_bounds__(32) prefetch_layout_kernel(const __grid_consta
         if (++attempt >= 10000u) k = N + 1;       // as the twin: give up with what there is
       }
       if (k > N) {
-        const U4 rr = draw(chosen + 1, 0u, 0u, 0u, kTagRot);
+        const U4 rr = draw(layout_seed, 0u, 0u, 0u, kTagRot);
+        const size_t sb = (size_t)slot * p.B;
         const float2 rb = placed[0][lane];
+        float2* nz = p.next_zone_xy + sb * N + e;
 #pragma unroll
-        for (int i = 0; i < N; ++i) p.next_zone_xy[(size_t)i * p.B + e] = placed[1 + i][lane];
-        p.next_origin[e] = make_float4(rb.x, rb.y, __fmul_rn(6.2831855f, u01(rr.x)), 0.f);
-        p.next_seed[e] = chosen;
+        for (int i = 0; i < N; ++i) nz[(size_t)i * p.B] = placed[1 + i][lane];
+        p.next_origin[sb + e] = make_float4(rb.x, rb.y, __fmul_rn(6.2831855f, u01(rr.x)), 0.f);
+        p.next_seed[sb + e] = layout_seed - 1;
         __threadfence();
-        st_release_u32(p.next_ready + e, done_state);
+        st_release_u32(p.next_ready + sb + e, done_state);
         have = false;
       }
     }
@@ -453,46 +527,43 @@ __global__ void __launch_bounds__(32) prefetch_layout_kernel(const __grid_consta
 }
 
 template <int TASK, int N>
-__global__ void __launch_bounds__(128) prefetch_task_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(128) prefetch_task_kernel(const __grid_constant__ KParams p, const WorkItem* work) {
+  const WorkHeader* hdr = reinterpret_cast<const WorkHeader*>(work);
+  const uint32_t count = hdr->count;
   const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-  const int n_chunks = (p.B + 31) / 32;
-  const int half = lane >> 4, zone = lane & 15;
-  for (int chunk = warp; chunk < n_chunks; chunk += n_warps) {
-    const int ce = chunk * 32 + lane;
-    unsigned m = __ballot_sync(kFull, ce < p.B && ld_acquire_u32(p.next_ready + ce) == kSlotLayoutDone);
-    while (m) {
-      const int e0 = chunk * 32 + __ffs(m) - 1;
-      m &= m - 1;
-      int e1 = -1;
-      if (m) { e1 = chunk * 32 + __ffs(m) - 1; m &= m - 1; }
-      const int e = half ? e1 : e0;
-      uint32_t my_draw = 0u;
-      if (e >= 0 && zone < N) {
-        const long long chosen = p.next_seed[e];  // task draws use the seed BEFORE the increment
-        if (TASK == CRL_TASK_TTSP) {
-          const double ga = gamma_draw(chosen, p.beta_a, (uint32_t)zone, 0u);
-          const double gb = gamma_draw(chosen, p.beta_b, (uint32_t)zone, 1u);
-          const int t = (int)((ga / (ga + gb)) * (double)p.num_steps);
-          my_draw = (uint32_t)min(max(t, 0), 65535);
-        } else {
-          my_draw = colour_draw(chosen, (uint32_t)zone);
-        }
-      }
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t half = lane >> 4, zone = lane & 15;
+  constexpr int T = TASK == CRL_TASK_TTSP ? (N + 1) / 2 : 1;
+  for (uint32_t pair = warp; 2u * pair < count; pair += n_warps) {
+    const uint32_t idx = 2u * pair + half;
+    const bool live = idx < count;
+    WorkItem it{-1, 0u, 0};
+    if (live) it = work[1u + idx];
+    const size_t sb = (size_t)it.slot * p.B;
+    uint32_t my_draw = 0u;
+    if (live && zone < N) {                       // task draws use the seed BEFORE the increment
       if (TASK == CRL_TASK_TTSP) {
-        const uint32_t hi = __shfl_down_sync(kFull, my_draw, 1);
-        if (e >= 0 && zone < N && !(zone & 1))
-          p.next_task[(size_t)(zone >> 1) * p.B + e] = my_draw | (zone + 1 < N ? hi << 16 : 0u);
+        const double ga = gamma_draw(it.seed, p.beta_a, zone, 0u);
+        const double gb = gamma_draw(it.seed, p.beta_b, zone, 1u);
+        const int t = (int)((ga / (ga + gb)) * (double)p.num_steps);
+        my_draw = (uint32_t)min(max(t, 0), 65535);
       } else {
-        uint32_t cw = zone < N ? my_draw << (2 * zone) : 0u;
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) cw |= __shfl_xor_sync(kFull, cw, o);   // within the half-warp
-        if (e >= 0 && zone == 0) p.next_task[e] = cw;
+        my_draw = colour_draw(it.seed, zone);
       }
-      __threadfence();
-      __syncwarp();
-      if (e >= 0 && zone == 0) st_release_u32(p.next_ready + e, kSlotReady);
     }
+    if (TASK == CRL_TASK_TTSP) {
+      const uint32_t hi = __shfl_down_sync(kFull, my_draw, 1);
+      if (live && zone < N && !(zone & 1))
+        p.next_task[(sb * T) + (size_t)(zone >> 1) * p.B + it.e] = my_draw | (zone + 1 < N ? hi << 16 : 0u);
+    } else {
+      uint32_t cw = zone < N ? my_draw << (2 * zone) : 0u;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) cw |= __shfl_xor_sync(kFull, cw, o);   // within the half-warp
+      if (live && zone == 0) p.next_task[sb + it.e] = cw;
+    }
+    __threadfence();
+    __syncwarp();
+    if (live && zone == 0) st_release_u32(p.next_ready + sb + it.e, kSlotReady);
   }
 }
 
@@ -1065,12 +1136,12 @@ int crl_plane_bytes(const CrlConfig* c, int64_t o[19]) {
   o[3] = c->task == CRL_TASK_TTSP ? 4 * ((N + 1) / 2) * B : 0;
   o[4] = c->task == CRL_TASK_CM ? 8 * B : 0;
   o[5] = 8 * B; o[6] = 4 * B; o[7] = 16 * B; o[8] = 8 * 8;
-  o[9] = 8 * N * B;
-  o[10] = c->task == CRL_TASK_TTSP ? 4 * ((N + 1) / 2) * B : (c->task == CRL_TASK_CM ? 4 * B : 0);
-  o[11] = 16 * B; o[12] = 8 * B; o[13] = 4 * B;
+  o[9] = 2 * 8 * N * B;
+  o[10] = 2 * (c->task == CRL_TASK_TTSP ? 4 * ((N + 1) / 2) * B : (c->task == CRL_TASK_CM ? 4 * B : 0));
+  o[11] = 2 * 16 * B; o[12] = 2 * 8 * B; o[13] = 2 * 4 * B;
   o[14] = 32 * B; o[15] = 4 * N * Z * B; o[16] = 8 * B;
   o[17] = 2 * 4 * ((B + 31) / 32);
-  o[18] = 16;
+  o[18] = 16 * (1 + 2 * B);
   return CRL_OK;
 }
 
@@ -1169,22 +1240,27 @@ int crl_prefetch_layouts(const CrlConfig* c, const CrlState* st, int32_t warps_p
   KParams p;
   int rc = fill_params(c, st, nullptr, p);
   if (rc) return rc;
-  if (!p.next_ready || !st->prefetch_cursor) return CRL_ERR_NULL;
+  if (!p.next_ready || !st->prefetch_work) return CRL_ERR_NULL;
+  if (!aligned16(st->prefetch_work)) return CRL_ERR_ALIGN;
   if (warps_per_sm <= 0) warps_per_sm = 2;
   if (warps_per_sm > 32) warps_per_sm = 32;
-  const int n_chunks = (p.B + 31) / 32;
+  WorkItem* work = reinterpret_cast<WorkItem*>(st->prefetch_work);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (cudaMemsetAsync(st->prefetch_cursor, 0, 16, s) != cudaSuccess) return CRL_ERR_DEVICE;
-  // (A) layouts: persistent lanes, one env each; a few warps per SM share it with the steps
-  const int blocks_a = min(n_chunks, 148 * warps_per_sm);
+  if (cudaMemsetAsync(work, 0, sizeof(WorkHeader), s) != cudaSuccess) return CRL_ERR_DEVICE;
+  // (0) empty slots -> dense work list
+  const int blocks_0 = min((p.B + 255) / 256, 148 * 4);
+#define CRL_CALL_PREFETCH_0(T, NN) { prefetch_scan_kernel<NN><<<blocks_0, 256, 0, s>>>(p, work); }
+  CRL_DISPATCH(c->task, c->num_zones, CRL_CALL_PREFETCH_0);
+  // (A) layouts: persistent lanes, one layout each; a few warps per SM share it with the steps
+  const int blocks_a = min((2 * p.B + 31) / 32, 148 * warps_per_sm);
   const uint32_t done_state = c->task == CRL_TASK_TSP ? kSlotReady : kSlotLayoutDone;
-#define CRL_CALL_PREFETCH_A(T, NN) { prefetch_layout_kernel<NN><<<blocks_a, 32, 0, s>>>(p, st->prefetch_cursor, done_state); }
+#define CRL_CALL_PREFETCH_A(T, NN) { prefetch_layout_kernel<NN><<<blocks_a, 32, 0, s>>>(p, work, done_state); }
   CRL_DISPATCH(c->task, c->num_zones, CRL_CALL_PREFETCH_A);
   rc = launch_status();
   if (rc || c->task == CRL_TASK_TSP) return rc;
-  // (B) task draws for the slots (A) just filled
-  const int blocks_b = min((n_chunks + 3) / 4, 148 * 2);
-#define CRL_CALL_PREFETCH_B(T, NN) { prefetch_task_kernel<T, NN><<<blocks_b, 128, 0, s>>>(p); }
+  // (B) task draws for the same work list
+  const int blocks_b = min((2 * p.B + 7) / 8, 148 * 2);
+#define CRL_CALL_PREFETCH_B(T, NN) { prefetch_task_kernel<T, NN><<<blocks_b, 128, 0, s>>>(p, work); }
   CRL_DISPATCH(c->task, c->num_zones, CRL_CALL_PREFETCH_B);
   return launch_status();
 }

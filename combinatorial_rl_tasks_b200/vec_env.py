@@ -76,17 +76,18 @@ class ZoneVecEnv:
         self.origin = z(B, 4)
         self.counters_dev = z(8, dtype=torch.float64)
         # next-layout slots, filled in the background by crl_prefetch_layouts
-        self.next_zone_xy = z(N, B, 2)
+        # (two slots per env: reset number n takes slot n & 1)
+        self.next_zone_xy = z(2, N, B, 2)
         if spec.task == _lib.TASK_TTSP:
-            self.next_task = z((N + 1) // 2, B, dtype=torch.int32)
+            self.next_task = z(2, (N + 1) // 2, B, dtype=torch.int32)
         elif spec.task == _lib.TASK_CM:
-            self.next_task = z(B, dtype=torch.int32)
+            self.next_task = z(2, B, dtype=torch.int32)
         else:
             self.next_task = None
-        self.next_origin = z(B, 4)
-        self.next_seed = z(B, dtype=torch.int64)
-        self.next_ready = z(B, dtype=torch.int32)
-        self._prefetch_cursor = z(4, dtype=torch.int32)
+        self.next_origin = z(2, B, 4)
+        self.next_seed = z(2, B, dtype=torch.int64)
+        self.next_ready = z(2, B, dtype=torch.int32)
+        self._prefetch_work = z(1 + 2 * B, 4, dtype=torch.int32)
         self._side = torch.cuda.Stream(device=dev)
         # per-warp completion stamps of crl_step (CRL_STEP_CHAINED)
         self.stamp = z(2, (B + 31) // 32, dtype=torch.int32)
@@ -107,7 +108,7 @@ class ZoneVecEnv:
                                    counters=ptr(self.counters_dev), next_zone_xy=ptr(self.next_zone_xy),
                                    next_task=ptr(self.next_task), next_origin=ptr(self.next_origin),
                                    next_seed=ptr(self.next_seed), next_ready=ptr(self.next_ready),
-                                   stamp=ptr(self.stamp), prefetch_cursor=ptr(self._prefetch_cursor))
+                                   stamp=ptr(self.stamp), prefetch_work=ptr(self._prefetch_work))
         self.out = _lib.CrlOut(obs=ptr(self.obs), zone_obs=ptr(self.zone_obs), result=ptr(self.result))
         self._actions_dev = z(B, 2)
         self._host = None
@@ -156,7 +157,7 @@ class ZoneVecEnv:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.crl_prefetch_layouts(self.cfg, self.state, warps_per_sm,
                                                      ctypes.c_void_p(stream.cuda_stream)))
-        self.gpu_launches += 1 if self.spec.task == _lib.TASK_TSP else 2
+        self.gpu_launches += 2 if self.spec.task == _lib.TASK_TSP else 3
 
     def reset(self, layout=None, mask=None, env_ids=None):
         """Engine.reset of all envs (or those in ``mask``).  ``layout`` switches to the

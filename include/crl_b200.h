@@ -41,13 +41,14 @@
  *                          (goal_met), sum of episode lengths, resets served from a
  *                          prefetched layout, resets sampled inline, 1 reserved, chained-step
  *                          waits that gave up (must stay 0)
- *  optional next-layout planes (all NULL = no prefetch): the draws of each env's NEXT
- *  Engine.reset, made in the background by crl_prefetch_layouts so that an auto-reset
- *  inside crl_step is a copy instead of a rejection-sampling loop
- *    next_zone_xy float2[N][B], next_task uint32[ceil(N/2)][B] (TimedTSP timeouts) or
- *    uint32[B] (ColourMatch colour codes), next_origin float4[B], next_seed int64[B]
- *    (the seed the parked layout was drawn for), next_ready uint32[B] (0 = slot empty, 1 =
- *    ready, 2 = layout parked and task draws pending)
+ *  optional next-layout planes (all NULL = no prefetch): the draws of each env's next TWO
+ *  Engine.resets (reset number n parks in slot n & 1), made in the background by
+ *  crl_prefetch_layouts so that an auto-reset inside crl_step is a copy instead of a
+ *  rejection-sampling loop
+ *    next_zone_xy float2[2][N][B], next_task uint32[2][ceil(N/2)][B] (TimedTSP timeouts) or
+ *    uint32[2][B] (ColourMatch colour codes), next_origin float4[2][B], next_seed int64[2][B]
+ *    (the seed the parked layout was drawn for), next_ready uint32[2][B] (0 = slot empty, 1 =
+ *    ready, 2 = layout parked and task draws pending, 3 = claimed by a running prefetch)
  *  optional stamp uint32[2][ceil(B/32)]: steps started / finished per group of 32 envs,
  *  see CRL_STEP_CHAINED
  *  outputs, the layout the reference's consumer builds (main/src/utils/format.py:27-28):
@@ -133,14 +134,15 @@ typedef struct CrlState {
   uint32_t* episode;    /* uint32[B] */
   float* origin;        /* float4[B] */
   double* counters;     /* double[8] */
-  float* next_zone_xy;  /* float2[N][B]; optional (prefetch) */
-  uint32_t* next_task;  /* TTSP: uint32[ceil(N/2)][B]; ColourMatch: uint32[B]; optional */
-  float* next_origin;   /* float4[B]; optional */
-  int64_t* next_seed;   /* int64[B]; optional */
-  uint32_t* next_ready; /* uint32[B]; optional.  Zero it whenever CrlState.seed is rewritten */
+  float* next_zone_xy;  /* float2[2][N][B]; optional (prefetch) */
+  uint32_t* next_task;  /* TTSP: uint32[2][ceil(N/2)][B]; ColourMatch: uint32[2][B]; optional */
+  float* next_origin;   /* float4[2][B]; optional */
+  int64_t* next_seed;   /* int64[2][B]; optional */
+  uint32_t* next_ready; /* uint32[2][B]; optional.  Zero it whenever CrlState.seed is rewritten */
   uint32_t* stamp;      /* uint32[2][ceil(B/32)]; optional, zero-initialised.  Steps started and
                            steps finished for each group of 32 envs (CRL_STEP_CHAINED) */
-  uint32_t* prefetch_cursor; /* uint32[4]; workspace of crl_prefetch_layouts (needed with next_*) */
+  uint32_t* prefetch_work; /* 16 (1 + 2 B) bytes, 16-byte aligned: work list of crl_prefetch_layouts
+                              (needed with next_*) */
 } CrlState;
 
 typedef struct CrlResult {
@@ -173,7 +175,7 @@ const char* crl_strerror(int code);
 /* Bytes the caller must allocate for each plane of CrlState / CrlOut, in the order
  * pose, aux, zone_xy, zone_tmax, cooldown, seed, episode, origin, counters, next_zone_xy,
  * next_task, next_origin, next_seed, next_ready, obs, zone_obs, result, stamp,
- * prefetch_cursor (19 entries; 0 = plane unused by this task). */
+ * prefetch_work (19 entries; 0 = plane unused by this task). */
 int crl_plane_bytes(const CrlConfig* cfg, int64_t out_bytes[19]);
 
 /* Algorithmic HBM bytes one env-step moves in this layout: read, written. */

@@ -618,8 +618,9 @@ void ph_reset(int task, int N, int num_steps, int seed_mode, int64_t min_seed, i
       int found = 0;
       for (int j = 0; j < 100 && !found; ++j) {
         uint32_t r[4];
-        ph_draw(seed, (uint32_t)j, (uint32_t)k, attempt, TAG_LAYOUT, r);
-        volatile float mx = span * ph_u01(r[0]), my = span * ph_u01(r[1]);
+        /* try j = half (j & 1) of Philox block (j >> 1, k, attempt) */
+        ph_draw(seed, (uint32_t)(j >> 1), (uint32_t)k, attempt, TAG_LAYOUT, r);
+        volatile float mx = span * ph_u01(r[(j & 1) ? 2 : 0]), my = span * ph_u01(r[(j & 1) ? 3 : 1]);
         const float x = lo + mx, y = lo + my;
         int valid = 1;
         for (int q = 0; q < k; ++q) {

@@ -25,6 +25,13 @@ What each piece follows:
                               files, ZoneWrapper.split_zone_obs wrappers.py:136-142
   per-episode seeding ....... FixedSeedsWrapper wrappers.py:10-23
   auto-reset ................ penv.py:4-21, 52-66
+  goal-conditioned variants . zone-goals/envs/TSP_next_city_env.py (PointTSP-v3),
+                              TTSP_next_city_env.py (PointTTSP-v3),
+                              colour_match_next_city_env.py (ColourMatch-v3): set_goal /
+                              get_goal / get_available_goals, info['shaped_reward'],
+                              info['need_next_goal']; worker RPCs
+                              zone-goals/src/torch_ac/torch_utils/penv.py:18-25
+  WaitWrapper ............... wrappers.py:29-54 (no-op zeros after the inner env is done)
 """
 import math
 
@@ -33,7 +40,9 @@ import numpy as np
 from . import mj_point
 
 TSP, TTSP, CM = 0, 1, 2
-TASK_OF_ENV_ID = {'PointTSP-v0': TSP, 'PointTTSP-v0': TTSP, 'ColourMatch-v0': CM}
+TASK_OF_ENV_ID = {'PointTSP-v0': TSP, 'PointTTSP-v0': TTSP, 'ColourMatch-v0': CM,
+                  'PointTSP-v3': TSP, 'PointTTSP-v3': TTSP, 'ColourMatch-v3': CM}
+GOAL_ENV_IDS = ('PointTSP-v3', 'PointTTSP-v3', 'ColourMatch-v3')   # zone-goals/envs/__init__.py
 
 NUM_STEPS = 2000            # envs/__init__.py:13, :49
 NUM_ZONES = {TSP: 15, TTSP: 15, CM: 6}   # envs/__init__.py:9, :45
@@ -103,8 +112,11 @@ class ZoneTaskEnv:
     xy0 (2,), rot0, zone_xy (N,2) and, per task, zone_max_steps (N,) / colours (N,).
     """
 
-    def __init__(self, task, num_zones=None, num_steps=NUM_STEPS):
+    def __init__(self, task, num_zones=None, num_steps=NUM_STEPS, goals=False):
         self.task = task
+        self.goals = goals          # the *_next_city_env.py variants
+        self.goal_zone = None
+        self.last_dist_to_goal = None
         self.N = NUM_ZONES[task] if num_zones is None else num_zones
         self.Z = ZONE_DIM[task]
         self.num_steps = num_steps
@@ -206,10 +218,55 @@ class ZoneTaskEnv:
         self.steps += 1
         if self.steps >= self.num_steps:
             self.done = True
+        if self.goals:
+            # TSP_next_city_env.py:57-75 / colour_match_next_city_env.py:110-133, evaluated right
+            # after Engine.step (post-physics position), before TimedTSP's timeout test
+            assert self.goal_zone is not None
+            reached = fired >= 0 and fired == self.goal_zone
+            if reached:
+                info['shaped_reward'] = 0.
+            else:
+                dist = self._dist_to_goal()
+                info['shaped_reward'] = self.last_dist_to_goal - dist
+                self.last_dist_to_goal = dist
+                if self.task == CM and fired >= 0:
+                    info['shaped_reward'] -= 1.
+            if reached or self.done:
+                info['need_next_goal'] = True
+                self.goal_zone = None
+            else:
+                info['need_next_goal'] = False
         if self.task == TTSP and not self.done:
             if (self._zone_times() <= 0).any():
                 self.done = True
+                if self.goals:          # TTSP_next_city_env.py:49-53
+                    info['need_next_goal'] = True
+                    self.goal_zone = None
         return self._obs(), reward, self.done, info
+
+    # -- goal RPCs (TSP_next_city_env.py:77-95, colour_match_next_city_env.py:135-148) ---
+    def _dist_to_goal(self):
+        p = self.sim.data.get_body_xpos('robot')[:2]
+        return np.sqrt(np.sum(np.square(self.zone_xy[self.goal_zone] - p)))
+
+    def set_goal(self, next_goal):
+        next_goal = int(next_goal)
+        if self.task == CM:
+            assert 0 <= next_goal < self.N
+        else:
+            assert not self.visited[next_goal]
+        self.goal_zone = next_goal
+        self.last_dist_to_goal = self._dist_to_goal()
+
+    def get_goal(self):
+        assert self.goal_zone is not None
+        return self.zone_xy[self.goal_zone] / 3.
+
+    def get_available_goals(self):
+        assert self.goal_zone is None
+        if self.task == CM:
+            return np.ones(self.N, dtype=bool)
+        return ~self.visited
 
     # -- observation -----------------------------------------------------------
     def _zone_times(self):
@@ -266,6 +323,9 @@ class FixedSeeds:
     def step(self, action):
         return self.env.step(action)
 
+    def __getattr__(self, name):            # gym.Wrapper forwards unknown attributes (set_goal, goal_zone, ...)
+        return getattr(self.env, name)
+
 
 class SerialVecEnv:
     """ParallelEnv (penv.py:23-69) without the processes: same results."""
@@ -291,9 +351,41 @@ class SerialVecEnv:
 
 def make_fixed_env(env_id, seed=1000, env_seed=0):
     """make_env.make_fixed_env (make_env.py:37-51) for the three zone tasks."""
-    return FixedSeeds(ZoneTaskEnv(TASK_OF_ENV_ID[env_id]), env_seed, env_seed, rng_seed=seed)
+    return FixedSeeds(ZoneTaskEnv(TASK_OF_ENV_ID[env_id], goals=env_id in GOAL_ENV_IDS), env_seed, env_seed,
+                      rng_seed=seed)
 
 
-def make_train_env(env_id, num_training_tasks=100, rng_seed=0):
-    """make_env.make_train_env (make_env.py:3-18), hier=False."""
-    return FixedSeeds(ZoneTaskEnv(TASK_OF_ENV_ID[env_id]), 1, num_training_tasks, rng_seed=rng_seed)
+def make_train_env(env_id, num_training_tasks=100, rng_seed=0, hier=False):
+    """make_env.make_train_env (make_env.py:3-18)."""
+    env = FixedSeeds(ZoneTaskEnv(TASK_OF_ENV_ID[env_id], goals=env_id in GOAL_ENV_IDS), 1, num_training_tasks,
+                     rng_seed=rng_seed)
+    return Wait(env) if hier else env
+
+
+class Wait:
+    """WaitWrapper (wrappers.py:29-54): stepping an env whose inner env is done is a no-op that
+    returns an all-zero observation, zero reward, done=True and an empty info."""
+
+    def __init__(self, env):
+        self.env = env
+        self.inner_done = False
+
+    def step(self, action):
+        if not self.inner_done:
+            obs, rew, done, info = self.env.step(action)
+            if done:
+                self.inner_done = True
+        else:
+            obs, rew, done, info = self.noop_obs(), 0, True, {}
+        return obs, rew, done, info
+
+    def noop_obs(self):
+        e = self.env.env if hasattr(self.env, 'env') else self.env
+        return {'zone_obs': np.zeros((e.N, e.Z)), 'obs': np.zeros(8)}
+
+    def reset(self):
+        self.inner_done = False
+        return self.env.reset()
+
+    def __getattr__(self, name):
+        return getattr(self.env, name)

@@ -313,7 +313,10 @@ def test_prefetched_resets_equal_inline_resets(crl, env_id):
     for e in (a, b):
         e.seed(31337); e.reset()
     torch.cuda.synchronize()
-    assert bool((a.next_ready == 1).all()) and bool((b.next_ready == 0).all())
+    # a full reset() parks the layouts of the next two resets and consumes the first; `a` then tops
+    # its slots up again, `b` (never prefetching) is stripped of its parked layout: all inline
+    assert bool((a.next_ready == 1).all()) and bool((b.next_ready[0] == 0).all()) and bool((b.next_ready[1] == 1).all())
+    b.next_ready.zero_()
     gen = torch.Generator(device='cuda'); gen.manual_seed(0)
     for rnd in range(3):
         for e in (a, b):                      # everyone finishes within the next 30 steps
