@@ -10,7 +10,8 @@ import pytest
 from oracle import zone_env as ze
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-EPISODES = sorted(f for f in glob.glob(os.path.join(GOLDEN, '*.npz')) if not f.endswith('_vector.npz'))
+EPISODES = sorted(f for f in glob.glob(os.path.join(GOLDEN, '*.npz'))
+                  if not f.endswith('_vector.npz') and not os.path.basename(f).startswith('goals_'))
 VECTORS = sorted(glob.glob(os.path.join(GOLDEN, '*_vector.npz')))
 
 
