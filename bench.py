@@ -226,25 +226,41 @@ def run_ours(args):
     if rank == 0 or world > 1:
         env = envs[0]
         host_actions = [np.random.RandomState(7 + i).uniform(-1, 1, (B, 2)).astype(np.float32) for i in range(4)]
-        for i in range(3):
-            env.step_host(host_actions[i % 4])
-        ke = args.e2e_steps
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for i in range(ke):
-            obs, rew, done, info = env.step_host(host_actions[i % 4])
-        torch.cuda.synchronize()
-        te = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([te], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            te = float(t.item())
         N, Z = env.spec.num_zones, env.spec.zone_dim
-        e2e = {'value': world * ke * B / te, 'unit': UNIT, 'h2d_bytes_per_step': 8 * B,
-               'd2h_bytes_per_step': (32 + 4 * N * Z + 8) * B, 'steps': ke,
-               'api': 'ZoneVecEnv.step_host -> crl_step_host (pinned staging, copies + sync inside)'}
+
+        def timed_host_steps(delta):
+            for i in range(3):
+                env.step_host(host_actions[i % 4], delta=delta)
+            ke = args.e2e_steps
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            rows = 0
+            t0 = time.perf_counter()
+            for i in range(ke):
+                obs, rew, done, info = env.step_host(host_actions[i % 4], delta=delta)
+                rows += env.delta_rows
+            torch.cuda.synchronize()
+            te = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([te], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                te = float(t.item())
+            return world * ke * B / te, rows / ke
+
+        full_rate, _ = timed_host_steps(False)
+        rate, rows_per_step = timed_host_steps(True)
+        is_delta = rows_per_step < B
+        e2e = {'value': rate, 'unit': UNIT, 'h2d_bytes_per_step': 8 * B,
+               'd2h_bytes_per_step': int((32 + 8) * B + rows_per_step * (4 * N * Z + (4 if is_delta else 0)) + (16 if is_delta else 0)),
+               'steps': args.e2e_steps,
+               'api': 'ZoneVecEnv.step_host: host numpy actions in, host numpy obs/zone_obs/reward/done out, pinned '
+                      'staging, copies + stream sync inside every call'
+                      + ('; crl_step_host_delta: obs and result whole, zone_obs rows that changed only (mean %.1f of %d '
+                         'rows per step), byte-identical host buffers' % (rows_per_step, B) if is_delta
+                         else '; crl_step_host: everything copied whole'),
+               'full_copy_value': full_rate,
+               'full_copy_d2h_bytes_per_step': (32 + 4 * N * Z + 8) * B}
 
     if rank != 0:
         if world > 1:
@@ -300,7 +316,7 @@ def main():
     ap.add_argument('--env', default='PointTSP-v0')
     ap.add_argument('--envs', type=int, default=65536)
     ap.add_argument('--repeats', type=int, default=1)
-    ap.add_argument('--e2e-steps', type=int, default=50)
+    ap.add_argument('--e2e-steps', type=int, default=200)
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-auto-reset', action='store_true', help='diagnostic: finished envs keep stepping')

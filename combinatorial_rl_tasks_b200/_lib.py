@@ -12,12 +12,14 @@ c_void_p, c_int32, c_int64, c_uint32, c_uint64, c_double = (
 
 TASK_TSP, TASK_TTSP, TASK_CM = 0, 1, 2
 SEED_INCREMENT, SEED_FIXED_RANGE = 0, 1
-STEP_AUTO_RESET, STEP_PHYSICS_ONLY, STEP_CHAINED, STEP_CHAIN_START = 1, 2, 4, 8
-ABI_VERSION = 3
+STEP_AUTO_RESET, STEP_PHYSICS_ONLY, STEP_CHAINED, STEP_CHAIN_START, STEP_TRACK_ROWS = 1, 2, 4, 8, 16
+STEP_GOALS, STEP_WAIT = 32, 64
+ABI_VERSION = 4
 
 # every symbol include/crl_b200.h declares
 SYMBOLS = ['crl_abi_version', 'crl_strerror', 'crl_plane_bytes', 'crl_step_bytes', 'crl_reset',
-           'crl_prefetch_layouts', 'crl_reset_from_layout', 'crl_step', 'crl_step_host', 'crl_set_qpos_qvel',
+           'crl_prefetch_layouts', 'crl_reset_from_layout', 'crl_step', 'crl_step_host', 'crl_step_host_delta',
+           'crl_set_goal', 'crl_goal_query', 'crl_set_qpos_qvel',
            'crl_get_qpos_qvel', 'crl_counters_read']
 
 
@@ -34,11 +36,11 @@ class CrlState(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in ('pose', 'aux', 'zone_xy', 'zone_tmax', 'cooldown', 'seed',
                                         'episode', 'origin', 'counters', 'next_zone_xy', 'next_task',
                                         'next_origin', 'next_seed', 'next_ready', 'stamp',
-                                        'prefetch_work')]
+                                        'prefetch_work', 'row_list', 'goal')]
 
 
 class CrlOut(ctypes.Structure):
-    _fields_ = [(n, c_void_p) for n in ('obs', 'zone_obs', 'result')]
+    _fields_ = [(n, c_void_p) for n in ('obs', 'zone_obs', 'result', 'shaped_reward')]
 
 
 class CrlLayoutIn(ctypes.Structure):
@@ -71,6 +73,10 @@ def load():
                              c_void_p]
     lib.crl_step_host.argtypes = [P(CrlConfig), P(CrlState), c_void_p, c_void_p, P(CrlOut), P(CrlOut),
                                   c_uint32, c_void_p]
+    lib.crl_step_host_delta.argtypes = [P(CrlConfig), P(CrlState), c_void_p, c_void_p, P(CrlOut), P(CrlOut),
+                                        c_void_p, c_int64, c_uint32, P(c_int32), c_void_p]
+    lib.crl_set_goal.argtypes = [P(CrlConfig), P(CrlState), c_void_p, c_void_p]
+    lib.crl_goal_query.argtypes = [P(CrlConfig), P(CrlState), c_void_p, c_void_p, c_void_p, c_void_p]
     lib.crl_set_qpos_qvel.argtypes = [P(CrlConfig), P(CrlState), c_void_p, c_void_p, c_void_p, c_int32,
                                       c_void_p]
     lib.crl_get_qpos_qvel.argtypes = [P(CrlConfig), P(CrlState), c_void_p, c_void_p, c_void_p, c_int32,

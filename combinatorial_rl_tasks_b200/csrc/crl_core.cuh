@@ -116,13 +116,14 @@ inline double sqrt_threshold(double r) {
 // n / d correctly rounded (== IEEE float division) for integer-valued n and the two
 // divisors the observation uses (num_steps, max_cooldown): q0 = RN(n y), y = RN(1/d),
 // one exact-remainder correction (Markstein).  div_const_ok() proves it on the host, for
-// the divisor in force, over every numerator the kernels can form; a divisor that failed
-// the proof would be divided with __fdiv_rn instead (DivConst::exact == 0).
+// the divisor in force, over every numerator the kernels can form; a configuration whose
+// divisor failed the proof is refused (CRL_ERR_CONFIG) -- none does: every divisor in
+// [1, 65534] passes for every numerator in [-65535, 65535] (checked exhaustively), so the
+// device path carries no fallback branch.
 struct DivConst { float d, y; int exact; };
 
 CRL_HD float div_const(float n, const DivConst& k) {
 #if defined(__CUDA_ARCH__)
-  if (!k.exact) return __fdiv_rn(n, k.d);
   const float q0 = __fmul_rn(n, k.y);
   return __fmaf_rn(__fmaf_rn(-q0, k.d, n), k.y, q0);
 #else

@@ -61,11 +61,14 @@ struct KParams {
   long long* next_seed;
   uint32_t* next_ready;
   uint32_t* stamp;
+  uint32_t* row_list;
+  int32_t* goal;
   // io
   const float2* actions;
   float4* obs;
   float* zone_obs;
   unsigned long long* result;  // CrlResult as one 8-byte word
+  float* shaped;               // info['shaped_reward'] (goal-conditioned variants)
   const uint8_t* mask;
 };
 
@@ -392,6 +395,7 @@ __device__ CRL_RESET_INLINING void warp_reset(const KParams& p, unsigned dm, int
     p.seed[e] = chosen + 1;                       // Engine.reset: self._seed += 1
     p.episode[e] = episode + 1u;
     p.origin[e] = make_float4(x0, y0, rot0, 0.f);
+    if (p.goal) p.goal[e] = -1;                   // a new episode has no goal until set_goal
     // hand the slot back to the prefetcher (release: our reads of it are done)
     if (slot_flag) st_release_u32(slot_flag, kSlotEmpty);
   }
@@ -612,9 +616,12 @@ __device__ __forceinline__ void zone_row(const KParams& p, const Env<N>& env, fl
 // run before the CTA exits (the copy reads shared memory asynchronously).
 template <int TASK, int N>
 __device__ __forceinline__ void zone_obs_send(const KParams& p, const Env<N>& env, bool valid,
-                                              float* stage, int lane, int warp_env0) {
+                                              float* stage, int lane, int warp_env0, bool zero_row = false) {
   constexpr int ROW = N * ZoneDim<TASK>::Z;
   if (valid) zone_row<TASK, N>(p, env, stage + lane * ROW);
+  if (zero_row) {                                  // WaitWrapper.noop_obs (wrappers.py:46-50)
+    for (int k = 0; k < ROW; ++k) stage[lane * ROW + k] = 0.f;
+  }
   const int n_valid = min(32, p.B - warp_env0);
   const uint32_t bytes = (uint32_t)n_valid * ROW * 4u;
   float* gdst = p.zone_obs + (size_t)warp_env0 * ROW;
@@ -642,11 +649,15 @@ __device__ __forceinline__ void zone_obs_wait(int lane) {
 // to float32 equals the correctly rounded float32 quotient (num_steps - steps)/num_steps
 // (the exact value is k/num_steps, never within 2^-53 of a float32 rounding boundary
 // unless it is one), so one IEEE float division reproduces it bit for bit.
+// `park`: the stored step count becomes the parked sentinel (CRL_STEP_WAIT); the observation
+// still shows the real count.
+constexpr int kParkedSteps = 0xffff;
 template <int TASK, int N>
-__device__ __forceinline__ void store_state_obs(const KParams& p, const Env<N>& env, int e, float c, float s) {
+__device__ __forceinline__ void store_state_obs(const KParams& p, const Env<N>& env, int e, float c, float s,
+                                                bool park = false) {
   p.pose[e] = make_float4(env.b.X, env.b.Y, env.b.phi, env.b.vx);
   p.aux[e] = make_float4(env.b.vy, env.b.w, env.ep_return,
-                         __int_as_float((int)((uint32_t)env.steps | (env.hi << 16))));
+                         __int_as_float((int)((uint32_t)(park ? kParkedSteps : env.steps) | (env.hi << 16))));
   if (TASK == CRL_TASK_CM) p.cooldown[e] = env.cd;
   const float remaining = div_const((float)(p.num_steps - env.steps), p.div_steps);
   p.obs[2 * (size_t)e] = make_float4(remaining, env.b.X * (1.0f / 3.0f), env.b.Y * (1.0f / 3.0f), c);
@@ -670,6 +681,13 @@ __device__ __forceinline__ void load_env(const KParams& p, int e, Env<N>& env) {
   const uint32_t bits = (uint32_t)__float_as_int(ax.w);
   env.steps = (int)(bits & 0xffffu);
   env.hi = bits >> 16;
+}
+
+// np.sqrt(np.sum(np.square(goal_pos - robot_pos))) in fp64, no fused multiply-add
+// (TSP_next_city_env.py:38-42 dist_to_goal).
+__device__ __forceinline__ double dist_np(float X, float Y, float zx, float zy) {
+  const double dx = (double)zx - (double)X, dy = (double)zy - (double)Y;
+  return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
 }
 
 // ---- chained steps (CRL_STEP_CHAINED) ------------------------------------------------
@@ -716,7 +734,9 @@ __device__ __forceinline__ void chain_release(const KParams& p, int w, int lane,
 // (SURVEY.md Appendix B), so the task logic, the result word, the auto-reset and the
 // whole zone_obs row come first and the bulk copy of zone_obs is in flight while the
 // frameskip substeps run; state and the 8-float obs row are written last.
-template <int TASK, int N>
+// EXT = true: the variant that also serves the goal-conditioned tasks (CRL_STEP_GOALS) and
+// WaitWrapper semantics (CRL_STEP_WAIT); the plain rollout kernel carries none of it.
+template <int TASK, int N, bool EXT>
 __global__ void __launch_bounds__(kThreads, min_blocks<N>()) step_kernel(const __grid_constant__ KParams p) {
   constexpr int ROW = N * ZoneDim<TASK>::Z;
   extern __shared__ __align__(128) float smem[];
@@ -767,10 +787,37 @@ __global__ void __launch_bounds__(kThreads, min_blocks<N>()) step_kernel(const _
     for (int j = 0; j < (N + 1) / 2; ++j) env.tmax[j] = 0xffffffffu;
   }
 
+  // WaitWrapper (wrappers.py:29-54): an env whose episode ended under CRL_STEP_WAIT is parked
+  // (stored step count = sentinel); stepping it is a no-op that reports zeros and done.
+  const bool parked = EXT && (p.flags & CRL_STEP_WAIT) && valid && env.steps == kParkedSteps;
+  const bool live = valid && !parked;
+  // goal-conditioned variants: the goal zone and the distance to it BEFORE the physics, which
+  // is the reference's last_dist_to_goal (set by set_goal or left by the previous step, both
+  // at the position this step starts from)
+  const bool goals = EXT && (p.flags & CRL_STEP_GOALS);
+  int goal_zone = -1;
+  float gzx = 0.f, gzy = 0.f;
+  double dist_before = 0.0;
+  Body old_b = env.b;
+  bool reached = false, park_now = false;
+  if (goals && live) {
+    goal_zone = p.goal[e];
+    if (goal_zone >= 0) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) if (j == goal_zone) { gzx = env.zone[j].x; gzy = env.zone[j].y; }
+      dist_before = dist_np(env.b.X, env.b.Y, gzx, gzy);
+    }
+  }
+  int fired_out = -1;
   bool fresh = false;   // true: this env was rebuilt by the auto-reset, no physics this call
   if (!(p.flags & CRL_STEP_PHYSICS_ONLY)) {
+    // does this step rewrite the env's zone_obs row with different bytes? (CRL_STEP_TRACK_ROWS)
+    bool row_changed = TASK == CRL_TASK_TTSP;                       // the time-left column moves
     // (1) ColourMatch cooldowns tick before anything else (colour_match_env.py:98-100)
-    if (TASK == CRL_TASK_CM) { env.cd.x = cd_dec4(env.cd.x); env.cd.y = cd_dec4(env.cd.y); }
+    if (TASK == CRL_TASK_CM) {
+      row_changed = (env.cd.x | env.cd.y) != 0u;
+      env.cd.x = cd_dec4(env.cd.x); env.cd.y = cd_dec4(env.cd.y);
+    }
     // (2) zone event on the pre-physics position: first eligible zone in index order.
     // fp32 screen of all N zones without branches; the (rare) candidates are confirmed
     // with the exact fp64 predicate, lowest index first.
@@ -835,14 +882,35 @@ __global__ void __launch_bounds__(kThreads, min_blocks<N>()) step_kernel(const _
       }
     }
     env.ep_return += reward;
-    done = done && valid;
-    goal = goal && valid;
+    done = done && live;
+    goal = goal && live;
+    if (EXT) {
+      fired_out = fired;
+      reached = goals && fired >= 0 && fired == goal_zone;
+      park_now = (p.flags & CRL_STEP_WAIT) && done && !(p.flags & CRL_STEP_AUTO_RESET);
+      if (parked) { reward = 0.f; event = 0; }
+    }
+    if (p.flags & CRL_STEP_TRACK_ROWS) {
+      // a finished env's row changes too, if it is rebuilt below
+      const bool ch = (live && (row_changed || fired >= 0 || (done && (p.flags & CRL_STEP_AUTO_RESET)))) || parked;
+      const unsigned cm = __ballot_sync(kFull, ch);
+      if (cm) {
+        uint32_t base = 0u;
+        if (lane == 0) base = atomicAdd(p.row_list, (uint32_t)__popc(cm));
+        base = __shfl_sync(kFull, base, 0);
+        if (ch) p.row_list[4u + base + (uint32_t)__popc(cm & ((1u << lane) - 1u))] = (uint32_t)e;
+      }
+    }
     // (4) result word and episode statistics
     if (valid) {
+      // need_next_goal (TSP_next_city_env.py:69-75, TTSP_next_city_env.py:49-53): the goal zone
+      // was reached, or the episode ended (timeouts included), or there is no goal to pursue
+      const bool need_next = goals && live && (reached || done || goal_zone < 0);
       const unsigned long long word = (unsigned long long)__float_as_uint(reward) |
-          ((unsigned long long)(done ? 1u : 0u) << 32) | ((unsigned long long)(goal ? 1u : 0u) << 40) |
-          ((unsigned long long)(uint8_t)(int8_t)event << 48);
+          ((unsigned long long)((done || parked) ? 1u : 0u) << 32) | ((unsigned long long)(goal ? 1u : 0u) << 40) |
+          ((unsigned long long)(uint8_t)(int8_t)event << 48) | ((unsigned long long)(need_next ? 1u : 0u) << 56);
       p.result[e] = word;
+      if (EXT && goals && live && need_next && goal_zone >= 0) p.goal[e] = -1;
     }
     const unsigned dm = __ballot_sync(kFull, done);
     if (dm) {
@@ -871,16 +939,45 @@ __global__ void __launch_bounds__(kThreads, min_blocks<N>()) step_kernel(const _
     }
   }
   // (6) zone_obs leaves now and drains under the physics
-  zone_obs_send<TASK, N>(p, env, valid, stage, lane, warp_env0);
+  zone_obs_send<TASK, N>(p, env, live, stage, lane, warp_env0, EXT && parked);
   // (7) physics: all frameskip substeps in registers
   float c, s;
-  if (fresh) {
-    sincosf(env.b.phi, &s, &c);
+  if (!EXT) {
+    if (fresh) {
+      sincosf(env.b.phi, &s, &c);
+    } else {
+      substeps(env.b, act.x, act.y, p.frameskip, c, s);
+      env.b.phi = wrap_pi(env.b.phi);
+    }
+    if (valid) store_state_obs<TASK, N>(p, env, e, c, s);
   } else {
-    substeps(env.b, act.x, act.y, p.frameskip, c, s);
-    env.b.phi = wrap_pi(env.b.phi);
+    // an env rebuilt by the auto-reset still integrates its OLD body: the shaped reward of the
+    // episode's last step is measured at the post-physics position (TSP_next_city_env.py:57-67)
+    Body pb = fresh ? old_b : env.b;
+    substeps(pb, act.x, act.y, p.frameskip, c, s);
+    if (fresh) {
+      sincosf(env.b.phi, &s, &c);
+    } else {
+      env.b = pb;
+      env.b.phi = wrap_pi(env.b.phi);
+    }
+    if (goals && live) {
+      double shaped = 0.0;
+      if (goal_zone >= 0 && !reached) {
+        shaped = dist_before - dist_np(pb.X, pb.Y, gzx, gzy);
+        // colour_match_next_city_env.py:125-127: a zone other than the goal changed colour
+        if (TASK == CRL_TASK_CM && fired_out >= 0) shaped -= 1.0;
+      }
+      p.shaped[e] = (float)shaped;
+    }
+    if (parked) {
+      if (goals) p.shaped[e] = 0.f;
+      p.obs[2 * (size_t)e] = make_float4(0.f, 0.f, 0.f, 0.f);
+      p.obs[2 * (size_t)e + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else if (valid) {
+      store_state_obs<TASK, N>(p, env, e, c, s, park_now);
+    }
   }
-  if (valid) store_state_obs<TASK, N>(p, env, e, c, s);
   if (ticketed) {
     chain_release(p, warp_env0 >> 5, lane, ticket);
   } else {
@@ -905,9 +1002,10 @@ __global__ void __launch_bounds__(kThreads) reset_kernel(const __grid_constant__
   if (m) warp_reset<TASK, N>(p, m, lane, e, reinterpret_cast<float2*>(stage), env);
   float c = 1.f, s = 0.f;
   if (valid) sincosf(env.b.phi, &s, &c);
-  // envs that were not reset are rewritten with the values just loaded (no change)
+  // the warp's 32 zone_obs rows leave as one bulk copy: rows of envs that were not reset are
+  // rewritten from the state just loaded (a parked env's row of zeros becomes its real row)
   zone_obs_send<TASK, N>(p, env, valid, stage, lane, warp_env0);
-  if (valid) store_state_obs<TASK, N>(p, env, e, c, s);
+  if (want) store_state_obs<TASK, N>(p, env, e, c, s);
   zone_obs_wait(lane);
 }
 
@@ -946,6 +1044,7 @@ __global__ void reset_from_layout_kernel(const KParams p, const LayoutParams L) 
     for (int j = 0; j < (N + 1) / 2; ++j) p.zone_tmax[(size_t)j * p.B + e] = env.tmax[j];
   }
   p.episode[e] += 1u;
+  if (p.goal) p.goal[e] = -1;
   p.origin[e] = make_float4(env.b.X, env.b.Y, rot0, 0.f);
   p.pose[e] = make_float4(env.b.X, env.b.Y, env.b.phi, 0.f);
   p.aux[e] = make_float4(0.f, 0.f, 0.f, __int_as_float((int)(env.hi << 16)));
@@ -1004,6 +1103,59 @@ __global__ void get_qpos_qvel_kernel(const KParams p, double* qpos, double* qvel
   qvel[3 * i + 2] = (double)ax.y;
 }
 
+// crl_step_host_delta: the rows the step listed, packed, written straight into the caller's
+// device-mapped pinned host memory.  One warp per row; `dst_rows` row i belongs to env
+// list[4 + i].  The header and the ids are mirrored to the host in front of the rows.
+__global__ void __launch_bounds__(256) gather_rows_kernel(const uint32_t* __restrict__ list, const float* __restrict__ zone_obs,
+                                                          uint32_t* host_list, float* host_rows, int row_floats, int B) {
+  const uint32_t count = min(list[0], (uint32_t)B);
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  if (warp == 0 && lane == 0) host_list[0] = count;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+    host_list[4u + i] = list[4u + i];
+  for (uint32_t i = warp; i < count; i += n_warps) {
+    const float* src = zone_obs + (size_t)list[4u + i] * row_floats;
+    float* dst = host_rows + (size_t)i * row_floats;
+    for (int k = lane; k < row_floats; k += 32) dst[k] = src[k];
+  }
+}
+
+// Goal RPCs of the goal-conditioned variants, batched (zone-goals penv.py:18-25, 75-99).
+// set_goal (TSP_next_city_env.py:77-80, colour_match_next_city_env.py:135-138): goals[e] < 0
+// leaves env e alone; an index out of range or (TSP/TimedTSP) an already visited zone is the
+// reference's assertion failure: the goal stays unset and counters[6] counts it.
+template <int TASK>
+__global__ void set_goal_kernel(const KParams p, const int32_t* goals, int N) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= p.B) return;
+  const int g = goals[e];
+  if (g < 0) return;
+  const uint32_t bits = (uint32_t)__float_as_int(p.aux[e].w);
+  const bool ok = g < N && (TASK == CRL_TASK_CM || !((bits >> 16 >> g) & 1u));
+  if (ok) p.goal[e] = g; else atomicAdd(p.counters + 6, 1.0);
+}
+
+// needs_goal (goal_zone is None), get_goal (zone centre / 3; zeros when there is none) and
+// get_available_goals (TSP: the unvisited zones; ColourMatch: all) for every env.
+template <int TASK>
+__global__ void goal_query_kernel(const KParams p, float2* goal_xy, uint8_t* needs, uint8_t* available, int N) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= p.B) return;
+  const int g = p.goal[e];
+  if (needs) needs[e] = g < 0 ? 1 : 0;
+  if (goal_xy) {
+    float2 z = make_float2(0.f, 0.f);
+    if (g >= 0 && g < N) z = p.zone_xy[(size_t)g * p.B + e];
+    goal_xy[e] = make_float2(z.x * (1.0f / 3.0f), z.y * (1.0f / 3.0f));
+  }
+  if (available) {
+    const uint32_t bits = (uint32_t)__float_as_int(p.aux[e].w);
+    for (int i = 0; i < N; ++i)
+      available[(size_t)e * N + i] = (TASK == CRL_TASK_CM || !((bits >> 16 >> i) & 1u)) ? 1 : 0;
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------
 static int zone_dim(int task) { return task == CRL_TASK_TSP ? 6 : 7; }
 
@@ -1012,7 +1164,7 @@ static int check_config(const CrlConfig* c) {
   if (c->task < 0 || c->task > 2) return CRL_ERR_CONFIG;
   if (c->num_envs <= 0 || c->num_zones <= 0 || c->num_zones > CRL_MAX_ZONES) return CRL_ERR_CONFIG;
   if (c->task == CRL_TASK_CM && c->num_zones > 8) return CRL_ERR_CONFIG;
-  if (c->num_steps <= 0 || c->num_steps > 65535) return CRL_ERR_CONFIG;
+  if (c->num_steps <= 0 || c->num_steps > 65534) return CRL_ERR_CONFIG;   // 65535 = parked sentinel
   if (c->frameskip < 0 || c->max_cooldown < 0 || c->max_cooldown > 255) return CRL_ERR_CONFIG;
   if (c->seed_mode == CRL_SEED_FIXED_RANGE && c->max_seed < c->min_seed) return CRL_ERR_CONFIG;
   if (!(c->zone_size > 0.0)) return CRL_ERR_CONFIG;
@@ -1052,6 +1204,7 @@ static int fill_params(const CrlConfig* c, const CrlState* st, const CrlOut* out
   // numerators: num_steps - steps and zone_max_steps - steps, both within +-65535
   p.div_steps = cached_div_const(c->num_steps, -65535, 65535);
   p.div_cd = cached_div_const(c->max_cooldown > 0 ? c->max_cooldown : 1, 0, 255);
+  if (!p.div_steps.exact || !p.div_cd.exact) return CRL_ERR_CONFIG;   // never happens, see crl_core.cuh
   p.robot_keepout = (float)c->robot_keepout; p.zone_keepout = (float)c->zone_keepout; p.extent = (float)c->extent;
   p.pose = reinterpret_cast<float4*>(st->pose); p.aux = reinterpret_cast<float4*>(st->aux);
   p.zone_xy = reinterpret_cast<float2*>(st->zone_xy); p.zone_tmax = st->zone_tmax;
@@ -1068,11 +1221,14 @@ static int fill_params(const CrlConfig* c, const CrlState* st, const CrlOut* out
     p.next_seed = reinterpret_cast<long long*>(st->next_seed); p.next_ready = st->next_ready;
   }
   p.stamp = st->stamp;
+  p.row_list = st->row_list;
+  p.goal = st->goal;
   if (out) {
     if (!out->obs || !out->zone_obs || !out->result) return CRL_ERR_NULL;
     if (!aligned16(out->obs) || !aligned16(out->zone_obs)) return CRL_ERR_ALIGN;
     p.obs = reinterpret_cast<float4*>(out->obs); p.zone_obs = out->zone_obs;
     p.result = reinterpret_cast<unsigned long long*>(out->result);
+    p.shaped = out->shaped_reward;
   }
   return CRL_OK;
 }
@@ -1127,7 +1283,7 @@ const char* crl_strerror(int code) {
   }
 }
 
-int crl_plane_bytes(const CrlConfig* c, int64_t o[19]) {
+int crl_plane_bytes(const CrlConfig* c, int64_t o[22]) {
   int rc = check_config(c);
   if (rc) return rc;
   if (!o) return CRL_ERR_NULL;
@@ -1142,6 +1298,9 @@ int crl_plane_bytes(const CrlConfig* c, int64_t o[19]) {
   o[14] = 32 * B; o[15] = 4 * N * Z * B; o[16] = 8 * B;
   o[17] = 2 * 4 * ((B + 31) / 32);
   o[18] = 16 * (1 + 2 * B);
+  o[19] = 4 * (4 + B);
+  o[20] = 4 * B;   /* goal */
+  o[21] = 4 * B;   /* shaped_reward */
   return CRL_OK;
 }
 
@@ -1168,6 +1327,9 @@ int crl_step(const CrlConfig* c, const CrlState* st, const float* actions, const
   p.flags = flags; p.action_seed = action_seed; p.step_index = step_index;
   const bool ticketed = (flags & (CRL_STEP_CHAINED | CRL_STEP_CHAIN_START)) != 0u;
   if (ticketed && !p.stamp) return CRL_ERR_NULL;
+  if ((flags & CRL_STEP_TRACK_ROWS) && !p.row_list) return CRL_ERR_NULL;
+  if ((flags & CRL_STEP_GOALS) && (!p.goal || !p.shaped)) return CRL_ERR_NULL;
+  const bool ext = (flags & (CRL_STEP_GOALS | CRL_STEP_WAIT)) != 0u;
   // Programmatic launch (this grid may start while its predecessor drains) is safe when the
   // kernel then waits for the whole predecessor (plain, chain start) or for its own previous
   // step (chained).  After a CHAINED launch, though, "the predecessor is complete" no longer
@@ -1182,7 +1344,8 @@ int crl_step(const CrlConfig* c, const CrlState* st, const float* actions, const
 #define CRL_CALL_STEP(T, NN)                                                        \
   {                                                                                 \
     const size_t sm = (size_t)kThreads * NN * ZoneDim<T>::Z * 4;                    \
-    rc = set_smem(step_kernel<T, NN>, sm);                                          \
+    void (*kern)(const KParams) = ext ? step_kernel<T, NN, true> : step_kernel<T, NN, false>; \
+    rc = set_smem(kern, sm);                                                        \
     if (rc) return rc;                                                              \
     cudaLaunchConfig_t lc = {};                                                     \
     lc.gridDim = dim3(blocks); lc.blockDim = dim3(kThreads);                        \
@@ -1191,7 +1354,7 @@ int crl_step(const CrlConfig* c, const CrlState* st, const float* actions, const
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                  \
     at[0].val.programmaticStreamSerializationAllowed = 1;                           \
     lc.attrs = at; lc.numAttrs = programmatic ? 1 : 0;                              \
-    if (cudaLaunchKernelEx(&lc, step_kernel<T, NN>, p) != cudaSuccess) {            \
+    if (cudaLaunchKernelEx(&lc, kern, p) != cudaSuccess) {                          \
       (void)cudaGetLastError();                                                     \
       return CRL_ERR_LAUNCH;                                                        \
     }                                                                               \
@@ -1265,6 +1428,34 @@ int crl_prefetch_layouts(const CrlConfig* c, const CrlState* st, int32_t warps_p
   return launch_status();
 }
 
+int crl_set_goal(const CrlConfig* c, const CrlState* st, const int32_t* goals, void* stream) {
+  KParams p;
+  if (!goals) return CRL_ERR_NULL;
+  int rc = fill_params(c, st, nullptr, p);
+  if (rc) return rc;
+  if (!p.goal) return CRL_ERR_NULL;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int blocks = (p.B + 255) / 256;
+  if (c->task == CRL_TASK_CM) set_goal_kernel<CRL_TASK_CM><<<blocks, 256, 0, s>>>(p, goals, c->num_zones);
+  else set_goal_kernel<CRL_TASK_TSP><<<blocks, 256, 0, s>>>(p, goals, c->num_zones);
+  return launch_status();
+}
+
+int crl_goal_query(const CrlConfig* c, const CrlState* st, float* goal_xy, uint8_t* needs_goal,
+                   uint8_t* available, void* stream) {
+  KParams p;
+  int rc = fill_params(c, st, nullptr, p);
+  if (rc) return rc;
+  if (!p.goal) return CRL_ERR_NULL;
+  if (goal_xy && (reinterpret_cast<uintptr_t>(goal_xy) & 7u)) return CRL_ERR_ALIGN;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int blocks = (p.B + 255) / 256;
+  float2* gx = reinterpret_cast<float2*>(goal_xy);
+  if (c->task == CRL_TASK_CM) goal_query_kernel<CRL_TASK_CM><<<blocks, 256, 0, s>>>(p, gx, needs_goal, available, c->num_zones);
+  else goal_query_kernel<CRL_TASK_TSP><<<blocks, 256, 0, s>>>(p, gx, needs_goal, available, c->num_zones);
+  return launch_status();
+}
+
 int crl_set_qpos_qvel(const CrlConfig* c, const CrlState* st, const double* qpos, const double* qvel,
                       const int32_t* env_ids, int32_t n, void* stream) {
   KParams p;
@@ -1305,6 +1496,52 @@ int crl_step_host(const CrlConfig* c, const CrlState* st, const float* actions_h
   if (cudaMemcpyAsync(host_out->result, out->result, B * 8, cudaMemcpyDeviceToHost, s) != cudaSuccess)
     return CRL_ERR_DEVICE;
   if (cudaStreamSynchronize(s) != cudaSuccess) return CRL_ERR_DEVICE;
+  return CRL_OK;
+}
+
+int crl_step_host_delta(const CrlConfig* c, const CrlState* st, const float* actions_host, float* actions_dev,
+                        const CrlOut* out, const CrlOut* host_out, void* host_delta, int64_t host_delta_bytes,
+                        uint32_t flags, int32_t* delta_rows, void* stream) {
+  if (!c || !st || !actions_host || !actions_dev || !out || !host_out || !host_out->obs || !host_out->zone_obs ||
+      !host_out->result || !host_delta || !st->row_list)
+    return CRL_ERR_NULL;
+  int rc = check_config(c);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t B = c->num_envs, N = c->num_zones, Z = zone_dim(c->task), row = N * Z;
+  const size_t rows_off = (16 + 4 * B + 15) & ~(size_t)15;
+  if (!aligned16(host_delta) || (size_t)host_delta_bytes < rows_off + B * row * 4) return CRL_ERR_CONFIG;
+  // the gather kernel writes into host memory: it must be page-locked and device-mapped
+  cudaPointerAttributes pa;
+  if (cudaPointerGetAttributes(&pa, host_delta) != cudaSuccess || pa.type != cudaMemoryTypeHost || !pa.devicePointer) {
+    (void)cudaGetLastError();
+    return CRL_ERR_CONFIG;
+  }
+  uint32_t* host_list = static_cast<uint32_t*>(host_delta);
+  float* host_rows = reinterpret_cast<float*>(static_cast<char*>(host_delta) + rows_off);
+  uint32_t* dev_host_list = static_cast<uint32_t*>(pa.devicePointer);
+  float* dev_host_rows = reinterpret_cast<float*>(static_cast<char*>(pa.devicePointer) + rows_off);
+  if (cudaMemsetAsync(st->row_list, 0, 16, s) != cudaSuccess) return CRL_ERR_DEVICE;
+  if (cudaMemcpyAsync(actions_dev, actions_host, B * 8, cudaMemcpyHostToDevice, s) != cudaSuccess) return CRL_ERR_DEVICE;
+  rc = crl_step(c, st, actions_dev, out, flags | CRL_STEP_TRACK_ROWS, 0, 0, stream);
+  if (rc) return rc;
+  // plain launch: ordered after the whole step kernel
+  gather_rows_kernel<<<148, 256, 0, s>>>(st->row_list, out->zone_obs, dev_host_list, dev_host_rows, (int)row, (int)B);
+  rc = launch_status();
+  if (rc) return rc;
+  if (cudaMemcpyAsync(host_out->obs, out->obs, B * 32, cudaMemcpyDeviceToHost, s) != cudaSuccess) return CRL_ERR_DEVICE;
+  if (cudaMemcpyAsync(host_out->result, out->result, B * 8, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+    return CRL_ERR_DEVICE;
+  if (cudaStreamSynchronize(s) != cudaSuccess) return CRL_ERR_DEVICE;
+  const uint32_t count = host_list[0];
+  if (count > B) return CRL_ERR_DEVICE;
+  float* hz = host_out->zone_obs;
+  for (uint32_t i = 0; i < count; ++i) {
+    const uint32_t e = host_list[4 + i];
+    if (e >= B) return CRL_ERR_DEVICE;
+    memcpy(hz + (size_t)e * row, host_rows + (size_t)i * row, row * 4);
+  }
+  if (delta_rows) *delta_rows = (int32_t)count;
   return CRL_OK;
 }
 

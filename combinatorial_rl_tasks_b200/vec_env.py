@@ -42,10 +42,25 @@ class _EnvView:
     def num_cities(self):
         return self._vec.spec.num_zones
 
+    # zone-goals scripts/train_skill_planner.py:134-135 and penv.py:23 probe these on envs[0]
+    @property
+    def goal_dim(self):
+        return 2
+
+    @property
+    def goal_zone(self):
+        g = int(self._vec.goal[self.index].item())
+        return None if g < 0 else g
+
+    def noop_obs(self):
+        """WaitWrapper.noop_obs (wrappers.py:46-50)."""
+        N, Z = self._vec.spec.num_zones, self._vec.spec.zone_dim
+        return {'zone_obs': np.zeros((N, Z)), 'obs': np.zeros(8)}
+
 
 class ZoneVecEnv:
     def __init__(self, env_id, num_envs, device='cuda:0', seed_mode='increment', min_seed=1, max_seed=100,
-                 env_offset=0, auto_reset=True, prefetch_every=8):
+                 env_offset=0, auto_reset=True, prefetch_every=8, wait=False):
         if not torch.cuda.is_available():
             raise RuntimeError('ZoneVecEnv needs a CUDA device (sm_100a); there is no CPU fallback')
         self.lib = _lib.load()
@@ -55,6 +70,10 @@ class ZoneVecEnv:
         self.device = torch.device(device)
         self.auto_reset = auto_reset
         self.prefetch_every = prefetch_every      # 0: never park next layouts (resets sample inline)
+        # WaitWrapper semantics (make_train_env(hier=True), wrappers.py:29-54): under
+        # step_no_reset an env whose episode ended is parked until it is reset
+        self.wait = bool(wait)
+        self._mode_flags = (_lib.STEP_GOALS if spec.goals else 0)
         N, Z = spec.num_zones, spec.zone_dim
         self.cfg = _lib.CrlConfig(
             task=spec.task, num_envs=B, num_zones=N, num_steps=spec.num_steps, frameskip=spec.frameskip,
@@ -92,6 +111,10 @@ class ZoneVecEnv:
         # per-warp completion stamps of crl_step (CRL_STEP_CHAINED)
         self.stamp = z(2, (B + 31) // 32, dtype=torch.int32)
         self._chain_ok = False                    # True: the last kernel enqueued for this state was a ticketed step
+        # envs whose zone_obs row changed in the last step (CRL_STEP_TRACK_ROWS, step_host)
+        self._row_list = z(4 + B, dtype=torch.int32)
+        self._mirror_ok = False                   # True: the host zone_obs buffer equals the device one
+        self.delta_rows = 0                       # rows the last step_host moved (B = all)
         # outputs
         self.obs = z(B, 8)
         self.zone_obs = z(B, N, Z)
@@ -100,7 +123,14 @@ class ZoneVecEnv:
         self.done = self.result[:, 4].view(torch.bool)
         self.goal_met = self.result[:, 5].view(torch.bool)
         self.event = self.result[:, 6].view(torch.int8)
+        self.need_next_goal = self.result[:, 7].view(torch.bool)
         self._cost = z(B)
+        # goal-conditioned variants (PointTSP-v3 ...): goal_zone per env (-1 = None), shaped reward
+        self.goal = torch.full((B,), -1, dtype=torch.int32, device=dev)
+        self.shaped_reward = z(B)
+        self._goal_xy = z(B, 2)
+        self._needs_goal = z(B, dtype=torch.uint8)
+        self._available = z(B, N, dtype=torch.uint8)
         ptr = lambda t: t.data_ptr() if t is not None else None
         self.state = _lib.CrlState(pose=ptr(self.pose), aux=ptr(self.aux), zone_xy=ptr(self.zone_xy),
                                    zone_tmax=ptr(self.zone_tmax), cooldown=ptr(self.cooldown),
@@ -108,8 +138,10 @@ class ZoneVecEnv:
                                    counters=ptr(self.counters_dev), next_zone_xy=ptr(self.next_zone_xy),
                                    next_task=ptr(self.next_task), next_origin=ptr(self.next_origin),
                                    next_seed=ptr(self.next_seed), next_ready=ptr(self.next_ready),
-                                   stamp=ptr(self.stamp), prefetch_work=ptr(self._prefetch_work))
-        self.out = _lib.CrlOut(obs=ptr(self.obs), zone_obs=ptr(self.zone_obs), result=ptr(self.result))
+                                   stamp=ptr(self.stamp), prefetch_work=ptr(self._prefetch_work),
+                                   row_list=ptr(self._row_list), goal=ptr(self.goal))
+        self.out = _lib.CrlOut(obs=ptr(self.obs), zone_obs=ptr(self.zone_obs), result=ptr(self.result),
+                               shaped_reward=ptr(self.shaped_reward))
         self._actions_dev = z(B, 2)
         self._host = None
         self._step_index = 0
@@ -129,7 +161,11 @@ class ZoneVecEnv:
         return {'zone_obs': self.zone_obs, 'obs': self.obs}
 
     def _info(self):
-        return {'goal_met': self.goal_met, 'cost': self._cost, 'event': self.event}
+        info = {'goal_met': self.goal_met, 'cost': self._cost, 'event': self.event}
+        if self.spec.goals:
+            info['shaped_reward'] = self.shaped_reward
+            info['need_next_goal'] = self.need_next_goal
+        return info
 
     def _as_dev(self, x, dtype):
         return torch.as_tensor(x, dtype=dtype, device=self.device).contiguous()
@@ -143,6 +179,7 @@ class ZoneVecEnv:
         self.episode.zero_()
         self.next_ready.zero_()          # parked layouts were drawn for the old seeds
         self._chain_ok = False
+        self._mirror_ok = False
 
     def prefetch(self, stream=None, warps_per_sm=0):
         """Fill the empty next-layout slots in the background (crl_prefetch_layouts) on a
@@ -188,6 +225,7 @@ class ZoneVecEnv:
                                                           self._stream()))
             self.gpu_launches += 1
             self._chain_ok = False
+            self._mirror_ok = False
             if self.prefetch_every and not torch.cuda.is_current_stream_capturing():
                 # the reset above must be visible to the prefetcher: same-stream launch
                 self.prefetch(torch.cuda.current_stream(self.device))
@@ -199,6 +237,8 @@ class ZoneVecEnv:
         (CRL_STEP_CHAINED: back-to-back rollout steps overlap across the launch boundary)."""
         if chained:
             flags |= _lib.STEP_CHAINED if self._chain_ok else _lib.STEP_CHAIN_START
+        if not flags & _lib.STEP_PHYSICS_ONLY:
+            flags |= self._mode_flags
         with torch.cuda.device(self.device):
             if actions is None:
                 aptr = None
@@ -213,6 +253,7 @@ class ZoneVecEnv:
         self._step_index += 1
         self.gpu_launches += 1
         self._chain_ok = bool(chained)
+        self._mirror_ok = False
         if (self.prefetch_every and self._step_index % self.prefetch_every == 0
                 and not torch.cuda.is_current_stream_capturing()):
             self.prefetch()
@@ -224,38 +265,122 @@ class ZoneVecEnv:
         return self._step(actions, _lib.STEP_AUTO_RESET if self.auto_reset else 0)
 
     def step_no_reset(self, actions):
-        """ParallelEnv.step_no_reset (penv.py:61-66)."""
-        return self._step(actions, 0)
+        """ParallelEnv.step_no_reset (penv.py:61-66).  With ``wait=True`` (the reference wraps each
+        env in WaitWrapper for the hierarchical collectors) an env that finished earlier is a
+        no-op: zero observation, reward 0, done True, until reset()."""
+        return self._step(actions, _lib.STEP_WAIT if self.wait else 0)
+
+    # -- goal RPCs of the goal-conditioned variants (zone-goals penv.py:75-99), batched ------
+    def _need_goals(self):
+        if not self.spec.goals:
+            raise RuntimeError(f'{self.env_id} is not a goal-conditioned variant (use PointTSP-v3, ...)')
+
+    def set_goal(self, goals, env_idx=None):
+        """env.set_goal for many envs at once: ``goals`` (B,) int, negative = leave that env alone;
+        or ``set_goal(env_idx, goal)`` order as penv.py:75-80 when env_idx is given as the first
+        argument and goal second (kept for callers that loop).  Invalid requests (visited zone,
+        index out of range: the reference's assertion) leave the goal unset and are counted in
+        counters()['goals_rejected']."""
+        self._need_goals()
+        if env_idx is not None:                   # penv signature: set_goal(env_idx, goal)
+            idx, goal = goals, env_idx
+            g = torch.full((self.num_envs,), -1, dtype=torch.int32, device=self.device)
+            g[int(idx)] = int(goal)
+        else:
+            g = self._as_dev(goals, torch.int32).reshape(self.num_envs)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.crl_set_goal(self.cfg, self.state, g.data_ptr(), self._stream()))
+        self._chain_ok = False
+
+    def _goal_query(self, xy=False, needs=False, available=False):
+        self._need_goals()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.crl_goal_query(self.cfg, self.state,
+                                               self._goal_xy.data_ptr() if xy else None,
+                                               self._needs_goal.data_ptr() if needs else None,
+                                               self._available.data_ptr() if available else None,
+                                               self._stream()))
+        self._chain_ok = False
+
+    def get_goal(self, env_idx=None):
+        """(B,2) goal coordinates / 3 (zeros where no goal is set); one env if env_idx is given."""
+        self._goal_query(xy=True)
+        return self._goal_xy if env_idx is None else self._goal_xy[env_idx]
+
+    def needs_goal(self):
+        """(B,) bool: goal_zone is None (penv.py:88-93)."""
+        self._goal_query(needs=True)
+        return self._needs_goal.view(torch.bool)
+
+    def available_goals(self, env_idx=None):
+        """(B,N) bool mask of eligible goal zones (penv.py:94-99)."""
+        self._goal_query(available=True)
+        a = self._available.view(torch.bool)
+        return a if env_idx is None else a[env_idx]
 
     def step_random(self, action_seed=1, auto_reset=True, chained=False):
         """A step with U(-1,1)^2 actions drawn in-kernel (Philox): action_space.sample().
         ``chained=True`` for back-to-back rollout steps with nothing else enqueued in between."""
         return self._step(None, _lib.STEP_AUTO_RESET if auto_reset else 0, action_seed, chained=chained)
 
-    def step_host(self, actions, auto_reset=True):
+    def step_host(self, actions, auto_reset=True, delta=True):
         """The reference-facing call with HOST buffers: numpy actions in, numpy obs /
-        reward / done out (pinned staging; host<->device copies inside the call)."""
+        reward / done out (pinned staging; host<->device copies inside the call).  The returned
+        arrays are persistent host buffers overwritten by the next call, as the device ones are.
+
+        ``delta=True`` (PointTSP, ColourMatch): once the host zone_obs buffer mirrors the device
+        one, later calls move only the rows that changed (crl_step_host_delta); the arrays
+        returned are byte-identical to a full copy.  TimedTSP's time-left column moves every
+        step, so it always copies whole."""
         B, N, Z = self.num_envs, self.spec.num_zones, self.spec.zone_dim
+        h = self._host_buffers()
+        a = np.asarray(actions, dtype=np.float32).reshape(B, 2)
+        if a is not h['np']['actions']:
+            np.copyto(h['np']['actions'], a)
+        flags = (_lib.STEP_AUTO_RESET if auto_reset else 0) | self._mode_flags
+        use_delta = delta and self._mirror_ok and self.spec.task != _lib.TASK_TTSP
+        with torch.cuda.device(self.device):
+            if use_delta:
+                if h['delta'] is None:
+                    nbytes = ((16 + 4 * B + 15) & ~15) + 4 * B * N * Z
+                    h['delta'] = torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
+                n = ctypes.c_int32(0)
+                _lib.check(self.lib.crl_step_host_delta(self.cfg, self.state, h['actions'].data_ptr(),
+                                                        self._actions_dev.data_ptr(), self.out, h['out'],
+                                                        h['delta'].data_ptr(), h['delta'].numel(), flags,
+                                                        ctypes.byref(n), self._stream()))
+                self.delta_rows = n.value
+                self.gpu_launches += 1                # the gather kernel
+            else:
+                _lib.check(self.lib.crl_step_host(self.cfg, self.state, h['actions'].data_ptr(),
+                                                  self._actions_dev.data_ptr(), self.out, h['out'],
+                                                  flags, self._stream()))
+                self.delta_rows = B
+        self._step_index += 1
+        self.gpu_launches += 1
+        self._chain_ok = False                    # memcpys follow the step kernel on the stream
+        self._mirror_ok = True
+        res = h['np']['result']
+        return ({'zone_obs': h['np']['zone_obs'], 'obs': h['np']['obs']}, res.view(np.float32)[:, 0],
+                res[:, 4].view(np.bool_), {'goal_met': res[:, 5].view(np.bool_), 'event': res[:, 6].view(np.int8)})
+
+    def _host_buffers(self):
         if self._host is None:
+            B, N, Z = self.num_envs, self.spec.num_zones, self.spec.zone_dim
             pin = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype).pin_memory()
             h = {'actions': pin(B, 2, dtype=torch.float32), 'obs': pin(B, 8, dtype=torch.float32),
                  'zone_obs': pin(B, N, Z, dtype=torch.float32), 'result': pin(B, 8, dtype=torch.uint8)}
             h['out'] = _lib.CrlOut(obs=h['obs'].data_ptr(), zone_obs=h['zone_obs'].data_ptr(),
                                    result=h['result'].data_ptr())
             h['np'] = {k: h[k].numpy() for k in ('actions', 'obs', 'zone_obs', 'result')}
+            h['delta'] = None
             self._host = h
-        h = self._host
-        np.copyto(h['np']['actions'], np.asarray(actions, dtype=np.float32).reshape(B, 2))
-        with torch.cuda.device(self.device):
-            _lib.check(self.lib.crl_step_host(self.cfg, self.state, h['actions'].data_ptr(),
-                                              self._actions_dev.data_ptr(), self.out, h['out'],
-                                              _lib.STEP_AUTO_RESET if auto_reset else 0, self._stream()))
-        self._step_index += 1
-        self.gpu_launches += 1
-        self._chain_ok = False                    # memcpys follow the step kernel on the stream
-        res = h['np']['result']
-        return ({'zone_obs': h['np']['zone_obs'], 'obs': h['np']['obs']}, res.view(np.float32)[:, 0],
-                res[:, 4].view(np.bool_), {'goal_met': res[:, 5].view(np.bool_), 'event': res[:, 6].view(np.int8)})
+        return self._host
+
+    def host_actions(self):
+        """The pinned (B,2) float32 action buffer step_host stages from; filling it in place and
+        passing it to step_host skips one host copy."""
+        return self._host_buffers()['np']['actions']
 
     # -- extras ----------------------------------------------------------------------
     @property
@@ -268,7 +393,8 @@ class ZoneVecEnv:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.crl_counters_read(self.state, out, self._stream()))
         return {'return_sum': out[0], 'episodes': out[1], 'successes': out[2], 'length_sum': out[3],
-                'resets_prefetched': out[4], 'resets_inline': out[5], 'chain_wait_timeouts': out[7]}
+                'resets_prefetched': out[4], 'resets_inline': out[5], 'goals_rejected': out[6],
+                'chain_wait_timeouts': out[7]}
 
     def set_qpos_qvel(self, qpos, qvel, env_ids=None):
         """Overwrite sim.data.qpos / qvel (fp64, reference coordinates) of some envs."""
@@ -279,6 +405,7 @@ class ZoneVecEnv:
                                                   None if ids is None else ids.data_ptr(), qp.shape[0],
                                                   self._stream()))
         self._chain_ok = False
+        self._mirror_ok = False
 
     def get_qpos_qvel(self, env_ids=None):
         n = self.num_envs if env_ids is None else len(env_ids)

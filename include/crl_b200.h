@@ -39,7 +39,7 @@
  *                          kept only to convert to/from qpos/qvel
  *    counters  double[8]   sum of episode returns, episodes finished, successes
  *                          (goal_met), sum of episode lengths, resets served from a
- *                          prefetched layout, resets sampled inline, 1 reserved, chained-step
+ *                          prefetched layout, resets sampled inline, rejected crl_set_goal requests, chained-step
  *                          waits that gave up (must stay 0)
  *  optional next-layout planes (all NULL = no prefetch): the draws of each env's next TWO
  *  Engine.resets (reset number n parks in slot n & 1), made in the background by
@@ -65,7 +65,7 @@
 extern "C" {
 #endif
 
-#define CRL_ABI_VERSION 3
+#define CRL_ABI_VERSION 4
 #define CRL_MAX_ZONES 16
 
 /* task ids; reference classes: main/envs/TSP_env.py:11, TTSP_env.py:12, colour_match_env.py:11 */
@@ -97,6 +97,22 @@ enum CrlError {
  * flag never touch the stamps. */
 #define CRL_STEP_CHAINED 4u
 #define CRL_STEP_CHAIN_START 8u
+/* Needs CrlState.row_list.  The step appends to it the index of every env whose zone_obs row
+ * differs from the row the previous step left there (a zone fired, the env was reset, a
+ * ColourMatch cooldown ticked; every TimedTSP env, whose time-left column moves each step).
+ * Used by crl_step_host_delta; the caller zeroes the list header before the step. */
+#define CRL_STEP_TRACK_ROWS 16u
+/* Goal-conditioned variants PointTSP-v3 / PointTTSP-v3 / ColourMatch-v3
+ * (zone-goals/envs/TSP_next_city_env.py:52-75, TTSP_next_city_env.py:45-56,
+ * colour_match_next_city_env.py:103-133): the step also reads CrlState.goal and writes
+ * CrlOut.shaped_reward (distance to the goal zone before minus after the physics; 0 when the
+ * goal zone fired; ColourMatch: minus 1 when another zone changed colour) and
+ * CrlResult.need_next_goal (goal reached, or episode over), clearing the goal when set. */
+#define CRL_STEP_GOALS 32u
+/* WaitWrapper (main/envs/wrappers.py:29-54), for step_no_reset rollouts: an env whose episode
+ * ends in a step without CRL_STEP_AUTO_RESET is parked; further steps of a parked env change
+ * nothing and report an all-zero observation, reward 0, done = 1, until it is reset. */
+#define CRL_STEP_WAIT 64u
 
 /* how a reset chooses the episode's seed; wrappers.py:10-23 and Engine.seed/reset */
 enum CrlSeedMode {
@@ -143,6 +159,10 @@ typedef struct CrlState {
                            steps finished for each group of 32 envs (CRL_STEP_CHAINED) */
   uint32_t* prefetch_work; /* 16 (1 + 2 B) bytes, 16-byte aligned: work list of crl_prefetch_layouts
                               (needed with next_*) */
+  uint32_t* row_list;   /* uint32[4 + B]; optional (CRL_STEP_TRACK_ROWS): word 0 = number of envs
+                           whose zone_obs row changed in the step, words 4.. = their indices */
+  int32_t* goal;        /* int32[B]; optional (CRL_STEP_GOALS): goal_zone of each env, -1 = None.
+                           Every reset clears it */
 } CrlState;
 
 typedef struct CrlResult {
@@ -150,13 +170,14 @@ typedef struct CrlResult {
   uint8_t done;
   uint8_t goal_met; /* info['goal_met'] */
   int8_t event;     /* integer reward component: new_city in {0,1} or Hamming delta in {-2..1} */
-  uint8_t reserved;
+  uint8_t need_next_goal; /* info['need_next_goal'] (CRL_STEP_GOALS), else 0 */
 } CrlResult;
 
 typedef struct CrlOut {
   float* obs;        /* float[B][8] */
   float* zone_obs;   /* float[B][N][Z] */
   CrlResult* result; /* [B] */
+  float* shaped_reward; /* float[B]: info['shaped_reward']; optional (CRL_STEP_GOALS) */
 } CrlOut;
 
 /* Host-supplied-layout mode (equivalence testing): n layouts in the reference's own
@@ -175,8 +196,8 @@ const char* crl_strerror(int code);
 /* Bytes the caller must allocate for each plane of CrlState / CrlOut, in the order
  * pose, aux, zone_xy, zone_tmax, cooldown, seed, episode, origin, counters, next_zone_xy,
  * next_task, next_origin, next_seed, next_ready, obs, zone_obs, result, stamp,
- * prefetch_work (19 entries; 0 = plane unused by this task). */
-int crl_plane_bytes(const CrlConfig* cfg, int64_t out_bytes[19]);
+ * prefetch_work, row_list, goal, shaped_reward (22 entries; 0 = plane unused by this task). */
+int crl_plane_bytes(const CrlConfig* cfg, int64_t out_bytes[22]);
 
 /* Algorithmic HBM bytes one env-step moves in this layout: read, written. */
 int crl_step_bytes(const CrlConfig* cfg, int64_t* bytes_read, int64_t* bytes_written);
@@ -220,6 +241,36 @@ int crl_step(const CrlConfig* cfg, const CrlState* st, const float* actions,
 int crl_step_host(const CrlConfig* cfg, const CrlState* st, const float* actions_host,
                   float* actions_dev, const CrlOut* out, const CrlOut* host_out,
                   uint32_t flags, void* stream);
+
+/* crl_step_host for a caller that keeps its host observation buffers between calls (as
+ * ParallelEnv's consumers do: the obs of step t is only read before step t+1).  zone_obs is
+ * 60-90 % of a step's output bytes and almost all of it repeats the previous step (zone
+ * centres never move inside an episode; a colour changes only when a zone fires), so only the
+ * rows that CHANGED cross PCIe: the step lists them (CRL_STEP_TRACK_ROWS), a gather kernel
+ * writes {count, env ids, rows} straight into the caller's pinned host memory
+ * (`host_delta`, device-mapped: uint32[4 + B] header and ids, then at byte offset
+ * 16 + 4 B rounded up to 16 the rows, float[B][N][Z] worst case), the stream is
+ * synchronised and the rows are scattered into `host_out->zone_obs` on the host.  obs and
+ * result are copied whole.  PRECONDITION: host_out->zone_obs holds the device zone_obs as of
+ * the previous step (e.g. left there by crl_step_host or by a full copy after crl_reset).
+ * The result is byte-identical to crl_step_host's.  `delta_rows`, if not NULL, receives the
+ * number of rows that crossed.  host_delta must be page-locked (cudaHostAlloc / pinned). */
+int crl_step_host_delta(const CrlConfig* cfg, const CrlState* st, const float* actions_host,
+                        float* actions_dev, const CrlOut* out, const CrlOut* host_out,
+                        void* host_delta, int64_t host_delta_bytes, uint32_t flags,
+                        int32_t* delta_rows, void* stream);
+
+/* Goal RPCs of the goal-conditioned variants, one call for the whole batch instead of one pipe
+ * message per env (zone-goals/src/torch_ac/torch_utils/penv.py:18-25, 75-99).
+ * crl_set_goal: env.set_goal(goals[e]) for every e with goals[e] >= 0 (device int32[B]); what
+ * the reference asserts (index in range; TSP / TimedTSP: zone not yet visited) is checked on
+ * the device: an invalid request leaves the goal unset and adds 1 to counters[6].
+ * crl_goal_query: any of needs_goal uint8[B] (goal_zone is None), goal_xy float[B][2]
+ * (get_goal: zone centre / 3; zeros where there is no goal), available uint8[B][N]
+ * (get_available_goals); NULL = not wanted.  All device pointers. */
+int crl_set_goal(const CrlConfig* cfg, const CrlState* st, const int32_t* goals, void* stream);
+int crl_goal_query(const CrlConfig* cfg, const CrlState* st, float* goal_xy, uint8_t* needs_goal,
+                   uint8_t* available, void* stream);
 
 /* Physics state in the reference's own coordinates (sim.data.qpos / qvel, fp64, device
  * arrays [n][3]) for envs env_ids[0..n) (NULL: 0..n).  set: teacher forcing for the

@@ -190,6 +190,45 @@ def test_step_host_equals_device_step(crl):
         assert np.array_equal(rew_h, rew_d.cpu().numpy()) and np.array_equal(done_h, done_d.cpu().numpy())
 
 
+@pytest.mark.parametrize('env_id', TASKS)
+def test_step_host_delta_is_byte_identical_to_full_copy(crl, env_id):
+    """crl_step_host_delta moves only the zone_obs rows that changed; what the caller sees in its
+    host buffers must be byte for byte what crl_step_host (full copy) delivers -- across zone
+    events, cooldown ticks, timeouts and auto-resets (episodes cut short to force many)."""
+    B = 1000
+    envs = []
+    for _ in range(2):
+        e = crl.ZoneVecEnv(env_id, B); e.seed(11); e.cfg.num_steps = 40; e.reset(); envs.append(e)
+    full, delta = envs
+    rs = np.random.RandomState(5)
+    moved = []
+    for t in range(130):
+        a = rs.uniform(-1, 1, (B, 2)).astype(np.float32)
+        if t == 70:                                   # device-side work in between invalidates the mirror
+            for e in envs:
+                e.step(torch.from_numpy(a).cuda())
+            continue
+        if t == 20:                                   # put 200 robots on zone 3: events through the delta path
+            for e in envs:
+                e.pose[:200, :2] = e.zone_xy[3, :200, :]
+        of, rf, df, inf_ = full.step_host(a, delta=False)
+        od, rd, dd, ind = delta.step_host(a, delta=True)
+        if t == 20:
+            assert delta.delta_rows >= 200 and (env_id == 'ColourMatch-v0' or int((ind['event'] != 0).sum()) >= 200)
+        assert np.array_equal(of['zone_obs'].view(np.uint32), od['zone_obs'].view(np.uint32)), t
+        assert np.array_equal(of['obs'].view(np.uint32), od['obs'].view(np.uint32)), t
+        assert np.array_equal(rf.view(np.uint32), rd.view(np.uint32)) and np.array_equal(df, dd), t
+        assert np.array_equal(inf_['event'], ind['event']) and np.array_equal(inf_['goal_met'], ind['goal_met'])
+        assert np.array_equal(od['zone_obs'], delta.zone_obs.cpu().numpy()), t
+        moved.append(delta.delta_rows)
+    assert moved[0] == B and moved[70] == B           # first call and the call after device-side work: full copy
+    if env_id == 'PointTTSP-v0':
+        assert all(m == B for m in moved)             # the time-left column moves every step
+    else:
+        assert max(moved[1:39]) < B // 4              # between resets only a few rows move
+        assert B in moved[39:42] or max(moved[38:42]) >= B // 2   # the step-limit reset rewrites every row
+
+
 @pytest.mark.parametrize('env_id,B', [('PointTSP-v0', 65536), ('PointTTSP-v0', 262144), ('ColourMatch-v0', 262144)])
 def test_full_size_properties(crl, env_id, B):
     """BASELINE.json configs 2-4 at full size: invariants that hold at any size."""

@@ -48,7 +48,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.crl_abi_version() == 3
+    assert lib.crl_abi_version() == 4
     assert b'NULL' in lib.crl_strerror(-1)
 
 
@@ -57,10 +57,10 @@ def test_argument_errors_are_detected_on_the_host():
     lib = _lib.load()
     cfg = _lib.CrlConfig(task=0, num_envs=64, num_zones=15, num_steps=2000, frameskip=10, max_cooldown=150,
                          zone_size=0.2)
-    sizes = (ctypes.c_int64 * 19)()
+    sizes = (ctypes.c_int64 * 20)()
     assert lib.crl_plane_bytes(cfg, sizes) == 0
     assert list(sizes) == [1024, 1024, 7680, 0, 0, 512, 256, 1024, 64, 2 * 7680, 0, 2 * 1024, 2 * 512, 2 * 256,
-                           2048, 64 * 90 * 4, 512, 16, 16 * 129]
+                           2048, 64 * 90 * 4, 512, 16, 16 * 129, 4 * 68]
     rd, wr = ctypes.c_int64(), ctypes.c_int64()
     assert lib.crl_step_bytes(cfg, ctypes.byref(rd), ctypes.byref(wr)) == 0 and (rd.value, wr.value) == (160, 432)
     bad = _lib.CrlConfig(task=7, num_envs=64, num_zones=15, num_steps=2000, zone_size=0.2)
@@ -75,6 +75,8 @@ def test_argument_errors_are_detected_on_the_host():
     out = _lib.CrlOut(obs=a16, zone_obs=a16, result=a16)
     assert lib.crl_step(cfg2, st, None, out, 0, 0, 0, None) == -4         # no kernel for N = 9
     assert lib.crl_step(cfg, st, None, out, _lib.STEP_CHAINED, 0, 0, None) == -1   # chained needs CrlState.stamp
+    assert lib.crl_step(cfg, st, None, out, _lib.STEP_TRACK_ROWS, 0, 0, None) == -1  # needs CrlState.row_list
+    assert lib.crl_step_host_delta(cfg, st, a16, a16, out, out, a16, 4096, 0, None, None) == -1  # no row_list
     st.pose = a16 + 4
     assert lib.crl_step(cfg, st, None, out, 0, 0, 0, None) == -3          # misaligned plane
 
