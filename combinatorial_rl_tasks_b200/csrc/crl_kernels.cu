@@ -522,7 +522,6 @@ __global__ void __launch_bounds__(32) prefetch_layout_kernel(const __grid_consta
         for (int i = 0; i < N; ++i) nz[(size_t)i * p.B] = placed[1 + i][lane];
         p.next_origin[sb + e] = make_float4(rb.x, rb.y, __fmul_rn(6.2831855f, u01(rr.x)), 0.f);
         p.next_seed[sb + e] = layout_seed - 1;
-        __threadfence();
         st_release_u32(p.next_ready + sb + e, done_state);
         have = false;
       }
@@ -721,10 +720,9 @@ __device__ __forceinline__ void chain_release(const KParams& p, int w, int lane,
   __syncwarp();
   if (lane == 0) {
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    if (w < (p.B + 31) / 32) {
-      __threadfence();
-      st_release_u32(p.stamp + (p.B + 31) / 32 + w, ticket + 1u);
-    }
+    // st.release is itself the fence (cumulative over the lanes' stores the warp barrier
+    // ordered before it); a __threadfence() in front of it would make the warp sit through two
+    if (w < (p.B + 31) / 32) st_release_u32(p.stamp + (p.B + 31) / 32 + w, ticket + 1u);
   }
 }
 
@@ -1495,6 +1493,9 @@ int crl_step_host(const CrlConfig* c, const CrlState* st, const float* actions_h
     return CRL_ERR_DEVICE;
   if (cudaMemcpyAsync(host_out->result, out->result, B * 8, cudaMemcpyDeviceToHost, s) != cudaSuccess)
     return CRL_ERR_DEVICE;
+  if ((flags & CRL_STEP_GOALS) && host_out->shaped_reward &&
+      cudaMemcpyAsync(host_out->shaped_reward, out->shaped_reward, B * 4, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+    return CRL_ERR_DEVICE;
   if (cudaStreamSynchronize(s) != cudaSuccess) return CRL_ERR_DEVICE;
   return CRL_OK;
 }
@@ -1531,6 +1532,9 @@ int crl_step_host_delta(const CrlConfig* c, const CrlState* st, const float* act
   if (rc) return rc;
   if (cudaMemcpyAsync(host_out->obs, out->obs, B * 32, cudaMemcpyDeviceToHost, s) != cudaSuccess) return CRL_ERR_DEVICE;
   if (cudaMemcpyAsync(host_out->result, out->result, B * 8, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+    return CRL_ERR_DEVICE;
+  if ((flags & CRL_STEP_GOALS) && host_out->shaped_reward &&
+      cudaMemcpyAsync(host_out->shaped_reward, out->shaped_reward, B * 4, cudaMemcpyDeviceToHost, s) != cudaSuccess)
     return CRL_ERR_DEVICE;
   if (cudaStreamSynchronize(s) != cudaSuccess) return CRL_ERR_DEVICE;
   const uint32_t count = host_list[0];

@@ -323,7 +323,7 @@ class ZoneVecEnv:
         ``chained=True`` for back-to-back rollout steps with nothing else enqueued in between."""
         return self._step(None, _lib.STEP_AUTO_RESET if auto_reset else 0, action_seed, chained=chained)
 
-    def step_host(self, actions, auto_reset=True, delta=True):
+    def step_host(self, actions, auto_reset=True, delta=True, wait=False):
         """The reference-facing call with HOST buffers: numpy actions in, numpy obs /
         reward / done out (pinned staging; host<->device copies inside the call).  The returned
         arrays are persistent host buffers overwritten by the next call, as the device ones are.
@@ -338,6 +338,8 @@ class ZoneVecEnv:
         if a is not h['np']['actions']:
             np.copyto(h['np']['actions'], a)
         flags = (_lib.STEP_AUTO_RESET if auto_reset else 0) | self._mode_flags
+        if wait and not auto_reset:
+            flags |= _lib.STEP_WAIT
         use_delta = delta and self._mirror_ok and self.spec.task != _lib.TASK_TTSP
         with torch.cuda.device(self.device):
             if use_delta:
@@ -361,18 +363,23 @@ class ZoneVecEnv:
         self._chain_ok = False                    # memcpys follow the step kernel on the stream
         self._mirror_ok = True
         res = h['np']['result']
+        info = {'goal_met': res[:, 5].view(np.bool_), 'event': res[:, 6].view(np.int8)}
+        if self.spec.goals:
+            info['shaped_reward'] = h['np']['shaped']
+            info['need_next_goal'] = res[:, 7].view(np.bool_)
         return ({'zone_obs': h['np']['zone_obs'], 'obs': h['np']['obs']}, res.view(np.float32)[:, 0],
-                res[:, 4].view(np.bool_), {'goal_met': res[:, 5].view(np.bool_), 'event': res[:, 6].view(np.int8)})
+                res[:, 4].view(np.bool_), info)
 
     def _host_buffers(self):
         if self._host is None:
             B, N, Z = self.num_envs, self.spec.num_zones, self.spec.zone_dim
             pin = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype).pin_memory()
             h = {'actions': pin(B, 2, dtype=torch.float32), 'obs': pin(B, 8, dtype=torch.float32),
-                 'zone_obs': pin(B, N, Z, dtype=torch.float32), 'result': pin(B, 8, dtype=torch.uint8)}
+                 'zone_obs': pin(B, N, Z, dtype=torch.float32), 'result': pin(B, 8, dtype=torch.uint8),
+                 'shaped': pin(B, dtype=torch.float32)}
             h['out'] = _lib.CrlOut(obs=h['obs'].data_ptr(), zone_obs=h['zone_obs'].data_ptr(),
-                                   result=h['result'].data_ptr())
-            h['np'] = {k: h[k].numpy() for k in ('actions', 'obs', 'zone_obs', 'result')}
+                                   result=h['result'].data_ptr(), shaped_reward=h['shaped'].data_ptr())
+            h['np'] = {k: h[k].numpy() for k in ('actions', 'obs', 'zone_obs', 'result', 'shaped')}
             h['delta'] = None
             self._host = h
         return self._host

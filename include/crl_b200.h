@@ -236,8 +236,8 @@ int crl_step(const CrlConfig* cfg, const CrlState* st, const float* actions,
              uint64_t step_index, void* stream);
 
 /* crl_step with HOST buffers (pinned or pageable): copies actions host->device into
- * `actions_dev`, steps, copies obs / zone_obs / result device->host into `host_out`,
- * then synchronises the stream.  The reference-facing call ParallelEnv.step makes. */
+ * `actions_dev`, steps, copies obs / zone_obs / result (and, with CRL_STEP_GOALS, shaped_reward
+ * if host_out has it) device->host into `host_out`, then synchronises the stream.  The reference-facing call ParallelEnv.step makes. */
 int crl_step_host(const CrlConfig* cfg, const CrlState* st, const float* actions_host,
                   float* actions_dev, const CrlOut* out, const CrlOut* host_out,
                   uint32_t flags, void* stream);

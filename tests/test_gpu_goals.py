@@ -264,3 +264,50 @@ def test_wait_wrapper_semantics(crl):
     env2.aux[:, 3] = (env2.aux[:, 3].view(torch.int32) & ~0xffff | 1999).view(torch.float32)
     o, rew, d, info = env2.step(torch.zeros(B, 2, device='cuda'))
     assert bool(d.all().item()) and bool((env2.steps == 0).all().item())
+
+
+def test_parallel_env_compat_has_the_reference_protocol(crl):
+    """compat.ParallelEnv: the call and return types of penv.py:46-66 and zone-goals
+    penv.py:75-99 (lists / tuples of per-env Python objects), values equal to the tensor API's."""
+    B = 6
+    pe = crl.ParallelEnv('PointTSP-v3', B, num_training_tasks=5, hier=True)
+    tw = crl.ZoneVecEnv('PointTSP-v3', B, seed_mode='fixed_range', min_seed=1, max_seed=5, wait=True)
+    obs = pe.reset()
+    tw.reset()
+    assert isinstance(obs, list) and len(obs) == B and obs[0]['zone_obs'].shape == (15, 6) and obs[0]['obs'].shape == (8,)
+    assert pe.envs[0].observation_space is pe.observation_space and pe.action_space.shape == (2,)
+    assert pe.envs[0].unwrapped.num_cities == 15 and pe.envs[0].unwrapped.goal_dim == 2 and pe.envs[0].goal_zone is None
+    assert pe.needs_goal() == [True] * B
+    av = pe.available_goals(2)
+    assert av.dtype == bool and av.shape == (15,) and av.all()
+    for i in range(B):
+        pe.set_goal(i, np.array(i))                           # the collector passes a 0-d array
+    tw.set_goal(torch.arange(B, dtype=torch.int32))
+    g = pe.get_goal(3)
+    assert g.shape == (2,) and np.allclose(g, obs[3]['zone_obs'][3, :2], atol=1e-6)
+    with pytest.raises(AssertionError):
+        pe.available_goals(0)                                 # a goal is set (TSP_next_city_env.py:88)
+    rs = np.random.RandomState(4)
+    tw.aux[:3, 3] = (tw.aux[:3, 3].view(torch.int32) & ~0xffff | 1998).view(torch.float32)
+    pe.vec.aux[:3, 3] = (pe.vec.aux[:3, 3].view(torch.int32) & ~0xffff | 1998).view(torch.float32)
+    for t in range(4):
+        a = [rs.uniform(-1, 1, 2) for _ in range(B)]          # list of per-env arrays, as the algos pass
+        o, r, d, info = pe.step_no_reset(a)
+        o2, r2, d2, i2 = tw.step_no_reset(torch.tensor(np.array(a), dtype=torch.float32).cuda())
+        assert all(isinstance(x, tuple) and len(x) == B for x in (o, r, d, info))
+        assert isinstance(r[0], float) and isinstance(d[0], bool) and isinstance(info[0], dict)
+        assert np.array_equal(np.stack([x['obs'] for x in o]), o2['obs'].cpu().numpy())
+        assert np.array_equal(np.stack([x['zone_obs'] for x in o]), o2['zone_obs'].cpu().numpy())
+        assert list(r) == [float(x) for x in r2.cpu().numpy()] and list(d) == [bool(x) for x in d2.cpu().numpy()]
+        for i in range(B):
+            if t >= 2 and i < 3:                              # parked by WaitWrapper after the step limit at t = 1
+                assert info[i] == {} and d[i] and r[i] == 0.0 and not o[i]['obs'].any() and not o[i]['zone_obs'].any()
+            else:
+                assert info[i]['cost'] == 0 and 'goal_met' not in info[i]
+                assert info[i]['need_next_goal'] == (t == 1 and i < 3)
+                assert abs(info[i]['shaped_reward'] - float(i2['shaped_reward'][i].item())) == 0.0
+    assert pe.needs_goal() == [True] * 3 + [False] * 3
+    first = pe.reset()
+    o, r, d, info = pe.step([np.zeros(2)] * B)                 # auto-reset variant: nobody is parked after reset
+    assert not any(d) and all(i_['need_next_goal'] for i_ in info)   # reset cleared the goals
+    assert first[0]['obs'][0] == 1.0 and o[0]['obs'][0] == np.float32(1999 / 2000)
