@@ -15,12 +15,13 @@ SEED_INCREMENT, SEED_FIXED_RANGE = 0, 1
 STEP_AUTO_RESET, STEP_PHYSICS_ONLY, STEP_CHAINED, STEP_CHAIN_START, STEP_TRACK_ROWS = 1, 2, 4, 8, 16
 STEP_GOALS, STEP_WAIT = 32, 64
 ABI_VERSION = 4
+NUM_PLANES = 22
 
 # every symbol include/crl_b200.h declares
 SYMBOLS = ['crl_abi_version', 'crl_strerror', 'crl_plane_bytes', 'crl_step_bytes', 'crl_reset',
            'crl_prefetch_layouts', 'crl_reset_from_layout', 'crl_step', 'crl_step_host', 'crl_step_host_delta',
            'crl_set_goal', 'crl_goal_query', 'crl_set_qpos_qvel',
-           'crl_get_qpos_qvel', 'crl_counters_read']
+           'crl_get_qpos_qvel', 'crl_gae', 'crl_counters_read']
 
 
 class CrlConfig(ctypes.Structure):
@@ -63,7 +64,7 @@ def load():
     lib.crl_abi_version.restype = ctypes.c_int
     lib.crl_strerror.restype = ctypes.c_char_p
     lib.crl_strerror.argtypes = [ctypes.c_int]
-    lib.crl_plane_bytes.argtypes = [P(CrlConfig), P(c_int64)]
+    lib.crl_plane_bytes.argtypes = [P(CrlConfig), P(c_int64), c_int32]
     lib.crl_step_bytes.argtypes = [P(CrlConfig), P(c_int64), P(c_int64)]
     lib.crl_reset.argtypes = [P(CrlConfig), P(CrlState), P(CrlOut), c_void_p, c_void_p]
     lib.crl_prefetch_layouts.argtypes = [P(CrlConfig), P(CrlState), c_int32, c_void_p]
@@ -81,6 +82,8 @@ def load():
                                       c_void_p]
     lib.crl_get_qpos_qvel.argtypes = [P(CrlConfig), P(CrlState), c_void_p, c_void_p, c_void_p, c_int32,
                                       c_void_p]
+    lib.crl_gae.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, c_int32, c_int32,
+                            c_void_p, c_void_p, c_void_p]
     lib.crl_counters_read.argtypes = [P(CrlState), P(c_double), c_void_p]
     for name in SYMBOLS:
         getattr(lib, name)

@@ -1154,6 +1154,35 @@ __global__ void goal_query_kernel(const KParams p, float2* goal_xy, uint8_t* nee
   }
 }
 
+// Generalised advantage estimation straight from the step's own result records
+// (main/src/torch_ac/algos/base.py:195-205).  One thread per env walks its column of the
+// [T+1][B] rollout backwards; every operation is a separate IEEE float32 operation in the order
+// torch evaluates the reference's expressions, so the result is bit-identical to it.
+__global__ void __launch_bounds__(256) gae_kernel(const unsigned long long* __restrict__ results,
+                                                  const float* __restrict__ reward_override,
+                                                  const float* __restrict__ values, const float* __restrict__ next_value,
+                                                  float g, float gl, int T, int B, float* __restrict__ adv_out,
+                                                  float* __restrict__ ret_out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B) return;
+  unsigned long long rec = results[(size_t)T * B + e];
+  float nm = ((rec >> 32) & 0xffu) ? 0.f : 1.f;        // the mask in force after the last step
+  float nv = next_value[e], na = 0.f;
+#pragma unroll 4
+  for (int t = T - 1; t >= 0; --t) {
+    const float reward = reward_override ? reward_override[(size_t)(t + 1) * B + e] : __uint_as_float((uint32_t)rec);
+    rec = results[(size_t)t * B + e];                   // slot t: outcome of step t-1, its done is masks[t]
+    const float v = values[(size_t)t * B + e];
+    const float delta = __fsub_rn(__fadd_rn(reward, __fmul_rn(__fmul_rn(g, nv), nm)), v);
+    const float a = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, na), nm));
+    adv_out[(size_t)t * B + e] = a;
+    if (ret_out) ret_out[(size_t)t * B + e] = __fadd_rn(v, a);
+    nm = ((rec >> 32) & 0xffu) ? 0.f : 1.f;
+    nv = v;
+    na = a;
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------
 static int zone_dim(int task) { return task == CRL_TASK_TSP ? 6 : 7; }
 
@@ -1281,10 +1310,12 @@ const char* crl_strerror(int code) {
   }
 }
 
-int crl_plane_bytes(const CrlConfig* c, int64_t o[22]) {
+int crl_plane_bytes(const CrlConfig* c, int64_t* out_bytes, int32_t n) {
   int rc = check_config(c);
   if (rc) return rc;
-  if (!o) return CRL_ERR_NULL;
+  if (!out_bytes) return CRL_ERR_NULL;
+  if (n < 0) return CRL_ERR_CONFIG;
+  int64_t o[CRL_NUM_PLANES];
   const int64_t B = c->num_envs, N = c->num_zones, Z = zone_dim(c->task);
   o[0] = 16 * B; o[1] = 16 * B; o[2] = 8 * N * B;
   o[3] = c->task == CRL_TASK_TTSP ? 4 * ((N + 1) / 2) * B : 0;
@@ -1299,6 +1330,7 @@ int crl_plane_bytes(const CrlConfig* c, int64_t o[22]) {
   o[19] = 4 * (4 + B);
   o[20] = 4 * B;   /* goal */
   o[21] = 4 * B;   /* shaped_reward */
+  for (int i = 0; i < n && i < CRL_NUM_PLANES; ++i) out_bytes[i] = o[i];
   return CRL_OK;
 }
 
@@ -1547,6 +1579,21 @@ int crl_step_host_delta(const CrlConfig* c, const CrlState* st, const float* act
   }
   if (delta_rows) *delta_rows = (int32_t)count;
   return CRL_OK;
+}
+
+int crl_gae(const CrlResult* results, const float* reward_override, const float* values, const float* next_value,
+            double discount, double gae_lambda, int32_t num_frames, int32_t num_envs, float* advantages,
+            float* returns, void* stream) {
+  if (!results || !values || !next_value || !advantages) return CRL_ERR_NULL;
+  if (num_frames <= 0 || num_envs <= 0) return CRL_ERR_CONFIG;
+  if (reinterpret_cast<uintptr_t>(results) & 7u) return CRL_ERR_ALIGN;
+  // torch rounds the Python doubles `discount` and `discount * gae_lambda` to float32 when they
+  // meet a float32 tensor
+  const float g = (float)discount, gl = (float)(discount * gae_lambda);
+  gae_kernel<<<(num_envs + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const unsigned long long*>(results), reward_override, values, next_value, g, gl, num_frames,
+      num_envs, advantages, returns);
+  return launch_status();
 }
 
 int crl_counters_read(const CrlState* st, double out[8], void* stream) {

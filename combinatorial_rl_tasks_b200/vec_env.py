@@ -116,18 +116,9 @@ class ZoneVecEnv:
         self._mirror_ok = False                   # True: the host zone_obs buffer equals the device one
         self.delta_rows = 0                       # rows the last step_host moved (B = all)
         # outputs
-        self.obs = z(B, 8)
-        self.zone_obs = z(B, N, Z)
-        self.result = z(B, 8, dtype=torch.uint8)
-        self.reward = self.result.view(torch.float32)[:, 0]
-        self.done = self.result[:, 4].view(torch.bool)
-        self.goal_met = self.result[:, 5].view(torch.bool)
-        self.event = self.result[:, 6].view(torch.int8)
-        self.need_next_goal = self.result[:, 7].view(torch.bool)
         self._cost = z(B)
         # goal-conditioned variants (PointTSP-v3 ...): goal_zone per env (-1 = None), shaped reward
         self.goal = torch.full((B,), -1, dtype=torch.int32, device=dev)
-        self.shaped_reward = z(B)
         self._goal_xy = z(B, 2)
         self._needs_goal = z(B, dtype=torch.uint8)
         self._available = z(B, N, dtype=torch.uint8)
@@ -140,8 +131,7 @@ class ZoneVecEnv:
                                    next_seed=ptr(self.next_seed), next_ready=ptr(self.next_ready),
                                    stamp=ptr(self.stamp), prefetch_work=ptr(self._prefetch_work),
                                    row_list=ptr(self._row_list), goal=ptr(self.goal))
-        self.out = _lib.CrlOut(obs=ptr(self.obs), zone_obs=ptr(self.zone_obs), result=ptr(self.result),
-                               shaped_reward=ptr(self.shaped_reward))
+        self.bind_outputs(z(B, 8), z(B, N, Z), z(B, 8, dtype=torch.uint8), z(B))
         self._actions_dev = z(B, 2)
         self._host = None
         self._step_index = 0
@@ -154,6 +144,28 @@ class ZoneVecEnv:
         self.seed(torch.arange(B, dtype=torch.int64) + env_offset)
 
     # -- plumbing ------------------------------------------------------------------
+    def bind_outputs(self, obs, zone_obs, result, shaped_reward=None):
+        """Point the env's outputs at caller-owned device tensors: the next reset / step writes
+        obs (B,8) f32, zone_obs (B,N,Z) f32, result (B,8) u8 and shaped_reward (B,) f32 there, in
+        place.  A rollout buffer hands in slot t+1 before step t, so storing a frame costs no copy
+        (rollout.py).  The tensors must be contiguous; obs / zone_obs 16-byte aligned."""
+        B, N, Z = self.num_envs, self.spec.num_zones, self.spec.zone_dim
+        assert obs.shape == (B, 8) and zone_obs.shape == (B, N, Z) and result.shape == (B, 8)
+        assert obs.dtype == zone_obs.dtype == torch.float32 and result.dtype == torch.uint8
+        assert obs.is_contiguous() and zone_obs.is_contiguous() and result.is_contiguous()
+        if shaped_reward is None:
+            shaped_reward = self.shaped_reward
+        self.obs, self.zone_obs, self.result, self.shaped_reward = obs, zone_obs, result, shaped_reward
+        self.reward = result.view(torch.float32)[:, 0]
+        self.done = result[:, 4].view(torch.bool)
+        self.goal_met = result[:, 5].view(torch.bool)
+        self.event = result[:, 6].view(torch.int8)
+        self.need_next_goal = result[:, 7].view(torch.bool)
+        self.out = _lib.CrlOut(obs=obs.data_ptr(), zone_obs=zone_obs.data_ptr(), result=result.data_ptr(),
+                               shaped_reward=shaped_reward.data_ptr())
+        self._mirror_ok = False
+        self._chain_ok = False
+
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 

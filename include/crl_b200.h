@@ -196,8 +196,10 @@ const char* crl_strerror(int code);
 /* Bytes the caller must allocate for each plane of CrlState / CrlOut, in the order
  * pose, aux, zone_xy, zone_tmax, cooldown, seed, episode, origin, counters, next_zone_xy,
  * next_task, next_origin, next_seed, next_ready, obs, zone_obs, result, stamp,
- * prefetch_work, row_list, goal, shaped_reward (22 entries; 0 = plane unused by this task). */
-int crl_plane_bytes(const CrlConfig* cfg, int64_t out_bytes[22]);
+ * prefetch_work, row_list, goal, shaped_reward (CRL_NUM_PLANES entries; 0 = plane unused by
+ * this task).  Writes the first min(n, CRL_NUM_PLANES) entries of out_bytes. */
+#define CRL_NUM_PLANES 22
+int crl_plane_bytes(const CrlConfig* cfg, int64_t* out_bytes, int32_t n);
 
 /* Algorithmic HBM bytes one env-step moves in this layout: read, written. */
 int crl_step_bytes(const CrlConfig* cfg, int64_t* bytes_read, int64_t* bytes_written);
@@ -279,6 +281,22 @@ int crl_set_qpos_qvel(const CrlConfig* cfg, const CrlState* st, const double* qp
                       const double* qvel, const int32_t* env_ids, int32_t n, void* stream);
 int crl_get_qpos_qvel(const CrlConfig* cfg, const CrlState* st, double* qpos, double* qvel,
                       const int32_t* env_ids, int32_t n, void* stream);
+
+/* Advantages of one rollout, on the device, from the records crl_step wrote
+ * (main/src/torch_ac/algos/base.py:195-205).  A rollout of T frames keeps
+ * T + 1 result slots [T+1][B]: slot t + 1 is CrlOut.result of step t (point CrlOut at the slot:
+ * the step writes its outputs in place, nothing is copied), slot 0 is the last slot of the
+ * previous rollout (zeros at first: no env finished yet).  reward[t] = slot[t+1].reward -- or
+ * reward_override[(t+1) B + e] if not NULL (info['shaped_reward'], base.py:155-159) --,
+ * masks[t] = 1 - slot[t].done, the mask after the last step = 1 - slot[T].done:
+ *   delta = reward[t] + discount v[t+1] mask[t+1] - v[t]
+ *   A[t]  = delta + discount gae_lambda A[t+1] mask[t+1],   v[T] = next_value, A[T] = 0
+ * evaluated in float32 operation by operation as torch does, so the result is bit-identical to
+ * the reference's.  values, advantages, returns (= values + advantages, may be NULL): float[T][B];
+ * next_value: float[B].  All device pointers. */
+int crl_gae(const CrlResult* results, const float* reward_override, const float* values,
+            const float* next_value, double discount, double gae_lambda, int32_t num_frames,
+            int32_t num_envs, float* advantages, float* returns, void* stream);
 
 /* Copies the eight counters to the host (synchronises `stream`).  The first four (sum of
  * returns, episodes, successes, sum of lengths) are what ranks all-reduce. */

@@ -1,5 +1,6 @@
 """Diagnostic (not a bench line): where does a step_host call spend its time?"""
-import time, ctypes
+import os, sys, time, ctypes
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import combinatorial_rl_tasks_b200 as crl
 from combinatorial_rl_tasks_b200 import _lib
