@@ -143,7 +143,7 @@ def run_ours(args):
     envs = []
     for r in range(R):
         e = crl.ZoneVecEnv(args.env, B, device=dev, env_offset=(rank * R + r) * B,
-                           prefetch_every=args.prefetch_every)
+                           prefetch_every=args.prefetch_every, prefetch_warps=args.prefetch_warps)
         e.seed(1 + (rank * R + r) * B)
         e.reset()
         envs.append(e)
@@ -172,7 +172,7 @@ def run_ours(args):
     launches = {'prefetch': 0}
 
     def run(n_steps):
-        # one graph replay = one step of every ring replica; every 8th cycle the next-layout
+        # one graph replay = one step of every ring replica; every --prefetch-every cycles the next-layout
         # slots are topped up on each replica's side stream (concurrent with the steps)
         for i in range(n_steps // R):
             graph.replay()
@@ -323,8 +323,9 @@ def main():
     ap.add_argument('--chained', type=int, default=-1,
                     help='1: back-to-back steps order themselves warp by warp (CRL_STEP_CHAINED); 0: whole-grid '
                          'wait; -1: chained when a launch is at most a wave or two (<= 131072 envs)')
-    ap.add_argument('--prefetch-every', type=int, default=8,
+    ap.add_argument('--prefetch-every', type=int, default=32,
                     help='top up the next-layout slots every N ring cycles (0: resets sample inline)')
+    ap.add_argument('--prefetch-warps', type=int, default=0, help='background sampler warps per SM (0: default)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

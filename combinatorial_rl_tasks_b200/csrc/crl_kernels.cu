@@ -460,10 +460,15 @@ __global__ void __launch_bounds__(256) prefetch_scan_kernel(const __grid_constan
   }
 }
 
+// The objects placed so far live in REGISTERS (written through a predicated unrolled select, read
+// with static indices): no shared memory, so that the sampler's resident CTAs never cost the
+// step kernel a CTA slot (4 x 53.8 KB of TimedTSP staging leave 9 KB of an SM's 228 KB).
 template <int N>
 __global__ void __launch_bounds__(32) prefetch_layout_kernel(const __grid_constant__ KParams p, WorkItem* work,
                                                              uint32_t done_state) {
-  __shared__ float2 placed[N + 1][32];            // [object][lane]: conflict-free for a common object index
+  float2 placed[N + 1];
+#pragma unroll
+  for (int q = 0; q <= N; ++q) placed[q] = make_float2(0.f, 0.f);
   WorkHeader* hdr = reinterpret_cast<WorkHeader*>(work);
   const int lane = threadIdx.x;
   const uint32_t count = hdr->count;              // final: the scan kernel precedes this one on the stream
@@ -500,14 +505,15 @@ __global__ void __launch_bounds__(32) prefetch_layout_kernel(const __grid_consta
       uint32_t bad = 0u;                          // bit q: too close to object q (no branches)
 #pragma unroll
       for (int q = 0; q < N; ++q) {
-        const float2 o = placed[q][lane];
+        const float2 o = placed[q];
         const float dx = __fsub_rn(x, o.x), dy = __fsub_rn(y, o.y);
         const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
         bad |= (d2 >= (q == 0 ? need_r2 : need_z2)) ? 0u : (1u << q);
       }
       bad &= (1u << k) - 1u;                      // objects >= k hold stale values
       if (bad == 0u) {
-        placed[k][lane] = make_float2(x, y);
+#pragma unroll
+        for (int q = 0; q <= N; ++q) if (q == k) placed[q] = make_float2(x, y);
         ++k; j = 0;
       } else if (++j >= 100) {                    // 100 misses abandon the layout
         j = 0; k = 0;
@@ -516,10 +522,10 @@ __global__ void __launch_bounds__(32) prefetch_layout_kernel(const __grid_consta
       if (k > N) {
         const U4 rr = draw(layout_seed, 0u, 0u, 0u, kTagRot);
         const size_t sb = (size_t)slot * p.B;
-        const float2 rb = placed[0][lane];
+        const float2 rb = placed[0];
         float2* nz = p.next_zone_xy + sb * N + e;
 #pragma unroll
-        for (int i = 0; i < N; ++i) nz[(size_t)i * p.B] = placed[1 + i][lane];
+        for (int i = 0; i < N; ++i) nz[(size_t)i * p.B] = placed[1 + i];
         p.next_origin[sb + e] = make_float4(rb.x, rb.y, __fmul_rn(6.2831855f, u01(rr.x)), 0.f);
         p.next_seed[sb + e] = layout_seed - 1;
         st_release_u32(p.next_ready + sb + e, done_state);

@@ -60,7 +60,7 @@ class _EnvView:
 
 class ZoneVecEnv:
     def __init__(self, env_id, num_envs, device='cuda:0', seed_mode='increment', min_seed=1, max_seed=100,
-                 env_offset=0, auto_reset=True, prefetch_every=8, wait=False):
+                 env_offset=0, auto_reset=True, prefetch_every=32, wait=False, prefetch_warps=0):
         if not torch.cuda.is_available():
             raise RuntimeError('ZoneVecEnv needs a CUDA device (sm_100a); there is no CPU fallback')
         self.lib = _lib.load()
@@ -70,6 +70,7 @@ class ZoneVecEnv:
         self.device = torch.device(device)
         self.auto_reset = auto_reset
         self.prefetch_every = prefetch_every      # 0: never park next layouts (resets sample inline)
+        self.prefetch_warps = prefetch_warps      # background sampler warps per SM (0: library default)
         # WaitWrapper semantics (make_train_env(hier=True), wrappers.py:29-54): under
         # step_no_reset an env whose episode ended is parked until it is reset
         self.wait = bool(wait)
@@ -204,7 +205,7 @@ class ZoneVecEnv:
             stream = self._side
             stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.crl_prefetch_layouts(self.cfg, self.state, warps_per_sm,
+            _lib.check(self.lib.crl_prefetch_layouts(self.cfg, self.state, warps_per_sm or self.prefetch_warps,
                                                      ctypes.c_void_p(stream.cuda_stream)))
         self.gpu_launches += 2 if self.spec.task == _lib.TASK_TSP else 3
 

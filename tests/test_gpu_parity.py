@@ -240,3 +240,27 @@ def test_closed_loop_identical_positions(crl, env_id, mode, seed):
             break
     if mode != 'random':
         assert n_events >= 3, 'the driver should have triggered task events'
+
+
+def test_integration_md_ctypes_stub_runs(crl):
+    """The raw ctypes binding printed in INTEGRATION.md section 2 is executed as written
+    (with B and `actions` supplied) and must step a batch through the C ABI."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md = open(os.path.join(root, 'INTEGRATION.md')).read()
+    sec = md[md.index('## 2. Bind the C ABI directly'):]
+    code = re.search(r'```python\n(.*?)```', sec, re.S).group(1)
+    B = 4096
+    ns = {'B': B, 'actions': torch.zeros(B, 2, device='cuda')}
+    cwd = os.getcwd()
+    os.chdir(root)                                   # the stub loads the library by its in-tree relative path
+    try:
+        exec(code, ns)
+    finally:
+        os.chdir(cwd)
+    torch.cuda.synchronize()
+    obs = ns['mem']['obs'].view(torch.float32).reshape(B, 8).cpu().numpy()
+    res = ns['mem']['result'].reshape(B, 8).cpu().numpy()
+    assert np.all(obs[:, 0] == np.float32(1999 / 2000)) and not res[:, 4].any()
+    zo = ns['mem']['zone_obs'].view(torch.float32).reshape(B, 15, 6).cpu().numpy()
+    assert np.all(zo[:, :, 5] == 0.25) and np.all(np.abs(zo[:, :, :2]) <= 2.45 / 3 + 1e-6)
