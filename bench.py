@@ -128,6 +128,8 @@ def run_ours(args):
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if world > 1:
+        # stdout carries the one JSON line and nothing else: NCCL's banner goes to stderr
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local}'))
     dev = torch.device(f'cuda:{local}')
     torch.cuda.set_device(dev)
