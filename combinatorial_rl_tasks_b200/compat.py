@@ -57,6 +57,7 @@ class ParallelEnv:
         was_parked = self._parked.copy()
         if auto_reset:
             obs, reward, done, info = v.step_host(a, auto_reset=True)
+            self._parked[:] = False                            # a parked env runs into the step limit and restarts
         else:
             obs, reward, done, info = v.step_host(a, auto_reset=False, wait=v.wait)
             if v.wait:
@@ -84,7 +85,7 @@ class ParallelEnv:
     # -- zone-goals penv.py:75-99 ----------------------------------------------------
     def set_goal(self, env_idx, goal):
         before = self.vec.counters()['goals_rejected']
-        self.vec.set_goal(int(env_idx), int(np.asarray(goal)))
+        self.vec.set_goal_at(int(env_idx), int(np.asarray(goal)))
         assert self.vec.counters()['goals_rejected'] == before, 'set_goal: zone already visited or out of range'
 
     def get_goal(self, env_idx):

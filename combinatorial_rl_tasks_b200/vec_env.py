@@ -288,22 +288,21 @@ class ZoneVecEnv:
         if not self.spec.goals:
             raise RuntimeError(f'{self.env_id} is not a goal-conditioned variant (use PointTSP-v3, ...)')
 
-    def set_goal(self, goals, env_idx=None):
-        """env.set_goal for many envs at once: ``goals`` (B,) int, negative = leave that env alone;
-        or ``set_goal(env_idx, goal)`` order as penv.py:75-80 when env_idx is given as the first
-        argument and goal second (kept for callers that loop).  Invalid requests (visited zone,
-        index out of range: the reference's assertion) leave the goal unset and are counted in
-        counters()['goals_rejected']."""
+    def set_goal(self, goals):
+        """env.set_goal for the whole batch (TSP_next_city_env.py:77-80): ``goals`` (B,) int,
+        negative = leave that env alone.  Invalid requests (visited zone, index out of range: the
+        reference's assertion) leave the goal unset and are counted in counters()['goals_rejected']."""
         self._need_goals()
-        if env_idx is not None:                   # penv signature: set_goal(env_idx, goal)
-            idx, goal = goals, env_idx
-            g = torch.full((self.num_envs,), -1, dtype=torch.int32, device=self.device)
-            g[int(idx)] = int(goal)
-        else:
-            g = self._as_dev(goals, torch.int32).reshape(self.num_envs)
+        g = self._as_dev(goals, torch.int32).reshape(self.num_envs)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.crl_set_goal(self.cfg, self.state, g.data_ptr(), self._stream()))
         self._chain_ok = False
+
+    def set_goal_at(self, env_idx, goal):
+        """ParallelEnv.set_goal(env_idx, goal) (zone-goals penv.py:75-80): one env."""
+        g = torch.full((self.num_envs,), -1, dtype=torch.int32, device=self.device)
+        g[int(env_idx)] = int(goal)
+        self.set_goal(g)
 
     def _goal_query(self, xy=False, needs=False, available=False):
         self._need_goals()

@@ -153,12 +153,12 @@ def test_goal_rpcs_batched_and_rejections(crl):
     xy = env.get_goal().cpu().numpy()
     want = env.zone_xy.cpu().numpy()[np.arange(32) % 15, np.arange(32)] / 3.0
     assert np.max(np.abs(xy[:32] - want)) <= 2e-6 and np.all(xy[32:] == 0.0)
-    # penv.py:75-80 signature: set_goal(env_idx, goal)
-    env.set_goal(50, 3)
+    # penv.py:75-80: one env at a time
+    env.set_goal_at(50, 3)
     assert int(env.goal[50].item()) == 3 and env.envs[0].goal_zone == 0
     # visit zone 2 in env 60, then ask for it
     env.pose[60, :2] = env.zone_xy[2, 60, :]
-    env.set_goal(60, 7)
+    env.set_goal_at(60, 7)
     env.step_no_reset(torch.zeros(B, 2, device='cuda'))
     assert not bool(env.available_goals()[60, 2].item()) and int(env.available_goals()[60].sum().item()) == 14
     assert int(env.goal[60].item()) == 7 and not bool(env.need_next_goal[60].item())
@@ -167,7 +167,7 @@ def test_goal_rpcs_batched_and_rejections(crl):
     env.step_no_reset(torch.zeros(B, 2, device='cuda'))
     assert bool(env.need_next_goal[60].item()) and float(env.shaped_reward[60].item()) == 0.0
     assert int(env.goal[60].item()) == -1
-    env.set_goal(60, 2)                                      # visited: rejected
+    env.set_goal_at(60, 2)                                      # visited: rejected
     assert int(env.goal[60].item()) == -1 and env.counters()['goals_rejected'] == 2
     # the step limit ends the episode: need_next_goal, goal cleared, auto-reset clears too
     twin = crl.ZoneVecEnv('PointTSP-v3', B)
