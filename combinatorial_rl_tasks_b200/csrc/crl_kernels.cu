@@ -620,13 +620,8 @@ __device__ __forceinline__ void zone_row(const KParams& p, const Env<N>& env, fl
 // the copy is issued early and drains while the warp integrates; zone_obs_wait() must
 // run before the CTA exits (the copy reads shared memory asynchronously).
 template <int TASK, int N>
-__device__ __forceinline__ void zone_obs_send(const KParams& p, const Env<N>& env, bool valid,
-                                              float* stage, int lane, int warp_env0, bool zero_row = false) {
+__device__ __forceinline__ void zone_obs_issue(const KParams& p, float* stage, int lane, int warp_env0) {
   constexpr int ROW = N * ZoneDim<TASK>::Z;
-  if (valid) zone_row<TASK, N>(p, env, stage + lane * ROW);
-  if (zero_row) {                                  // WaitWrapper.noop_obs (wrappers.py:46-50)
-    for (int k = 0; k < ROW; ++k) stage[lane * ROW + k] = 0.f;
-  }
   const int n_valid = min(32, p.B - warp_env0);
   const uint32_t bytes = (uint32_t)n_valid * ROW * 4u;
   float* gdst = p.zone_obs + (size_t)warp_env0 * ROW;
@@ -643,6 +638,17 @@ __device__ __forceinline__ void zone_obs_send(const KParams& p, const Env<N>& en
     __syncwarp();
     for (int i = lane; i < n_valid * ROW; i += 32) gdst[i] = stage[i];
   }
+}
+
+template <int TASK, int N>
+__device__ __forceinline__ void zone_obs_send(const KParams& p, const Env<N>& env, bool valid,
+                                              float* stage, int lane, int warp_env0, bool zero_row = false) {
+  constexpr int ROW = N * ZoneDim<TASK>::Z;
+  if (valid) zone_row<TASK, N>(p, env, stage + lane * ROW);
+  if (zero_row) {                                  // WaitWrapper.noop_obs (wrappers.py:46-50)
+    for (int k = 0; k < ROW; ++k) stage[lane * ROW + k] = 0.f;
+  }
+  zone_obs_issue<TASK, N>(p, stage, lane, warp_env0);
 }
 
 __device__ __forceinline__ void zone_obs_wait(int lane) {
@@ -942,11 +948,11 @@ __global__ void __launch_bounds__(kThreads, min_blocks<N>()) step_kernel(const _
       }
     }
   }
-  // (6) zone_obs leaves now and drains under the physics
-  zone_obs_send<TASK, N>(p, env, live, stage, lane, warp_env0, EXT && parked);
-  // (7) physics: all frameskip substeps in registers
   float c, s;
   if (!EXT) {
+    // (6) zone_obs leaves now and drains under the physics
+    zone_obs_send<TASK, N>(p, env, live, stage, lane, warp_env0, false);
+    // (7) physics: all frameskip substeps in registers
     if (fresh) {
       sincosf(env.b.phi, &s, &c);
     } else {
@@ -955,6 +961,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks<N>()) step_kernel(const _
     }
     if (valid) store_state_obs<TASK, N>(p, env, e, c, s);
   } else {
+    zone_obs_send<TASK, N>(p, env, live, stage, lane, warp_env0, parked);
     // an env rebuilt by the auto-reset still integrates its OLD body: the shaped reward of the
     // episode's last step is measured at the post-physics position (TSP_next_city_env.py:57-67)
     Body pb = fresh ? old_b : env.b;
