@@ -128,9 +128,20 @@ def run_ours(args):
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if world > 1:
-        # stdout carries the one JSON line and nothing else: NCCL's banner goes to stderr
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
-        dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local}'))
+        # stdout carries the one JSON line and nothing else: while NCCL initialises (it prints its
+        # version banner on stdout), file descriptor 1 points at stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local}'))
+            torch.cuda.set_device(local)
+            dist.barrier()                                         # creates the communicator now
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     dev = torch.device(f'cuda:{local}')
     torch.cuda.set_device(dev)
     B = args.envs
@@ -269,11 +280,12 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     peak, peak_src = measured_peaks()
-    traffic = None
+    traffic = traffic_note = None
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(f'{args.env}:{B}')
+            tj = json.load(f)
+        traffic, traffic_note = tj.get(f'{args.env}:{B}'), tj.get('_note')
     achieved = step_bytes * B / (ms_per_step * 1e-3) / 1e9
     canon = {'PointTSP-v0': 614, 'PointTTSP-v0': 734, 'ColourMatch-v0': 374}.get(args.env)
     out = {
@@ -287,7 +299,8 @@ def run_ours(args):
                          f'cycle) > 2x the 126 MB L2, so every launch reads HBM',
                    'launch': 'CUDA graph of one ring cycle, replayed', 'repeats': n_rep, 'timing': 'best of repeats'},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': traffic, 'algorithmic_bytes_per_launch': step_bytes * B, 'peak_source': peak_src, 'kernel': 'step_kernel',
+                     'traffic': traffic, 'traffic_note': traffic_note if traffic is not None else None,
+                     'algorithmic_bytes_per_launch': step_bytes * B, 'peak_source': peak_src, 'kernel': 'step_kernel',
                      'bytes_per_env_step': step_bytes,
                      'canonical_bytes_per_env_step': canon,
                      'achieved_canonical': canon * B / (ms_per_step * 1e-3) / 1e9 if canon else None,
@@ -312,8 +325,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=16000)
-    ap.add_argument('--warmup', type=int, default=1600)
+    ap.add_argument('--steps', type=int, default=64000)
+    ap.add_argument('--warmup', type=int, default=6400)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--env', default='PointTSP-v0')
     ap.add_argument('--envs', type=int, default=65536)

@@ -22,7 +22,7 @@ host arrays in, host arrays out); there is no CPU path here either.
 import numpy as np
 import torch
 
-from .vec_env import ZoneVecEnv
+from .vec_env import ZoneVecEnv, _EnvView
 
 
 class ParallelEnv:
@@ -34,7 +34,7 @@ class ParallelEnv:
         kw.setdefault('min_seed', 1)
         kw.setdefault('max_seed', num_training_tasks)
         self.vec = ZoneVecEnv(env_id, num_envs, device=device, wait=hier, **kw)
-        self.envs = [_View(self, i) for i in range(num_envs)]
+        self.envs = [_EnvView(self.vec, i) for i in range(num_envs)]   # the probes callers make on penv.envs[i]
         self.observation_space = self.vec.observation_space
         self.action_space = self.vec.action_space
         self._parked = np.zeros(num_envs, dtype=bool)
@@ -102,32 +102,3 @@ class ParallelEnv:
 
     def render(self):
         raise NotImplementedError
-
-
-class _View:
-    """penv.envs[i]: the attribute probes the reference's callers make."""
-
-    def __init__(self, penv, i):
-        self._p, self._i = penv, i
-        self.observation_space, self.action_space = penv.vec.observation_space, penv.vec.action_space
-
-    @property
-    def unwrapped(self):
-        return self
-
-    @property
-    def num_cities(self):
-        return self._p.vec.spec.num_zones
-
-    @property
-    def goal_dim(self):
-        return 2
-
-    @property
-    def goal_zone(self):
-        g = int(self._p.vec.goal[self._i].item())
-        return None if g < 0 else g
-
-    def noop_obs(self):
-        N, Z = self._p.vec.spec.num_zones, self._p.vec.spec.zone_dim
-        return {'zone_obs': np.zeros((N, Z)), 'obs': np.zeros(8)}

@@ -28,7 +28,7 @@
 namespace crl {
 
 #ifndef CRL_THREADS
-#define CRL_THREADS 128
+#define CRL_THREADS 64
 #endif
 constexpr int kThreads = CRL_THREADS;
 constexpr unsigned kFull = 0xffffffffu;
