@@ -1171,28 +1171,42 @@ __global__ void goal_query_kernel(const KParams p, float2* goal_xy, uint8_t* nee
 // (main/src/torch_ac/algos/base.py:195-205).  One thread per env walks its column of the
 // [T+1][B] rollout backwards; every operation is a separate IEEE float32 operation in the order
 // torch evaluates the reference's expressions, so the result is bit-identical to it.
-__global__ void __launch_bounds__(256) gae_kernel(const unsigned long long* __restrict__ results,
+__global__ void __launch_bounds__(128) gae_kernel(const unsigned long long* __restrict__ results,
                                                   const float* __restrict__ reward_override,
                                                   const float* __restrict__ values, const float* __restrict__ next_value,
                                                   float g, float gl, int T, int B, float* __restrict__ adv_out,
                                                   float* __restrict__ ret_out) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= B) return;
-  unsigned long long rec = results[(size_t)T * B + e];
-  float nm = ((rec >> 32) & 0xffu) ? 0.f : 1.f;        // the mask in force after the last step
+  constexpr int U = 8;   // frames per batch of independent loads (the recurrence itself is serial)
+  unsigned long long rec_next = results[(size_t)T * B + e];   // slot t+1 while frame t is processed
+  float nm = ((rec_next >> 32) & 0xffu) ? 0.f : 1.f;          // the mask in force after the last step
   float nv = next_value[e], na = 0.f;
-#pragma unroll 4
-  for (int t = T - 1; t >= 0; --t) {
-    const float reward = reward_override ? reward_override[(size_t)(t + 1) * B + e] : __uint_as_float((uint32_t)rec);
-    rec = results[(size_t)t * B + e];                   // slot t: outcome of step t-1, its done is masks[t]
-    const float v = values[(size_t)t * B + e];
-    const float delta = __fsub_rn(__fadd_rn(reward, __fmul_rn(__fmul_rn(g, nv), nm)), v);
-    const float a = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, na), nm));
-    adv_out[(size_t)t * B + e] = a;
-    if (ret_out) ret_out[(size_t)t * B + e] = __fadd_rn(v, a);
-    nm = ((rec >> 32) & 0xffu) ? 0.f : 1.f;
-    nv = v;
-    na = a;
+  for (int t0 = T - 1; t0 >= 0; t0 -= U) {
+    unsigned long long rec[U];
+    float val[U], ovr[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {                             // all loads of the batch in flight at once
+      const int t = t0 - u;
+      rec[u] = t >= 0 ? results[(size_t)t * B + e] : 0ull;    // slot t: outcome of step t-1, its done is masks[t]
+      val[u] = t >= 0 ? values[(size_t)t * B + e] : 0.f;
+      ovr[u] = (reward_override && t >= 0) ? reward_override[(size_t)(t + 1) * B + e] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int t = t0 - u;
+      if (t < 0) break;
+      const float reward = reward_override ? ovr[u] : __uint_as_float((uint32_t)rec_next);
+      const float v = val[u];
+      const float delta = __fsub_rn(__fadd_rn(reward, __fmul_rn(__fmul_rn(g, nv), nm)), v);
+      const float a = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, na), nm));
+      adv_out[(size_t)t * B + e] = a;
+      if (ret_out) ret_out[(size_t)t * B + e] = __fadd_rn(v, a);
+      rec_next = rec[u];
+      nm = ((rec_next >> 32) & 0xffu) ? 0.f : 1.f;
+      nv = v;
+      na = a;
+    }
   }
 }
 
@@ -1603,7 +1617,7 @@ int crl_gae(const CrlResult* results, const float* reward_override, const float*
   // torch rounds the Python doubles `discount` and `discount * gae_lambda` to float32 when they
   // meet a float32 tensor
   const float g = (float)discount, gl = (float)(discount * gae_lambda);
-  gae_kernel<<<(num_envs + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  gae_kernel<<<(num_envs + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const unsigned long long*>(results), reward_override, values, next_value, g, gl, num_frames,
       num_envs, advantages, returns);
   return launch_status();
