@@ -47,13 +47,18 @@ class Rollout:
         self.rewards = self.result.view(torch.float32)[1:, :, 0]         # (T, B) view: reward of step t
         self.dones = self.result[1:, :, 4].view(torch.bool)              # (T, B) view
         self._started = False
+        assert B % 4 == 0, 'slots of zone_obs must start 16-byte aligned: num_envs must be a multiple of 4'
+        # one validated output binding per slot, installed with a few attribute stores per step
+        self._bindings = [env.prepare_outputs(self.obs[t], self.zone_obs[t], self.result[t],
+                                              None if self.shaped is None else self.shaped[t]) for t in range(T + 1)]
+        self._obs_views = [{'zone_obs': self.zone_obs[t], 'obs': self.obs[t]} for t in range(T + 1)]
+        self._action_views = [self.actions[t] for t in range(T)]
 
     def _bind(self, t):
-        self.env.bind_outputs(self.obs[t], self.zone_obs[t], self.result[t],
-                              None if self.shaped is None else self.shaped[t])
+        self.env.bind_outputs(binding=self._bindings[t])
 
     def obs_at(self, t):
-        return {'zone_obs': self.zone_obs[t], 'obs': self.obs[t]}
+        return self._obs_views[t]
 
     def begin(self, reset=None):
         """Start a rollout: the first one (or ``reset=True``) resets every env into slot 0; later
@@ -74,14 +79,16 @@ class Rollout:
 
     def step(self, t, actions, values=None, log_probs=None):
         """ParallelEnv.step for frame t (auto-reset on), outputs written into slot t + 1."""
-        self.actions[t].copy_(actions)
+        a = self._action_views[t]
+        if actions.data_ptr() != a.data_ptr():            # a policy may also write into ro.actions[t] directly
+            a.copy_(actions)
         if values is not None:
             self.values[t].copy_(values)
         if log_probs is not None:
             self.log_probs[t].copy_(log_probs)
         self._bind(t + 1)
-        _, reward, done, info = self.env.step(self.actions[t])
-        return self.obs_at(t + 1), reward, done, info
+        _, reward, done, info = self.env.step(a)
+        return self._obs_views[t + 1], reward, done, info
 
     def masks(self):
         """(T, B) float: masks[t] = 1 - done of the step before frame t (base.py:151-152)."""

@@ -16,6 +16,7 @@ reference (main/src/torch_ac/torch_utils/penv.py:23-69 over main/envs/make_env.p
 All arithmetic happens in libcrl_b200.so (include/crl_b200.h); torch only owns the
 memory.  There is no CPU path.
 """
+import contextlib
 import ctypes
 
 import numpy as np
@@ -24,6 +25,9 @@ import torch
 from . import _lib
 from .config import ENV_SPECS
 from .spaces import Box, Dict
+
+
+_NO_GUARD = contextlib.nullcontext()
 
 
 class _EnvView:
@@ -68,6 +72,7 @@ class ZoneVecEnv:
         self.spec = spec = ENV_SPECS[env_id]
         self.num_envs = B = int(num_envs)
         self.device = torch.device(device)
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.auto_reset = auto_reset
         self.prefetch_every = prefetch_every      # 0: never park next layouts (resets sample inline)
         self.prefetch_warps = prefetch_warps      # background sampler warps per SM (0: library default)
@@ -145,27 +150,38 @@ class ZoneVecEnv:
         self.seed(torch.arange(B, dtype=torch.int64) + env_offset)
 
     # -- plumbing ------------------------------------------------------------------
-    def bind_outputs(self, obs, zone_obs, result, shaped_reward=None):
-        """Point the env's outputs at caller-owned device tensors: the next reset / step writes
-        obs (B,8) f32, zone_obs (B,N,Z) f32, result (B,8) u8 and shaped_reward (B,) f32 there, in
-        place.  A rollout buffer hands in slot t+1 before step t, so storing a frame costs no copy
-        (rollout.py).  The tensors must be contiguous; obs / zone_obs 16-byte aligned."""
+    def prepare_outputs(self, obs, zone_obs, result, shaped_reward=None):
+        """Validate a set of caller-owned output tensors once and return a binding that
+        ``bind_outputs(binding=...)`` installs with a few attribute stores (rollout.py prepares
+        one per slot)."""
         B, N, Z = self.num_envs, self.spec.num_zones, self.spec.zone_dim
         assert obs.shape == (B, 8) and zone_obs.shape == (B, N, Z) and result.shape == (B, 8)
         assert obs.dtype == zone_obs.dtype == torch.float32 and result.dtype == torch.uint8
         assert obs.is_contiguous() and zone_obs.is_contiguous() and result.is_contiguous()
         if shaped_reward is None:
-            shaped_reward = self.shaped_reward
-        self.obs, self.zone_obs, self.result, self.shaped_reward = obs, zone_obs, result, shaped_reward
-        self.reward = result.view(torch.float32)[:, 0]
-        self.done = result[:, 4].view(torch.bool)
-        self.goal_met = result[:, 5].view(torch.bool)
-        self.event = result[:, 6].view(torch.int8)
-        self.need_next_goal = result[:, 7].view(torch.bool)
-        self.out = _lib.CrlOut(obs=obs.data_ptr(), zone_obs=zone_obs.data_ptr(), result=result.data_ptr(),
-                               shaped_reward=shaped_reward.data_ptr())
+            shaped_reward = getattr(self, 'shaped_reward', None)
+            if shaped_reward is None:
+                shaped_reward = torch.zeros(B, dtype=torch.float32, device=self.device)
+        out = _lib.CrlOut(obs=obs.data_ptr(), zone_obs=zone_obs.data_ptr(), result=result.data_ptr(),
+                          shaped_reward=shaped_reward.data_ptr())
+        return (obs, zone_obs, result, shaped_reward, result.view(torch.float32)[:, 0], result[:, 4].view(torch.bool),
+                result[:, 5].view(torch.bool), result[:, 6].view(torch.int8), result[:, 7].view(torch.bool), out)
+
+    def bind_outputs(self, obs=None, zone_obs=None, result=None, shaped_reward=None, binding=None):
+        """Point the env's outputs at caller-owned device tensors: the next reset / step writes
+        obs (B,8) f32, zone_obs (B,N,Z) f32, result (B,8) u8 and shaped_reward (B,) f32 there, in
+        place.  A rollout buffer hands in slot t+1 before step t, so storing a frame costs no copy
+        (rollout.py).  The tensors must be contiguous; obs / zone_obs 16-byte aligned."""
+        if binding is None:
+            binding = self.prepare_outputs(obs, zone_obs, result, shaped_reward)
+        (self.obs, self.zone_obs, self.result, self.shaped_reward, self.reward, self.done, self.goal_met, self.event,
+         self.need_next_goal, self.out) = binding
         self._mirror_ok = False
         self._chain_ok = False
+
+    def _guard(self):
+        """Make this env's device current for the call; free when it already is (the usual case)."""
+        return _NO_GUARD if torch.cuda.current_device() == self._dev_index else torch.cuda.device(self.device)
 
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -204,7 +220,7 @@ class ZoneVecEnv:
             # run far ahead of the device), but never blocking it
             stream = self._side
             stream.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.device(self.device):
+        with self._guard():
             _lib.check(self.lib.crl_prefetch_layouts(self.cfg, self.state, warps_per_sm or self.prefetch_warps,
                                                      ctypes.c_void_p(stream.cuda_stream)))
         self.gpu_launches += 2 if self.spec.task == _lib.TASK_TSP else 3
@@ -213,7 +229,7 @@ class ZoneVecEnv:
         """Engine.reset of all envs (or those in ``mask``).  ``layout`` switches to the
         host-supplied-layout mode: dict with xy0 (n,2), rot0 (n,), zone_xy (n,N,2) and
         zone_max_steps (n,N) / colours (n,N) per task, for envs ``env_ids`` (default 0..n)."""
-        with torch.cuda.device(self.device):
+        with self._guard():
             if layout is None:
                 m = None if mask is None else self._as_dev(mask, torch.uint8)
                 if mask is None and not torch.cuda.is_current_stream_capturing():
@@ -252,7 +268,7 @@ class ZoneVecEnv:
             flags |= _lib.STEP_CHAINED if self._chain_ok else _lib.STEP_CHAIN_START
         if not flags & _lib.STEP_PHYSICS_ONLY:
             flags |= self._mode_flags
-        with torch.cuda.device(self.device):
+        with self._guard():
             if actions is None:
                 aptr = None
             else:
@@ -294,7 +310,7 @@ class ZoneVecEnv:
         reference's assertion) leave the goal unset and are counted in counters()['goals_rejected']."""
         self._need_goals()
         g = self._as_dev(goals, torch.int32).reshape(self.num_envs)
-        with torch.cuda.device(self.device):
+        with self._guard():
             _lib.check(self.lib.crl_set_goal(self.cfg, self.state, g.data_ptr(), self._stream()))
         self._chain_ok = False
 
@@ -306,7 +322,7 @@ class ZoneVecEnv:
 
     def _goal_query(self, xy=False, needs=False, available=False):
         self._need_goals()
-        with torch.cuda.device(self.device):
+        with self._guard():
             _lib.check(self.lib.crl_goal_query(self.cfg, self.state,
                                                self._goal_xy.data_ptr() if xy else None,
                                                self._needs_goal.data_ptr() if needs else None,
@@ -353,7 +369,7 @@ class ZoneVecEnv:
         if wait and not auto_reset:
             flags |= _lib.STEP_WAIT
         use_delta = delta and self._mirror_ok and self.spec.task != _lib.TASK_TTSP
-        with torch.cuda.device(self.device):
+        with self._guard():
             if use_delta:
                 if h['delta'] is None:
                     nbytes = ((16 + 4 * B + 15) & ~15) + 4 * B * N * Z
@@ -409,7 +425,7 @@ class ZoneVecEnv:
     def counters(self):
         """Episode statistics accumulated in-kernel since construction."""
         out = (ctypes.c_double * 8)()
-        with torch.cuda.device(self.device):
+        with self._guard():
             _lib.check(self.lib.crl_counters_read(self.state, out, self._stream()))
         return {'return_sum': out[0], 'episodes': out[1], 'successes': out[2], 'length_sum': out[3],
                 'resets_prefetched': out[4], 'resets_inline': out[5], 'goals_rejected': out[6],
@@ -419,7 +435,7 @@ class ZoneVecEnv:
         """Overwrite sim.data.qpos / qvel (fp64, reference coordinates) of some envs."""
         qp, qv = self._as_dev(qpos, torch.float64).reshape(-1, 3), self._as_dev(qvel, torch.float64).reshape(-1, 3)
         ids = None if env_ids is None else self._as_dev(env_ids, torch.int32)
-        with torch.cuda.device(self.device):
+        with self._guard():
             _lib.check(self.lib.crl_set_qpos_qvel(self.cfg, self.state, qp.data_ptr(), qv.data_ptr(),
                                                   None if ids is None else ids.data_ptr(), qp.shape[0],
                                                   self._stream()))
@@ -431,7 +447,7 @@ class ZoneVecEnv:
         qp = torch.empty(n, 3, dtype=torch.float64, device=self.device)
         qv = torch.empty_like(qp)
         ids = None if env_ids is None else self._as_dev(env_ids, torch.int32)
-        with torch.cuda.device(self.device):
+        with self._guard():
             _lib.check(self.lib.crl_get_qpos_qvel(self.cfg, self.state, qp.data_ptr(), qv.data_ptr(),
                                                   None if ids is None else ids.data_ptr(), n, self._stream()))
         self._chain_ok = False
