@@ -157,6 +157,9 @@ def run_ours(args):
     for r in range(R):
         e = crl.ZoneVecEnv(args.env, B, device=dev, env_offset=(rank * R + r) * B,
                            prefetch_every=args.prefetch_every, prefetch_warps=args.prefetch_warps)
+        for kv in args.cfg:                                        # diagnostic overrides, e.g. --cfg beta_a=1000
+            k, v = kv.split('=')
+            setattr(e.cfg, k, type(getattr(e.cfg, k))(float(v)))
         e.seed(1 + (rank * R + r) * B)
         e.reset()
         envs.append(e)
@@ -340,6 +343,7 @@ def main():
                          'wait; -1: chained when a launch is at most a wave or two (<= 131072 envs)')
     ap.add_argument('--prefetch-every', type=int, default=32,
                     help='top up the next-layout slots every N ring cycles (0: resets sample inline)')
+    ap.add_argument('--cfg', action='append', default=[], help='diagnostic: override a CrlConfig field, key=value')
     ap.add_argument('--prefetch-warps', type=int, default=0, help='background sampler warps per SM (0: default)')
     args = ap.parse_args()
     if args.impl == 'reference':

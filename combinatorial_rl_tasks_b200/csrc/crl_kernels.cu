@@ -298,13 +298,15 @@ __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
 // it: no sampling latency on the step's critical path.  The others are rebuilt one at a
 // time by the whole warp.  Both ways produce the same layout: it is a pure function of
 // the seed.
-#ifdef CRL_INLINE_RESET
-#define CRL_RESET_INLINING __forceinline__
-#else
-#define CRL_RESET_INLINING __noinline__
-#endif
+//
+// The function is out of line (cold, register-hungry); `out` (the caller's Env copy) therefore
+// lives in local memory.  It is WRITE-ONLY here: with the L1 thrashed by the step's streaming
+// loads and invalidated by the acquire load below, a local load is an L2 round trip, and the 23
+// plane stores used to read their values back from it one after the other (~14 us per resetting
+// warp, profiles/r01_notes.md).  Now the new zone centres / timeouts go straight from registers
+// to their planes, and the caller reads its copy back once, in one batch of independent loads.
 template <int TASK, int N>
-__device__ CRL_RESET_INLINING void warp_reset(const KParams& p, unsigned dm, int lane, int e, float2* placed, Env<N>& env) {
+__device__ __noinline__ void warp_reset(const KParams& p, unsigned dm, int lane, int e, float2* placed, Env<N>& out) {
   const bool mine = (dm >> lane) & 1u;
   long long chosen = 0;
   uint32_t episode = 0;
@@ -313,13 +315,13 @@ __device__ CRL_RESET_INLINING void warp_reset(const KParams& p, unsigned dm, int
   uint32_t col_word = 0u;
   const int B = p.B;
   uint32_t* slot_flag = nullptr;
+  float2* zp = p.zone_xy + e;
+  uint32_t* tp = p.zone_tmax + e;
   if (mine) {
     episode = p.episode[e];
     chosen = choose_seed(p, e, episode);
     if (p.next_ready) {
-      // reset number n takes slot n & 1.  Everything is loaded into registers first, in one
-      // batch of independent loads, and only then written into `env` (which lives in local
-      // memory across this out-of-line call).
+      // reset number n takes slot n & 1: one batch of independent loads, then straight out again
       const size_t sb = (size_t)(episode & 1u) * (size_t)B;
       slot_flag = p.next_ready + sb + e;
       if (ld_acquire_u32(slot_flag) == kSlotReady) {
@@ -340,10 +342,10 @@ __device__ CRL_RESET_INLINING void warp_reset(const KParams& p, unsigned dm, int
           fast = true;
           x0 = o.x; y0 = o.y; rot0 = o.z;
 #pragma unroll
-          for (int i = 0; i < N; ++i) env.zone[i] = z[i];
+          for (int i = 0; i < N; ++i) { zp[(size_t)i * B] = z[i]; out.zone[i] = z[i]; }
           if (TASK == CRL_TASK_TTSP) {
 #pragma unroll
-            for (int j = 0; j < (N + 1) / 2; ++j) env.tmax[j] = t[j];
+            for (int j = 0; j < (N + 1) / 2; ++j) { tp[(size_t)j * B] = t[j]; out.tmax[j] = t[j]; }
           }
           if (TASK == CRL_TASK_CM) col_word = t[0];
         }
@@ -359,39 +361,34 @@ __device__ CRL_RESET_INLINING void warp_reset(const KParams& p, unsigned dm, int
     float r0;
     warp_generate<TASK, N>(p, ch, placed, lane, my_draw, r0);
     uint32_t cw = 0u;
+    uint32_t tm[(N + 1) / 2];
+#pragma unroll
+    for (int j = 0; j < (N + 1) / 2; ++j) tm[j] = 0u;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       const uint32_t d = __shfl_sync(kFull, my_draw, i);
-      if (lane == src) {
-        if (TASK == CRL_TASK_TTSP) {
-          if (i & 1) env.tmax[i >> 1] |= d << 16; else env.tmax[i >> 1] = d;
-        }
-        cw |= d << (2 * i);
-      }
+      tm[i >> 1] |= d << (16 * (i & 1));
+      cw |= d << (2 * i);
     }
     if (lane == src) {
       const float2 rb = placed[0];
       x0 = rb.x; y0 = rb.y; rot0 = r0; col_word = cw;
 #pragma unroll
-      for (int i = 0; i < N; ++i) env.zone[i] = placed[1 + i];
+      for (int i = 0; i < N; ++i) { const float2 z = placed[1 + i]; zp[(size_t)i * B] = z; out.zone[i] = z; }
+      if (TASK == CRL_TASK_TTSP) {
+#pragma unroll
+        for (int j = 0; j < (N + 1) / 2; ++j) { tp[(size_t)j * B] = tm[j]; out.tmax[j] = tm[j]; }
+      }
     }
     __syncwarp();
   }
   if (mine) {
-    env.b.X = x0; env.b.Y = y0; env.b.phi = wrap_pi(rot0);
-    env.b.vx = env.b.vy = env.b.w = 0.f;
-    env.ep_return = 0.f;
-    env.steps = 0;
-    env.hi = TASK == CRL_TASK_CM ? col_word : 0u;
-    env.cd = make_uint2(0u, 0u);
-    float2* zp = p.zone_xy + e;
-    uint32_t* tp = p.zone_tmax + e;
-#pragma unroll
-    for (int i = 0; i < N; ++i) zp[(size_t)i * B] = env.zone[i];
-    if (TASK == CRL_TASK_TTSP) {
-#pragma unroll
-      for (int j = 0; j < (N + 1) / 2; ++j) tp[(size_t)j * B] = env.tmax[j];
-    }
+    out.b.X = x0; out.b.Y = y0; out.b.phi = wrap_pi(rot0);
+    out.b.vx = out.b.vy = out.b.w = 0.f;
+    out.ep_return = 0.f;
+    out.steps = 0;
+    out.hi = TASK == CRL_TASK_CM ? col_word : 0u;
+    out.cd = make_uint2(0u, 0u);
     p.seed[e] = chosen + 1;                       // Engine.reset: self._seed += 1
     p.episode[e] = episode + 1u;
     p.origin[e] = make_float4(x0, y0, rot0, 0.f);
@@ -940,7 +937,8 @@ __global__ void __launch_bounds__(kThreads, min_blocks<N>()) step_kernel(const _
       }
       // (5) auto-reset, penv.py:9-10: only the finished envs are rebuilt
       if (p.flags & CRL_STEP_AUTO_RESET) {
-        // a copy crosses the (cold, out-of-line) call so that `env` itself stays in registers
+        // a copy crosses the (cold, out-of-line) call so that `env` itself is dead across it and
+        // stays in registers everywhere else (keeping it live costs spills in the hot path)
         Env<N> next = env;
         warp_reset<TASK, N>(p, dm, lane, e, reinterpret_cast<float2*>(stage), next);
         env = next;
