@@ -272,8 +272,9 @@ def run_ours(args):
                'steps': args.e2e_steps,
                'api': 'ZoneVecEnv.step_host: host numpy actions in, host numpy obs/zone_obs/reward/done out, pinned '
                       'staging, copies + stream sync inside every call'
-                      + ('; crl_step_host_delta: obs and result whole, zone_obs rows that changed only (mean %.1f of %d '
-                         'rows per step), byte-identical host buffers' % (rows_per_step, B) if is_delta
+                      + ('; crl_step_host_delta, zero-copy: the step kernel reads the actions from and writes obs and result to the '
+                         'pinned host buffers itself; of zone_obs only the rows that changed cross PCIe (mean %.1f of %d '
+                         'rows per step); host buffers byte-identical to a full copy' % (rows_per_step, B) if is_delta
                          else '; crl_step_host: everything copied whole'),
                'full_copy_value': full_rate,
                'full_copy_d2h_bytes_per_step': (32 + 4 * N * Z + 8) * B}

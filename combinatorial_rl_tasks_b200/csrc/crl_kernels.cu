@@ -1580,19 +1580,46 @@ int crl_step_host_delta(const CrlConfig* c, const CrlState* st, const float* act
   uint32_t* dev_host_list = static_cast<uint32_t*>(pa.devicePointer);
   float* dev_host_rows = reinterpret_cast<float*>(static_cast<char*>(pa.devicePointer) + rows_off);
   if (cudaMemsetAsync(st->row_list, 0, 16, s) != cudaSuccess) return CRL_ERR_DEVICE;
-  if (cudaMemcpyAsync(actions_dev, actions_host, B * 8, cudaMemcpyHostToDevice, s) != cudaSuccess) return CRL_ERR_DEVICE;
-  rc = crl_step(c, st, actions_dev, out, flags | CRL_STEP_TRACK_ROWS, 0, 0, stream);
-  if (rc) return rc;
-  // plain launch: ordered after the whole step kernel
-  gather_rows_kernel<<<148, 256, 0, s>>>(st->row_list, out->zone_obs, dev_host_list, dev_host_rows, (int)row, (int)B);
-  rc = launch_status();
-  if (rc) return rc;
-  if (cudaMemcpyAsync(host_out->obs, out->obs, B * 32, cudaMemcpyDeviceToHost, s) != cudaSuccess) return CRL_ERR_DEVICE;
-  if (cudaMemcpyAsync(host_out->result, out->result, B * 8, cudaMemcpyDeviceToHost, s) != cudaSuccess)
-    return CRL_ERR_DEVICE;
-  if ((flags & CRL_STEP_GOALS) && host_out->shaped_reward &&
-      cudaMemcpyAsync(host_out->shaped_reward, out->shaped_reward, B * 4, cudaMemcpyDeviceToHost, s) != cudaSuccess)
-    return CRL_ERR_DEVICE;
+  const bool zero_copy = (flags & CRL_STEP_HOST_ZERO_COPY) != 0u;
+  flags &= ~CRL_STEP_HOST_ZERO_COPY;
+  if (zero_copy) {
+    // the step kernel itself reads the actions from, and writes obs / result (/ shaped_reward) to,
+    // the caller's pinned device-mapped host buffers: no copy-engine transfers, no staging
+    auto mapped = [](const void* h) -> void* {
+      cudaPointerAttributes a;
+      if (!h || cudaPointerGetAttributes(&a, h) != cudaSuccess || a.type != cudaMemoryTypeHost) {
+        (void)cudaGetLastError();
+        return nullptr;
+      }
+      return a.devicePointer;
+    };
+    CrlOut direct = *out;
+    direct.obs = static_cast<float*>(mapped(host_out->obs));
+    direct.result = static_cast<CrlResult*>(mapped(host_out->result));
+    const float* act = static_cast<const float*>(mapped(actions_host));
+    if ((flags & CRL_STEP_GOALS) && host_out->shaped_reward)
+      direct.shaped_reward = static_cast<float*>(mapped(host_out->shaped_reward));
+    if (!direct.obs || !direct.result || !act || !direct.shaped_reward) return CRL_ERR_CONFIG;
+    rc = crl_step(c, st, act, &direct, flags | CRL_STEP_TRACK_ROWS, 0, 0, stream);
+    if (rc) return rc;
+    gather_rows_kernel<<<148, 256, 0, s>>>(st->row_list, out->zone_obs, dev_host_list, dev_host_rows, (int)row, (int)B);
+    rc = launch_status();
+    if (rc) return rc;
+  } else {
+    if (cudaMemcpyAsync(actions_dev, actions_host, B * 8, cudaMemcpyHostToDevice, s) != cudaSuccess) return CRL_ERR_DEVICE;
+    rc = crl_step(c, st, actions_dev, out, flags | CRL_STEP_TRACK_ROWS, 0, 0, stream);
+    if (rc) return rc;
+    // plain launch: ordered after the whole step kernel
+    gather_rows_kernel<<<148, 256, 0, s>>>(st->row_list, out->zone_obs, dev_host_list, dev_host_rows, (int)row, (int)B);
+    rc = launch_status();
+    if (rc) return rc;
+    if (cudaMemcpyAsync(host_out->obs, out->obs, B * 32, cudaMemcpyDeviceToHost, s) != cudaSuccess) return CRL_ERR_DEVICE;
+    if (cudaMemcpyAsync(host_out->result, out->result, B * 8, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+      return CRL_ERR_DEVICE;
+    if ((flags & CRL_STEP_GOALS) && host_out->shaped_reward &&
+        cudaMemcpyAsync(host_out->shaped_reward, out->shaped_reward, B * 4, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+      return CRL_ERR_DEVICE;
+  }
   if (cudaStreamSynchronize(s) != cudaSuccess) return CRL_ERR_DEVICE;
   const uint32_t count = host_list[0];
   if (count > B) return CRL_ERR_DEVICE;

@@ -351,7 +351,7 @@ class ZoneVecEnv:
         ``chained=True`` for back-to-back rollout steps with nothing else enqueued in between."""
         return self._step(None, _lib.STEP_AUTO_RESET if auto_reset else 0, action_seed, chained=chained)
 
-    def step_host(self, actions, auto_reset=True, delta=True, wait=False):
+    def step_host(self, actions, auto_reset=True, delta=True, wait=False, zero_copy=True):
         """The reference-facing call with HOST buffers: numpy actions in, numpy obs /
         reward / done out (pinned staging; host<->device copies inside the call).  The returned
         arrays are persistent host buffers overwritten by the next call, as the device ones are.
@@ -359,7 +359,10 @@ class ZoneVecEnv:
         ``delta=True`` (PointTSP, ColourMatch): once the host zone_obs buffer mirrors the device
         one, later calls move only the rows that changed (crl_step_host_delta); the arrays
         returned are byte-identical to a full copy.  TimedTSP's time-left column moves every
-        step, so it always copies whole."""
+        step, so it always copies whole.  ``zero_copy=True`` (with the delta path): the step kernel
+        reads the actions from, and writes obs / result / shaped_reward to, the pinned host buffers
+        itself -- no staging copies; the DEVICE tensors ``env.obs`` / ``env.result`` are then not
+        updated by the call (``env.zone_obs`` is)."""
         B, N, Z = self.num_envs, self.spec.num_zones, self.spec.zone_dim
         h = self._host_buffers()
         a = np.asarray(actions, dtype=np.float32).reshape(B, 2)
@@ -375,6 +378,8 @@ class ZoneVecEnv:
                     nbytes = ((16 + 4 * B + 15) & ~15) + 4 * B * N * Z
                     h['delta'] = torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
                 n = ctypes.c_int32(0)
+                if zero_copy:                         # the kernel reads / writes the pinned host buffers itself
+                    flags |= _lib.STEP_HOST_ZERO_COPY
                 _lib.check(self.lib.crl_step_host_delta(self.cfg, self.state, h['actions'].data_ptr(),
                                                         self._actions_dev.data_ptr(), self.out, h['out'],
                                                         h['delta'].data_ptr(), h['delta'].numel(), flags,

@@ -113,6 +113,11 @@ enum CrlError {
  * ends in a step without CRL_STEP_AUTO_RESET is parked; further steps of a parked env change
  * nothing and report an all-zero observation, reward 0, done = 1, until it is reset. */
 #define CRL_STEP_WAIT 64u
+/* crl_step_host_delta only: no staging and no copy-engine transfers -- the step kernel reads the
+ * actions from, and writes obs / result / shaped_reward straight to, the caller's host buffers,
+ * which must be page-locked and device-mapped (cudaHostAlloc; CRL_ERR_CONFIG otherwise).  The
+ * device copies CrlOut.obs / result / shaped_reward are NOT updated by such a call. */
+#define CRL_STEP_HOST_ZERO_COPY 256u
 
 /* how a reset chooses the episode's seed; wrappers.py:10-23 and Engine.seed/reset */
 enum CrlSeedMode {
