@@ -1,20 +1,24 @@
 // crl_kernels.cu -- sm_100a kernels and the C ABI (include/crl_b200.h) of the
 // batched Point-robot zone-task simulator.
 //
-// One thread per env.  Per env-step a thread
+// One thread per env.  Per env-step a thread (order as executed, see step_kernel)
 //   1. loads its state planes (two float4), its action (float2) and its N zone
 //      centres (float2 each, plane-major so every load is a coalesced 256-B row),
 //   2. tests the zone event on the PRE-physics position (TSP_env.py:54-69,
 //      colour_match_env.py:106-120) -- fp32 screen, exact fp64 confirm,
-//   3. integrates all frameskip substeps in registers (crl_core.cuh),
-//   4. applies reward / goal / timeout / done (TSP_env.py:37-42,71-72,
-//      TTSP_env.py:62-71, colour_match_env.py:86-93,122-123, Engine.step),
-//   5. if the env finished and auto-reset is on, its warp builds the next
-//      episode's layout cooperatively (32 rejection-sampling candidates per round),
-//   6. writes state, CrlResult, obs, and stages its zone_obs row in shared memory,
-//      from where each warp's 32 rows (one contiguous span of B x N x Z) leave with a
-//      single cp.async.bulk shared->global copy.
-// Episode statistics go through warp ballots and one atomic per warp.
+//   3. applies reward / goal / timeout / done (TSP_env.py:37-42,71-72,
+//      TTSP_env.py:62-71, colour_match_env.py:86-93,122-123, Engine.step) -- none of it
+//      depends on the post-physics state -- and writes the CrlResult record,
+//   4. if the env finished and auto-reset is on, takes its next layout from the slot the
+//      background sampler parked it in (prefetch_*_kernel); only if the slot is empty does
+//      its warp build the layout cooperatively (32 rejection-sampling candidates per round),
+//   5. stages its zone_obs row in shared memory, from where each warp's 32 rows (one
+//      contiguous span of B x N x Z) leave with a single cp.async.bulk shared->global copy,
+//   6. integrates all frameskip substeps in registers (crl_core.cuh) while that copy drains,
+//   7. writes state and the 8-float obs row.
+// Episode statistics go through warp ballots and one atomic per warp.  Also here: the
+// goal-conditioned / WaitWrapper variant of the step (EXT), the host-facing steps
+// (crl_step_host, crl_step_host_delta + gather_rows_kernel), goal RPC kernels and crl_gae.
 #include <cuda_runtime.h>
 
 #include <atomic>

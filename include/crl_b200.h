@@ -39,8 +39,8 @@
  *                          kept only to convert to/from qpos/qvel
  *    counters  double[8]   sum of episode returns, episodes finished, successes
  *                          (goal_met), sum of episode lengths, resets served from a
- *                          prefetched layout, resets sampled inline, rejected crl_set_goal requests, chained-step
- *                          waits that gave up (must stay 0)
+ *                          prefetched layout, resets sampled inline, rejected crl_set_goal
+ *                          requests, chained-step waits that gave up (must stay 0)
  *  optional next-layout planes (all NULL = no prefetch): the draws of each env's next TWO
  *  Engine.resets (reset number n parks in slot n & 1), made in the background by
  *  crl_prefetch_layouts so that an auto-reset inside crl_step is a copy instead of a
@@ -51,10 +51,13 @@
  *    ready, 2 = layout parked and task draws pending, 3 = claimed by a running prefetch)
  *  optional stamp uint32[2][ceil(B/32)]: steps started / finished per group of 32 envs,
  *  see CRL_STEP_CHAINED
+ *  optional row_list uint32[4 + B] (CRL_STEP_TRACK_ROWS, crl_step_host_delta) and goal int32[B]
+ *  (goal-conditioned variants, CRL_STEP_GOALS): see CrlState
  *  outputs, the layout the reference's consumer builds (main/src/utils/format.py:27-28):
  *    obs       float[B][8]      remaining, pos/3 (2), dir (2), vel/1.5 (2), yaw rate/3
  *    zone_obs  float[B][N][Z]   x/3, y/3, r, g, b, 0.25 [, time left | cooldown/150]
- *    result    CrlResult[B]     reward, done, goal_met, integer reward component
+ *    result    CrlResult[B]     reward, done, goal_met, integer reward component, need_next_goal
+ *    shaped_reward float[B]     info['shaped_reward'] of the goal-conditioned variants
  */
 #ifndef CRL_B200_H_
 #define CRL_B200_H_
