@@ -32,6 +32,12 @@ The sphere/floor contact has signed distance exactly 0.0 == margin, which
 MuJoCo lists but excludes (``dist < includemargin`` is false), so
 ``constraint_force`` returns zero; it is kept as an isolated hook.
 
+tests/test_oracle_physics_first_principles.py re-derives the equations of motion used below
+(mass matrix, centrifugal bias, generalized actuator forces, the damped semi-implicit Euler
+step) symbolically from the model geometry and checks this file against them to 1e-12; that
+removes transcription and derivation errors, not the dependence on the recalled model
+constants, integrator choice and contact exclusion.
+
 The mass matrix is assembled generically (composite rigid body of the two
 geoms) and the 3x3 system is solved with ``numpy.linalg.solve`` on purpose: the
 CUDA kernel uses an independently derived closed form, so agreement between the
