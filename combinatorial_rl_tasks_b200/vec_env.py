@@ -436,6 +436,33 @@ class ZoneVecEnv:
                 'resets_prefetched': out[4], 'resets_inline': out[5], 'goals_rejected': out[6],
                 'chain_wait_timeouts': out[7]}
 
+    _STATE_KEYS = ('pose', 'aux', 'zone_xy', 'zone_tmax', 'cooldown', 'seeds', 'episode', 'origin', 'counters_dev',
+                   'goal', 'obs', 'zone_obs', 'result', 'shaped_reward')
+
+    def state_dict(self):
+        """Everything needed to continue a run bit for bit (the reference has no equivalent: its
+        envs live in worker processes and die with them): clones of the state and output planes.
+        Parked next layouts are not saved -- they are pure functions of the seeds and are redrawn."""
+        torch.cuda.current_stream(self.device).synchronize()
+        d = {k: getattr(self, k).clone() for k in self._STATE_KEYS if getattr(self, k) is not None}
+        d['step_index'] = self._step_index
+        d['env_id'], d['num_envs'], d['num_steps'] = self.env_id, self.num_envs, int(self.cfg.num_steps)
+        return d
+
+    def load_state_dict(self, d):
+        assert d['env_id'] == self.env_id and d['num_envs'] == self.num_envs
+        for k in self._STATE_KEYS:
+            if getattr(self, k) is not None:
+                getattr(self, k).copy_(d[k])
+        self.cfg.num_steps = d['num_steps']
+        self._step_index = d['step_index']
+        self.next_ready.zero_()                   # parked layouts belong to the run that was interrupted
+        self.stamp.zero_()
+        self._chain_ok = False
+        self._mirror_ok = False
+        if self.prefetch_every:
+            self.prefetch(torch.cuda.current_stream(self.device))
+
     def set_qpos_qvel(self, qpos, qvel, env_ids=None):
         """Overwrite sim.data.qpos / qvel (fp64, reference coordinates) of some envs."""
         qp, qv = self._as_dev(qpos, torch.float64).reshape(-1, 3), self._as_dev(qvel, torch.float64).reshape(-1, 3)

@@ -436,3 +436,35 @@ def test_chained_steps_equal_plain_steps(crl, env_id):
     assert chain.counters()['episodes'] > B // 2     # resets did happen under chaining
     st = chain2.stamp.cpu().numpy()
     assert np.all(st[0] == st[1]) and np.all(st[0] == 2 * n_graph + 2)
+
+
+@pytest.mark.parametrize('env_id', ['PointTTSP-v0', 'ColourMatch-v3'])
+def test_state_dict_resumes_bit_for_bit(crl, env_id):
+    """A run restored from state_dict() continues exactly as the original did, through auto-resets
+    (layouts are pure functions of the seeds, so the parked ones need not be saved)."""
+    B = 512
+    env = crl.ZoneVecEnv(env_id, B)
+    env.seed(31)
+    env.cfg.num_steps = 25
+    env.reset()
+    rs = np.random.RandomState(8)
+    acts = [torch.from_numpy(rs.uniform(-1, 1, (B, 2)).astype(np.float32)).cuda() for _ in range(90)]
+    goals = torch.zeros(B, dtype=torch.int32, device='cuda')
+    def run(e, lo, hi):
+        out = []
+        for t in range(lo, hi):
+            if e.spec.goals:
+                e.set_goal(torch.where(e.needs_goal(), goals + t % 6, goals - 1))
+            o, r, d, info = e.step(acts[t])
+            out.append((o['obs'].clone(), o['zone_obs'].clone(), e.result.clone(), e.shaped_reward.clone()))
+        return out
+    run(env, 0, 40)
+    snap = env.state_dict()
+    first = run(env, 40, 90)
+    other = crl.ZoneVecEnv(env_id, B)                    # a fresh object, as after a restart
+    other.load_state_dict(snap)
+    second = run(other, 40, 90)
+    for t, (a, b) in enumerate(zip(first, second)):
+        assert all(torch.equal(x, y) for x, y in zip(a, b)), t
+    assert other.counters()['episodes'] == env.counters()['episodes'] > B
+    assert torch.equal(other.seeds, env.seeds) and torch.equal(other.zone_xy, env.zone_xy)
