@@ -21,7 +21,7 @@ NUM_PLANES = 22
 SYMBOLS = ['crl_abi_version', 'crl_strerror', 'crl_plane_bytes', 'crl_step_bytes', 'crl_reset',
            'crl_prefetch_layouts', 'crl_reset_from_layout', 'crl_step', 'crl_step_host', 'crl_step_host_delta',
            'crl_set_goal', 'crl_goal_query', 'crl_set_qpos_qvel',
-           'crl_get_qpos_qvel', 'crl_gae', 'crl_counters_read']
+           'crl_get_qpos_qvel', 'crl_gae', 'crl_check_state', 'crl_counters_read']
 
 
 class CrlConfig(ctypes.Structure):
@@ -84,6 +84,7 @@ def load():
                                       c_void_p]
     lib.crl_gae.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, c_int32, c_int32,
                             c_void_p, c_void_p, c_void_p]
+    lib.crl_check_state.argtypes = [P(CrlConfig), P(CrlState), c_void_p, c_void_p]
     lib.crl_counters_read.argtypes = [P(CrlState), P(c_double), c_void_p]
     for name in SYMBOLS:
         getattr(lib, name)

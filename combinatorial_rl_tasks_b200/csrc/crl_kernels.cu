@@ -1212,6 +1212,52 @@ __global__ void __launch_bounds__(128) gae_kernel(const unsigned long long* __re
   }
 }
 
+// Invariants of the state planes, counted per kind (crl_check_state): what a stray write or a
+// broken reset would violate.  compute-sanitizer is not available on every pool; this is cheap
+// enough to run after any rollout.
+__global__ void check_state_kernel(const KParams p, int task, int N, unsigned long long* bad) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= p.B) return;
+  const float4 ps = p.pose[e], ax = p.aux[e];
+  const uint32_t bits = (uint32_t)__float_as_int(ax.w);
+  const int steps = (int)(bits & 0xffffu);
+  const uint32_t hi = bits >> 16;
+  if (!(isfinite(ps.x) && isfinite(ps.y) && isfinite(ps.z) && isfinite(ps.w) && isfinite(ax.x) && isfinite(ax.y) &&
+        isfinite(ax.z)))
+    atomicAdd(bad + 0, 1ull);
+  if (!(fabsf(ps.z) <= 3.1415935f)) atomicAdd(bad + 1, 1ull);                       // heading wrapped
+  if (steps > p.num_steps && steps != kParkedSteps) atomicAdd(bad + 2, 1ull);
+  const float lim = p.extent - p.zone_keepout + 1e-5f;
+  bool zone_bad = false;
+  for (int i = 0; i < N; ++i) {
+    const float2 z = p.zone_xy[(size_t)i * p.B + e];
+    zone_bad |= !(fabsf(z.x) <= lim && fabsf(z.y) <= lim);
+  }
+  if (zone_bad) atomicAdd(bad + 3, 1ull);
+  bool hi_bad = false;
+  if (task == CRL_TASK_CM) {
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t c = (hi >> (2 * i)) & 3u;
+      hi_bad |= i < N ? c == 3u : c != 0u;
+    }
+    const uint2 cd = p.cooldown[e];
+    for (int i = 0; i < 8; ++i) hi_bad |= cd_get(cd, i) > (uint32_t)p.max_cd || (i >= N && cd_get(cd, i) != 0u);
+  } else {
+    hi_bad = (hi >> N) != 0u;
+  }
+  if (hi_bad) atomicAdd(bad + 4, 1ull);
+  if (p.next_ready && (p.next_ready[e] > 3u || p.next_ready[(size_t)p.B + e] > 3u)) atomicAdd(bad + 5, 1ull);
+  if (p.goal && (p.goal[e] < -1 || p.goal[e] >= N)) atomicAdd(bad + 6, 1ull);
+  if (task == CRL_TASK_TTSP) {
+    bool t_bad = false;
+    for (int i = 0; i < N; ++i) {
+      const uint32_t tm = (p.zone_tmax[(size_t)(i >> 1) * p.B + e] >> (16 * (i & 1))) & 0xffffu;
+      t_bad |= tm > (uint32_t)p.num_steps;
+    }
+    if (t_bad) atomicAdd(bad + 7, 1ull);
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------
 static int zone_dim(int task) { return task == CRL_TASK_TSP ? 6 : 7; }
 
@@ -1649,6 +1695,18 @@ int crl_gae(const CrlResult* results, const float* reward_override, const float*
   gae_kernel<<<(num_envs + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const unsigned long long*>(results), reward_override, values, next_value, g, gl, num_frames,
       num_envs, advantages, returns);
+  return launch_status();
+}
+
+int crl_check_state(const CrlConfig* c, const CrlState* st, uint64_t* violations, void* stream) {
+  KParams p;
+  if (!violations) return CRL_ERR_NULL;
+  int rc = fill_params(c, st, nullptr, p);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(violations, 0, 8 * sizeof(uint64_t), s) != cudaSuccess) return CRL_ERR_DEVICE;
+  check_state_kernel<<<(p.B + 255) / 256, 256, 0, s>>>(p, c->task, c->num_zones,
+                                                       reinterpret_cast<unsigned long long*>(violations));
   return launch_status();
 }
 

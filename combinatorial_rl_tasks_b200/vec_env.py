@@ -436,6 +436,14 @@ class ZoneVecEnv:
                 'resets_prefetched': out[4], 'resets_inline': out[5], 'goals_rejected': out[6],
                 'chain_wait_timeouts': out[7]}
 
+    def check_state(self):
+        """Invariant check of the state planes (crl_check_state); returns the eight violation counts
+        as a list of ints -- all zero on a healthy env.  Synchronises."""
+        v = torch.zeros(8, dtype=torch.int64, device=self.device)
+        with self._guard():
+            _lib.check(self.lib.crl_check_state(self.cfg, self.state, v.data_ptr(), self._stream()))
+        return [int(x) for x in v.cpu()]
+
     _STATE_KEYS = ('pose', 'aux', 'zone_xy', 'zone_tmax', 'cooldown', 'seeds', 'episode', 'origin', 'counters_dev',
                    'goal', 'obs', 'zone_obs', 'result', 'shaped_reward')
 

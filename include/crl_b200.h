@@ -306,6 +306,14 @@ int crl_gae(const CrlResult* results, const float* reward_override, const float*
             const float* next_value, double discount, double gae_lambda, int32_t num_frames,
             int32_t num_envs, float* advantages, float* returns, void* stream);
 
+/* Failure detection: counts, per kind, the envs whose state planes violate an invariant that
+ * only a stray write or a broken reset could violate.  violations: device uint64[8] =
+ * {non-finite body state, heading outside [-pi, pi], step count above num_steps (and not the
+ * parked sentinel), zone centre outside the placement extents, visited / colour / cooldown bits
+ * out of range, next-layout flag out of range, goal outside [-1, N), TimedTSP timeout above
+ * num_steps}.  All zeros = healthy.  Asynchronous on `stream`. */
+int crl_check_state(const CrlConfig* cfg, const CrlState* st, uint64_t* violations, void* stream);
+
 /* Copies the eight counters to the host (synchronises `stream`).  The first four (sum of
  * returns, episodes, successes, sum of lengths) are what ranks all-reduce. */
 int crl_counters_read(const CrlState* st, double out[8], void* stream);

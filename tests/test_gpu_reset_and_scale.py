@@ -253,6 +253,7 @@ def test_full_size_properties(crl, env_id, B):
         ret_sum += float(ep_ret[done].double().sum())
         ep_ret[done] = 0
     torch.cuda.synchronize()
+    assert env.check_state() == [0] * 8                     # crl_check_state: no invariant violated anywhere
     c = env.counters()
     assert c['episodes'] == n_done and n_done >= B
     assert abs(c['return_sum'] - ret_sum) <= 1e-3 * max(1.0, abs(ret_sum))
@@ -468,3 +469,25 @@ def test_state_dict_resumes_bit_for_bit(crl, env_id):
         assert all(torch.equal(x, y) for x, y in zip(a, b)), t
     assert other.counters()['episodes'] == env.counters()['episodes'] > B
     assert torch.equal(other.seeds, env.seeds) and torch.equal(other.zone_xy, env.zone_xy)
+
+
+def test_check_state_detects_corruption(crl):
+    """crl_check_state counts, per kind, what a stray write would break."""
+    env = crl.ZoneVecEnv('PointTTSP-v3', 256)
+    env.reset()
+    assert env.check_state() == [0] * 8
+    env.pose[3, 0] = float('nan')
+    env.pose[4, 2] = 7.0
+    env.aux[5, 3] = torch.tensor(2001, dtype=torch.int32).view(torch.float32)
+    env.zone_xy[2, 6, 0] = 2.9
+    env.aux[7, 3] = torch.tensor(1 << 31, dtype=torch.int64).to(torch.int32).view(torch.float32)
+    env.next_ready[1, 8] = 9
+    env.goal[9] = 15
+    env.zone_tmax[0, 10] = 2001
+    assert env.check_state() == [1] * 8
+    cm = crl.ZoneVecEnv('ColourMatch-v0', 64)
+    cm.reset()
+    assert cm.check_state() == [0] * 8
+    cm.cooldown[1, 0] = 151
+    cm.aux[2, 3] = torch.tensor(3 << 16, dtype=torch.int32).view(torch.float32)   # colour code 3 does not exist
+    assert cm.check_state()[4] == 2

@@ -30,5 +30,28 @@ for env_id in ('PointTSP-v0', 'PointTTSP-v0', 'ColourMatch-v0', 'PointTSP-v1'):
     env.set_qpos_qvel(rs.uniform(-1, 1, (5, 3)), rs.uniform(-1, 1, (5, 3)), env_ids=[0, 7, 33, 299, 300])
     qp, qv = env.get_qpos_qvel()
     env.physics_substeps(torch.zeros(B, 2, device='cuda'), 3)
+    for t in range(6):                       # chained back-to-back steps (per-warp ticket / stamp ordering)
+        env.step_random(action_seed=9, chained=True)
+    env.step_host(np.zeros((B, 2), np.float32))                       # full copy: the host mirror becomes valid
+    env.step_host(np.zeros((B, 2), np.float32))                       # delta rows + zero-copy obs / result
+    env.step_host(np.zeros((B, 2), np.float32), zero_copy=False)      # delta rows, staged copies
     torch.cuda.synchronize()
     print(env_id, 'ok', env.counters())
+
+# goal-conditioned variant + WaitWrapper + rollout slots + GAE
+from combinatorial_rl_tasks_b200.rollout import Rollout  # noqa: E402
+env = crl.ZoneVecEnv('PointTTSP-v3', 300, wait=True)
+env.seed(3)
+env.cfg.num_steps = 9
+ro = Rollout(env, 6)
+ro.begin()
+for t in range(6):
+    env.set_goal(torch.where(env.needs_goal(), torch.full((300,), t % 15, dtype=torch.int32, device='cuda'),
+                             torch.full((300,), -1, dtype=torch.int32, device='cuda')))
+    ro.step(t, torch.zeros(300, 2, device='cuda'), torch.zeros(300, device='cuda'))
+ro.finish(torch.zeros(300, device='cuda'))
+env.get_goal(); env.available_goals()
+for t in range(8):
+    env.step_no_reset(torch.zeros(300, 2, device='cuda'))            # envs park as they finish
+torch.cuda.synchronize()
+print('PointTTSP-v3 ok', env.counters())
