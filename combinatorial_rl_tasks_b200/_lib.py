@@ -37,7 +37,8 @@ class CrlState(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in ('pose', 'aux', 'zone_xy', 'zone_tmax', 'cooldown', 'seed',
                                         'episode', 'origin', 'counters', 'next_zone_xy', 'next_task',
                                         'next_origin', 'next_seed', 'next_ready', 'stamp',
-                                        'prefetch_work', 'row_list', 'goal')]
+                                        'prefetch_work', 'row_list', 'goal', 'bank_zone_xy', 'bank_origin',
+                                        'bank_task')]
 
 
 class CrlOut(ctypes.Structure):

@@ -67,6 +67,9 @@ struct KParams {
   uint32_t* stamp;
   uint32_t* row_list;
   int32_t* goal;
+  const float2* bank_zone_xy;
+  const float4* bank_origin;
+  const uint32_t* bank_task;
   // io
   const float2* actions;
   float4* obs;
@@ -324,7 +327,24 @@ __device__ __noinline__ void warp_reset(const KParams& p, unsigned dm, int lane,
   if (mine) {
     episode = p.episode[e];
     chosen = choose_seed(p, e, episode);
-    if (p.next_ready) {
+    if (p.bank_zone_xy && chosen >= p.min_seed && chosen <= p.max_seed) {
+      // fixed task set: the map of seed `chosen` is entry chosen - min_seed of the layout bank
+      // (a few KB, cache resident): copy it, nothing to sample
+      const size_t k = (size_t)(chosen - p.min_seed);
+      const float4 o = p.bank_origin[k];
+      fast = true;
+      x0 = o.x; y0 = o.y; rot0 = o.z;
+#pragma unroll
+      for (int i = 0; i < N; ++i) { const float2 z = p.bank_zone_xy[k * N + i]; zp[(size_t)i * B] = z; out.zone[i] = z; }
+      if (TASK == CRL_TASK_TTSP) {
+#pragma unroll
+        for (int j = 0; j < (N + 1) / 2; ++j) {
+          const uint32_t t = p.bank_task[k * ((N + 1) / 2) + j];
+          tp[(size_t)j * B] = t; out.tmax[j] = t;
+        }
+      }
+      if (TASK == CRL_TASK_CM) col_word = p.bank_task[k];
+    } else if (p.next_ready) {
       // reset number n takes slot n & 1: one batch of independent loads, then straight out again
       const size_t sb = (size_t)(episode & 1u) * (size_t)B;
       slot_flag = p.next_ready + sb + e;
@@ -1325,6 +1345,14 @@ static int fill_params(const CrlConfig* c, const CrlState* st, const CrlOut* out
   p.stamp = st->stamp;
   p.row_list = st->row_list;
   p.goal = st->goal;
+  if (st->bank_zone_xy || st->bank_origin || st->bank_task) {
+    if (!st->bank_zone_xy || !st->bank_origin || (c->task != CRL_TASK_TSP && !st->bank_task)) return CRL_ERR_NULL;
+    if (c->max_seed < c->min_seed) return CRL_ERR_CONFIG;              // the bank is indexed by seed - min_seed
+    if (!aligned16(st->bank_origin) || (reinterpret_cast<uintptr_t>(st->bank_zone_xy) & 7u)) return CRL_ERR_ALIGN;
+    p.bank_zone_xy = reinterpret_cast<const float2*>(st->bank_zone_xy);
+    p.bank_origin = reinterpret_cast<const float4*>(st->bank_origin);
+    p.bank_task = st->bank_task;
+  }
   if (out) {
     if (!out->obs || !out->zone_obs || !out->result) return CRL_ERR_NULL;
     if (!aligned16(out->obs) || !aligned16(out->zone_obs)) return CRL_ERR_ALIGN;

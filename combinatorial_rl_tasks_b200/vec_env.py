@@ -64,7 +64,7 @@ class _EnvView:
 
 class ZoneVecEnv:
     def __init__(self, env_id, num_envs, device='cuda:0', seed_mode='increment', min_seed=1, max_seed=100,
-                 env_offset=0, auto_reset=True, prefetch_every=32, wait=False, prefetch_warps=0):
+                 env_offset=0, auto_reset=True, prefetch_every=32, wait=False, prefetch_warps=0, layout_bank=None):
         if not torch.cuda.is_available():
             raise RuntimeError('ZoneVecEnv needs a CUDA device (sm_100a); there is no CPU fallback')
         self.lib = _lib.load()
@@ -137,6 +137,8 @@ class ZoneVecEnv:
                                    next_seed=ptr(self.next_seed), next_ready=ptr(self.next_ready),
                                    stamp=ptr(self.stamp), prefetch_work=ptr(self._prefetch_work),
                                    row_list=ptr(self._row_list), goal=ptr(self.goal))
+        if layout_bank is not None:
+            self._install_layout_bank(layout_bank, seed_mode, min_seed, max_seed)
         self.bind_outputs(z(B, 8), z(B, N, Z), z(B, 8, dtype=torch.uint8), z(B))
         self._actions_dev = z(B, 2)
         self._host = None
@@ -150,6 +152,37 @@ class ZoneVecEnv:
         self.seed(torch.arange(B, dtype=torch.int64) + env_offset)
 
     # -- plumbing ------------------------------------------------------------------
+    def _install_layout_bank(self, bank, seed_mode, min_seed, max_seed):
+        """The maps of a fixed task set (CrlState.bank_*): ``bank`` = dict with xy0 (K,2), rot0 (K,),
+        zone_xy (K,N,2) and, per task, zone_max_steps (K,N) / colours (K,N), entry k being the map
+        of seed ``min_seed + k`` -- e.g. what the reference's own ``env.seed(s); env.reset()`` builds
+        for each of make_train_env's ``num_training_tasks`` seeds.  Every reset then copies the
+        entry of its seed: the device runs on exactly those maps and needs no sampler."""
+        N, spec = self.spec.num_zones, self.spec
+        xy0 = np.asarray(bank['xy0'], dtype=np.float64).reshape(-1, 2)
+        K = xy0.shape[0]
+        if K != max_seed - min_seed + 1:
+            raise ValueError('a layout bank needs one entry per seed in [min_seed, max_seed]')
+        origin = np.zeros((K, 4), dtype=np.float32)
+        origin[:, :2], origin[:, 2] = xy0, np.asarray(bank['rot0'], dtype=np.float64).reshape(K)
+        zxy = np.asarray(bank['zone_xy'], dtype=np.float64).reshape(K, N, 2).astype(np.float32)
+        task = None
+        if spec.task == _lib.TASK_TTSP:
+            tm = np.clip(np.asarray(bank['zone_max_steps']).reshape(K, N), 0, 65535).astype(np.uint32)
+            tm = np.concatenate([tm, np.zeros((K, (-N) % 2), dtype=np.uint32)], axis=1)
+            task = (tm[:, 0::2] | (tm[:, 1::2] << 16)).astype(np.uint32).view(np.int32)
+        elif spec.task == _lib.TASK_CM:
+            col = np.asarray(bank['colours']).reshape(K, N).astype(np.uint32)
+            task = (col << (2 * np.arange(N, dtype=np.uint32))).sum(axis=1).astype(np.uint32).view(np.int32).reshape(K, 1)
+        dev = self.device
+        self._bank = (torch.from_numpy(zxy).to(dev).contiguous(), torch.from_numpy(origin).to(dev).contiguous(),
+                      None if task is None else torch.from_numpy(np.ascontiguousarray(task)).to(dev))
+        self.state.bank_zone_xy = self._bank[0].data_ptr()
+        self.state.bank_origin = self._bank[1].data_ptr()
+        self.state.bank_task = None if self._bank[2] is None else self._bank[2].data_ptr()
+        if seed_mode == 'fixed_range':
+            self.prefetch_every = 0               # every seed is in the bank: nothing to sample
+
     def prepare_outputs(self, obs, zone_obs, result, shaped_reward=None):
         """Validate a set of caller-owned output tensors once and return a binding that
         ``bind_outputs(binding=...)`` installs with a few attribute stores (rollout.py prepares
@@ -232,7 +265,7 @@ class ZoneVecEnv:
         with self._guard():
             if layout is None:
                 m = None if mask is None else self._as_dev(mask, torch.uint8)
-                if mask is None and not torch.cuda.is_current_stream_capturing():
+                if mask is None and self.state.bank_zone_xy is None and not torch.cuda.is_current_stream_capturing():
                     # a full reset: sample every layout with the one-lane-per-env sampler first
                     # (all SMs, nothing else is running), then crl_reset only copies
                     self.prefetch(torch.cuda.current_stream(self.device), warps_per_sm=16)
@@ -468,7 +501,7 @@ class ZoneVecEnv:
         self.stamp.zero_()
         self._chain_ok = False
         self._mirror_ok = False
-        if self.prefetch_every:
+        if self.prefetch_every and self.state.bank_zone_xy is None:
             self.prefetch(torch.cuda.current_stream(self.device))
 
     def set_qpos_qvel(self, qpos, qvel, env_ids=None):

@@ -171,6 +171,16 @@ typedef struct CrlState {
                            whose zone_obs row changed in the step, words 4.. = their indices */
   int32_t* goal;        /* int32[B]; optional (CRL_STEP_GOALS): goal_zone of each env, -1 = None.
                            Every reset clears it */
+  /* optional LAYOUT BANK (all three NULL = none): the maps of the K = max_seed - min_seed + 1
+   * seeds min_seed..max_seed, e.g. exported from the reference (make_train_env's
+   * num_training_tasks maps, make_env.py:3-18; evaluate.py's seeds).  A reset that runs with a
+   * seed s in that range COPIES entry s - min_seed instead of sampling (in either seed mode;
+   * seeds outside the range are sampled as usual), so the device trains / evaluates on exactly
+   * the reference's maps, and with CRL_SEED_FIXED_RANGE no sampler is needed at all. */
+  const float* bank_zone_xy;   /* float2[K][N] zone centres */
+  const float* bank_origin;    /* float4[K]: x0, y0, rot0, 0 */
+  const uint32_t* bank_task;   /* TTSP: uint32[K][ceil(N/2)] timeouts packed like zone_tmax;
+                                  ColourMatch: uint32[K] colour codes, 2 bits per zone; TSP: NULL */
 } CrlState;
 
 typedef struct CrlResult {

@@ -102,11 +102,14 @@ def record_vector(env_id, n_envs, n_steps):
     rs = np.random.RandomState(5)
     obs = [e.reset() for e in es]
     layouts = [[snapshot_layout(e)] for e in es]
-    rec = {k: [] for k in ('actions', 'obs', 'zone_obs', 'reward', 'done', 'goal_met')}
+    rec = {k: [] for k in ('actions', 'obs', 'zone_obs', 'reward', 'done', 'goal_met', 'qpos', 'qvel')}
     rec['obs'].append(np.array([o['obs'] for o in obs]))
     rec['zone_obs'].append(np.array([o['zone_obs'] for o in obs]))
     for t in range(n_steps):
         acts, row = [], []
+        # physics state each env steps FROM (after a reset: the new episode's), for teacher forcing
+        rec['qpos'].append(np.array([e.unwrapped.data.qpos.copy() for e in es]))
+        rec['qvel'].append(np.array([e.unwrapped.data.qvel.copy() for e in es]))
         for i, e in enumerate(es):
             a = policy(env_id, obs[i], rs, 'greedy', t)
             o, r, d, info = e.step(a)

@@ -275,3 +275,59 @@ def test_integration_md_ctypes_stub_runs(crl):
     assert np.all(obs[:, 0] == np.float32(1999 / 2000)) and not res[:, 4].any()
     zo = ns['mem']['zone_obs'].view(torch.float32).reshape(B, 15, 6).cpu().numpy()
     assert np.all(zo[:, :, 5] == 0.25) and np.all(np.abs(zo[:, :, :2]) <= 2.45 / 3 + 1e-6)
+
+
+VECTORS = sorted(glob.glob(os.path.join(GOLDEN, '*_vector.npz')))
+
+
+@pytest.mark.parametrize('path', VECTORS, ids=os.path.basename)
+def test_vector_fixture_with_in_kernel_auto_reset(crl, path):
+    """The REAL reference ParallelEnv trace (penv.py worker protocol over make_train_env envs,
+    recorded by gen_golden.py: several episodes per env, auto-reset on done) replayed through
+    crl_step's in-kernel auto-reset: the maps of every episode come from a layout bank holding
+    the reference's own layouts, the physics state is forced to the recorded qpos/qvel before
+    every step.  reward / done / goal_met of the finished episode and the FIRST observation of
+    the next one must come out of the same call, exactly as penv.py:7-11 returns them."""
+    g = np.load(path)
+    env_id = str(g['env_id'])
+    task = ze.TASK_OF_ENV_ID[env_id]
+    n = g['actions'].shape[1]
+    N = ze.NUM_ZONES[task]
+    stride = 100                                             # env i, episode j -> bank entry 100 i + j
+    K = stride * n
+    bank = {'xy0': np.zeros((K, 2)), 'rot0': np.zeros(K), 'zone_xy': np.zeros((K, N, 2)),
+            'zone_max_steps': np.zeros((K, N), dtype=np.int64), 'colours': np.zeros((K, N), dtype=np.int64)}
+    for i in range(n):
+        for j in range(int(g['n_layouts'][i])):
+            for k in bank:
+                if f'layout_{i}_{j}_{k}' in g.files:
+                    bank[k][stride * i + j] = g[f'layout_{i}_{j}_{k}']
+    env = crl.ZoneVecEnv(env_id, n, seed_mode='increment', min_seed=0, max_seed=K - 1, layout_bank=bank)
+    env.seed(torch.arange(n, dtype=torch.int64) * stride)
+    obs = env.reset()
+    for i in range(n):
+        check_obs(task, obs['obs'][i].cpu().numpy(), obs['zone_obs'][i].cpu().numpy(), g['obs'][0][i], g['zone_obs'][0][i], ('reset', i))
+    acts, qpos, qvel = (torch.from_numpy(g[k]).cuda() for k in ('actions', 'qpos', 'qvel'))
+    T = len(g['actions'])
+    rec = {k: [] for k in ('obs', 'zobs', 'res')}
+    for t in range(T):
+        env.set_qpos_qvel(qpos[t], qvel[t])
+        o, r, d, info = env.step(acts[t])                    # auto-reset inside the call
+        rec['obs'].append(o['obs'].clone()); rec['zobs'].append(o['zone_obs'].clone()); rec['res'].append(env.result.clone())
+    res = torch.stack(rec['res']).cpu().numpy()              # (T, n, 8)
+    assert np.array_equal(res[:, :, 4].astype(bool), g['done']), 'done flags'
+    assert np.array_equal(res[:, :, 5].astype(bool), g['goal_met']), 'goal_met'
+    assert int(g['done'].sum()) >= 3
+    reward = res.view(np.float32)[:, :, 0].astype(np.float64)
+    assert np.max(np.abs(reward - g['reward'])) <= REWARD_ATOL
+    obs_g, zobs_g = torch.stack(rec['obs']).cpu().numpy(), torch.stack(rec['zobs']).cpu().numpy()
+    resets = np.argwhere(g['done'])
+    check_at = set(range(0, T, 9)) | {int(t) for t, _ in resets} | {int(t) + 1 for t, _ in resets if t + 1 < T}
+    for t in sorted(check_at):
+        for i in range(n):
+            check_obs(task, obs_g[t, i], zobs_g[t, i], g['obs'][t + 1][i], g['zone_obs'][t + 1][i], (t, i))
+    for t, i in resets:                                      # the observation returned WITH done is the new episode's first
+        assert obs_g[t, i, 0] == 1.0 and not obs_g[t, i, 5:].any(), (t, i)
+    assert np.array_equal(env.episode.cpu().numpy(), g['n_layouts'])
+    c = env.counters()
+    assert c['episodes'] == g['done'].sum() and c['resets_inline'] == 0

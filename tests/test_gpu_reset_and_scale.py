@@ -491,3 +491,50 @@ def test_check_state_detects_corruption(crl):
     cm.cooldown[1, 0] = 151
     cm.aux[2, 3] = torch.tensor(3 << 16, dtype=torch.int32).view(torch.float32)   # colour code 3 does not exist
     assert cm.check_state()[4] == 2
+
+
+@pytest.mark.parametrize('env_id', TASKS)
+def test_layout_bank_reproduces_the_reference_maps(crl, env_id):
+    """A fixed task set exported from the reference side (here: the oracle's numpy-legacy
+    Engine.reset for seeds 1..12, as make_train_env(num_training_tasks=12) would build them) is
+    installed as a layout bank; every reset -- the first one and every in-step auto-reset -- must
+    land on exactly the map of the seed it ran with, timeouts / colours included."""
+    from oracle import zone_env as ze
+    task = ze.TASK_OF_ENV_ID[env_id]
+    K, B = 12, 700
+    bank = {'xy0': [], 'rot0': [], 'zone_xy': [], 'zone_max_steps': [], 'colours': []}
+    for s in range(1, K + 1):
+        e = ze.ZoneTaskEnv(task)
+        e.seed(s)
+        e.reset()
+        bank['xy0'].append(e.xy0); bank['rot0'].append(e.rot0); bank['zone_xy'].append(e.zone_xy)
+        bank['zone_max_steps'].append(e.zone_max_steps if task == ze.TTSP else np.zeros(e.N, int))
+        bank['colours'].append(e.colours if task == ze.CM else np.zeros(e.N, int))
+    bank = {k: np.array(v) for k, v in bank.items()}
+    env = crl.ZoneVecEnv(env_id, B, seed_mode='fixed_range', min_seed=1, max_seed=K, layout_bank=bank)
+    env.cfg.num_steps = 7
+    seen = set()
+    env.reset()
+    for t in range(40):
+        if t:
+            env.step_random(action_seed=4)
+        torch.cuda.synchronize()
+        seeds = env.seeds.cpu().numpy() - 1                  # Engine.reset left seed + 1 behind
+        k = seeds - 1
+        seen |= set(int(x) for x in k)
+        assert k.min() >= 0 and k.max() < K
+        assert np.array_equal(env.zone_xy.cpu().numpy().transpose(1, 0, 2), bank['zone_xy'][k].astype(np.float32)), t
+        o = env.origin.cpu().numpy()
+        assert np.array_equal(o[:, :2], bank['xy0'][k].astype(np.float32)) and np.array_equal(o[:, 2], bank['rot0'][k].astype(np.float32))
+        if task == ze.TTSP:
+            assert np.array_equal(tmax_of(env), bank['zone_max_steps'][k]), t
+        if task == ze.CM and t % 7 == 0:                     # right after a reset the colours are the bank's
+            col = (bits_of(env)[:, None] >> 16 >> (2 * np.arange(6))) & 3
+            assert np.array_equal(col, bank['colours'][k]), t
+    assert seen == set(range(K))
+    c = env.counters()
+    assert c['resets_inline'] == 0 and c['resets_prefetched'] == B * (1 + 40 // 7)
+    env.cfg.num_steps = 2000                                 # the bank's timeouts belong to 2000-step episodes
+    assert env.check_state() == [0] * 8
+    with pytest.raises(ValueError):
+        crl.ZoneVecEnv(env_id, 8, seed_mode='fixed_range', min_seed=1, max_seed=K + 1, layout_bank=bank)
