@@ -153,10 +153,29 @@ def run_ours(args):
     R = max(2, -(-2 * L2_BYTES // (B * step_bytes)))             # ring > 2x L2
     K = max(1, args.steps)
     W = max(3, args.warmup)
+    bank_kw = {}
+    if args.bank:
+        # the training configuration of the reference: a fixed set of K maps (make_train_env), here
+        # K maps drawn by the device sampler itself and installed as a layout bank
+        helper = crl.ZoneVecEnv(args.env, args.bank, device=dev)
+        helper.seed(1)
+        helper.reset()
+        torch.cuda.synchronize()
+        N = helper.spec.num_zones
+        o = helper.origin.cpu().numpy()
+        bank = {'xy0': o[:, :2], 'rot0': o[:, 2], 'zone_xy': helper.zone_xy.cpu().numpy().transpose(1, 0, 2)}
+        if helper.zone_tmax is not None:
+            w = helper.zone_tmax.cpu().numpy().astype(np.int64) & 0xffffffff
+            bank['zone_max_steps'] = np.stack([w & 0xffff, w >> 16], 1).reshape(-1, w.shape[1])[:N].T
+        if helper.cooldown is not None:
+            bits = helper.aux[:, 3].view(torch.int32).cpu().numpy().astype(np.int64) & 0xffffffff
+            bank['colours'] = (bits[:, None] >> 16 >> (2 * np.arange(N))) & 3
+        bank_kw = dict(seed_mode='fixed_range', min_seed=1, max_seed=args.bank, layout_bank=bank)
+        del helper
     envs = []
     for r in range(R):
         e = crl.ZoneVecEnv(args.env, B, device=dev, env_offset=(rank * R + r) * B,
-                           prefetch_every=args.prefetch_every, prefetch_warps=args.prefetch_warps)
+                           prefetch_every=args.prefetch_every, prefetch_warps=args.prefetch_warps, **bank_kw)
         for kv in args.cfg:                                        # diagnostic overrides, e.g. --cfg beta_a=1000
             k, v = kv.split('=')
             setattr(e.cfg, k, type(getattr(e.cfg, k))(float(v)))
@@ -192,7 +211,7 @@ def run_ours(args):
         # slots are topped up on each replica's side stream (concurrent with the steps)
         for i in range(n_steps // R):
             graph.replay()
-            if args.prefetch_every and i % args.prefetch_every == args.prefetch_every - 1:
+            if args.prefetch_every and not args.bank and i % args.prefetch_every == args.prefetch_every - 1:
                 for e in envs:
                     e.prefetch()
                 launches['prefetch'] += R * (2 if envs[0].spec.task == _lib.TASK_TSP else 3)
@@ -298,6 +317,7 @@ def run_ours(args):
         'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': f'{args.env}, {B} batched envs per launch, random actions, auto-reset {"off" if args.no_auto_reset else "on"}',
                    'prefetch_every': args.prefetch_every, 'chained_steps': bool(args.chained),
+                   'layout_bank': args.bank or None,
                    'envs_per_gpu_per_launch': B, 'ring_replicas': R,
                    'l2': f'ring of {R} independent {B}-env replicas ({R * B * step_bytes / 1e6:.0f} MB touched per '
                          f'cycle) > 2x the 126 MB L2, so every launch reads HBM',
@@ -344,6 +364,8 @@ def main():
                          'wait; -1: chained when a launch is at most a wave or two (<= 131072 envs)')
     ap.add_argument('--prefetch-every', type=int, default=32,
                     help='top up the next-layout slots every N ring cycles (0: resets sample inline)')
+    ap.add_argument('--bank', type=int, default=0,
+                    help='fixed task set of K maps (make_train_env): resets copy from a layout bank, no sampler')
     ap.add_argument('--cfg', action='append', default=[], help='diagnostic: override a CrlConfig field, key=value')
     ap.add_argument('--prefetch-warps', type=int, default=0, help='background sampler warps per SM (0: default)')
     args = ap.parse_args()
