@@ -207,14 +207,14 @@ def run_ours(args):
     launches = {'prefetch': 0}
 
     def run(n_steps):
-        # one graph replay = one step of every ring replica; every --prefetch-every cycles the next-layout
+        # one graph replay = one step of every ring replica; at most every --prefetch-every steps the next-layout
         # slots are topped up on each replica's side stream (concurrent with the steps)
         for i in range(n_steps // R):
             graph.replay()
-            if args.prefetch_every and not args.bank and i % args.prefetch_every == args.prefetch_every - 1:
-                for e in envs:
-                    e.prefetch()
-                launches['prefetch'] += R * (2 if envs[0].spec.task == _lib.TASK_TSP else 3)
+            if not args.bank:
+                for e in envs:                                     # the envs' own sampler cadence (ZoneVecEnv.tick)
+                    if e.tick():
+                        launches['prefetch'] += 2 if e.spec.task == _lib.TASK_TSP else 3
         if n_steps % R:
             tails[n_steps % R].replay()
 
@@ -316,7 +316,7 @@ def run_ours(args):
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': f'{args.env}, {B} batched envs per launch, random actions, auto-reset {"off" if args.no_auto_reset else "on"}',
-                   'prefetch_every': args.prefetch_every, 'chained_steps': bool(args.chained),
+                   'prefetch_every': args.prefetch_every, 'prefetch_cadence': 'adaptive: interval doubles (up to 16x) while a round finds no empty slot', 'chained_steps': bool(args.chained),
                    'layout_bank': args.bank or None,
                    'envs_per_gpu_per_launch': B, 'ring_replicas': R,
                    'l2': f'ring of {R} independent {B}-env replicas ({R * B * step_bytes / 1e6:.0f} MB touched per '

@@ -74,7 +74,10 @@ class ZoneVecEnv:
         self.device = torch.device(device)
         self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.auto_reset = auto_reset
-        self.prefetch_every = prefetch_every      # 0: never park next layouts (resets sample inline)
+        # top up the parked next layouts every `prefetch_every` steps at most (0: never, resets then
+        # sample inline); the interval stretches up to 16x while the sampler finds nothing to do
+        self.prefetch_every = prefetch_every
+        self._pf_interval, self._pf_due = max(prefetch_every, 1), max(prefetch_every, 1)
         self.prefetch_warps = prefetch_warps      # background sampler warps per SM (0: library default)
         # WaitWrapper semantics (make_train_env(hier=True), wrappers.py:29-54): under
         # step_no_reset an env whose episode ended is parked until it is reset
@@ -113,6 +116,7 @@ class ZoneVecEnv:
         self.next_seed = z(2, B, dtype=torch.int64)
         self.next_ready = z(2, B, dtype=torch.int32)
         self._prefetch_work = z(1 + 2 * B, 4, dtype=torch.int32)
+        self._pf_found = torch.zeros(1, dtype=torch.int32).pin_memory()   # empty slots the last round found
         self._side = torch.cuda.Stream(device=dev)
         # per-warp completion stamps of crl_step (CRL_STEP_CHAINED)
         self.stamp = z(2, (B + 31) // 32, dtype=torch.int32)
@@ -240,6 +244,7 @@ class ZoneVecEnv:
         self.seeds.copy_(self._as_dev(seeds, torch.int64))
         self.episode.zero_()
         self.next_ready.zero_()          # parked layouts were drawn for the old seeds
+        self._pf_interval = self._pf_due = max(self.prefetch_every, 1)
         self._chain_ok = False
         self._mirror_ok = False
 
@@ -256,7 +261,28 @@ class ZoneVecEnv:
         with self._guard():
             _lib.check(self.lib.crl_prefetch_layouts(self.cfg, self.state, warps_per_sm or self.prefetch_warps,
                                                      ctypes.c_void_p(stream.cuda_stream)))
+            if not torch.cuda.is_current_stream_capturing():
+                with torch.cuda.stream(stream):           # how much there was to do, read by tick() later
+                    self._pf_found.copy_(self._prefetch_work[0, :1], non_blocking=True)
         self.gpu_launches += 2 if self.spec.task == _lib.TASK_TSP else 3
+
+    def tick(self, steps=1):
+        """Cadence of the background sampler, called once per step (step() does; a caller that
+        replays captured steps calls it itself).  A round is launched when `prefetch_every` steps
+        have passed -- stretched up to 16x while the previous rounds found no empty slot (PointTSP
+        under random actions resets once in 2000 steps), back to the base interval as soon as one
+        finds work.  The count read here may be one round old; an env whose slot is empty when it
+        needs it samples inline, so the cadence never affects results."""
+        if not self.prefetch_every:
+            return False
+        self._pf_due -= steps
+        if self._pf_due > 0:
+            return False
+        found = int(self._pf_found[0])
+        self._pf_interval = min(2 * self._pf_interval, 16 * self.prefetch_every) if found == 0 else self.prefetch_every
+        self._pf_due = self._pf_interval
+        self.prefetch()
+        return True
 
     def reset(self, layout=None, mask=None, env_ids=None):
         """Engine.reset of all envs (or those in ``mask``).  ``layout`` switches to the
@@ -316,9 +342,8 @@ class ZoneVecEnv:
         self.gpu_launches += 1
         self._chain_ok = bool(chained)
         self._mirror_ok = False
-        if (self.prefetch_every and self._step_index % self.prefetch_every == 0
-                and not torch.cuda.is_current_stream_capturing()):
-            self.prefetch()
+        if self.prefetch_every and not torch.cuda.is_current_stream_capturing():
+            self.tick()
         return self._obs_dict(), self.reward, self.done, self._info()
 
     def step(self, actions):
