@@ -26,14 +26,24 @@ from .vec_env import ZoneVecEnv, _EnvView
 
 
 class ParallelEnv:
-    def __init__(self, env_id, num_envs, num_training_tasks=100, hier=False, device='cuda:0', **kw):
+    def __init__(self, env_id, num_envs=None, num_training_tasks=100, hier=False, device='cuda:0', **kw):
         """``ParallelEnv([make_train_env(env_id, hier, num_training_tasks, rng_seed=...) for _ in
         range(num_envs)])`` (main/scripts/train_ppo.py:108-113, make_env.py:3-18): every reset
-        re-seeds uniformly in [1, num_training_tasks]; ``hier=True`` wraps in WaitWrapper."""
+        re-seeds uniformly in [1, num_training_tasks]; ``hier=True`` wraps in WaitWrapper.
+        The first argument may also be that very list, built with this module's make_train_env /
+        make_test_env / make_fixed_env: the batch then takes its size from the list and its task,
+        seeding rule and wrapper from the first element (the reference's lists are homogeneous)."""
+        if isinstance(env_id, (list, tuple)):
+            first, num_envs = env_id[0], len(env_id)
+            env_id, hier, device = first.env_id, first.hier, first.device
+            kw = dict(first.seeding, **kw)
         kw.setdefault('seed_mode', 'fixed_range')
         kw.setdefault('min_seed', 1)
         kw.setdefault('max_seed', num_training_tasks)
+        first_seed = kw.pop('first_seed', None)
         self.vec = ZoneVecEnv(env_id, num_envs, device=device, wait=hier, **kw)
+        if first_seed is not None:
+            self.vec.seed(int(first_seed))
         self.envs = [_EnvView(self.vec, i) for i in range(num_envs)]   # the probes callers make on penv.envs[i]
         self.observation_space = self.vec.observation_space
         self.action_space = self.vec.action_space
@@ -102,3 +112,79 @@ class ParallelEnv:
 
     def render(self):
         raise NotImplementedError
+
+
+class GymEnv:
+    """One env with the reference's single-env surface -- ``seed(s)``, ``reset() -> obs``,
+    ``step(a) -> (obs, float, bool, info)`` without auto-reset (evaluate.py:48-60), the probes
+    ``observation_space / action_space / unwrapped.num_cities`` -- as returned by the factories
+    below.  Cheap to construct (no GPU work until the first reset), so a list of them can be
+    handed to ParallelEnv exactly as train_ppo.py:108-113 does; used on its own it is a batch of
+    one."""
+
+    def __init__(self, env_id, hier, seeding, device='cuda:0'):
+        from .config import ENV_SPECS
+        from .spaces import Box, Dict
+        self.env_id, self.hier, self.seeding, self.device = env_id, hier, dict(seeding), device
+        spec = ENV_SPECS[env_id]
+        N, Z = spec.num_zones, spec.zone_dim
+        self.observation_space = Dict({'zone_obs': Box(-np.inf, np.inf, (N, Z)), 'obs': Box(-np.inf, np.inf, (8,))})
+        self.action_space = Box(-1.0, 1.0, (2,))
+        self.num_cities, self.goal_dim = N, 2
+        self._pe = None
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def _batch(self):
+        if self._pe is None:
+            self._pe = ParallelEnv([self])
+        return self._pe
+
+    def seed(self, seed):
+        """Engine.seed: the next reset builds the map of seed + 1 (and, under a FixedSeedsWrapper,
+        re-seeds first)."""
+        self.seeding['first_seed'] = int(seed)
+        if self._pe is not None:
+            self._pe.vec.seed(int(seed))
+
+    def reset(self):
+        return self._batch().reset()[0]
+
+    def step(self, action):
+        obs, reward, done, info = self._batch().step_no_reset([action])
+        return obs[0], reward[0], done[0], info[0]
+
+    @property
+    def goal_zone(self):
+        return self._batch().envs[0].goal_zone
+
+    def set_goal(self, goal):
+        self._batch().set_goal(0, goal)
+
+    def get_goal(self):
+        return self._batch().get_goal(0)
+
+    def get_available_goals(self):
+        return self._batch().available_goals(0)
+
+    def noop_obs(self):
+        return self._batch().envs[0].noop_obs()
+
+
+def make_train_env(env_name, hier=False, num_training_tasks=100, rng_seed=0, device='cuda:0'):
+    """make_env.make_train_env (make_env.py:3-18): FixedSeedsWrapper over [1, num_training_tasks].
+    ``rng_seed`` only decorrelated the per-process seed choosers; here the chooser is keyed by
+    the env index."""
+    return GymEnv(env_name, hier, dict(seed_mode='fixed_range', min_seed=1, max_seed=num_training_tasks), device)
+
+
+def make_test_env(env_name, hier=False, seed=1000, device='cuda:0'):
+    """make_env.make_test_env (:20-35): seeded once, every reset moves on to the next seed."""
+    return GymEnv(env_name, False, dict(seed_mode='increment', first_seed=seed), device)
+
+
+def make_fixed_env(env_name, hier=False, seed=1000, env_seed=0, device='cuda:0'):
+    """make_env.make_fixed_env (:37-51): the same map (seed ``env_seed``) at every reset."""
+    return GymEnv(env_name, False, dict(seed_mode='fixed_range', min_seed=env_seed, max_seed=env_seed), device)

@@ -311,3 +311,40 @@ def test_parallel_env_compat_has_the_reference_protocol(crl):
     o, r, d, info = pe.step([np.zeros(2)] * B)                 # auto-reset variant: nobody is parked after reset
     assert not any(d) and all(i_['need_next_goal'] for i_ in info)   # reset cleared the goals
     assert first[0]['obs'][0] == 1.0 and o[0]['obs'][0] == np.float32(1999 / 2000)
+
+
+def test_reference_factories_and_single_env_api(crl):
+    """make_train_env / make_test_env / make_fixed_env (make_env.py:3-51) and the single-env gym
+    surface evaluate.py:48-60 drives: same call shapes, and the seeding rules behind them."""
+    envs = [crl.make_train_env('ColourMatch-v0', hier=False, num_training_tasks=4, rng_seed=1 + 10000 * i) for i in range(5)]
+    assert envs[0].observation_space.spaces['zone_obs'].shape == (6, 7) and envs[0].action_space.shape == (2,)
+    pe = crl.ParallelEnv(envs)                                # exactly what base.py:50 does with the list
+    obs = pe.reset()
+    assert len(obs) == 5 and set((pe.vec.seeds.cpu().numpy() - 1).tolist()) <= {1, 2, 3, 4}
+    o, r, d, info = pe.step([np.zeros(2)] * 5)
+    assert len(o) == 5 and info[0]['cost'] == 0
+    # one fixed map, as evaluate.py:48-56 builds it; step() does not auto-reset
+    single = crl.make_fixed_env('PointTSP-v0', hier=False, seed=3, env_seed=1000007)
+    first = single.reset()
+    z0 = first['zone_obs'].copy()
+    assert first['obs'].shape == (8,) and first['obs'][0] == 1.0
+    for t in range(5):
+        o, r, d, info = single.step(np.array([0.5, -0.2]))
+        assert isinstance(r, float) and isinstance(d, bool) and info == {'cost': 0} and o['zone_obs'].shape == (15, 6)
+    assert o['obs'][0] == np.float32(1995 / 2000)
+    assert np.array_equal(single.reset()['zone_obs'], z0)     # FixedSeedsWrapper(min = max = env_seed): same map again
+    # make_test_env: seeded once, the next reset moves on to the next seed; its first map is make_fixed_env's of that seed
+    test = crl.make_test_env('PointTSP-v0', seed=1000007)
+    a = test.reset()['zone_obs'].copy()
+    b = test.reset()['zone_obs'].copy()
+    assert np.array_equal(a, z0) and not np.array_equal(a, b)
+    nxt = crl.make_fixed_env('PointTSP-v0', env_seed=1000008)
+    assert np.array_equal(nxt.reset()['zone_obs'], b)
+    # goal variant through the single-env surface (visualize_hier.py:60-72)
+    g = crl.make_fixed_env('PointTSP-v3', env_seed=5)
+    ob = g.reset()
+    assert g.goal_zone is None and g.get_available_goals().all()
+    g.set_goal(np.array(4))
+    assert g.goal_zone == 4 and np.allclose(g.get_goal(), ob['zone_obs'][4, :2], atol=1e-6)
+    o, r, d, info = g.step(np.zeros(2))
+    assert set(info) == {'cost', 'shaped_reward', 'need_next_goal'} and info['need_next_goal'] is False
