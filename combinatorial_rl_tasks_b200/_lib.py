@@ -14,7 +14,7 @@ TASK_TSP, TASK_TTSP, TASK_CM = 0, 1, 2
 SEED_INCREMENT, SEED_FIXED_RANGE = 0, 1
 STEP_AUTO_RESET, STEP_PHYSICS_ONLY, STEP_CHAINED, STEP_CHAIN_START, STEP_TRACK_ROWS = 1, 2, 4, 8, 16
 STEP_GOALS, STEP_WAIT, STEP_HOST_ZERO_COPY = 32, 64, 256
-ABI_VERSION = 4
+ABI_VERSION = 5
 NUM_PLANES = 22
 
 # every symbol include/crl_b200.h declares
@@ -30,7 +30,7 @@ class CrlConfig(ctypes.Structure):
                 ('env_offset', c_int32), ('min_seed', c_int64), ('max_seed', c_int64),
                 ('zone_size', c_double), ('time_saved_reward', c_double), ('beta_a', c_double),
                 ('beta_b', c_double), ('robot_keepout', c_double), ('zone_keepout', c_double),
-                ('extent', c_double)]
+                ('extent', c_double), ('initial_visited', c_uint32), ('reserved_', c_uint32)]
 
 
 class CrlState(ctypes.Structure):
@@ -38,7 +38,7 @@ class CrlState(ctypes.Structure):
                                         'episode', 'origin', 'counters', 'next_zone_xy', 'next_task',
                                         'next_origin', 'next_seed', 'next_ready', 'stamp',
                                         'prefetch_work', 'row_list', 'goal', 'bank_zone_xy', 'bank_origin',
-                                        'bank_task')]
+                                        'bank_task', 'fixed_layout')]
 
 
 class CrlOut(ctypes.Structure):

@@ -20,6 +20,42 @@ class TaskSpec:
     zone_keepout: float = 0.55     # ZoneEnvBase.py:50
     extent: float = 3.0            # ZoneEnvBase.py:41
     goals: bool = False            # goal-conditioned "next city" variant (zone-goals/envs/*_next_city_env.py)
+    # hard instances (TSP_hard_env.py over main/envs/__init__.py:52-81): Engine's robot_locations[0],
+    # robot_rot, zones_locations (the first len() zones) and zones_colours (5 = Yellow = starts visited,
+    # 6 = Cyan = a city; zone enum ZoneEnvBase.py:13-21)
+    robot_location: tuple = None
+    robot_rot: float = None
+    zones_locations: tuple = ()
+    zones_colours: tuple = None
+
+    @property
+    def initial_visited(self):
+        if self.zones_colours is None:
+            return 0
+        return sum(1 << i for i, c in enumerate(self.zones_colours) if c == 5)
+
+    def fixed_layout(self):
+        """The float32 (1 + N, 4) table of CrlState.fixed_layout, or None when nothing is fixed.
+        Raises if two fixed objects violate each other's keepout (the reference would then retry its
+        layout 10,000 times and fail, Engine.build_layout)."""
+        if self.robot_location is None and self.robot_rot is None and not self.zones_locations:
+            return None
+        import numpy as np
+        t = np.zeros((1 + self.num_zones, 4), dtype=np.float32)
+        if self.robot_location is not None:
+            t[0, :2], t[0, 3] = self.robot_location, 1
+        if self.robot_rot is not None:
+            t[0, 2] = self.robot_rot
+            t[0, 3] += 2
+        for i, xy in enumerate(self.zones_locations):
+            t[1 + i, :2], t[1 + i, 3] = xy, 1
+        keep = [self.robot_keepout] + [self.zone_keepout] * self.num_zones
+        pinned = [k for k in range(1 + self.num_zones) if t[k, 3] in (1, 3)]
+        for a in pinned:
+            for b in pinned:
+                if a < b and np.hypot(*(t[a, :2].astype(np.float64) - t[b, :2])) < keep[a] + keep[b]:
+                    raise ValueError(f'fixed objects {a} and {b} are closer than their keepouts allow')
+        return t
 
 
 # main/envs/__init__.py:7-14 (config_point), :16-23 (config_point_easy), :43-50 (config_point_colour)
@@ -35,3 +71,23 @@ ENV_SPECS = {
     'PointTTSP-v3': TaskSpec(_lib.TASK_TTSP, 15, 2000, 7, goals=True),
     'ColourMatch-v3': TaskSpec(_lib.TASK_CM, 6, 2000, 7, goals=True),
 }
+
+# Hard instances, main/envs/__init__.py:52-81 and :110-118 (TSPHardEnv, TSP_hard_env.py): a few cities
+# at fixed places, a fixed start, and distractor zones that are visited from the start.
+_ZONES_1 = ((-2.6, -1.6), (-0., -0.5), (1., 0.5), (1.8, 1.5), (2.6, 2.6))
+_ZONES_2 = ((-2.6, -2.6), (-2, -1.6), (2, 1))
+ENV_SPECS.update({
+    'PointTSP-v4': TaskSpec(_lib.TASK_TSP, 15, 1000, 6, robot_location=(-0.9, -0.9), robot_rot=-1.0,
+                            zones_locations=_ZONES_1, zones_colours=(6,) * 5 + (5,) * 10),
+    'PointTSP-v5': TaskSpec(_lib.TASK_TSP, 15, 250, 6, robot_location=(0.8, 0.8),
+                            zones_locations=_ZONES_2, zones_colours=(6,) * 3 + (5,) * 12),
+})
+# the zone-goals registrations of the same ids (zone-goals/envs/__init__.py:52-81, :111-119; TSPHardEnv over
+# TSPNextCityEnv, zone-goals/envs/TSP_hard_env.py): goal-conditioned, v5 with 300 steps
+ENV_SPECS.update({
+    'zone-goals/PointTSP-v4': TaskSpec(_lib.TASK_TSP, 15, 1000, 6, goals=True, robot_location=(-0.9, -0.9),
+                                       robot_rot=-1.0, zones_locations=_ZONES_1,
+                                       zones_colours=(6,) * 5 + (5,) * 10),
+    'zone-goals/PointTSP-v5': TaskSpec(_lib.TASK_TSP, 15, 300, 6, goals=True, robot_location=(0.8, 0.8),
+                                       zones_locations=_ZONES_2, zones_colours=(6,) * 3 + (5,) * 12),
+})

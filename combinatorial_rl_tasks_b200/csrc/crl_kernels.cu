@@ -70,6 +70,8 @@ struct KParams {
   const float2* bank_zone_xy;
   const float4* bank_origin;
   const uint32_t* bank_task;
+  const float4* fixed;          // fixed placements (CrlState.fixed_layout), or nullptr
+  uint32_t init_hi;             // visited mask an episode starts with (CrlConfig.initial_visited)
   // io
   const float2* actions;
   float4* obs;
@@ -200,7 +202,11 @@ __device__ uint32_t colour_draw(long long seed, uint32_t zone) {
 // function of (seed, j, k, L) -- half (j & 1) of Philox block (j >> 1, k, L) -- so the
 // outcome equals the sequential procedure's.
 // `placed` is warp-private shared scratch of N+1 float2 (16-byte aligned).
-template <int N>
+// FIXED: honour CrlState.fixed_layout (hard instances).  A template parameter, not a run-time test,
+// so that the step kernels of the registrations without fixed placements are compiled exactly as if
+// the feature did not exist (ptxas' register allocation of the whole step kernel moved with it:
+// TimedTSP 262,144 envs lost 9 % with the run-time test, profiles/r01_notes.md).
+template <int N, bool FIXED>
 __device__ void warp_layout(const KParams& p, long long seed, float2* placed, int lane) {
   const float ext = p.extent;
   constexpr int NP = (N + 2) / 2;                 // float4 pairs covering placed[0..N]
@@ -210,7 +216,13 @@ __device__ void warp_layout(const KParams& p, long long seed, float2* placed, in
 #pragma unroll 1
     for (int k = 0; k <= N && ok_layout; ++k) {
       const float keep = k == 0 ? p.robot_keepout : p.zone_keepout;
-      const float lo = -ext + keep, span = (ext - keep) - lo;
+      float lo_x = -ext + keep, lo_y = lo_x, span = (ext - keep) - lo_x;
+      // an object with a fixed location (CrlState.fixed_layout): a box of width 0 at that location,
+      // so every try is the location itself (x = lo + 0 * u) and one miss means a hundred
+      if (FIXED && p.fixed) {
+        const float4 fx = p.fixed[k];
+        if (fx.w == 1.f || fx.w == 3.f) { lo_x = fx.x; lo_y = fx.y; span = 0.f; }
+      }
       // everything placed so far, read once per object with independent 16-byte loads
       float4 pl[NP];
 #pragma unroll
@@ -221,8 +233,8 @@ __device__ void warp_layout(const KParams& p, long long seed, float2* placed, in
         const int j = base + lane;
         // try j = half (j & 1) of Philox block (j >> 1): one block serves two tries
         const U4 r = draw(seed, (uint32_t)(j >> 1), (uint32_t)k, attempt, kTagLayout);
-        const float x = __fadd_rn(lo, __fmul_rn(span, u01((j & 1) ? r.z : r.x)));
-        const float y = __fadd_rn(lo, __fmul_rn(span, u01((j & 1) ? r.w : r.y)));
+        const float x = __fadd_rn(lo_x, __fmul_rn(span, u01((j & 1) ? r.z : r.x)));
+        const float y = __fadd_rn(lo_y, __fmul_rn(span, u01((j & 1) ? r.w : r.y)));
         bool valid = j < 100;
 #pragma unroll
         for (int q = 0; q < N; ++q) {             // slots >= k hold stale values and are ignored
@@ -266,7 +278,7 @@ __device__ __forceinline__ long long choose_seed(const KParams& p, int e, uint32
 // heading with chosen + 1 (Engine.reset: self._seed += 1).  On return placed[0] = robot,
 // placed[1..N] = zones (shared memory), lane i < N holds zone i's timeout / colour in
 // `my_draw`, every lane holds rot0.
-template <int TASK, int N>
+template <int TASK, int N, bool FIXED>
 __device__ void warp_generate(const KParams& p, long long chosen, float2* placed, int lane,
                               uint32_t& my_draw, float& rot0) {
   my_draw = 0u;
@@ -277,9 +289,10 @@ __device__ void warp_generate(const KParams& p, long long chosen, float2* placed
     my_draw = (uint32_t)min(max(t, 0), 65535);
   }
   if (TASK == CRL_TASK_CM && lane < N) my_draw = colour_draw(chosen, (uint32_t)lane);
-  warp_layout<N>(p, chosen + 1, placed, lane);
+  warp_layout<N, FIXED>(p, chosen + 1, placed, lane);
   const U4 rr = draw(chosen + 1, 0u, 0u, 0u, kTagRot);
   rot0 = __fmul_rn(6.2831855f, u01(rr.x));
+  if (FIXED && p.fixed) { const float4 f0 = p.fixed[0]; if (f0.w >= 2.f) rot0 = f0.z; }   // Engine.robot_rot
   __syncwarp();
 }
 
@@ -312,7 +325,7 @@ __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
 // plane stores used to read their values back from it one after the other (~14 us per resetting
 // warp, profiles/r01_notes.md).  Now the new zone centres / timeouts go straight from registers
 // to their planes, and the caller reads its copy back once, in one batch of independent loads.
-template <int TASK, int N>
+template <int TASK, int N, bool FIXED>
 __device__ __noinline__ void warp_reset(const KParams& p, unsigned dm, int lane, int e, float2* placed, Env<N>& out) {
   const bool mine = (dm >> lane) & 1u;
   long long chosen = 0;
@@ -383,7 +396,7 @@ __device__ __noinline__ void warp_reset(const KParams& p, unsigned dm, int lane,
     const long long ch = __shfl_sync(kFull, chosen, src);
     uint32_t my_draw;
     float r0;
-    warp_generate<TASK, N>(p, ch, placed, lane, my_draw, r0);
+    warp_generate<TASK, N, FIXED>(p, ch, placed, lane, my_draw, r0);
     uint32_t cw = 0u;
     uint32_t tm[(N + 1) / 2];
 #pragma unroll
@@ -411,7 +424,7 @@ __device__ __noinline__ void warp_reset(const KParams& p, unsigned dm, int lane,
     out.b.vx = out.b.vy = out.b.w = 0.f;
     out.ep_return = 0.f;
     out.steps = 0;
-    out.hi = TASK == CRL_TASK_CM ? col_word : 0u;
+    out.hi = TASK == CRL_TASK_CM ? col_word : p.init_hi;
     out.cd = make_uint2(0u, 0u);
     p.seed[e] = chosen + 1;                       // Engine.reset: self._seed += 1
     p.episode[e] = episode + 1u;
@@ -517,10 +530,15 @@ __global__ void __launch_bounds__(32) prefetch_layout_kernel(const __grid_consta
     if (have) {
       // one try of Engine.sample_layout's sequential procedure
       const float keep = k == 0 ? rk : zk;
-      const float lo = -ext + keep, span = (ext - keep) - lo;
+      float lo_x = -ext + keep, lo_y = lo_x, span = (ext - keep) - lo_x;
+      bool pinned = false;                        // fixed location: a box of width 0, one try
+      if (p.fixed) {
+        const float4 fx = p.fixed[min(k, N)];
+        if (fx.w == 1.f || fx.w == 3.f) { lo_x = fx.x; lo_y = fx.y; span = 0.f; pinned = true; }
+      }
       if (!(j & 1)) r = draw(layout_seed, (uint32_t)(j >> 1), (uint32_t)k, attempt, kTagLayout);
-      const float x = __fadd_rn(lo, __fmul_rn(span, u01((j & 1) ? r.z : r.x)));
-      const float y = __fadd_rn(lo, __fmul_rn(span, u01((j & 1) ? r.w : r.y)));
+      const float x = __fadd_rn(lo_x, __fmul_rn(span, u01((j & 1) ? r.z : r.x)));
+      const float y = __fadd_rn(lo_y, __fmul_rn(span, u01((j & 1) ? r.w : r.y)));
       const float need_r = __fadd_rn(rk, keep), need_z = __fadd_rn(zk, keep);
       const float need_r2 = __fmul_rn(need_r, need_r), need_z2 = __fmul_rn(need_z, need_z);
       uint32_t bad = 0u;                          // bit q: too close to object q (no branches)
@@ -536,18 +554,20 @@ __global__ void __launch_bounds__(32) prefetch_layout_kernel(const __grid_consta
 #pragma unroll
         for (int q = 0; q <= N; ++q) if (q == k) placed[q] = make_float2(x, y);
         ++k; j = 0;
-      } else if (++j >= 100) {                    // 100 misses abandon the layout
+      } else if (++j >= (pinned ? 1 : 100)) {     // 100 misses abandon the layout
         j = 0; k = 0;
         if (++attempt >= 10000u) k = N + 1;       // as the twin: give up with what there is
       }
       if (k > N) {
         const U4 rr = draw(layout_seed, 0u, 0u, 0u, kTagRot);
+        float rot0 = __fmul_rn(6.2831855f, u01(rr.x));
+        if (p.fixed) { const float4 f0 = p.fixed[0]; if (f0.w >= 2.f) rot0 = f0.z; }
         const size_t sb = (size_t)slot * p.B;
         const float2 rb = placed[0];
         float2* nz = p.next_zone_xy + sb * N + e;
 #pragma unroll
         for (int i = 0; i < N; ++i) nz[(size_t)i * p.B] = placed[1 + i];
-        p.next_origin[sb + e] = make_float4(rb.x, rb.y, __fmul_rn(6.2831855f, u01(rr.x)), 0.f);
+        p.next_origin[sb + e] = make_float4(rb.x, rb.y, rot0, 0.f);
         p.next_seed[sb + e] = layout_seed - 1;
         st_release_u32(p.next_ready + sb + e, done_state);
         have = false;
@@ -767,7 +787,7 @@ __device__ __forceinline__ void chain_release(const KParams& p, int w, int lane,
 // frameskip substeps run; state and the 8-float obs row are written last.
 // EXT = true: the variant that also serves the goal-conditioned tasks (CRL_STEP_GOALS) and
 // WaitWrapper semantics (CRL_STEP_WAIT); the plain rollout kernel carries none of it.
-template <int TASK, int N, bool EXT>
+template <int TASK, int N, bool EXT, bool FIXED = false>
 __global__ void __launch_bounds__(kThreads, min_blocks<N>()) step_kernel(const __grid_constant__ KParams p) {
   constexpr int ROW = N * ZoneDim<TASK>::Z;
   extern __shared__ __align__(128) float smem[];
@@ -964,7 +984,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks<N>()) step_kernel(const _
         // a copy crosses the (cold, out-of-line) call so that `env` itself is dead across it and
         // stays in registers everywhere else (keeping it live costs spills in the hot path)
         Env<N> next = env;
-        warp_reset<TASK, N>(p, dm, lane, e, reinterpret_cast<float2*>(stage), next);
+        warp_reset<TASK, N, FIXED>(p, dm, lane, e, reinterpret_cast<float2*>(stage), next);
         env = next;
         fresh = done;
       }
@@ -1032,7 +1052,7 @@ __global__ void __launch_bounds__(kThreads) reset_kernel(const __grid_constant__
   if (valid) load_env<TASK, N>(p, e, env);
   const bool want = valid && (p.mask == nullptr || p.mask[e] != 0);
   const unsigned m = __ballot_sync(kFull, want);
-  if (m) warp_reset<TASK, N>(p, m, lane, e, reinterpret_cast<float2*>(stage), env);
+  if (m) warp_reset<TASK, N, true>(p, m, lane, e, reinterpret_cast<float2*>(stage), env);
   float c = 1.f, s = 0.f;
   if (valid) sincosf(env.b.phi, &s, &c);
   // the warp's 32 zone_obs rows leave as one bulk copy: rows of envs that were not reset are
@@ -1059,7 +1079,7 @@ __global__ void reset_from_layout_kernel(const KParams p, const LayoutParams L) 
   Env<N> env;
   const float rot0 = (float)L.rot0[i];
   env.b = Body{(float)L.xy0[2 * i], (float)L.xy0[2 * i + 1], wrap_pi(rot0), 0.f, 0.f, 0.f};
-  env.ep_return = 0.f; env.steps = 0; env.hi = 0u; env.cd = make_uint2(0u, 0u);
+  env.ep_return = 0.f; env.steps = 0; env.hi = TASK == CRL_TASK_CM ? 0u : p.init_hi; env.cd = make_uint2(0u, 0u);
 #pragma unroll
   for (int j = 0; j < (N + 1) / 2; ++j) env.tmax[j] = 0u;
 #pragma unroll
@@ -1251,7 +1271,8 @@ __global__ void check_state_kernel(const KParams p, int task, int N, unsigned lo
   bool zone_bad = false;
   for (int i = 0; i < N; ++i) {
     const float2 z = p.zone_xy[(size_t)i * p.B + e];
-    zone_bad |= !(fabsf(z.x) <= lim && fabsf(z.y) <= lim);
+    const bool pinned = p.fixed && p.fixed[1 + i].w == 1.f;     // a fixed location may lie anywhere
+    zone_bad |= !pinned && !(fabsf(z.x) <= lim && fabsf(z.y) <= lim);
   }
   if (zone_bad) atomicAdd(bad + 3, 1ull);
   bool hi_bad = false;
@@ -1290,6 +1311,7 @@ static int check_config(const CrlConfig* c) {
   if (c->frameskip < 0 || c->max_cooldown < 0 || c->max_cooldown > 255) return CRL_ERR_CONFIG;
   if (c->seed_mode == CRL_SEED_FIXED_RANGE && c->max_seed < c->min_seed) return CRL_ERR_CONFIG;
   if (!(c->zone_size > 0.0)) return CRL_ERR_CONFIG;
+  if (c->task != CRL_TASK_CM && (c->initial_visited >> c->num_zones) != 0u) return CRL_ERR_CONFIG;
   return CRL_OK;
 }
 
@@ -1342,6 +1364,11 @@ static int fill_params(const CrlConfig* c, const CrlState* st, const CrlOut* out
     p.next_origin = reinterpret_cast<float4*>(st->next_origin);
     p.next_seed = reinterpret_cast<long long*>(st->next_seed); p.next_ready = st->next_ready;
   }
+  if (st->fixed_layout) {
+    if (!aligned16(st->fixed_layout)) return CRL_ERR_ALIGN;
+    p.fixed = reinterpret_cast<const float4*>(st->fixed_layout);
+  }
+  p.init_hi = c->task == CRL_TASK_CM ? 0u : c->initial_visited;
   p.stamp = st->stamp;
   p.row_list = st->row_list;
   p.goal = st->goal;
@@ -1375,6 +1402,17 @@ static int launch_status() { return cudaGetLastError() == cudaSuccess ? CRL_OK :
     else if ((task) == CRL_TASK_CM && (n) == 6) { CALL(CRL_TASK_CM, 6); }        \
     else return CRL_ERR_UNSUPPORTED;                                             \
   } while (0)
+
+// The step kernel of a configuration.  Fixed placements (CrlState.fixed_layout) have kernels for the
+// 15-zone TSP only -- the hard instances PointTSP-v4 / v5 and their goal-conditioned flavours.
+template <int T, int NN>
+static void (*pick_step_kernel(bool ext, bool fixed))(const KParams) {
+  if (fixed) {
+    if constexpr (T == CRL_TASK_TSP && NN == 15) return ext ? step_kernel<T, NN, true, true> : step_kernel<T, NN, false, true>;
+    else return nullptr;
+  }
+  return ext ? step_kernel<T, NN, true> : step_kernel<T, NN, false>;
+}
 
 // opt in to > 48 KB dynamic shared memory once per kernel
 static int set_smem(void (*kernel)(const KParams), size_t bytes) {
@@ -1477,7 +1515,8 @@ int crl_step(const CrlConfig* c, const CrlState* st, const float* actions, const
 #define CRL_CALL_STEP(T, NN)                                                        \
   {                                                                                 \
     const size_t sm = (size_t)kThreads * NN * ZoneDim<T>::Z * 4;                    \
-    void (*kern)(const KParams) = ext ? step_kernel<T, NN, true> : step_kernel<T, NN, false>; \
+    void (*kern)(const KParams) = pick_step_kernel<T, NN>(ext, p.fixed != nullptr); \
+    if (!kern) return CRL_ERR_UNSUPPORTED;                                          \
     rc = set_smem(kern, sm);                                                        \
     if (rc) return rc;                                                              \
     cudaLaunchConfig_t lc = {};                                                     \

@@ -90,7 +90,8 @@ class ZoneVecEnv:
             seed_mode=_lib.SEED_FIXED_RANGE if seed_mode == 'fixed_range' else _lib.SEED_INCREMENT,
             env_offset=env_offset, min_seed=min_seed, max_seed=max_seed, zone_size=spec.zone_size,
             time_saved_reward=spec.time_saved_reward, beta_a=spec.beta_a, beta_b=spec.beta_b,
-            robot_keepout=spec.robot_keepout, zone_keepout=spec.zone_keepout, extent=spec.extent)
+            robot_keepout=spec.robot_keepout, zone_keepout=spec.zone_keepout, extent=spec.extent,
+            initial_visited=spec.initial_visited)
         dev = self.device
         z = lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype, device=dev)
         # state planes (layout documented in include/crl_b200.h)
@@ -141,6 +142,10 @@ class ZoneVecEnv:
                                    next_seed=ptr(self.next_seed), next_ready=ptr(self.next_ready),
                                    stamp=ptr(self.stamp), prefetch_work=ptr(self._prefetch_work),
                                    row_list=ptr(self._row_list), goal=ptr(self.goal))
+        fixed = spec.fixed_layout()               # hard instances: fixed robot / city placements
+        if fixed is not None:
+            self._fixed = torch.from_numpy(fixed).to(dev).contiguous()
+            self.state.fixed_layout = self._fixed.data_ptr()
         if layout_bank is not None:
             self._install_layout_bank(layout_bank, seed_mode, min_seed, max_seed)
         self.bind_outputs(z(B, 8), z(B, N, Z), z(B, 8, dtype=torch.uint8), z(B))

@@ -68,7 +68,7 @@
 extern "C" {
 #endif
 
-#define CRL_ABI_VERSION 4
+#define CRL_ABI_VERSION 5
 #define CRL_MAX_ZONES 16
 
 /* task ids; reference classes: main/envs/TSP_env.py:11, TTSP_env.py:12, colour_match_env.py:11 */
@@ -146,6 +146,12 @@ typedef struct CrlConfig {
   double robot_keepout;  /* 0.4 (Engine default) */
   double zone_keepout;   /* 0.55 (ZoneEnvBase.py:50) */
   double extent;         /* 3.0 (ZoneEnvBase.py:41) */
+  /* TSP / TimedTSP zones that START an episode visited (bit i = zone i): the hard instances
+   * PointTSP-v4 / v5 (main/envs/TSP_hard_env.py:27-30, `zones_colours` of
+   * main/envs/__init__.py:52-81: Cyan = a city, Yellow = a distractor that counts as visited).
+   * 0 for every other registration.  Ignored by ColourMatch. */
+  uint32_t initial_visited;
+  uint32_t reserved_;    /* keep 0 */
 } CrlConfig;
 
 typedef struct CrlState {
@@ -181,6 +187,16 @@ typedef struct CrlState {
   const float* bank_origin;    /* float4[K]: x0, y0, rot0, 0 */
   const uint32_t* bank_task;   /* TTSP: uint32[K][ceil(N/2)] timeouts packed like zone_tmax;
                                   ColourMatch: uint32[K] colour codes, 2 bits per zone; TSP: NULL */
+  /* optional FIXED PLACEMENTS (NULL = none): float4[1 + N], entry 0 the robot, entry 1 + i zone i.
+   * Engine's `robot_locations` / `zones_locations` / `robot_rot` (Safety Gym
+   * placements_dict_from_object: an object with a location is drawn inside a 2e-9-wide box
+   * around it -- here: AT it -- and still has to pass the keepout test against the objects
+   * placed before it, else the layout attempt is abandoned), as the hard instances use them
+   * (main/envs/__init__.py:52-81).  Entry 0 = (x, y, rot, f) with f = 1 position fixed, 2 heading
+   * fixed, 3 both, 0 neither; entry 1 + i = (x, y, 0, f) with f = 1 fixed, 0 sampled.  Read by
+   * every sampler (crl_reset, the auto-reset of crl_step, crl_prefetch_layouts); layout banks and
+   * crl_reset_from_layout take their positions as given. */
+  const float* fixed_layout;
 } CrlState;
 
 typedef struct CrlResult {

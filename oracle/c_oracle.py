@@ -8,7 +8,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, 'libcrl_oracle.so')
 TASKS = {'PointTSP-v0': (0, 15, 2000), 'PointTTSP-v0': (1, 15, 2000), 'ColourMatch-v0': (2, 6, 2000),
-         'PointTSP-v1': (0, 5, 1000), 'PointTTSP-v1': (1, 5, 1000)}
+         'PointTSP-v1': (0, 5, 1000), 'PointTTSP-v1': (1, 5, 1000),
+         'PointTSP-v4': (0, 15, 1000), 'PointTSP-v5': (0, 15, 250)}
 _lib = None
 dp = ctypes.POINTER(ctypes.c_double)
 ip = ctypes.POINTER(ctypes.c_int64)
@@ -43,7 +44,7 @@ def lib():
         L.oe_timed_rollout.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ip]
         L.ph_reset.argtypes = ([ctypes.c_int] * 4 + [ctypes.c_int64] * 3 + [ctypes.c_uint32, ctypes.c_int64,
                                ctypes.c_double, ctypes.c_double, ctypes.c_float, ctypes.c_float, ctypes.c_float]
-                               + [ctypes.c_void_p] * 6)
+                               + [ctypes.c_void_p] * 7)
         L.ph_action.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_void_p]
         L.ph_philox.argtypes = [ctypes.c_void_p] * 3
         L.ph_gamma_sample.restype = ctypes.c_double
@@ -152,14 +153,17 @@ def timed_rollout(env_id, threads, seconds):
 
 
 def philox_reset(env_id, seed_in, seed_mode=0, min_seed=0, max_seed=0, global_env=0, episode=0,
-                 beta=(3.0, 1.5), keepouts=(0.4, 0.55), extent=3.0):
-    """Design twin of the device reset (crl_reset / auto-reset) for one env."""
+                 beta=(3.0, 1.5), keepouts=(0.4, 0.55), extent=3.0, fixed=None):
+    """Design twin of the device reset (crl_reset / auto-reset) for one env.  ``fixed``: the
+    float32 (1 + N, 4) table of CrlState.fixed_layout (hard instances), or None."""
     task, N, num_steps = TASKS[env_id]
+    if fixed is not None:
+        fixed = np.ascontiguousarray(fixed, dtype=np.float32).reshape(1 + N, 4)
     xy0, rot0, zxy = np.zeros(2, np.float32), np.zeros(1, np.float32), np.zeros((N, 2), np.float32)
     tm, col, after = np.zeros(N, np.int32), np.zeros(N, np.int32), np.zeros(1, np.int64)
     lib().ph_reset(task, N, num_steps, seed_mode, min_seed, max_seed, global_env, episode, seed_in,
                    beta[0], beta[1], keepouts[0], keepouts[1], extent,
-                   xy0.ctypes.data, rot0.ctypes.data, zxy.ctypes.data, tm.ctypes.data, col.ctypes.data,
+                   None if fixed is None else fixed.ctypes.data, xy0.ctypes.data, rot0.ctypes.data, zxy.ctypes.data, tm.ctypes.data, col.ctypes.data,
                    after.ctypes.data)
     return {'xy0': xy0, 'rot0': float(rot0[0]), 'zone_xy': zxy, 'zone_max_steps': tm, 'colours': col,
             'seed_after': int(after[0])}

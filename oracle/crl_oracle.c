@@ -581,6 +581,7 @@ double ph_gamma_sample(int64_t seed, double a, uint32_t zone, uint32_t which) { 
 void ph_reset(int task, int N, int num_steps, int seed_mode, int64_t min_seed, int64_t max_seed,
               int64_t global_env, uint32_t episode, int64_t seed_in, double beta_a, double beta_b,
               float robot_keepout, float zone_keepout, float extent,
+              const float* fixed /* CrlState.fixed_layout: float4[1 + N] or NULL */,
               float* xy0, float* rot0, float* zone_xy, int32_t* tmax, int32_t* colours, int64_t* seed_after) {
   int64_t seed = seed_in;
   if (seed_mode == 1) {
@@ -616,12 +617,13 @@ void ph_reset(int task, int N, int num_steps, int seed_mode, int64_t min_seed, i
       const float keep = k == 0 ? robot_keepout : zone_keepout;
       const float lo = -extent + keep, span = (extent - keep) - lo;
       int found = 0;
-      for (int j = 0; j < 100 && !found; ++j) {
+      const int pinned = fixed && (fixed[4 * k + 3] == 1.f || fixed[4 * k + 3] == 3.f);
+      for (int j = 0; j < (pinned ? 1 : 100) && !found; ++j) {
         uint32_t r[4];
         /* try j = half (j & 1) of Philox block (j >> 1, k, attempt) */
         ph_draw(seed, (uint32_t)(j >> 1), (uint32_t)k, attempt, TAG_LAYOUT, r);
         volatile float mx = span * ph_u01(r[(j & 1) ? 2 : 0]), my = span * ph_u01(r[(j & 1) ? 3 : 1]);
-        const float x = lo + mx, y = lo + my;
+        const float x = pinned ? fixed[4 * k] : lo + mx, y = pinned ? fixed[4 * k + 1] : lo + my;
         int valid = 1;
         for (int q = 0; q < k; ++q) {
           const float need = (q == 0 ? robot_keepout : zone_keepout) + keep;
@@ -640,6 +642,7 @@ void ph_reset(int task, int N, int num_steps, int seed_mode, int64_t min_seed, i
   ph_draw(seed, 0u, 0u, 0u, TAG_ROT, rr);
   xy0[0] = px[0]; xy0[1] = py[0];
   *rot0 = 6.2831855f * ph_u01(rr[0]);
+  if (fixed && fixed[3] >= 2.f) *rot0 = fixed[2];
   for (int i = 0; i < N; ++i) { zone_xy[2 * i] = px[i + 1]; zone_xy[2 * i + 1] = py[i + 1]; }
   *seed_after = seed;
 }

@@ -32,6 +32,10 @@ What each piece follows:
                               info['need_next_goal']; worker RPCs
                               zone-goals/src/torch_ac/torch_utils/penv.py:18-25
   WaitWrapper ............... wrappers.py:29-54 (no-op zeros after the inner env is done)
+  hard instances ............ PointTSP-v4 / v5: TSP_hard_env.py:11-31 over the configs of
+                              main/envs/__init__.py:52-81 (fixed robot / city locations,
+                              `zones_colours`: Cyan cities + Yellow distractors that start
+                              visited); the goal-conditioned flavour zone-goals/envs/TSP_hard_env.py
 """
 import math
 
@@ -42,7 +46,23 @@ from . import mj_point
 TSP, TTSP, CM = 0, 1, 2
 TASK_OF_ENV_ID = {'PointTSP-v0': TSP, 'PointTTSP-v0': TTSP, 'ColourMatch-v0': CM,
                   'PointTSP-v3': TSP, 'PointTTSP-v3': TTSP, 'ColourMatch-v3': CM}
-GOAL_ENV_IDS = ('PointTSP-v3', 'PointTTSP-v3', 'ColourMatch-v3')   # zone-goals/envs/__init__.py
+GOAL_ENV_IDS = ('PointTSP-v3', 'PointTTSP-v3', 'ColourMatch-v3',   # zone-goals/envs/__init__.py
+                'zone-goals/PointTSP-v4', 'zone-goals/PointTSP-v5')
+
+# Hard instances (main/envs/__init__.py:52-81; zone enum ZoneEnvBase.py:13-21: 6 = Cyan = a city,
+# 5 = Yellow = visited from the start).  The zone-goals registrations differ in v5's num_steps
+# only (zone-goals/envs/__init__.py:69-81) and step through TSPNextCityEnv.
+HARD = {
+    'PointTSP-v4': dict(num_zones=15, num_steps=1000,
+                        zones_locations=[(-2.6, -1.6), (-0., -0.5), (1., 0.5), (1.8, 1.5), (2.6, 2.6)],
+                        zones_colours=[6] * 5 + [5] * 10, robot_locations=[(-0.9, -0.9)], robot_rot=-1),
+    'PointTSP-v5': dict(num_zones=15, num_steps=250,
+                        zones_locations=[(-2.6, -2.6), (-2, -1.6), (2, 1)],
+                        zones_colours=[6] * 3 + [5] * 12, robot_locations=[(0.8, 0.8)], robot_rot=None),
+}
+HARD['zone-goals/PointTSP-v4'] = dict(HARD['PointTSP-v4'])
+HARD['zone-goals/PointTSP-v5'] = dict(HARD['PointTSP-v5'], num_steps=300)
+TASK_OF_ENV_ID.update({k: TSP for k in HARD})
 
 NUM_STEPS = 2000            # envs/__init__.py:13, :49
 NUM_ZONES = {TSP: 15, TTSP: 15, CM: 6}   # envs/__init__.py:9, :45
@@ -72,21 +92,32 @@ def hamming_to_goal(colours):
     return min(2 * ng + nr, 2 * nr + nb, 2 * nb + ng)
 
 
-def sample_layout(rs, num_zones):
+def sample_layout(rs, num_zones, robot_locations=(), zones_locations=(), robot_rot=None):
     """Engine.build_layout / sample_layout / build_world_config [upstream],
     specialised to: robot (keepout .4) then ``num_zones`` zones (keepout .55),
-    extents +-3, no fixed locations.  Consumes ``rs`` exactly as upstream does
+    extents +-3.  Consumes ``rs`` exactly as upstream does
     (x then y per candidate; robot_rot after the layout; one cosmetic
-    ``random_rot`` per zone, ZoneEnvBase.py:132).  Returns xy0, rot0, zone_xy."""
+    ``random_rot`` per zone, ZoneEnvBase.py:132).  An object with a fixed location
+    (``robot_locations[0]``, ``zones_locations[i]``; placements_dict_from_object) is drawn
+    -- still consuming two uniforms -- from the box of half-width keepout + 1e-9 around it
+    shrunk by keepout, i.e. within 1e-9 of the location, and must pass the same keepout
+    test.  A fixed ``robot_rot`` draws nothing.  Returns xy0, rot0, zone_xy."""
     keepouts = [ROBOT_KEEPOUT] + [ZONE_KEEPOUT] * num_zones
+    locations = [robot_locations[0] if len(robot_locations) else None]
+    locations += [zones_locations[i] if i < len(zones_locations) else None for i in range(num_zones)]
     for _ in range(10000):
         placed = []
         ok_layout = True
-        for k in keepouts:
-            lo, hi = -EXTENT + k, EXTENT - k
+        for k, loc in zip(keepouts, locations):
+            if loc is None:
+                xlo = ylo = -EXTENT + k
+                xhi = yhi = EXTENT - k
+            else:
+                kk = k + 1e-9
+                xlo, ylo, xhi, yhi = loc[0] - kk + k, loc[1] - kk + k, loc[0] + kk - k, loc[1] + kk - k
             found = False
             for _try in range(100):
-                xy = np.array([rs.uniform(lo, hi), rs.uniform(lo, hi)])
+                xy = np.array([rs.uniform(xlo, xhi), rs.uniform(ylo, yhi)])
                 if all(np.sqrt(np.sum(np.square(xy - oxy))) >= ok + k for oxy, ok in placed):
                     found = True
                     break
@@ -98,7 +129,7 @@ def sample_layout(rs, num_zones):
             break
     else:
         raise RuntimeError('layout sampling failed')
-    rot0 = rs.uniform(0, 2 * np.pi)
+    rot0 = rs.uniform(0, 2 * np.pi) if robot_rot is None else float(robot_rot)
     for _ in range(num_zones):
         rs.uniform(0, 2 * np.pi)
     return placed[0][0], rot0, np.array([p for p, _ in placed[1:]])
@@ -112,8 +143,10 @@ class ZoneTaskEnv:
     xy0 (2,), rot0, zone_xy (N,2) and, per task, zone_max_steps (N,) / colours (N,).
     """
 
-    def __init__(self, task, num_zones=None, num_steps=NUM_STEPS, goals=False):
+    def __init__(self, task, num_zones=None, num_steps=NUM_STEPS, goals=False, hard=None):
         self.task = task
+        # hard instance: dict with zones_locations, zones_colours, robot_locations, robot_rot
+        self.hard = hard
         self.goals = goals          # the *_next_city_env.py variants
         self.goal_zone = None
         self.last_dist_to_goal = None
@@ -140,7 +173,9 @@ class ZoneTaskEnv:
                 self.colours = np.array([int(rs.choice(3)) for _ in range(N)])
             self._seed += 1
             self.rs = np.random.RandomState(self._seed)
-            xy0, rot0, zone_xy = sample_layout(self.rs, N)
+            h = self.hard or {}
+            xy0, rot0, zone_xy = sample_layout(self.rs, N, h.get('robot_locations', ()),
+                                               h.get('zones_locations', ()), h.get('robot_rot'))
         else:
             xy0, rot0, zone_xy = layout['xy0'], layout['rot0'], layout['zone_xy']
             if self.task == TTSP:
@@ -152,6 +187,8 @@ class ZoneTaskEnv:
         self.rot0 = float(rot0)
         self.zone_xy = np.asarray(zone_xy, dtype=np.float64).reshape(N, 2)
         self.visited = np.zeros(N, dtype=bool)
+        if self.hard is not None:       # TSP_hard_env.py:27-30: zones restart from zones_colours
+            self.visited = np.array([c == 5 for c in self.hard['zones_colours']], dtype=bool)
         if self.task == CM:
             self.cooldown = np.zeros(N, dtype=np.int64)
             self.goal_dist = hamming_to_goal(self.colours)
@@ -349,16 +386,23 @@ class SerialVecEnv:
         return tuple(zip(*[e.step(a) for e, a in zip(self.envs, actions)]))
 
 
+def make_task_env(env_id):
+    """gym.make(env_id) for the registrations this oracle covers."""
+    if env_id in HARD:
+        h = HARD[env_id]
+        return ZoneTaskEnv(TSP, num_zones=h['num_zones'], num_steps=h['num_steps'], goals=env_id in GOAL_ENV_IDS,
+                           hard=h)
+    return ZoneTaskEnv(TASK_OF_ENV_ID[env_id], goals=env_id in GOAL_ENV_IDS)
+
+
 def make_fixed_env(env_id, seed=1000, env_seed=0):
     """make_env.make_fixed_env (make_env.py:37-51) for the three zone tasks."""
-    return FixedSeeds(ZoneTaskEnv(TASK_OF_ENV_ID[env_id], goals=env_id in GOAL_ENV_IDS), env_seed, env_seed,
-                      rng_seed=seed)
+    return FixedSeeds(make_task_env(env_id), env_seed, env_seed, rng_seed=seed)
 
 
 def make_train_env(env_id, num_training_tasks=100, rng_seed=0, hier=False):
     """make_env.make_train_env (make_env.py:3-18)."""
-    env = FixedSeeds(ZoneTaskEnv(TASK_OF_ENV_ID[env_id], goals=env_id in GOAL_ENV_IDS), 1, num_training_tasks,
-                     rng_seed=rng_seed)
+    env = FixedSeeds(make_task_env(env_id), 1, num_training_tasks, rng_seed=rng_seed)
     return Wait(env) if hier else env
 
 

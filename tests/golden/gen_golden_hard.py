@@ -1,0 +1,52 @@
+"""Generate tests/golden/hard_*.npz and hardgoals_*.npz by running the REAL hard-instance code.
+
+Run in the build container only (needs /root/reference), once per tree (the two reference
+packages both call themselves ``envs``):
+
+    python tests/golden/gen_golden_hard.py main
+    python tests/golden/gen_golden_hard.py zone-goals
+
+``main``: PointTSP-v4 / PointTSP-v5 as registered in main/envs/__init__.py:52-81, :110-118 --
+``envs/TSP_hard_env.py`` (TSPHardEnv over TSPEnv) imported unmodified, driven through
+make_env.make_fixed_env exactly like the other fixtures (recorder: gen_golden.record_episode).
+``zone-goals``: the goal-conditioned registrations of the same ids (zone-goals/envs/__init__.py:52-81,
+zone-goals/envs/TSP_hard_env.py over TSPNextCityEnv; recorder: gen_golden_goals.record_episode);
+stored under the ids 'zone-goals/PointTSP-v4' / 'zone-goals/PointTSP-v5'.
+Stubs as in gen_golden.py: Safety Gym's Engine (fixed ``robot_locations`` / ``zones_locations`` /
+``robot_rot`` included) is the oracle's restatement, oracle/sg_engine.py.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+MAIN = [('PointTSP-v4', 1000000, 'greedy', 1000), ('PointTSP-v4', 1000001, 'random', 1000),
+        ('PointTSP-v5', 1000000, 'greedy', 250), ('PointTSP-v5', 1000002, 'idle', 250)]
+GOALS = [('PointTSP-v4', 1000000, 'near', 1000), ('PointTSP-v5', 1000001, 'far', 300)]
+
+
+def main(tree):
+    if tree == 'main':
+        from tests.golden import gen_golden as gg
+        for env_id, seed, mode, max_len in MAIN:
+            out = gg.record_episode(env_id, seed, mode, max_len)
+            name = f'hard_{env_id}_{seed}_{mode}.npz'
+            np.savez_compressed(os.path.join(HERE, name), **out)
+            print(name, 'steps', len(out['reward']), 'return', out['reward'].sum(), 'goal_met', bool(out['goal_met'].any()),
+                  'first colours', out['zone_obs'][0][:, 2].astype(int))
+    else:
+        from tests.golden import gen_golden_goals as gg
+        for env_id, seed, mode, max_len in GOALS:
+            out = gg.record_episode(env_id, seed, mode, max_len)
+            out['env_id'] = np.array('zone-goals/' + env_id)
+            name = f'hardgoals_{env_id}_{seed}_{mode}.npz'
+            np.savez_compressed(os.path.join(HERE, name), **out)
+            print(name, 'steps', len(out['reward']), 'return', out['reward'].sum(), 'shaped', out['shaped_reward'].sum(),
+                  'reached', int(out['need_next_goal'].sum()), 'goal_met', bool(out['goal_met'].any()))
+
+
+if __name__ == '__main__':
+    main(sys.argv[1])

@@ -20,7 +20,8 @@ from tests.golden.gen_golden_goals_pick import pick_goal  # noqa: E402
 from tests.test_gpu_parity import REWARD_ATOL, batched, check_obs, load_layout, world_state  # noqa: E402
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-EPISODES = sorted(glob.glob(os.path.join(GOLDEN, 'goals_*_*_*.npz')))
+EPISODES = sorted(glob.glob(os.path.join(GOLDEN, 'goals_*_*_*.npz')) +
+                  glob.glob(os.path.join(GOLDEN, 'hardgoals_*.npz')))     # + zone-goals PointTSP-v4 / v5
 SHAPED_FIXTURE_ATOL = 2e-6
 
 

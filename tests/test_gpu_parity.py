@@ -21,7 +21,7 @@ from tests._driver import policy  # noqa: E402
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 EPISODES = sorted(f for f in glob.glob(os.path.join(GOLDEN, '*.npz'))
-                  if not f.endswith('_vector.npz') and not os.path.basename(f).startswith(('goals_', 'gae_')))
+                  if not f.endswith('_vector.npz') and not os.path.basename(f).startswith(('goals_', 'gae_', 'hardgoals_')))   # incl. hard_*: PointTSP-v4 / v5
 
 PHYS_RTOL = 1e-5       # per substep, from identical inputs (the north-star bar)
 REWARD_ATOL = 1e-6
@@ -83,7 +83,7 @@ def check_obs(task, obs_gpu, zobs_gpu, obs_ref, zobs_ref, where):
 def test_library_is_the_cuda_one(crl):
     from combinatorial_rl_tasks_b200 import _lib
     lib = _lib.load()
-    assert lib.crl_abi_version() == _lib.ABI_VERSION == 4
+    assert lib.crl_abi_version() == _lib.ABI_VERSION == 5
     with open('/proc/self/maps') as f:
         assert 'libcrl_b200.so' in f.read()
 
@@ -172,7 +172,7 @@ def test_fixture_episode_teacher_forced(crl, path):
     assert np.array_equal(res[:, 4].astype(bool), g['done']), 'done flags'
     assert np.array_equal(res[:, 5].astype(bool), g['goal_met']), 'goal_met'
     # integer reward component: the reference's dense reward (bonus removed)
-    dense_ref = np.where(g['goal_met'], np.round(g['reward'] - (2000 - np.arange(T)) * 0.01), g['reward']).astype(np.int8)
+    dense_ref = np.where(g['goal_met'], np.round(g['reward'] - (env.spec.num_steps - np.arange(T)) * 0.01), g['reward']).astype(np.int8)
     assert np.array_equal(res[:, 6].view(np.int8), dense_ref), 'integer reward components'
     assert np.max(np.abs(reward_g.astype(np.float64) - g['reward'])) <= REWARD_ATOL
     for t in range(T):
@@ -191,7 +191,8 @@ EASY = {'PointTSP-v1': (ze.TSP, 'PointTSP-v0'), 'PointTTSP-v1': (ze.TTSP, 'Point
     ('PointTSP-v0', 'greedy', 11), ('PointTSP-v0', 'random', 12),
     ('PointTTSP-v0', 'greedy', 13), ('PointTTSP-v0', 'deadline', 14),
     ('ColourMatch-v0', 'greedy', 15), ('ColourMatch-v0', 'greedy', 16),
-    ('PointTSP-v1', 'greedy', 17), ('PointTTSP-v1', 'deadline', 18), ('PointTTSP-v1', 'idle', 19)])
+    ('PointTSP-v1', 'greedy', 17), ('PointTTSP-v1', 'deadline', 18), ('PointTTSP-v1', 'idle', 19),
+    ('PointTSP-v4', 'greedy', 20), ('PointTSP-v5', 'greedy', 21)])
 def test_closed_loop_identical_positions(crl, env_id, mode, seed):
     """Oracle and CUDA path stepped side by side from IDENTICAL positions: before every
     step the oracle is set to the kernel's own fp32 state (exactly representable), so
@@ -200,6 +201,9 @@ def test_closed_loop_identical_positions(crl, env_id, mode, seed):
     if env_id in EASY:
         task, drive_as = EASY[env_id]
         ref_env = ze.ZoneTaskEnv(task, num_zones=5, num_steps=1000)
+    elif env_id in ze.HARD:              # fixed cities + distractors that start visited (TSP_hard_env.py)
+        task, drive_as = ze.TSP, 'PointTSP-v0'
+        ref_env = ze.make_task_env(env_id)
     else:
         task, drive_as = ze.TASK_OF_ENV_ID[env_id], env_id
         ref_env = ze.ZoneTaskEnv(task)
@@ -248,7 +252,9 @@ def test_closed_loop_identical_positions(crl, env_id, mode, seed):
         if d_ref:
             break
     if mode not in ('random', 'idle'):
-        assert n_events >= 3, 'the driver should have triggered task events'
+        assert n_events >= (1 if env_id == 'PointTSP-v5' else 3), 'the driver should have triggered task events'
+    if env_id in ze.HARD:
+        assert ref_env.done and t < ref_env.num_steps and ref_env.visited.sum() >= 12
     if env_id in EASY:
         assert ref_env.done and t < 1000             # ended by success, a timeout or the 1000-step limit
 

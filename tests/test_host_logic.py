@@ -48,7 +48,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.crl_abi_version() == 4
+    assert lib.crl_abi_version() == 5
     assert b'NULL' in lib.crl_strerror(-1)
 
 
@@ -79,6 +79,62 @@ def test_argument_errors_are_detected_on_the_host():
     assert lib.crl_step_host_delta(cfg, st, a16, a16, out, out, a16, 4096, 0, None, None) == -1  # no row_list
     st.pose = a16 + 4
     assert lib.crl_step(cfg, st, None, out, 0, 0, 0, None) == -3          # misaligned plane
+
+
+def test_hard_instance_specs_and_config_checks():
+    """PointTSP-v4 / v5 (main/envs/__init__.py:52-81): the product's registry against the oracle's
+    independent restatement of the same configs; the fixed-placement table; initial_visited is
+    validated on the host."""
+    from combinatorial_rl_tasks_b200 import _lib
+    from combinatorial_rl_tasks_b200.config import ENV_SPECS, TaskSpec
+    from oracle import zone_env as ze
+    for env_id, h in ze.HARD.items():
+        spec = ENV_SPECS[env_id]
+        assert (spec.task, spec.num_zones, spec.num_steps) == (_lib.TASK_TSP, h['num_zones'], h['num_steps'])
+        assert spec.goals == (env_id in ze.GOAL_ENV_IDS)
+        assert spec.initial_visited == sum(1 << i for i, c in enumerate(h['zones_colours']) if c == 5)
+        t = spec.fixed_layout()
+        assert t.shape == (16, 4) and t.dtype == np.float32
+        assert tuple(t[0, :2]) == tuple(np.float32(h['robot_locations'][0]))
+        assert t[0, 3] == (3 if h['robot_rot'] is not None else 1)
+        n = len(h['zones_locations'])
+        assert np.array_equal(t[1:1 + n, :2], np.array(h['zones_locations'], dtype=np.float32))
+        assert np.all(t[1:1 + n, 3] == 1) and not t[1 + n:].any()
+        # the cities are exactly the zones that do not start visited
+        assert spec.initial_visited == ((1 << 15) - 1) & ~((1 << n) - 1)
+    assert ENV_SPECS['PointTSP-v0'].fixed_layout() is None and ENV_SPECS['PointTSP-v0'].initial_visited == 0
+    with pytest.raises(ValueError):                      # two fixed zones closer than 2 x 0.55
+        TaskSpec(_lib.TASK_TSP, 5, 1000, 6, zones_locations=((0, 0), (0.5, 0.5))).fixed_layout()
+    lib = _lib.load()
+    sizes = (ctypes.c_int64 * 22)()
+    ok = _lib.CrlConfig(task=0, num_envs=64, num_zones=15, num_steps=1000, zone_size=0.2, initial_visited=0x7fe0)
+    assert lib.crl_plane_bytes(ok, sizes, 22) == 0
+    bad = _lib.CrlConfig(task=0, num_envs=64, num_zones=15, num_steps=1000, zone_size=0.2, initial_visited=0x8000)
+    assert lib.crl_plane_bytes(bad, sizes, 22) == -2     # a bit beyond zone N - 1
+    assert ctypes.sizeof(_lib.CrlConfig) == 112 and ctypes.sizeof(_lib.CrlState) == 22 * 8
+
+
+def test_design_twin_honours_fixed_placements():
+    """oracle/crl_oracle.c ph_reset with the fixed-placement table: fixed objects at their
+    places, sampled ones inside the arena and clear of every keepout, v4's heading fixed."""
+    from combinatorial_rl_tasks_b200.config import ENV_SPECS
+    for env_id in ('PointTSP-v4', 'PointTSP-v5'):
+        spec = ENV_SPECS[env_id]
+        t = spec.fixed_layout()
+        n = len(spec.zones_locations)
+        rots = []
+        for seed in range(40):
+            tw = co.philox_reset(env_id, seed, fixed=t)
+            assert np.array_equal(tw['xy0'], t[0, :2]) and np.array_equal(tw['zone_xy'][:n], t[1:1 + n, :2])
+            pts = np.concatenate([tw['xy0'][None], tw['zone_xy']]).astype(np.float64)
+            keep = np.array([0.4] + [0.55] * 15)
+            d = np.linalg.norm(pts[:, None] - pts[None], axis=2) + 1e9 * np.eye(16)
+            assert np.all(d >= keep[:, None] + keep[None] - 1e-5)
+            assert np.abs(tw['zone_xy'][n:]).max() <= 2.45 + 1e-6
+            rots.append(tw['rot0'])
+        assert (set(rots) == {-1.0}) if spec.robot_rot is not None else (len(set(rots)) == 40)
+        free = co.philox_reset(env_id, 3)                # same seed, nothing fixed: a different map
+        assert not np.array_equal(free['xy0'], t[0, :2])
 
 
 def test_vec_env_fails_loudly_without_cuda():

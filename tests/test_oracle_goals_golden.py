@@ -12,11 +12,12 @@ import pytest
 from oracle import zone_env as ze
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-EPISODES = sorted(glob.glob(os.path.join(GOLDEN, 'goals_*_*_*.npz')))
+EPISODES = sorted(glob.glob(os.path.join(GOLDEN, 'goals_*_*_*.npz')) +
+                  glob.glob(os.path.join(GOLDEN, 'hardgoals_*.npz')))     # + zone-goals PointTSP-v4 / v5
 
 
 def test_fixtures_present():
-    assert len(EPISODES) == 9 and os.path.exists(os.path.join(GOLDEN, 'goals_wait_PointTSP.npz'))
+    assert len(EPISODES) == 11 and os.path.exists(os.path.join(GOLDEN, 'goals_wait_PointTSP.npz'))
 
 
 @pytest.mark.parametrize('path', EPISODES, ids=os.path.basename)

@@ -11,12 +11,13 @@ from oracle import zone_env as ze
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 EPISODES = sorted(f for f in glob.glob(os.path.join(GOLDEN, '*.npz'))
-                  if not f.endswith('_vector.npz') and not os.path.basename(f).startswith(('goals_', 'gae_')))
+                  if not f.endswith('_vector.npz') and not os.path.basename(f).startswith(('goals_', 'gae_', 'hardgoals_')))
 VECTORS = sorted(glob.glob(os.path.join(GOLDEN, '*_vector.npz')))
 
 
 def test_fixtures_present():
-    assert len(EPISODES) >= 12 and len(VECTORS) == 3
+    assert len(EPISODES) >= 16 and len(VECTORS) == 3
+    assert sum(os.path.basename(f).startswith('hard_') for f in EPISODES) == 4     # PointTSP-v4 / v5
 
 
 @pytest.mark.parametrize('path', EPISODES, ids=os.path.basename)
