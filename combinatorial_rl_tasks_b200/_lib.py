@@ -21,7 +21,8 @@ NUM_PLANES = 22
 SYMBOLS = ['crl_abi_version', 'crl_strerror', 'crl_plane_bytes', 'crl_step_bytes', 'crl_reset',
            'crl_prefetch_layouts', 'crl_reset_from_layout', 'crl_step', 'crl_step_host', 'crl_step_host_delta',
            'crl_set_goal', 'crl_goal_query', 'crl_set_qpos_qvel',
-           'crl_get_qpos_qvel', 'crl_gae', 'crl_check_state', 'crl_counters_read']
+           'crl_get_qpos_qvel', 'crl_gae', 'crl_check_state', 'crl_counters_read',
+           'crl_encoder_packed_bytes', 'crl_encoder_pack', 'crl_zone_encode']
 
 
 class CrlConfig(ctypes.Structure):
@@ -43,6 +44,10 @@ class CrlState(ctypes.Structure):
 
 class CrlOut(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in ('obs', 'zone_obs', 'result', 'shaped_reward')]
+
+
+class CrlEncoderShape(ctypes.Structure):
+    _fields_ = [('obs_dim', c_int32), ('zone_dim', c_int32), ('hidden', c_int32), ('num_zones', c_int32)]
 
 
 class CrlLayoutIn(ctypes.Structure):
@@ -87,6 +92,10 @@ def load():
                             c_void_p, c_void_p, c_void_p]
     lib.crl_check_state.argtypes = [P(CrlConfig), P(CrlState), c_void_p, c_void_p]
     lib.crl_counters_read.argtypes = [P(CrlState), P(c_double), c_void_p]
+    lib.crl_encoder_packed_bytes.argtypes = [P(CrlEncoderShape), P(c_int64)]
+    lib.crl_encoder_pack.argtypes = [P(CrlEncoderShape)] + [c_void_p] * 8
+    lib.crl_zone_encode.argtypes = [P(CrlEncoderShape), c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p]
     for name in SYMBOLS:
         getattr(lib, name)
     if lib.crl_abi_version() != ABI_VERSION:

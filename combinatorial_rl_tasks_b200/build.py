@@ -4,8 +4,9 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'csrc', 'crl_kernels.cu')
+SRC_ENCODE = os.path.join(HERE, 'csrc', 'crl_encode.cu')     # own translation unit: see its header
 LIB = os.path.join(HERE, 'libcrl_b200.so')
-DEPS = [SRC, os.path.join(HERE, 'csrc', 'crl_core.cuh'),
+DEPS = [SRC, SRC_ENCODE, os.path.join(HERE, 'csrc', 'crl_core.cuh'),
         os.path.join(os.path.dirname(HERE), 'include', 'crl_b200.h')]
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
@@ -27,7 +28,7 @@ def build(force=False, verbose=False, defines=None, out=None):
         return LIB
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
     dflags = [f'-D{k}={v}' for k, v in (defines or {}).items()]
-    cmd = [nvcc] + NVCC_FLAGS + dflags + (['-Xptxas', '-v'] if verbose else []) + ['-o', out, SRC]
+    cmd = [nvcc] + NVCC_FLAGS + dflags + (['-Xptxas', '-v'] if verbose else []) + ['-o', out, SRC, SRC_ENCODE]
     subprocess.run(cmd, check=True)
     return out
 

@@ -1,0 +1,125 @@
+"""crl_zone_encode (tcgen05 kernel, csrc/crl_encode.cu) = ZoneEnvModel's zone_net_ + mean-pool
+(main/src/env_model.py:56-78).  The kernel multiplies bf16 operands with fp32 accumulation, the
+reference runs in fp32; bars (written here, measured values printed), relative to the largest
+reference value of the batch (and at least 1):
+  vs a torch reference that rounds the same operands to bf16 (same arithmetic) ... 1e-3
+     (what remains are activations that round to the neighbouring bf16 because one side summed in
+      fp32 and the other in fp64; measured 1e-7 .. 4e-4)
+  vs the REAL module's fp32 output (fixture) and vs torch fp32 ................... 1e-2
+     (bf16 operand rounding through three layers; measured 3e-3 .. 5e-3)
+"""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip('torch')
+pytestmark = pytest.mark.gpu
+
+from oracle import zone_model as zm  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'model_zone_env.npz')
+BF16_TWIN_RTOL = 1e-3
+FP32_RTOL = 1e-2
+
+
+@pytest.fixture(scope='module')
+def crl():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    import combinatorial_rl_tasks_b200 as m
+    return m
+
+
+def bf16_twin(sd, obs, zone_obs):
+    """The kernel's arithmetic in torch: operands rounded to bf16, products and sums in fp32 (fp64 here)."""
+    r = lambda t: t.to(torch.bfloat16).to(torch.float64)
+    B, N, _ = zone_obs.shape
+    x = r(torch.cat([obs[:, None, :].expand(B, N, obs.shape[1]), zone_obs], dim=-1))
+    for i in (0, 2, 4):
+        x = x @ r(sd[f'zone_net_.{i}.weight']).T + sd[f'zone_net_.{i}.bias'].to(torch.float64)
+        if i != 4:
+            x = r(torch.relu(x).to(torch.float32))
+    return (x.sum(dim=1) / N).to(torch.float32)
+
+
+def fp32_ref(sd, obs, zone_obs):
+    B, N, _ = zone_obs.shape
+    x = torch.cat([obs[:, None, :].expand(B, N, obs.shape[1]), zone_obs], dim=-1).to(torch.float64)
+    for i in (0, 2, 4):
+        x = x @ sd[f'zone_net_.{i}.weight'].to(torch.float64).T + sd[f'zone_net_.{i}.bias'].to(torch.float64)
+        if i != 4:
+            x = torch.relu(x)
+    return (x.sum(dim=1) / N).to(torch.float32)
+
+
+@pytest.mark.parametrize('tag,n', [('tsp', 15), ('cm', 6)])
+def test_fixture_of_the_real_module(crl, tag, n):
+    g = np.load(GOLDEN)
+    sd = {k[len(tag) + 4:]: torch.from_numpy(g[k]).cuda() for k in g.files if k.startswith(tag + '_sd_')}
+    enc = crl.ZoneEncoder(sd, num_zones=n)
+    obs, zobs = torch.from_numpy(g[f'{tag}_obs']).cuda(), torch.from_numpy(g[f'{tag}_zone_obs']).cuda()
+    emb = enc.zone_embedding(obs, zobs)
+    out = enc(obs, zobs)
+    torch.cuda.synchronize()
+    assert enc.healthy()
+    e_twin = float((emb - bf16_twin(sd, obs, zobs)).abs().max())
+    e_emb = float(np.abs(emb.cpu().numpy() - g[f'{tag}_zone_emb']).max())
+    e_out = float(np.abs(out.cpu().numpy() - g[f'{tag}_out']).max())
+    scale = max(1.0, float(np.abs(g[f'{tag}_zone_emb']).max()))
+    print(f'{tag}: vs bf16 twin {e_twin:.2e}, vs real module zone_emb {e_emb:.2e}, forward {e_out:.2e}, scale {scale:.2f}')
+    assert e_twin <= BF16_TWIN_RTOL * scale and e_emb <= FP32_RTOL * scale and e_out <= FP32_RTOL * scale
+    # the numpy oracle agrees with what was compared against
+    assert np.abs(zm.zone_embedding({k: v.cpu().numpy() for k, v in sd.items()}, g[f'{tag}_obs'], g[f'{tag}_zone_obs'])
+                  - g[f'{tag}_zone_emb']).max() <= 2e-6
+
+
+@pytest.mark.parametrize('B,N,Z,h', [(4099, 15, 6, 185), (1, 15, 7, 185), (777, 5, 6, 96), (20000, 6, 7, 32)])
+def test_random_batches_against_torch(crl, B, N, Z, h):
+    """Ragged batch sizes (partial tiles, more tiles than SMs), every supported width class."""
+    gen = torch.Generator(device='cuda').manual_seed(B + h)
+    rn = lambda *s, scale=1.0: (torch.randn(*s, device='cuda', generator=gen) * scale)
+    sd = {'zone_net_.0.weight': rn(h, 8 + Z, scale=0.4), 'zone_net_.0.bias': rn(h, scale=0.2),
+          'zone_net_.2.weight': rn(h, h, scale=1.5 / h ** 0.5), 'zone_net_.2.bias': rn(h, scale=0.2),
+          'zone_net_.4.weight': rn(h, h, scale=1.5 / h ** 0.5), 'zone_net_.4.bias': rn(h, scale=0.2),
+          'combine_net_.weight': rn(h, 8 + h, scale=0.1), 'combine_net_.bias': rn(h, scale=0.1)}
+    obs, zobs = rn(B, 8), rn(B, N, Z)
+    enc = crl.ZoneEncoder(sd, num_zones=N)
+    out = torch.full((B + 3, h), 7.0, device='cuda')           # guard rows: nothing may be written past B
+    emb = enc.zone_embedding(obs, zobs, out=out[:B])
+    torch.cuda.synchronize()
+    assert enc.healthy() and bool((out[B:] == 7.0).all())
+    twin, ref = bf16_twin(sd, obs, zobs), fp32_ref(sd, obs, zobs)
+    e_twin, e_ref = float((emb - twin).abs().max()), float((emb - ref).abs().max())
+    print(f'B={B} N={N} Z={Z} h={h}: vs bf16 twin {e_twin:.2e}, vs fp32 {e_ref:.2e}, |ref| max {float(ref.abs().max()):.2f}')
+    scale = max(1.0, float(ref.abs().max()))
+    assert e_twin <= BF16_TWIN_RTOL * scale and e_ref <= FP32_RTOL * scale
+    # second call on the same encoder (barrier phases, TMEM re-allocation) gives the same bits
+    assert torch.equal(enc.zone_embedding(obs, zobs), emb)
+
+
+def test_encoder_on_the_env_outputs(crl):
+    """The fused step's outputs feed the encoder directly (obs (B,8), zone_obs (B,N,Z) as CrlOut lays them out)."""
+    g = np.load(GOLDEN)
+    sd = {k[7:]: torch.from_numpy(g[k]).cuda() for k in g.files if k.startswith('tsp_sd_')}
+    env = crl.ZoneVecEnv('PointTSP-v0', 4096)
+    env.seed(3)
+    obs = env.reset()
+    for _ in range(5):
+        obs, *_ = env.step_random(action_seed=2)
+    enc = crl.ZoneEncoder(sd, num_zones=15)
+    y = enc(obs)
+    ref = torch.nn.functional.linear(torch.cat([obs['obs'], fp32_ref(sd, obs['obs'], obs['zone_obs'])], -1),
+                                     sd['combine_net_.weight'], sd['combine_net_.bias'])
+    assert enc.healthy() and y.shape == (4096, 185)
+    assert float((y - ref).abs().max()) <= FP32_RTOL * max(1.0, float(ref.abs().max()))
+
+
+def test_unsupported_shapes_are_refused(crl):
+    from combinatorial_rl_tasks_b200 import _lib
+    import ctypes
+    lib = _lib.load()
+    n = ctypes.c_int64()
+    assert lib.crl_encoder_packed_bytes(_lib.CrlEncoderShape(8, 6, 185, 15), ctypes.byref(n)) == 0 and n.value == 2 * 192 * 192 * 2 + 192 * 32 + 3 * 192 * 4
+    assert lib.crl_encoder_packed_bytes(_lib.CrlEncoderShape(8, 6, 256, 15), ctypes.byref(n)) == -4    # two resident weights do not fit
+    assert lib.crl_encoder_packed_bytes(_lib.CrlEncoderShape(8, 9, 64, 15), ctypes.byref(n)) == -2     # input wider than 16
