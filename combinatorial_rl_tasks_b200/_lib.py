@@ -93,7 +93,7 @@ def load():
     lib.crl_check_state.argtypes = [P(CrlConfig), P(CrlState), c_void_p, c_void_p]
     lib.crl_counters_read.argtypes = [P(CrlState), P(c_double), c_void_p]
     lib.crl_encoder_packed_bytes.argtypes = [P(CrlEncoderShape), P(c_int64)]
-    lib.crl_encoder_pack.argtypes = [P(CrlEncoderShape)] + [c_void_p] * 8
+    lib.crl_encoder_pack.argtypes = [P(CrlEncoderShape)] + [c_void_p] * 6
     lib.crl_zone_encode.argtypes = [P(CrlEncoderShape), c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p]
     for name in SYMBOLS:

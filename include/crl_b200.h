@@ -342,12 +342,15 @@ int crl_check_state(const CrlConfig* cfg, const CrlState* st, uint64_t* violatio
 
 /* ---- the consumer of the observation: ZoneEnvModel's zone encoder ----
  * main/src/env_model.py:56-78: zone_net_ = Linear(obs_dim + Z, h), ReLU, Linear(h, h), ReLU, Linear(h, h)
- * applied to [obs[e], zone_obs[e][z]] for every zone, then the mean over the env's zones.  One fused
- * kernel on the tensor cores (tcgen05, bf16 operands, fp32 accumulation in TMEM; csrc/crl_encode.cu):
- * the three (B N, h) activations the reference materialises never leave the SM.  Inference only
- * (the rollout-time forward of BaseAlgo.collect_experiences, base.py:133-140); combine_net_ stays a
- * library GEMM on the caller's side.  hidden <= 192 (the default is 185, scripts/train_ppo.py:66),
- * obs_dim + zone_dim <= 16, num_zones <= 16. */
+ * applied to [obs[e], zone_obs[e][z]] for every zone, then the mean over the env's zones.  The third
+ * Linear is affine, so the mean commutes with it:
+ *     zone_emb = W3 pooled + b3,   pooled[e] = mean_z relu(W2 relu(W1 [obs[e], zone_obs[e][z]] + b1) + b2)
+ * crl_zone_encode computes `pooled` in one fused kernel on the tensor cores (tcgen05, bf16 operands,
+ * fp32 accumulation in TMEM; csrc/crl_encode.cu): the (B N, h) activations the reference materialises
+ * never leave the SM, and the third Linear shrinks from B N to B rows -- it and combine_net_ stay
+ * fp32 library GEMMs on the caller's side.  Inference only (the rollout-time forward of
+ * BaseAlgo.collect_experiences, base.py:133-140).  hidden <= 192 (the default is 185,
+ * scripts/train_ppo.py:66), obs_dim + zone_dim <= 16, num_zones <= 16. */
 typedef struct CrlEncoderShape {
   int32_t obs_dim;    /* 8 */
   int32_t zone_dim;   /* Z */
@@ -356,14 +359,15 @@ typedef struct CrlEncoderShape {
 } CrlEncoderShape;
 /* bytes of the packed-weights buffer (device, 16-byte aligned) */
 int crl_encoder_packed_bytes(const CrlEncoderShape* shape, int64_t* bytes);
-/* fp32 torch-layout weights ([out][in], device) -> the bf16 shared-memory image the kernel keeps resident */
+/* fp32 torch-layout weights of the first two Linears ([out][in], device) -> the bf16 shared-memory
+ * image the kernel keeps resident */
 int crl_encoder_pack(const CrlEncoderShape* shape, const float* w1, const float* b1, const float* w2,
-                     const float* b2, const float* w3, const float* b3, void* packed, void* stream);
-/* zone_emb float[B][h] = mean_z zone_net_([obs, zone_obs[:, z]]).  obs float[B][obs_dim], zone_obs
- * float[B][N][Z] (CrlOut's layout), all device.  status: optional device int32, set to 1 if a
- * tensor-core completion wait expired (results then undefined); never hangs. */
+                     const float* b2, void* packed, void* stream);
+/* pooled float[B][h] (see above).  obs float[B][obs_dim], zone_obs float[B][N][Z] (CrlOut's layout),
+ * all device.  status: optional device int32, set to 1 if a tensor-core completion wait expired
+ * (results then undefined); the kernel never hangs. */
 int crl_zone_encode(const CrlEncoderShape* shape, int32_t num_envs, const float* obs, const float* zone_obs,
-                    const void* packed, float* zone_emb, int32_t* status, void* stream);
+                    const void* packed, float* pooled, int32_t* status, void* stream);
 
 /* Copies the eight counters to the host (synchronises `stream`).  The first four (sum of
  * returns, episodes, successes, sum of lengths) are what ranks all-reduce. */
