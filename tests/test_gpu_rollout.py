@@ -127,12 +127,14 @@ def test_rollout_stores_in_place_and_matches_stepwise(crl, env_id):
     assert env.counters()['episodes'] == twin.counters()['episodes'] > 0
 
 
-def test_example_collect_loop_runs(crl):
-    """examples/collect_ppo.py end to end at a small size: rollout in place, GAE, one update."""
+@pytest.mark.parametrize('extra', [[], ['--fused-encoder']], ids=['torch', 'fused-encoder'])
+def test_example_collect_loop_runs(crl, extra):
+    """examples/collect_ppo.py end to end at a small size: rollout in place, GAE, one update; also with the
+    collection forward on the tcgen05 zone encoder (weights re-packed after each update)."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, os.path.join(root, 'examples', 'collect_ppo.py'), '--envs', '2048', '--frames', '16',
-                          '--updates', '2', '--env', 'ColourMatch-v0'], capture_output=True, text=True, timeout=300)
+                          '--updates', '2', '--env', 'ColourMatch-v0'] + extra, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.count('update ') >= 2 and 'loss' in out.stdout
