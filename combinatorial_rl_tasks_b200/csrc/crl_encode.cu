@@ -5,41 +5,48 @@
 //               = L3( pooled[e] ),   pooled[e] = 1/N * sum_z relu( L2( relu( L1( . ))))    (L3 is affine)
 //
 // The reference materialises three (B*N, h) activations (h = 185 by default,
-// main/scripts/train_ppo.py:66).  Here the kernel produces `pooled` (B, h) and nothing else: the two
-// wide GEMMs run on the 5th-gen tensor cores (tcgen05.mma, kind::f16 with bf16 operands, fp32
-// accumulators in TMEM, M = 128, N = HP = h padded to a multiple of 32, K = 16 per instruction),
-// W1 / W2 stay resident in shared memory for the whole (persistent) kernel, the epilogue of layer 1
-// (TMEM -> registers -> bias, ReLU, bf16 -> shared memory in the canonical K-major operand layout)
-// feeds layer 2, and the epilogue of layer 2 pools each env's zones with a butterfly of warp
-// shuffles.  The mean is taken BEFORE the third Linear, which turns L3 from a (B N, h) x (h, h) GEMM
-// into a (B, h) x (h, h) one: a third of the tensor work disappears, and L3 / combine_net_
-// (env_model.py:79) stay plain fp32 library GEMMs on the caller's side.
+// main/scripts/train_ppo.py:66).  Here the kernel produces `pooled` (B, h) and nothing else; the
+// mean is taken BEFORE the third Linear, which turns L3 from a (B N, h) x (h, h) GEMM into a
+// (B, h) x (h, h) one (a third of the tensor work gone): L3 and combine_net_ (env_model.py:79) stay
+// plain fp32 library GEMMs on the caller's side.
 //
-// A CTA = two independent groups of 256 threads, each walking its own sequence of tiles (8 envs =
-// 128 (env, zone) rows; zone slot 15 of an env is padding) with its own accumulator, operand buffers
-// and mbarrier: while one group is in an epilogue (CUDA cores) the other group's MMAs occupy the
-// tensor pipe.  Within a group, warps w and w + 4 share TMEM lane quadrant w % 4 (rows 32 (w % 4) ..)
-// and split the accumulator's columns.  The next tile's inputs are prefetched into registers.
+// The two wide GEMMs run TRANSPOSED on the 5th-gen tensor cores: H^T = W X^T, i.e. the weights are
+// the A operand (M = hidden units, in blocks of 128 = the TMEM lanes) and a tile of 8 envs = 128
+// (env, zone) rows is the N dimension (TMEM columns; zone slot 15 of an env is padding).
+// tcgen05.mma.cta_group::1.kind::f16: bf16 operands, fp32 accumulators in TMEM, M = 128, N = 128,
+// K = 16 per instruction.  Why transposed: an accumulator row lives in ONE thread's registers after
+// tcgen05.ld, so with the 16 zone slots of an env on consecutive COLUMNS the mean over zones is 15
+// register adds per env -- no shuffles -- and lane j stores hidden unit j, i.e. coalesced rows of the
+// output.  (The first version had rows = (env, zone) on the lanes: half of its instructions were a
+// shuffle butterfly.)  W1 / W2 stay resident in shared memory for the whole persistent kernel.
 //
-// The epilogues are the bottleneck of such a narrow MLP (K = 192 gives the tensor pipe 13 x 96 cycles
-// per tile, while 2 x 96 KB of accumulator have to come back through registers), so they are kept
-// minimal: the BIASES ARE FOLDED INTO THE GEMMS -- the operand rows carry constant-1 columns (layer 1:
-// columns in_dim, in_dim + 1 of the 16; layer 2: columns h, h + 1 of HP, produced by two "generator"
-// rows of W1) that multiply the bias split into a bf16 high and low part -- so epilogue 1 is one
-// cvt.rn.relu.bf16x2 per pair of values and epilogue 2 one max per value plus the pooling butterfly.
+// Epilogues are the bottleneck of such a narrow MLP (K <= 192 gives the tensor pipe ~1,700 cycles per
+// tile while 2 x 96 KB of accumulator come back through registers), so they are minimal:
+//  * the BIASES ARE FOLDED INTO THE GEMMS -- the K dimension carries constant-1 entries (layer 1:
+//    input columns in_dim, in_dim + 1; layer 2: hidden rows h, h + 1, produced by two "generator" rows
+//    of W1) that multiply the bias split into a bf16 high and low part;
+//  * epilogue 1 = one cvt.rn.relu.bf16x2.f32 per pair of values + 16-byte stores: 8 consecutive rows m of
+//    one hidden unit j are exactly one 16-byte unit of the layer-2 B operand in MN-major layout;
+//  * epilogue 2 = one max per value + the register adds + two coalesced stores per 32 values.
 // A padding row is all zeros including its ones, hence stays exactly zero through both layers and
 // drops out of the mean by itself.
+//
+// A CTA = two independent groups of 256 threads, each walking its own sequence of tiles with its own
+// accumulators, operand buffers and mbarrier: while one group is in an epilogue (CUDA cores) the other
+// group's MMAs occupy the tensor pipe.  Warp w of a group owns TMEM lane quadrant w % 4 of M-block
+// w / 4.  The next tile's inputs are prefetched into registers.  Every wait is bounded.
 //
 // A separate translation unit on purpose: nothing here can move the register allocation of the
 // step kernels (crl_kernels.cu; see profiles/r01_notes.md on how easily that happens).
 //
-// Operand layout in shared memory (no swizzle, "interleaved" K-major canonical layout of
-// cute::UMMA, mma_traits_sm100.hpp: ((8,n),2):((1,SBO),LBO) in 16-byte units): element (row r,
-// column k) of an R x K bf16 matrix lives at byte
-//     (r % 8) * 16 + (r / 8) * (16 K) + (k / 8) * 128 + (k % 8) * 2
-// i.e. 8x8 core matrices of 128 contiguous bytes, consecutive along K (LBO = 128 B), 8-row groups
-// 16 K bytes apart (SBO).  One tcgen05.mma consumes K = 16 = two core matrices; k-step s starts
-// 256 s bytes into the image.
+// Shared-memory operand images (no swizzle; canonical layouts of cute::UMMA, mma_traits_sm100.hpp), all
+// made of 8 x 8 core matrices of 128 contiguous bytes:
+//  K-major (W1, W2 as A; the input rows X as B of layer 1): element (r, k) of an R x K matrix at
+//      (r % 8) * 16 + (r / 8) * (16 K) + (k / 8) * 128 + (k % 8) * 2      LBO = 128 (next core matrix along K),
+//                                                                         SBO = 16 K (next 8 rows)
+//  MN-major (the layer-1 activations H1 as B of layer 2, N = row m, K = hidden unit j): element (m, j) at
+//      (j % 8) * 16 + (j / 8) * 2048 + (m / 8) * 128 + (m % 8) * 2        LBO = 2048 (next 8 j), SBO = 128 (next 8 m)
+// One tcgen05.mma consumes K = 16 = two core matrices along K.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -48,34 +55,37 @@
 
 namespace crl_enc {
 
-constexpr int kRows = 128;          // rows of a tile = TMEM lanes
-constexpr int kGroupThreads = 256;  // 8 warps: two per TMEM lane quadrant
+constexpr int kRows = 128;          // (env, zone) rows of a tile = the N of every MMA = accumulator columns
+constexpr int kGroupThreads = 256;  // 8 warps: one per (M-block, TMEM lane quadrant)
 constexpr int kGroups = 2;          // independent groups per CTA
 constexpr int kEnvsPerTile = 8;     // 16 row slots per env (N <= 16)
 constexpr int kK1 = 16;             // padded input width of layer 1 (obs_dim + zone_dim + a ones column <= 16)
-constexpr uint32_t kTmemCols = 512; // one accumulator of up to 256 columns per group; the CTA owns the SM
+constexpr uint32_t kTmemCols = 512; // two M-blocks x 128 columns per group; the CTA owns the SM
 constexpr uint32_t kSpinLimit = 1u << 24;
 
-// accumulator width: h plus at least one spare column (the ones column of layer 2), multiple of 32
-__host__ __device__ inline int padded_hidden(int h) { return (h + 1 + 31) & ~31; }
+// K of layer 2: the h hidden units plus the two ones rows, multiple of 16
+__host__ __device__ inline int padded_k(int h) { return (h + 2 + 15) & ~15; }
+// M of both layers: blocks of 128 lanes covering padded_k (the ones rows are outputs of layer 1)
+__host__ __device__ inline int padded_m(int h) { return (padded_k(h) + 127) & ~127; }
 
-// byte offset of element (r, k) in the canonical image of a matrix with K columns
+// byte offset of element (r, k) in the K-major image of a matrix with K columns
 __host__ __device__ inline uint32_t canon(int r, int k, int K) {
   return (uint32_t)((r & 7) * 16 + (r >> 3) * (16 * K) + (k >> 3) * 128 + (k & 7) * 2);
 }
 
 struct Offsets {   // byte offsets: packed weight buffer == start of shared memory; then per-group buffers
-  uint32_t w2, w1, packed_end, group0, abuf, a1buf, bar, group_bytes, tmem_slot, smem_end;
+  uint32_t w2, w1, packed_end, group0, h1, xbuf, bar, group_bytes, tmem_slot, smem_end;
 };
-__host__ __device__ inline Offsets offsets(int HP) {
+__host__ __device__ inline Offsets offsets(int h) {
+  const int KP = padded_k(h), MP = padded_m(h);
   Offsets o;
   o.w2 = 0;
-  o.w1 = o.w2 + (uint32_t)HP * HP * 2;
-  o.packed_end = o.w1 + (uint32_t)HP * kK1 * 2;
+  o.w1 = o.w2 + (uint32_t)MP * KP * 2;
+  o.packed_end = o.w1 + (uint32_t)MP * kK1 * 2;
   o.group0 = (o.packed_end + 127u) & ~127u;
-  o.abuf = 0;                                            // relative to the group's base
-  o.a1buf = o.abuf + (uint32_t)kRows * HP * 2;
-  o.bar = o.a1buf + (uint32_t)kRows * kK1 * 2;
+  o.h1 = 0;                                              // relative to the group's base
+  o.xbuf = o.h1 + (uint32_t)KP * kRows * 2;
+  o.bar = o.xbuf + (uint32_t)kRows * kK1 * 2;
   o.group_bytes = (o.bar + 8 + 127u) & ~127u;
   o.tmem_slot = o.group0 + kGroups * o.group_bytes;
   o.smem_end = o.tmem_slot + 16;
@@ -86,19 +96,19 @@ __host__ __device__ inline Offsets offsets(int HP) {
 struct PackArgs {
   const float *w1, *b1, *w2, *b2;
   uint8_t* out;
-  int in_dim, h, HP;
+  int in_dim, h;
 };
 
 __global__ void pack_kernel(const PackArgs a) {
-  const Offsets o = offsets(a.HP);
-  const int HP = a.HP;
-  const int n_w = HP * HP, n_w1 = HP * kK1;
+  const Offsets o = offsets(a.h);
+  const int KP = padded_k(a.h), MP = padded_m(a.h);
+  const int n_w = MP * KP, n_w1 = MP * kK1;
   const int total = n_w + n_w1;
-  // bias = hi + lo with hi = bf16(bias), lo = bf16(bias - hi): column `ones` of the operand carries 1
-  // and multiplies hi, column `ones + 1` (when the matrix has one) multiplies lo
+  // bias = hi + lo with hi = bf16(bias), lo = bf16(bias - hi): entry `ones` of the K dimension carries 1
+  // and multiplies hi, entry `ones + 1` multiplies lo (layer 1 has the second one only if in_dim < 15)
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const bool second = i < n_w;
-    const int K = second ? HP : kK1, ones = second ? a.h : a.in_dim;
+    const int K = second ? KP : kK1, ones = second ? a.h : a.in_dim;
     const int j = second ? i : i - n_w, n = j / K, k = j % K;
     const float* w = second ? a.w2 : a.w1;
     const float* b = second ? a.b2 : a.b1;
@@ -108,7 +118,7 @@ __global__ void pack_kernel(const PackArgs a) {
       else if (k == ones) v = __bfloat162float(__float2bfloat16_rn(b[n]));
       else if (k == ones + 1) v = b[n] - __bfloat162float(__float2bfloat16_rn(b[n]));
     } else if (!second && (n == a.h || n == a.h + 1) && k == ones) {
-      v = 1.f;                                   // generator rows of W1: layer 2's ones columns h, h + 1
+      v = 1.f;                                   // generator rows of W1: layer 2's ones entries h, h + 1
     }
     *reinterpret_cast<__nv_bfloat16*>(a.out + (second ? o.w2 : o.w1) + canon(n, k, K)) = __float2bfloat16_rn(v);
   }
@@ -121,10 +131,10 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// shared-memory matrix descriptor: start address, LBO = 128 B, SBO, version 1 (sm_100), no swizzle
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t sbo_bytes) {
-  return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) |
-         (1ull << 46);
+// shared-memory matrix descriptor: start address, LBO, SBO, version 1 (sm_100), no swizzle
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, issued by one thread
@@ -190,10 +200,10 @@ struct EncArgs {
   const uint8_t* packed;
   float* out;              // [B][h]: pooled hidden activation
   int* status;             // device int: set to 1 if a tensor-core wait expired
-  int B, N, Z, obs_dim, h, HP, n_tiles;
+  int B, N, Z, obs_dim, h, n_tiles;
 };
 
-// eight consecutive values (k = 8 half .. 8 half + 7) of row (e, slot) of the layer-1 operand
+// eight consecutive values (k = 8 half .. 8 half + 7) of row (e, slot) of the layer-1 input
 // [obs[e], zone_obs[e][slot], 1, 1, 0...]; all zeros -- the ones included -- for a padding row
 __device__ __forceinline__ void load_half_row(const EncArgs& a, int tile, int m, int half, float (&x)[8]) {
 #pragma unroll
@@ -213,55 +223,43 @@ __device__ __forceinline__ void load_half_row(const EncArgs& a, int tile, int m,
   }
 }
 
-// relu(acc) of 32 columns of this thread's row -> bf16 -> the next layer's A operand
-__device__ __forceinline__ void relu_to_smem(const uint32_t (&v)[32], uint8_t* abuf, uint32_t row_off, int c) {
+// relu of 32 consecutive rows m of this thread's hidden unit -> bf16 -> four 16-byte units of H1
+__device__ __forceinline__ void relu_to_h1(const uint32_t (&v)[32], uint8_t* h1_row, int c) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    *reinterpret_cast<uint4*>(abuf + row_off + (uint32_t)((c * 4 + q) * 128)) =
+    *reinterpret_cast<uint4*>(h1_row + (uint32_t)((c * 4 + q) * 128)) =
         make_uint4(relu_pack_bf16(v[q * 8 + 0], v[q * 8 + 1]), relu_pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
                    relu_pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), relu_pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
   }
 }
 
-// relu(acc) of 32 columns, summed over the 16 rows (lanes) of an env.  A butterfly in which every
-// step halves what a lane carries: with partner lane ^ off, the lane whose bit `off` is clear keeps
-// the lower half of its values and receives the partner's lower half, the other lane the upper
-// halves: 16 + 8 + 4 + 2 = 30 shuffles instead of 32 x 4.  Lane L of the half-warp ends up with the
-// sums of columns 2L and 2L + 1 of the chunk, which it stores scaled by 1/N.
-__device__ __forceinline__ void relu_pool_store(const uint32_t (&v)[32], int lane, float inv_n, float* dst_row, int c, int h) {
-  float x[32];
+// 32 consecutive rows m = the 16 zone slots of envs e0 and e0 + 1: relu, sum in registers, store column j
+__device__ __forceinline__ void relu_pool_store(const uint32_t (&v)[32], const EncArgs& a, int e0, int j, float inv_n) {
+  float s0[8], s1[8];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) x[j] = fmaxf(__uint_as_float(v[j]), 0.f);
-#define CRL_BUTTERFLY(HALF, OFF)                                        \
-  {                                                                     \
-    const bool upper = (lane & OFF) != 0;                               \
-    _Pragma("unroll") for (int i = 0; i < HALF; ++i) {                  \
-      const float send = upper ? x[i] : x[i + HALF];                    \
-      const float keep = upper ? x[i + HALF] : x[i];                    \
-      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);            \
-    }                                                                   \
+  for (int i = 0; i < 8; ++i) {
+    s0[i] = fmaxf(__uint_as_float(v[2 * i]), 0.f) + fmaxf(__uint_as_float(v[2 * i + 1]), 0.f);
+    s1[i] = fmaxf(__uint_as_float(v[16 + 2 * i]), 0.f) + fmaxf(__uint_as_float(v[16 + 2 * i + 1]), 0.f);
   }
-  CRL_BUTTERFLY(16, 8)
-  CRL_BUTTERFLY(8, 4)
-  CRL_BUTTERFLY(4, 2)
-  CRL_BUTTERFLY(2, 1)
-#undef CRL_BUTTERFLY
-  if (dst_row) {
-    const int col = c * 32 + 2 * (lane & 15);
-    if (col < h) dst_row[col] = x[0] * inv_n;
-    if (col + 1 < h) dst_row[col + 1] = x[1] * inv_n;
+  const float p0 = ((s0[0] + s0[1]) + (s0[2] + s0[3])) + ((s0[4] + s0[5]) + (s0[6] + s0[7]));
+  const float p1 = ((s1[0] + s1[1]) + (s1[2] + s1[3])) + ((s1[4] + s1[5]) + (s1[6] + s1[7]));
+  if (j < a.h) {
+    if (e0 < a.B) a.out[(size_t)e0 * a.h + j] = p0 * inv_n;
+    if (e0 + 1 < a.B) a.out[(size_t)(e0 + 1) * a.h + j] = p1 * inv_n;
   }
 }
 
 __global__ void __launch_bounds__(kGroupThreads * kGroups, 1) zone_encode_kernel(const EncArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const Offsets o = offsets(a.HP);
+  const Offsets o = offsets(a.h);
+  const int KP = padded_k(a.h), MP = padded_m(a.h);
+  const int n_mblocks = MP / 128;
   const int group = threadIdx.x / kGroupThreads;              // 0 / 1
   const int t = threadIdx.x % kGroupThreads;
-  const int m = t & (kRows - 1);                              // row of the tile = TMEM lane
-  const int half = t >> 7;                                    // which half of the columns / of the input row
-  const int quad = (t >> 5) & 3, lane = t & 31;               // TMEM lane quadrant of this warp
-  const int HP = a.HP;
+  const int m = t & (kRows - 1), half = t >> 7;               // input row / half of it this thread stages
+  const int warp = t >> 5, lane = t & 31;
+  const int mblock = warp >> 2, quad = warp & 3;              // accumulator rows this warp drains
+  const int j = mblock * 128 + quad * 32 + lane;              // hidden unit (accumulator row) of this thread
   uint8_t* gbase = smem + o.group0 + (uint32_t)group * o.group_bytes;
   uint64_t* bar = reinterpret_cast<uint64_t*>(gbase + o.bar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + o.tmem_slot);
@@ -288,19 +286,19 @@ __global__ void __launch_bounds__(kGroupThreads * kGroups, 1) zone_encode_kernel
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t acc = tmem_base + (uint32_t)group * 256u;    // this group's accumulator columns
-  const uint32_t my_acc = acc + ((uint32_t)(quad * 32) << 16);
-  // instruction descriptor: D fp32, A and B bf16, both K-major, N = HP, M = 128
-  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HP >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
-  uint8_t* abuf = gbase + o.abuf;
-  uint8_t* a1buf = gbase + o.a1buf;
-  const uint32_t abuf_addr = smem_u32(abuf), a1_addr = smem_u32(a1buf);
+  const uint32_t acc = tmem_base + (uint32_t)group * 256u;    // this group's accumulators: M-block b at + 128 b
+  const uint32_t my_acc = acc + (uint32_t)(mblock * 128) + ((uint32_t)(quad * 32) << 16);
+  // instruction descriptors: D fp32, A and B bf16, M = 128, N = 128; layer 1: both K-major; layer 2: B MN-major
+  const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kRows >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint32_t idesc2 = idesc1 | (1u << 16);
+  uint8_t* h1buf = gbase + o.h1;
+  uint8_t* xbuf = gbase + o.xbuf;
+  const uint32_t h1_addr = smem_u32(h1buf), x_addr = smem_u32(xbuf);
   const uint32_t w1_addr = smem_u32(smem + o.w1), w2_addr = smem_u32(smem + o.w2);
-  const uint32_t a1_off = (uint32_t)((m & 7) * 16 + (m >> 3) * (16 * kK1) + half * 128);
-  const uint32_t a_off = (uint32_t)((m & 7) * 16 + (m >> 3) * (16 * HP));
-  const int n_chunks = HP / 32;
-  const int c_split = (n_chunks + 1) / 2;
-  const int c_begin = half ? c_split : 0, c_end = half ? n_chunks : c_split;   // this warp's column chunks
+  const uint32_t x_off = (uint32_t)((m & 7) * 16 + (m >> 3) * (16 * kK1) + half * 128);
+  const uint32_t h1_off = (uint32_t)((j & 7) * 16 + (j >> 3) * 2048);
+  const bool drains1 = mblock < n_mblocks && mblock * 128 + quad * 32 < KP;     // layer 2 reads hidden rows < KP
+  const bool drains2 = mblock < n_mblocks && mblock * 128 + quad * 32 < a.h;    // the output has h columns
   const float inv_n = 1.0f / (float)a.N;
   uint32_t parity = 0u;
   bool healthy = true;
@@ -310,52 +308,67 @@ __global__ void __launch_bounds__(kGroupThreads * kGroups, 1) zone_encode_kernel
   float x[8];
   load_half_row(a, tile, m, half, x);
   for (; tile < a.n_tiles; tile += tile_stride) {
-    const int e = tile * kEnvsPerTile + (m >> 4);
-    // ---- layer-1 operand from the prefetched registers ---------------------------------------
-    *reinterpret_cast<uint4*>(a1buf + a1_off) =
+    // ---- layer-1 B operand (the tile's 128 input rows) from the prefetched registers ----------
+    *reinterpret_cast<uint4*>(xbuf + x_off) =
         make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
     fence_async_smem();
     tc_fence_before();
     group_sync(group);
-    // ---- layer 1: [128 x 16] x [16 x HP] -> acc ---------------------------------------------
+    // ---- layer 1: H1^T[128 b ..][m] = W1[128 b ..][16] X^T -------------------------------------
     if (t == 0) {
       tc_fence_after();
-      mma_bf16(acc, smem_desc(a1_addr, 16 * kK1), smem_desc(w1_addr, 16 * kK1), idesc, 0u);
+      for (int b = 0; b < n_mblocks; ++b)
+        mma_bf16(acc + (uint32_t)(b * 128), smem_desc(w1_addr + (uint32_t)(b * 16 * 16 * kK1), 128u, 16 * kK1),
+                 smem_desc(x_addr, 128u, 16 * kK1), idesc1, 0u);
       mma_commit(bar_addr);
     }
     load_half_row(a, tile + tile_stride, m, half, x);         // prefetch: in flight for the rest of the tile
     healthy = mbar_wait(bar_addr, parity) && healthy;
     parity ^= 1u;
     tc_fence_after();
-    for (int c = c_begin; c < c_end; ++c) {
-      uint32_t v[32];
-      tmem_ld32(my_acc + (uint32_t)(c * 32), v);
-      tmem_ld_wait(v);
-      relu_to_smem(v, abuf, a_off, c);
+    if (drains1) {
+      // this thread: hidden unit j, rows m = 32 c .. 32 c + 31 -> relu -> bf16 -> four 16-byte units of H1
+#pragma unroll 1
+      for (int c = 0; c < kRows / 32; c += 2) {               // two TMEM loads in flight
+        uint32_t v0[32], v1[32];
+        tmem_ld32(my_acc + (uint32_t)(c * 32), v0);
+        tmem_ld32(my_acc + (uint32_t)(c * 32 + 32), v1);
+        tmem_ld_wait(v0);
+        relu_to_h1(v0, h1buf + h1_off, c);
+        tmem_ld_wait(v1);
+        relu_to_h1(v1, h1buf + h1_off, c + 1);
+      }
     }
     fence_async_smem();
     tc_fence_before();
     group_sync(group);
-    // ---- layer 2: [128 x HP] x [HP x HP] -> acc (layer 1's values have been read) -------------
+    // ---- layer 2: H2^T[128 b ..][m] = W2[128 b ..][KP] H1^T (layer 1's values have been read) ---
     if (t == 0) {
       tc_fence_after();
-      for (int s = 0; s < HP / 16; ++s)
-        mma_bf16(acc, smem_desc(abuf_addr + 256u * s, 16 * HP), smem_desc(w2_addr + 256u * s, 16 * HP), idesc, s > 0);
+      for (int b = 0; b < n_mblocks; ++b)
+        for (int s = 0; s < KP / 16; ++s)
+          mma_bf16(acc + (uint32_t)(b * 128), smem_desc(w2_addr + (uint32_t)(b * 16 * 16 * KP) + 256u * s, 128u, 16 * KP),
+                   smem_desc(h1_addr + 4096u * s, 2048u, 128u), idesc2, s > 0);
       mma_commit(bar_addr);
     }
     healthy = mbar_wait(bar_addr, parity) && healthy;
     parity ^= 1u;
     tc_fence_after();
-    // ---- ReLU, mean over the env's zones, store ----------------------------------------------
-    float* dst_row = e < a.B ? a.out + (size_t)e * a.h : nullptr;
-    for (int c = c_begin; c < c_end; ++c) {
-      uint32_t v[32];
-      tmem_ld32(my_acc + (uint32_t)(c * 32), v);
-      tmem_ld_wait(v);
-      relu_pool_store(v, lane, inv_n, dst_row, c, a.h);
+    // ---- ReLU, mean over each env's 16 zone slots (register adds), coalesced stores -----------
+    if (drains2) {
+#pragma unroll 1
+      for (int c = 0; c < kRows / 32; c += 2) {               // two TMEM loads in flight
+        uint32_t v0[32], v1[32];
+        tmem_ld32(my_acc + (uint32_t)(c * 32), v0);
+        tmem_ld32(my_acc + (uint32_t)(c * 32 + 32), v1);
+        tmem_ld_wait(v0);
+        relu_pool_store(v0, a, tile * kEnvsPerTile + 2 * c, j, inv_n);
+        tmem_ld_wait(v1);
+        relu_pool_store(v1, a, tile * kEnvsPerTile + 2 * c + 2, j, inv_n);
+      }
     }
-    // the next tile's layer-1 MMA overwrites acc: ordered after these loads by the fence and the
-    // group barrier that precede it
+    // the next tile's layer-1 MMA overwrites the accumulators: ordered after these loads by the fence
+    // and the group barrier that precede it
   }
   if (!healthy && a.status) atomicExch(a.status, 1);
   tc_fence_before();
@@ -370,7 +383,7 @@ static int check_shape(const CrlEncoderShape* s) {
   if (s->obs_dim <= 0 || s->zone_dim <= 0 || s->obs_dim + s->zone_dim >= kK1) return CRL_ERR_CONFIG;   // + a ones column
   if (s->num_zones <= 0 || s->num_zones > 16) return CRL_ERR_CONFIG;
   if (s->hidden <= 0) return CRL_ERR_CONFIG;
-  if (padded_hidden(s->hidden) > 192) return CRL_ERR_UNSUPPORTED;   // resident W2 + two operand buffers must fit an SM
+  if (padded_k(s->hidden) > 192) return CRL_ERR_UNSUPPORTED;   // resident W2 + two groups' operand buffers must fit an SM
   return CRL_OK;
 }
 
@@ -384,7 +397,7 @@ int crl_encoder_packed_bytes(const CrlEncoderShape* s, int64_t* bytes) {
   const int rc = check_shape(s);
   if (rc) return rc;
   if (!bytes) return CRL_ERR_NULL;
-  *bytes = (int64_t)offsets(padded_hidden(s->hidden)).packed_end;
+  *bytes = (int64_t)offsets(s->hidden).packed_end;
   return CRL_OK;
 }
 
@@ -394,7 +407,7 @@ int crl_encoder_pack(const CrlEncoderShape* s, const float* w1, const float* b1,
   if (rc) return rc;
   if (!w1 || !b1 || !w2 || !b2 || !packed) return CRL_ERR_NULL;
   if (reinterpret_cast<uintptr_t>(packed) & 15u) return CRL_ERR_ALIGN;
-  PackArgs a{w1, b1, w2, b2, static_cast<uint8_t*>(packed), s->obs_dim + s->zone_dim, s->hidden, padded_hidden(s->hidden)};
+  PackArgs a{w1, b1, w2, b2, static_cast<uint8_t*>(packed), s->obs_dim + s->zone_dim, s->hidden};
   pack_kernel<<<148, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   return cudaGetLastError() == cudaSuccess ? CRL_OK : CRL_ERR_LAUNCH;
 }
@@ -406,8 +419,7 @@ int crl_zone_encode(const CrlEncoderShape* s, int32_t num_envs, const float* obs
   if (!obs || !zone_obs || !packed || !pooled) return CRL_ERR_NULL;
   if (num_envs <= 0) return CRL_ERR_CONFIG;
   if (reinterpret_cast<uintptr_t>(packed) & 15u) return CRL_ERR_ALIGN;
-  const int HP = padded_hidden(s->hidden);
-  const Offsets o = offsets(HP);
+  const Offsets o = offsets(s->hidden);
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(zone_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
@@ -415,7 +427,7 @@ int crl_zone_encode(const CrlEncoderShape* s, int32_t num_envs, const float* obs
     attr_set = true;
   }
   EncArgs a{obs, zone_obs, static_cast<const uint8_t*>(packed), pooled, status, num_envs, s->num_zones, s->zone_dim,
-            s->obs_dim, s->hidden, HP, (num_envs + kEnvsPerTile - 1) / kEnvsPerTile};
+            s->obs_dim, s->hidden, (num_envs + kEnvsPerTile - 1) / kEnvsPerTile};
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int want = (a.n_tiles + kGroups - 1) / kGroups;

@@ -349,8 +349,8 @@ int crl_check_state(const CrlConfig* cfg, const CrlState* st, uint64_t* violatio
  * fp32 accumulation in TMEM; csrc/crl_encode.cu): the (B N, h) activations the reference materialises
  * never leave the SM, and the third Linear shrinks from B N to B rows -- it and combine_net_ stay
  * fp32 library GEMMs on the caller's side.  Inference only (the rollout-time forward of
- * BaseAlgo.collect_experiences, base.py:133-140).  hidden <= 192 (the default is 185,
- * scripts/train_ppo.py:66), obs_dim + zone_dim <= 16, num_zones <= 16. */
+ * BaseAlgo.collect_experiences, base.py:133-140).  hidden <= 190 (the default is 185,
+ * scripts/train_ppo.py:66), obs_dim + zone_dim <= 15, num_zones <= 16. */
 typedef struct CrlEncoderShape {
   int32_t obs_dim;    /* 8 */
   int32_t zone_dim;   /* Z */

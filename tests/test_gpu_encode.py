@@ -42,7 +42,7 @@ def bf16_twin(sd, obs, zone_obs):
         return hi + r(b.to(torch.float64) - hi) if room_for_lo else hi
     h, in_dim = sd['zone_net_.0.weight'].shape
     x = r(torch.relu(x @ r(sd['zone_net_.0.weight']).T + bias(sd['zone_net_.0.bias'], in_dim + 1 < 16)).to(torch.float32))
-    x = torch.relu(x @ r(sd['zone_net_.2.weight']).T + bias(sd['zone_net_.2.bias'], (h + 1) % 32 != 0))
+    x = torch.relu(x @ r(sd['zone_net_.2.weight']).T + bias(sd['zone_net_.2.bias'], True))
     pooled = x.sum(dim=1) / N                        # the kernel's output; the third Linear is fp32 on (B, h)
     return (pooled @ sd['zone_net_.4.weight'].to(torch.float64).T + sd['zone_net_.4.bias'].to(torch.float64)).to(torch.float32)
 
@@ -125,6 +125,6 @@ def test_unsupported_shapes_are_refused(crl):
     import ctypes
     lib = _lib.load()
     n = ctypes.c_int64()
-    assert lib.crl_encoder_packed_bytes(_lib.CrlEncoderShape(8, 6, 185, 15), ctypes.byref(n)) == 0 and n.value == 192 * 192 * 2 + 192 * 32
+    assert lib.crl_encoder_packed_bytes(_lib.CrlEncoderShape(8, 6, 185, 15), ctypes.byref(n)) == 0 and n.value == 256 * 192 * 2 + 256 * 32
     assert lib.crl_encoder_packed_bytes(_lib.CrlEncoderShape(8, 6, 256, 15), ctypes.byref(n)) == -4    # two resident weights do not fit
     assert lib.crl_encoder_packed_bytes(_lib.CrlEncoderShape(8, 8, 64, 15), ctypes.byref(n)) == -2     # no room for the ones column in the 16-wide input
