@@ -420,16 +420,17 @@ int crl_zone_encode(const CrlEncoderShape* s, int32_t num_envs, const float* obs
   if (num_envs <= 0) return CRL_ERR_CONFIG;
   if (reinterpret_cast<uintptr_t>(packed) & 15u) return CRL_ERR_ALIGN;
   const Offsets o = offsets(s->hidden);
-  static bool attr_set = false;
-  if (!attr_set) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess) return CRL_ERR_DEVICE;
+  static bool attr_set[64] = {false};                       // per device: opt in to > 48 KB of dynamic shared memory
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     if (cudaFuncSetAttribute(zone_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return CRL_ERR_DEVICE;
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   EncArgs a{obs, zone_obs, static_cast<const uint8_t*>(packed), pooled, status, num_envs, s->num_zones, s->zone_dim,
             s->obs_dim, s->hidden, (num_envs + kEnvsPerTile - 1) / kEnvsPerTile};
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int want = (a.n_tiles + kGroups - 1) / kGroups;
   const int grid = want < sms ? want : sms;                   // persistent: one CTA per SM, weights loaded once
   zone_encode_kernel<<<grid, kGroupThreads * kGroups, o.smem_end, static_cast<cudaStream_t>(stream)>>>(a);

@@ -65,6 +65,7 @@ class ZoneEncoder:
         assert obs.dtype == zone_obs.dtype == torch.float32 and obs.is_contiguous() and zone_obs.is_contiguous()
         if out is None:
             out = torch.empty(B, self.hidden, dtype=torch.float32, device=self.device)
+        assert out.shape == (B, self.hidden) and out.dtype == torch.float32 and out.is_contiguous()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.crl_zone_encode(self.shape, B, obs.data_ptr(), zone_obs.data_ptr(),
                                                 self.packed.data_ptr(), out.data_ptr(), self._status.data_ptr(),

@@ -137,6 +137,31 @@ def test_design_twin_honours_fixed_placements():
         assert not np.array_equal(free['xy0'], t[0, :2])
 
 
+def test_encoder_shape_checks_run_on_the_host():
+    """crl_encoder_packed_bytes: limits of the tcgen05 zone encoder are refused before anything is launched."""
+    from combinatorial_rl_tasks_b200 import _lib
+    lib = _lib.load()
+    n = ctypes.c_int64()
+    S = _lib.CrlEncoderShape
+    assert lib.crl_encoder_packed_bytes(S(8, 6, 185, 15), ctypes.byref(n)) == 0 and n.value == 256 * 192 * 2 + 256 * 32
+    assert lib.crl_encoder_packed_bytes(S(8, 7, 64, 6), ctypes.byref(n)) == 0 and n.value == 128 * 80 * 2 + 128 * 32
+    assert lib.crl_encoder_packed_bytes(S(8, 6, 190, 15), ctypes.byref(n)) == 0
+    assert lib.crl_encoder_packed_bytes(S(8, 6, 191, 15), ctypes.byref(n)) == -4     # W2 + operand buffers exceed an SM
+    assert lib.crl_encoder_packed_bytes(S(8, 8, 64, 15), ctypes.byref(n)) == -2      # no room for the ones column
+    assert lib.crl_encoder_packed_bytes(S(8, 6, 64, 17), ctypes.byref(n)) == -2      # more than 16 zone slots
+    assert lib.crl_encoder_packed_bytes(None, ctypes.byref(n)) == -1
+    assert lib.crl_zone_encode(S(8, 6, 185, 15), 64, None, None, None, None, None, None) == -1
+
+
+def test_encoder_fails_loudly_without_cuda():
+    torch = pytest.importorskip('torch')
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    import combinatorial_rl_tasks_b200 as crl
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        crl.ZoneEncoder({}, num_zones=15)
+
+
 def test_vec_env_fails_loudly_without_cuda():
     torch = pytest.importorskip('torch')
     if torch.cuda.is_available():
