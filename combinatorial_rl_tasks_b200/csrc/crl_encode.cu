@@ -11,8 +11,9 @@
 // plain fp32 library GEMMs on the caller's side.
 //
 // The two wide GEMMs run TRANSPOSED on the 5th-gen tensor cores: H^T = W X^T, i.e. the weights are
-// the A operand (M = hidden units, in blocks of 128 = the TMEM lanes) and a tile of 8 envs = 128
-// (env, zone) rows is the N dimension (TMEM columns; zone slot 15 of an env is padding).
+// the A operand (M = hidden units, in blocks of 128 = the TMEM lanes) and a tile of 128 (env, zone) rows
+// -- 8 envs of 16 zone slots, or 16 envs of 8 slots when N <= 8; slots beyond N are padding -- is the N
+// dimension (TMEM columns).
 // tcgen05.mma.cta_group::1.kind::f16: bf16 operands, fp32 accumulators in TMEM, M = 128, N = 128,
 // K = 16 per instruction.  Why transposed: an accumulator row lives in ONE thread's registers after
 // tcgen05.ld, so with the 16 zone slots of an env on consecutive COLUMNS the mean over zones is 15
@@ -58,7 +59,8 @@ namespace crl_enc {
 constexpr int kRows = 128;          // (env, zone) rows of a tile = the N of every MMA = accumulator columns
 constexpr int kGroupThreads = 256;  // 8 warps: one per (M-block, TMEM lane quadrant)
 constexpr int kGroups = 2;          // independent groups per CTA
-constexpr int kEnvsPerTile = 8;     // 16 row slots per env (N <= 16)
+// an env owns S = 8 (N <= 8) or 16 consecutive row slots of a tile; the slots beyond N are padding rows
+__host__ __device__ inline int slots_per_env(int n_zones) { return n_zones <= 8 ? 8 : 16; }
 constexpr int kK1 = 16;             // padded input width of layer 1 (obs_dim + zone_dim + a ones column <= 16)
 constexpr uint32_t kTmemCols = 512; // two M-blocks x 128 columns per group; the CTA owns the SM
 constexpr uint32_t kSpinLimit = 1u << 24;
@@ -200,7 +202,7 @@ struct EncArgs {
   const uint8_t* packed;
   float* out;              // [B][h]: pooled hidden activation
   int* status;             // device int: set to 1 if a tensor-core wait expired
-  int B, N, Z, obs_dim, h, n_tiles;
+  int B, N, Z, obs_dim, h, n_tiles, S;   // S = slots_per_env(N)
 };
 
 // eight consecutive values (k = 8 half .. 8 half + 7) of row (e, slot) of the layer-1 input
@@ -208,7 +210,7 @@ struct EncArgs {
 __device__ __forceinline__ void load_half_row(const EncArgs& a, int tile, int m, int half, float (&x)[8]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) x[j] = 0.f;
-  const int e = tile * kEnvsPerTile + (m >> 4), slot = m & 15;
+  const int e = tile * (kRows / a.S) + m / a.S, slot = m % a.S;
   if (tile < a.n_tiles && e < a.B && slot < a.N) {
     const float* ob = a.obs + (size_t)e * a.obs_dim;
     const float* zo = a.zone_obs + ((size_t)e * a.N + slot) * a.Z;
@@ -233,19 +235,26 @@ __device__ __forceinline__ void relu_to_h1(const uint32_t (&v)[32], uint8_t* h1_
   }
 }
 
-// 32 consecutive rows m = the 16 zone slots of envs e0 and e0 + 1: relu, sum in registers, store column j
+// 32 consecutive rows m = the zone slots of envs e0 .. e0 + 32 / S - 1: relu, sum in registers, store column j
 __device__ __forceinline__ void relu_pool_store(const uint32_t (&v)[32], const EncArgs& a, int e0, int j, float inv_n) {
-  float s0[8], s1[8];
+  float q[4];                                                 // sums of 8 consecutive rows
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    s0[i] = fmaxf(__uint_as_float(v[2 * i]), 0.f) + fmaxf(__uint_as_float(v[2 * i + 1]), 0.f);
-    s1[i] = fmaxf(__uint_as_float(v[16 + 2 * i]), 0.f) + fmaxf(__uint_as_float(v[16 + 2 * i + 1]), 0.f);
+  for (int g = 0; g < 4; ++g) {
+    float s[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      s[i] = fmaxf(__uint_as_float(v[8 * g + 2 * i]), 0.f) + fmaxf(__uint_as_float(v[8 * g + 2 * i + 1]), 0.f);
+    q[g] = (s[0] + s[1]) + (s[2] + s[3]);
   }
-  const float p0 = ((s0[0] + s0[1]) + (s0[2] + s0[3])) + ((s0[4] + s0[5]) + (s0[6] + s0[7]));
-  const float p1 = ((s1[0] + s1[1]) + (s1[2] + s1[3])) + ((s1[4] + s1[5]) + (s1[6] + s1[7]));
   if (j < a.h) {
-    if (e0 < a.B) a.out[(size_t)e0 * a.h + j] = p0 * inv_n;
-    if (e0 + 1 < a.B) a.out[(size_t)(e0 + 1) * a.h + j] = p1 * inv_n;
+    if (a.S == 16) {
+      if (e0 < a.B) a.out[(size_t)e0 * a.h + j] = (q[0] + q[1]) * inv_n;
+      if (e0 + 1 < a.B) a.out[(size_t)(e0 + 1) * a.h + j] = (q[2] + q[3]) * inv_n;
+    } else {
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if (e0 + g < a.B) a.out[(size_t)(e0 + g) * a.h + j] = q[g] * inv_n;
+    }
   }
 }
 
@@ -362,9 +371,10 @@ __global__ void __launch_bounds__(kGroupThreads * kGroups, 1) zone_encode_kernel
         tmem_ld32(my_acc + (uint32_t)(c * 32), v0);
         tmem_ld32(my_acc + (uint32_t)(c * 32 + 32), v1);
         tmem_ld_wait(v0);
-        relu_pool_store(v0, a, tile * kEnvsPerTile + 2 * c, j, inv_n);
+        const int per_chunk = 32 / a.S, e0 = tile * (kRows / a.S) + c * per_chunk;
+        relu_pool_store(v0, a, e0, j, inv_n);
         tmem_ld_wait(v1);
-        relu_pool_store(v1, a, tile * kEnvsPerTile + 2 * c + 2, j, inv_n);
+        relu_pool_store(v1, a, e0 + per_chunk, j, inv_n);
       }
     }
     // the next tile's layer-1 MMA overwrites the accumulators: ordered after these loads by the fence
@@ -429,7 +439,8 @@ int crl_zone_encode(const CrlEncoderShape* s, int32_t num_envs, const float* obs
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   EncArgs a{obs, zone_obs, static_cast<const uint8_t*>(packed), pooled, status, num_envs, s->num_zones, s->zone_dim,
-            s->obs_dim, s->hidden, (num_envs + kEnvsPerTile - 1) / kEnvsPerTile};
+            s->obs_dim, s->hidden, 0, slots_per_env(s->num_zones)};
+  a.n_tiles = (num_envs + kRows / a.S - 1) / (kRows / a.S);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int want = (a.n_tiles + kGroups - 1) / kGroups;
   const int grid = want < sms ? want : sms;                   // persistent: one CTA per SM, weights loaded once
