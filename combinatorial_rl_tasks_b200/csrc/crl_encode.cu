@@ -61,7 +61,10 @@ constexpr int kGroupThreads = 256;  // 8 warps: one per (M-block, TMEM lane quad
 constexpr int kGroups = 2;          // independent groups per CTA
 // an env owns S = 8 (N <= 8) or 16 consecutive row slots of a tile; the slots beyond N are padding rows
 __host__ __device__ inline int slots_per_env(int n_zones) { return n_zones <= 8 ? 8 : 16; }
-constexpr int kK1 = 16;             // padded input width of layer 1 (obs_dim + zone_dim + a ones column <= 16)
+// padded input width of layer 1: the per-env features (obs, and goal / one-hot skill for the reference's
+// ZoneEnvGoalModel / ZoneEnvSkillModel, which the caller concatenates to obs), the zone row and at
+// least one ones column; one or two K = 16 steps
+__host__ __device__ inline int padded_k1(int in_dim) { return in_dim + 1 <= 16 ? 16 : 32; }
 constexpr uint32_t kTmemCols = 512; // two M-blocks x 128 columns per group; the CTA owns the SM
 constexpr uint32_t kSpinLimit = 1u << 24;
 
@@ -78,8 +81,8 @@ __host__ __device__ inline uint32_t canon(int r, int k, int K) {
 struct Offsets {   // byte offsets: packed weight buffer == start of shared memory; then per-group buffers
   uint32_t w2, w1, packed_end, group0, h1, xbuf, bar, group_bytes, tmem_slot, smem_end;
 };
-__host__ __device__ inline Offsets offsets(int h) {
-  const int KP = padded_k(h), MP = padded_m(h);
+__host__ __device__ inline Offsets offsets(int h, int in_dim) {
+  const int KP = padded_k(h), MP = padded_m(h), kK1 = padded_k1(in_dim);
   Offsets o;
   o.w2 = 0;
   o.w1 = o.w2 + (uint32_t)MP * KP * 2;
@@ -102,8 +105,8 @@ struct PackArgs {
 };
 
 __global__ void pack_kernel(const PackArgs a) {
-  const Offsets o = offsets(a.h);
-  const int KP = padded_k(a.h), MP = padded_m(a.h);
+  const Offsets o = offsets(a.h, a.in_dim);
+  const int KP = padded_k(a.h), MP = padded_m(a.h), kK1 = padded_k1(a.in_dim);
   const int n_w = MP * KP, n_w1 = MP * kK1;
   const int total = n_w + n_w1;
   // bias = hi + lo with hi = bf16(bias), lo = bf16(bias - hi): entry `ones` of the K dimension carries 1
@@ -205,9 +208,9 @@ struct EncArgs {
   int B, N, Z, obs_dim, h, n_tiles, S;   // S = slots_per_env(N)
 };
 
-// eight consecutive values (k = 8 half .. 8 half + 7) of row (e, slot) of the layer-1 input
+// eight consecutive values (k = 8 kc .. 8 kc + 7) of row (e, slot) of the layer-1 input
 // [obs[e], zone_obs[e][slot], 1, 1, 0...]; all zeros -- the ones included -- for a padding row
-__device__ __forceinline__ void load_half_row(const EncArgs& a, int tile, int m, int half, float (&x)[8]) {
+__device__ __forceinline__ void load_half_row(const EncArgs& a, int tile, int m, int kc, float (&x)[8]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) x[j] = 0.f;
   const int e = tile * (kRows / a.S) + m / a.S, slot = m % a.S;
@@ -217,7 +220,7 @@ __device__ __forceinline__ void load_half_row(const EncArgs& a, int tile, int m,
     const int in_dim = a.obs_dim + a.Z;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int k = 8 * half + j;
+      const int k = 8 * kc + j;
       if (k < a.obs_dim) x[j] = __ldg(ob + k);
       else if (k < in_dim) x[j] = __ldg(zo + (k - a.obs_dim));
       else if (k <= in_dim + 1) x[j] = 1.f;
@@ -260,8 +263,8 @@ __device__ __forceinline__ void relu_pool_store(const uint32_t (&v)[32], const E
 
 __global__ void __launch_bounds__(kGroupThreads * kGroups, 1) zone_encode_kernel(const EncArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const Offsets o = offsets(a.h);
-  const int KP = padded_k(a.h), MP = padded_m(a.h);
+  const Offsets o = offsets(a.h, a.obs_dim + a.Z);
+  const int KP = padded_k(a.h), MP = padded_m(a.h), kK1 = padded_k1(a.obs_dim + a.Z);
   const int n_mblocks = MP / 128;
   const int group = threadIdx.x / kGroupThreads;              // 0 / 1
   const int t = threadIdx.x % kGroupThreads;
@@ -314,12 +317,16 @@ __global__ void __launch_bounds__(kGroupThreads * kGroups, 1) zone_encode_kernel
 
   const int tile_stride = kGroups * gridDim.x;
   int tile = kGroups * blockIdx.x + group;
-  float x[8];
+  float x[8], x2[8];                                         // 16-byte units `half` and, for 32-wide inputs, `half + 2`
   load_half_row(a, tile, m, half, x);
+  if (kK1 == 32) load_half_row(a, tile, m, half + 2, x2);
   for (; tile < a.n_tiles; tile += tile_stride) {
     // ---- layer-1 B operand (the tile's 128 input rows) from the prefetched registers ----------
     *reinterpret_cast<uint4*>(xbuf + x_off) =
         make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+    if (kK1 == 32)
+      *reinterpret_cast<uint4*>(xbuf + x_off + 256) =
+          make_uint4(pack_bf16(x2[0], x2[1]), pack_bf16(x2[2], x2[3]), pack_bf16(x2[4], x2[5]), pack_bf16(x2[6], x2[7]));
     fence_async_smem();
     tc_fence_before();
     group_sync(group);
@@ -327,11 +334,13 @@ __global__ void __launch_bounds__(kGroupThreads * kGroups, 1) zone_encode_kernel
     if (t == 0) {
       tc_fence_after();
       for (int b = 0; b < n_mblocks; ++b)
-        mma_bf16(acc + (uint32_t)(b * 128), smem_desc(w1_addr + (uint32_t)(b * 16 * 16 * kK1), 128u, 16 * kK1),
-                 smem_desc(x_addr, 128u, 16 * kK1), idesc1, 0u);
+        for (int s = 0; s < kK1 / 16; ++s)
+          mma_bf16(acc + (uint32_t)(b * 128), smem_desc(w1_addr + (uint32_t)(b * 16 * 16 * kK1) + 256u * s, 128u, 16 * kK1),
+                   smem_desc(x_addr + 256u * s, 128u, 16 * kK1), idesc1, s > 0);
       mma_commit(bar_addr);
     }
     load_half_row(a, tile + tile_stride, m, half, x);         // prefetch: in flight for the rest of the tile
+    if (kK1 == 32) load_half_row(a, tile + tile_stride, m, half + 2, x2);
     healthy = mbar_wait(bar_addr, parity) && healthy;
     parity ^= 1u;
     tc_fence_after();
@@ -390,7 +399,7 @@ __global__ void __launch_bounds__(kGroupThreads * kGroups, 1) zone_encode_kernel
 
 static int check_shape(const CrlEncoderShape* s) {
   if (!s) return CRL_ERR_NULL;
-  if (s->obs_dim <= 0 || s->zone_dim <= 0 || s->obs_dim + s->zone_dim >= kK1) return CRL_ERR_CONFIG;   // + a ones column
+  if (s->obs_dim <= 0 || s->zone_dim <= 0 || s->obs_dim + s->zone_dim + 1 > 32) return CRL_ERR_CONFIG;   // + a ones column
   if (s->num_zones <= 0 || s->num_zones > 16) return CRL_ERR_CONFIG;
   if (s->hidden <= 0) return CRL_ERR_CONFIG;
   if (padded_k(s->hidden) > 192) return CRL_ERR_UNSUPPORTED;   // resident W2 + two groups' operand buffers must fit an SM
@@ -407,7 +416,7 @@ int crl_encoder_packed_bytes(const CrlEncoderShape* s, int64_t* bytes) {
   const int rc = check_shape(s);
   if (rc) return rc;
   if (!bytes) return CRL_ERR_NULL;
-  *bytes = (int64_t)offsets(s->hidden).packed_end;
+  *bytes = (int64_t)offsets(s->hidden, s->obs_dim + s->zone_dim).packed_end;
   return CRL_OK;
 }
 
@@ -429,7 +438,7 @@ int crl_zone_encode(const CrlEncoderShape* s, int32_t num_envs, const float* obs
   if (!obs || !zone_obs || !packed || !pooled) return CRL_ERR_NULL;
   if (num_envs <= 0) return CRL_ERR_CONFIG;
   if (reinterpret_cast<uintptr_t>(packed) & 15u) return CRL_ERR_ALIGN;
-  const Offsets o = offsets(s->hidden);
+  const Offsets o = offsets(s->hidden, s->obs_dim + s->zone_dim);
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) != cudaSuccess) return CRL_ERR_DEVICE;
   static bool attr_set[64] = {false};                       // per device: opt in to > 48 KB of dynamic shared memory

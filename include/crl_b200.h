@@ -350,7 +350,8 @@ int crl_check_state(const CrlConfig* cfg, const CrlState* st, uint64_t* violatio
  * never leave the SM, and the third Linear shrinks from B N to B rows -- it and combine_net_ stay
  * fp32 library GEMMs on the caller's side.  Inference only (the rollout-time forward of
  * BaseAlgo.collect_experiences, base.py:133-140).  hidden <= 190 (the default is 185,
- * scripts/train_ppo.py:66), obs_dim + zone_dim <= 15, num_zones <= 16. */
+ * scripts/train_ppo.py:66), obs_dim + zone_dim <= 31 (one K step up to 15, two beyond: ZoneEnvGoalModel /
+ * ZoneEnvSkillModel, whose per-env goal / one-hot skill the caller concatenates to obs), num_zones <= 16. */
 typedef struct CrlEncoderShape {
   int32_t obs_dim;    /* 8 */
   int32_t zone_dim;   /* Z */

@@ -41,7 +41,7 @@ def bf16_twin(sd, obs, zone_obs):
         hi = r(b)
         return hi + r(b.to(torch.float64) - hi) if room_for_lo else hi
     h, in_dim = sd['zone_net_.0.weight'].shape
-    x = r(torch.relu(x @ r(sd['zone_net_.0.weight']).T + bias(sd['zone_net_.0.bias'], in_dim + 1 < 16)).to(torch.float32))
+    x = r(torch.relu(x @ r(sd['zone_net_.0.weight']).T + bias(sd['zone_net_.0.bias'], in_dim + 1 not in (16, 32))).to(torch.float32))
     x = torch.relu(x @ r(sd['zone_net_.2.weight']).T + bias(sd['zone_net_.2.bias'], True))
     pooled = x.sum(dim=1) / N                        # the kernel's output; the third Linear is fp32 on (B, h)
     return (pooled @ sd['zone_net_.4.weight'].to(torch.float64).T + sd['zone_net_.4.bias'].to(torch.float64)).to(torch.float32)
@@ -78,16 +78,20 @@ def test_fixture_of_the_real_module(crl, tag, n):
                   - g[f'{tag}_zone_emb']).max() <= 2e-6
 
 
-@pytest.mark.parametrize('B,N,Z,h', [(4099, 15, 6, 185), (1, 15, 7, 185), (777, 5, 6, 96), (20000, 6, 7, 32)])
-def test_random_batches_against_torch(crl, B, N, Z, h):
-    """Ragged batch sizes (partial tiles, more tiles than SMs), every supported width class."""
+@pytest.mark.parametrize('B,N,Z,h,D', [(4099, 15, 6, 185, 8), (1, 15, 7, 185, 8), (777, 5, 6, 96, 8), (20000, 6, 7, 32, 8),
+                                       (3001, 15, 7, 185, 10), (515, 6, 7, 64, 16)])
+def test_random_batches_against_torch(crl, B, N, Z, h, D):
+    """Ragged batch sizes (partial tiles, more tiles than SMs), every supported width class.  D = per-env
+    features: 8 for ZoneEnvModel; 8 + goal_dim (ZoneEnvGoalModel, zone-goals/src/env_model.py) or 8 + n_skills
+    (ZoneEnvSkillModel, main/src/env_model.py:81-117) when the caller concatenates goal / one-hot skill to obs --
+    then the layer-1 input is 32 wide (two K steps)."""
     gen = torch.Generator(device='cuda').manual_seed(B + h)
     rn = lambda *s, scale=1.0: (torch.randn(*s, device='cuda', generator=gen) * scale)
-    sd = {'zone_net_.0.weight': rn(h, 8 + Z, scale=0.4), 'zone_net_.0.bias': rn(h, scale=0.2),
+    sd = {'zone_net_.0.weight': rn(h, D + Z, scale=0.4), 'zone_net_.0.bias': rn(h, scale=0.2),
           'zone_net_.2.weight': rn(h, h, scale=1.5 / h ** 0.5), 'zone_net_.2.bias': rn(h, scale=0.2),
           'zone_net_.4.weight': rn(h, h, scale=1.5 / h ** 0.5), 'zone_net_.4.bias': rn(h, scale=0.2),
-          'combine_net_.weight': rn(h, 8 + h, scale=0.1), 'combine_net_.bias': rn(h, scale=0.1)}
-    obs, zobs = rn(B, 8), rn(B, N, Z)
+          'combine_net_.weight': rn(h, D + h, scale=0.1), 'combine_net_.bias': rn(h, scale=0.1)}
+    obs, zobs = rn(B, D), rn(B, N, Z)
     enc = crl.ZoneEncoder(sd, num_zones=N)
     out = torch.full((B + 3, h), 7.0, device='cuda')           # guard rows: nothing may be written past B
     pooled = enc.pooled(obs, zobs, out=out[:B])
@@ -96,7 +100,7 @@ def test_random_batches_against_torch(crl, B, N, Z, h):
     assert enc.healthy() and bool((out[B:] == 7.0).all()) and bool((pooled >= 0).all())
     twin, ref = bf16_twin(sd, obs, zobs), fp32_ref(sd, obs, zobs)
     e_twin, e_ref = float((emb - twin).abs().max()), float((emb - ref).abs().max())
-    print(f'B={B} N={N} Z={Z} h={h}: vs bf16 twin {e_twin:.2e}, vs fp32 {e_ref:.2e}, |ref| max {float(ref.abs().max()):.2f}')
+    print(f'B={B} N={N} Z={Z} h={h} D={D}: vs bf16 twin {e_twin:.2e}, vs fp32 {e_ref:.2e}, |ref| max {float(ref.abs().max()):.2f}')
     scale = max(1.0, float(ref.abs().max()))
     assert e_twin <= BF16_TWIN_RTOL * scale and e_ref <= FP32_RTOL * scale
     # second call on the same encoder (barrier phases, TMEM re-allocation) gives the same bits
@@ -127,4 +131,4 @@ def test_unsupported_shapes_are_refused(crl):
     n = ctypes.c_int64()
     assert lib.crl_encoder_packed_bytes(_lib.CrlEncoderShape(8, 6, 185, 15), ctypes.byref(n)) == 0 and n.value == 256 * 192 * 2 + 256 * 32
     assert lib.crl_encoder_packed_bytes(_lib.CrlEncoderShape(8, 6, 256, 15), ctypes.byref(n)) == -4    # two resident weights do not fit
-    assert lib.crl_encoder_packed_bytes(_lib.CrlEncoderShape(8, 8, 64, 15), ctypes.byref(n)) == -2     # no room for the ones column in the 16-wide input
+    assert lib.crl_encoder_packed_bytes(_lib.CrlEncoderShape(20, 12, 64, 15), ctypes.byref(n)) == -2     # no room for the ones column in the 32-wide input

@@ -147,7 +147,8 @@ def test_encoder_shape_checks_run_on_the_host():
     assert lib.crl_encoder_packed_bytes(S(8, 7, 64, 6), ctypes.byref(n)) == 0 and n.value == 128 * 80 * 2 + 128 * 32
     assert lib.crl_encoder_packed_bytes(S(8, 6, 190, 15), ctypes.byref(n)) == 0
     assert lib.crl_encoder_packed_bytes(S(8, 6, 191, 15), ctypes.byref(n)) == -4     # W2 + operand buffers exceed an SM
-    assert lib.crl_encoder_packed_bytes(S(8, 8, 64, 15), ctypes.byref(n)) == -2      # no room for the ones column
+    assert lib.crl_encoder_packed_bytes(S(10, 7, 185, 15), ctypes.byref(n)) == 0 and n.value == 256 * 192 * 2 + 256 * 64   # 32-wide input
+    assert lib.crl_encoder_packed_bytes(S(20, 12, 64, 15), ctypes.byref(n)) == -2    # no room for the ones column
     assert lib.crl_encoder_packed_bytes(S(8, 6, 64, 17), ctypes.byref(n)) == -2      # more than 16 zone slots
     assert lib.crl_encoder_packed_bytes(None, ctypes.byref(n)) == -1
     assert lib.crl_zone_encode(S(8, 6, 185, 15), 64, None, None, None, None, None, None) == -1
