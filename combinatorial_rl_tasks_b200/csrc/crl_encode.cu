@@ -346,8 +346,13 @@ __global__ void __launch_bounds__(kGroupThreads * kGroups, 1) zone_encode_kernel
     tc_fence_after();
     if (drains1) {
       // this thread: hidden unit j, rows m = 32 c .. 32 c + 31 -> relu -> bf16 -> four 16-byte units of H1
+#ifdef CRL_ENC_DIAG_HALF_DRAIN                                // timing diagnostic (wrong results): half of epilogue 1's TMEM reads
+      const int c_stop = kRows / 64;
+#else
+      const int c_stop = kRows / 32;
+#endif
 #pragma unroll 1
-      for (int c = 0; c < kRows / 32; c += 2) {               // two TMEM loads in flight
+      for (int c = 0; c < c_stop; c += 2) {                   // two TMEM loads in flight
         uint32_t v0[32], v1[32];
         tmem_ld32(my_acc + (uint32_t)(c * 32), v0);
         tmem_ld32(my_acc + (uint32_t)(c * 32 + 32), v1);
@@ -363,8 +368,13 @@ __global__ void __launch_bounds__(kGroupThreads * kGroups, 1) zone_encode_kernel
     // ---- layer 2: H2^T[128 b ..][m] = W2[128 b ..][KP] H1^T (layer 1's values have been read) ---
     if (t == 0) {
       tc_fence_after();
+#ifdef CRL_ENC_DIAG_HALF_MMA                                  // timing diagnostic (wrong results): half of layer 2's K steps
+      const int s_stop = KP / 32;
+#else
+      const int s_stop = KP / 16;
+#endif
       for (int b = 0; b < n_mblocks; ++b)
-        for (int s = 0; s < KP / 16; ++s)
+        for (int s = 0; s < s_stop; ++s)
           mma_bf16(acc + (uint32_t)(b * 128), smem_desc(w2_addr + (uint32_t)(b * 16 * 16 * KP) + 256u * s, 128u, 16 * KP),
                    smem_desc(h1_addr + 4096u * s, 2048u, 128u), idesc2, s > 0);
       mma_commit(bar_addr);
