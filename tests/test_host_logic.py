@@ -137,6 +137,26 @@ def test_design_twin_honours_fixed_placements():
         assert not np.array_equal(free['xy0'], t[0, :2])
 
 
+def test_integration_md_structs_match_the_binding():
+    """The ctypes structs printed in INTEGRATION.md section 2 (executed as written by a GPU test) declare the
+    same fields, in the same order and of the same size, as the product's own binding and the C header."""
+    from combinatorial_rl_tasks_b200 import _lib
+    md = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    sec = md[md.index('## 2. Bind the C ABI directly'):]
+    code = re.search(r'```python\n(.*?)```', sec, re.S).group(1)
+    defs = code[code.index('class CrlConfig'):code.index('cfg = CrlConfig')]
+    ns = {'ctypes': ctypes}
+    exec(defs, ns)
+    for name in ('CrlConfig', 'CrlState', 'CrlOut'):
+        mine, theirs = getattr(_lib, name), ns[name]
+        assert [f[0] for f in mine._fields_] == [f[0] for f in theirs._fields_], name
+        assert ctypes.sizeof(mine) == ctypes.sizeof(theirs), name
+    hdr = open(os.path.join(ROOT, 'include', 'crl_b200.h')).read()
+    body = hdr[hdr.index('typedef struct CrlState {'):hdr.index('} CrlState;')]
+    fields = re.findall(r'\b(\w+);', re.sub(r'/\*.*?\*/', '', body, flags=re.S))
+    assert fields == [f[0] for f in _lib.CrlState._fields_]
+
+
 def test_encoder_shape_checks_run_on_the_host():
     """crl_encoder_packed_bytes: limits of the tcgen05 zone encoder are refused before anything is launched."""
     from combinatorial_rl_tasks_b200 import _lib
