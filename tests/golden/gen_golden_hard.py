@@ -37,6 +37,33 @@ def main(tree):
             np.savez_compressed(os.path.join(HERE, name), **out)
             print(name, 'steps', len(out['reward']), 'return', out['reward'].sum(), 'goal_met', bool(out['goal_met'].any()),
                   'first colours', out['zone_obs'][0][:, 2].astype(int))
+        # the vector-env protocol (penv.py: step, reset on done) over make_test_env envs of the 250-step instance
+        # (the reference's make_train_env refuses the hard instances, make_env.py:3-18; evaluation seeds once and
+        # lets Engine.reset increment the seed): every env auto-resets twice in 600 steps, each time re-sampling its
+        # distractors around the fixed cities
+        from envs.make_env import make_test_env
+        es = [make_test_env('PointTSP-v5', seed=1000 + 50 * i) for i in range(3)]
+        rs = np.random.RandomState(5)
+        obs = [e.reset() for e in es]
+        rec = {k: [] for k in ('actions', 'obs', 'zone_obs', 'reward', 'done', 'goal_met')}
+        rec['obs'].append(np.array([o['obs'] for o in obs])); rec['zone_obs'].append(np.array([o['zone_obs'] for o in obs]))
+        for t in range(600):
+            acts, row = [], []
+            for i, e in enumerate(es):
+                a = gg.policy('PointTSP-v5', obs[i], rs, 'greedy', t)
+                o, r, d, info = e.step(a)
+                if d:
+                    o = e.reset()
+                obs[i] = o
+                acts.append(a); row.append((float(r), bool(d), bool(info.get('goal_met', False))))
+            rec['actions'].append(np.array(acts))
+            rec['obs'].append(np.array([o['obs'] for o in obs])); rec['zone_obs'].append(np.array([o['zone_obs'] for o in obs]))
+            rec['reward'].append([x[0] for x in row]); rec['done'].append([x[1] for x in row]); rec['goal_met'].append([x[2] for x in row])
+        out = {k: np.array(v) for k, v in rec.items()}
+        out['actions'] = out['actions'].astype(np.float32)
+        out['env_id'] = np.array('PointTSP-v5')
+        np.savez_compressed(os.path.join(HERE, 'hardvec_PointTSP-v5.npz'), **out)
+        print('hardvec_PointTSP-v5.npz', 'resets', int(out['done'].sum()), 'return', out['reward'].sum())
     else:
         from tests.golden import gen_golden_goals as gg
         for env_id, seed, mode, max_len in GOALS:

@@ -21,7 +21,7 @@ from tests._driver import policy  # noqa: E402
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 EPISODES = sorted(f for f in glob.glob(os.path.join(GOLDEN, '*.npz'))
-                  if not f.endswith('_vector.npz') and not os.path.basename(f).startswith(('goals_', 'gae_', 'model_', 'hardgoals_')))   # incl. hard_*: PointTSP-v4 / v5
+                  if not f.endswith('_vector.npz') and not os.path.basename(f).startswith(('goals_', 'gae_', 'model_', 'hardgoals_', 'hardvec_')))   # incl. hard_*: PointTSP-v4 / v5
 
 PHYS_RTOL = 1e-5       # per substep, from identical inputs (the north-star bar)
 REWARD_ATOL = 1e-6

@@ -11,7 +11,7 @@ from oracle import zone_env as ze
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 EPISODES = sorted(f for f in glob.glob(os.path.join(GOLDEN, '*.npz'))
-                  if not f.endswith('_vector.npz') and not os.path.basename(f).startswith(('goals_', 'gae_', 'model_', 'hardgoals_')))
+                  if not f.endswith('_vector.npz') and not os.path.basename(f).startswith(('goals_', 'gae_', 'model_', 'hardgoals_', 'hardvec_')))
 VECTORS = sorted(glob.glob(os.path.join(GOLDEN, '*_vector.npz')))
 
 
@@ -66,6 +66,25 @@ def test_host_supplied_layout_matches_reference(path):
             assert np.array_equal(obs['obs'], g['obs'][t + 1]), t
             assert np.array_equal(obs['zone_obs'], g['zone_obs'][t + 1]), t
         assert reward == g['reward'][t] and done == g['done'][t], t
+
+
+def test_hard_instance_vector_trace_matches_reference():
+    """Three make_test_env('PointTSP-v5') envs (seeded once, Engine.reset increments the seed) under the vector-env
+    protocol, recorded from the REAL TSPHardEnv: two auto-resets each, the distractors re-sampled around the fixed
+    cities every time."""
+    g = np.load(os.path.join(GOLDEN, 'hardvec_PointTSP-v5.npz'))
+    envs = [ze.make_task_env('PointTSP-v5') for _ in range(3)]
+    for i, e in enumerate(envs):
+        e.seed(1000 + 50 * i)
+    vec = ze.SerialVecEnv(envs)
+    obs = vec.reset()
+    assert np.array_equal(np.array([o['zone_obs'] for o in obs]), g['zone_obs'][0])
+    for t, acts in enumerate(g['actions']):
+        obs, reward, done, info = vec.step(acts)
+        assert np.array_equal(np.array([o['obs'] for o in obs]), g['obs'][t + 1]), t
+        assert np.array_equal(np.array([o['zone_obs'] for o in obs]), g['zone_obs'][t + 1]), t
+        assert np.array_equal(np.array(reward, dtype=np.float64), g['reward'][t]) and np.array_equal(np.array(done), g['done'][t]), t
+    assert int(g['done'].sum()) == 6 and all(e._seed == 1000 + 50 * i + 3 for i, e in enumerate(envs))
 
 
 @pytest.mark.parametrize('path', VECTORS, ids=os.path.basename)
