@@ -13,13 +13,13 @@ c_void_p, c_int32, c_int64, c_uint32, c_uint64, c_double = (
 TASK_TSP, TASK_TTSP, TASK_CM = 0, 1, 2
 SEED_INCREMENT, SEED_FIXED_RANGE = 0, 1
 STEP_AUTO_RESET, STEP_PHYSICS_ONLY, STEP_CHAINED, STEP_CHAIN_START, STEP_TRACK_ROWS = 1, 2, 4, 8, 16
-STEP_GOALS, STEP_WAIT, STEP_HOST_ZERO_COPY = 32, 64, 256
-ABI_VERSION = 5
-NUM_PLANES = 22
+STEP_GOALS, STEP_WAIT, STEP_ACTION_COUNTER, STEP_HOST_ZERO_COPY = 32, 64, 128, 256
+ABI_VERSION = 6
+NUM_PLANES = 23
 
 # every symbol include/crl_b200.h declares
 SYMBOLS = ['crl_abi_version', 'crl_strerror', 'crl_plane_bytes', 'crl_step_bytes', 'crl_reset',
-           'crl_prefetch_layouts', 'crl_reset_from_layout', 'crl_step', 'crl_step_host', 'crl_step_host_delta',
+           'crl_prefetch_layouts', 'crl_prefetch_publish', 'crl_reset_from_layout', 'crl_step', 'crl_step_host', 'crl_step_host_delta',
            'crl_set_goal', 'crl_goal_query', 'crl_set_qpos_qvel',
            'crl_get_qpos_qvel', 'crl_gae', 'crl_check_state', 'crl_counters_read',
            'crl_encoder_packed_bytes', 'crl_encoder_pack', 'crl_zone_encode']
@@ -39,7 +39,7 @@ class CrlState(ctypes.Structure):
                                         'episode', 'origin', 'counters', 'next_zone_xy', 'next_task',
                                         'next_origin', 'next_seed', 'next_ready', 'stamp',
                                         'prefetch_work', 'row_list', 'goal', 'bank_zone_xy', 'bank_origin',
-                                        'bank_task', 'fixed_layout')]
+                                        'bank_task', 'fixed_layout', 'prefetch_epoch')]
 
 
 class CrlOut(ctypes.Structure):
@@ -73,7 +73,8 @@ def load():
     lib.crl_plane_bytes.argtypes = [P(CrlConfig), P(c_int64), c_int32]
     lib.crl_step_bytes.argtypes = [P(CrlConfig), P(c_int64), P(c_int64)]
     lib.crl_reset.argtypes = [P(CrlConfig), P(CrlState), P(CrlOut), c_void_p, c_void_p]
-    lib.crl_prefetch_layouts.argtypes = [P(CrlConfig), P(CrlState), c_int32, c_void_p]
+    lib.crl_prefetch_layouts.argtypes = [P(CrlConfig), P(CrlState), c_int32, c_uint32, c_void_p]
+    lib.crl_prefetch_publish.argtypes = [P(CrlState), c_uint32, c_void_p]
     lib.crl_reset_from_layout.argtypes = [P(CrlConfig), P(CrlState), P(CrlOut), P(CrlLayoutIn), c_void_p,
                                           c_int32, c_void_p]
     lib.crl_step.argtypes = [P(CrlConfig), P(CrlState), c_void_p, P(CrlOut), c_uint32, c_uint64, c_uint64,

@@ -66,8 +66,10 @@ class ParallelEnv:
         a = np.asarray([np.asarray(x, dtype=np.float32).reshape(2) for x in actions], dtype=np.float32)
         was_parked = self._parked.copy()
         if auto_reset:
-            obs, reward, done, info = v.step_host(a, auto_reset=True)
-            self._parked[:] = False                            # a parked env runs into the step limit and restarts
+            # a parked env is WaitWrapper's no-op followed by the worker's reset (wrappers.py:36-44,
+            # penv.py:7-10): (first obs of its new episode, 0, True, {})
+            obs, reward, done, info = v.step_host(a, auto_reset=True, wait=v.wait)
+            self._parked[:] = False
         else:
             obs, reward, done, info = v.step_host(a, auto_reset=False, wait=v.wait)
             if v.wait:

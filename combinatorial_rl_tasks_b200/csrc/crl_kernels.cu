@@ -65,6 +65,9 @@ struct KParams {
   long long* next_seed;
   uint32_t* next_ready;
   uint32_t* stamp;
+  uint32_t* act_count;          // stamp plane 2: NULL-action steps taken per 32 envs (CRL_STEP_ACTION_COUNTER)
+  const uint32_t* epoch;        // CrlState.prefetch_epoch: last sampler round whose slots the step may trust
+  uint32_t round;               // crl_prefetch_layouts: the round being run
   uint32_t* row_list;
   int32_t* goal;
   const float2* bank_zone_xy;
@@ -80,6 +83,8 @@ struct KParams {
   float* shaped;               // info['shaped_reward'] (goal-conditioned variants)
   const uint8_t* mask;
 };
+
+constexpr uint32_t kParBit = 0x8000u, kHiMask = 0x7fffu;
 
 template <int TASK>
 struct ZoneDim { static constexpr int Z = (TASK == CRL_TASK_TSP) ? 6 : 7; };
@@ -103,7 +108,8 @@ struct Env {
   Body b;
   float ep_return;
   int steps;
-  uint32_t hi;        // visited mask or colour codes
+  uint32_t hi;        // bits 0-14: visited mask or colour codes; bit 15: parity of the env's episode
+                      // counter (= the next-layout slot its next reset takes, kParBit)
   float2 zone[N];
   uint32_t tmax[(N + 1) / 2];
   uint2 cd;
@@ -297,7 +303,12 @@ __device__ void warp_generate(const KParams& p, long long chosen, float2* placed
 }
 
 // next-layout slot states (CrlState.next_ready)
-constexpr uint32_t kSlotEmpty = 0u, kSlotReady = 1u, kSlotLayoutDone = 2u, kSlotClaimed = 3u;
+// kSlotReady + r: ready, filled by sampler round r.  A step trusts such a slot only if r <= *epoch, the
+// last round the HOST has ordered before it (crl_prefetch_publish): everything that round wrote is then
+// visible by stream order, so the step reads flag, seed and layout with plain independent loads -- one
+// round trip, no acquire (each acquire used to invalidate the L1 under the warp's siblings) and no
+// release when it hands the slot back (the next round's scan is ordered after the step by the host).
+constexpr uint32_t kSlotEmpty = 0u, kSlotLayoutDone = 2u, kSlotClaimed = 3u, kSlotReady = 16u;
 
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
   uint32_t v;
@@ -321,12 +332,13 @@ __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
 //
 // The function is out of line (cold, register-hungry); `out` (the caller's Env copy) therefore
 // lives in local memory.  It is WRITE-ONLY here: with the L1 thrashed by the step's streaming
-// loads and invalidated by the acquire load below, a local load is an L2 round trip, and the 23
+// loads, a local load is an L2 round trip, and the 23
 // plane stores used to read their values back from it one after the other (~14 us per resetting
 // warp, profiles/r01_notes.md).  Now the new zone centres / timeouts go straight from registers
 // to their planes, and the caller reads its copy back once, in one batch of independent loads.
-template <int TASK, int N, bool FIXED>
-__device__ __noinline__ void warp_reset(const KParams& p, unsigned dm, int lane, int e, float2* placed, Env<N>& out) {
+template <int TASK, int N, bool FIXED, bool PAR_FROM_EPISODE = false>
+__device__ __noinline__ void warp_reset(const KParams& p, unsigned dm, int lane, int e, float2* placed, uint32_t par_in,
+                                        Env<N>& out) {
   const bool mine = (dm >> lane) & 1u;
   long long chosen = 0;
   uint32_t episode = 0;
@@ -338,9 +350,8 @@ __device__ __noinline__ void warp_reset(const KParams& p, unsigned dm, int lane,
   float2* zp = p.zone_xy + e;
   uint32_t* tp = p.zone_tmax + e;
   if (mine) {
-    episode = p.episode[e];
-    chosen = choose_seed(p, e, episode);
-    if (p.bank_zone_xy && chosen >= p.min_seed && chosen <= p.max_seed) {
+    if (p.bank_zone_xy || !p.next_ready || PAR_FROM_EPISODE) episode = p.episode[e];
+    if (p.bank_zone_xy && (chosen = choose_seed(p, e, episode)) >= p.min_seed && chosen <= p.max_seed) {
       // fixed task set: the map of seed `chosen` is entry chosen - min_seed of the layout bank
       // (a few KB, cache resident): copy it, nothing to sample
       const size_t k = (size_t)(chosen - p.min_seed);
@@ -358,35 +369,48 @@ __device__ __noinline__ void warp_reset(const KParams& p, unsigned dm, int lane,
       }
       if (TASK == CRL_TASK_CM) col_word = p.bank_task[k];
     } else if (p.next_ready) {
-      // reset number n takes slot n & 1: one batch of independent loads, then straight out again
-      const size_t sb = (size_t)(episode & 1u) * (size_t)B;
+      // Reset number n takes slot n & 1, and that parity rides in the env's state word: the slot is
+      // known without a load, so the episode counter, the env's seed, the slot's flag / seed / origin
+      // / zone centres / task draws and the trusted epoch are ONE batch of independent loads.
+      const uint32_t par = PAR_FROM_EPISODE ? (episode & 1u) : par_in;
+      const size_t sb = (size_t)par * (size_t)B;
       slot_flag = p.next_ready + sb + e;
-      if (ld_acquire_u32(slot_flag) == kSlotReady) {
-        const float2* nz = p.next_zone_xy + sb * N + e;
-        const uint32_t* nt = p.next_task ? p.next_task + sb * (TASK == CRL_TASK_TTSP ? (N + 1) / 2 : 1) + e : nullptr;
-        const long long parked_for = p.next_seed[sb + e];
-        const float4 o = p.next_origin[sb + e];
-        float2 z[N];
-        uint32_t t[(N + 1) / 2];
+      const float2* nz = p.next_zone_xy + sb * N + e;
+      const uint32_t* nt = p.next_task ? p.next_task + sb * (TASK == CRL_TASK_TTSP ? (N + 1) / 2 : 1) + e : nullptr;
+      const uint32_t flag = ld_relaxed_u32(slot_flag);
+      const uint32_t trusted = ld_relaxed_u32(p.epoch);
+      if (!PAR_FROM_EPISODE) episode = p.episode[e];
+      const long long parked_for = __ldcg(p.next_seed + sb + e);
+      const float4 o = __ldcg(p.next_origin + sb + e);
+      float2 z[N];
+      uint32_t t[(N + 1) / 2];
 #pragma unroll
-        for (int i = 0; i < N; ++i) z[i] = nz[(size_t)i * B];
+      for (int i = 0; i < N; ++i) z[i] = __ldcg(nz + (size_t)i * B);
+      if (TASK == CRL_TASK_TTSP) {
+#pragma unroll
+        for (int j = 0; j < (N + 1) / 2; ++j) t[j] = __ldcg(nt + (size_t)j * B);
+      }
+      if (TASK == CRL_TASK_CM) t[0] = __ldcg(nt);
+      chosen = choose_seed(p, e, episode);
+      const bool ready = flag >= kSlotReady && flag - kSlotReady <= trusted;
+      if (ready && parked_for == chosen && (episode & 1u) == par) {
+        fast = true;
+        x0 = o.x; y0 = o.y; rot0 = o.z;
+#pragma unroll
+        for (int i = 0; i < N; ++i) { zp[(size_t)i * B] = z[i]; out.zone[i] = z[i]; }
         if (TASK == CRL_TASK_TTSP) {
 #pragma unroll
-          for (int j = 0; j < (N + 1) / 2; ++j) t[j] = nt[(size_t)j * B];
+          for (int j = 0; j < (N + 1) / 2; ++j) { tp[(size_t)j * B] = t[j]; out.tmax[j] = t[j]; }
         }
-        if (TASK == CRL_TASK_CM) t[0] = nt[0];
-        if (parked_for == chosen) {
-          fast = true;
-          x0 = o.x; y0 = o.y; rot0 = o.z;
-#pragma unroll
-          for (int i = 0; i < N; ++i) { zp[(size_t)i * B] = z[i]; out.zone[i] = z[i]; }
-          if (TASK == CRL_TASK_TTSP) {
-#pragma unroll
-            for (int j = 0; j < (N + 1) / 2; ++j) { tp[(size_t)j * B] = t[j]; out.tmax[j] = t[j]; }
-          }
-          if (TASK == CRL_TASK_CM) col_word = t[0];
-        }
+        if (TASK == CRL_TASK_CM) col_word = t[0];
       }
+      // hand the slot back only if it held a finished layout (now consumed, or stale: drawn for a seed
+      // this env has moved past); a slot the running sampler round owns is left alone.  The slot of
+      // THIS reset is (episode & 1); a state word whose parity disagrees (seed() without a reset)
+      // just samples inline and is corrected below.
+      if (!ready || (episode & 1u) != par) slot_flag = nullptr;
+    } else {
+      chosen = choose_seed(p, e, episode);
     }
   }
   unsigned slow = __ballot_sync(kFull, mine && !fast);
@@ -424,14 +448,15 @@ __device__ __noinline__ void warp_reset(const KParams& p, unsigned dm, int lane,
     out.b.vx = out.b.vy = out.b.w = 0.f;
     out.ep_return = 0.f;
     out.steps = 0;
-    out.hi = TASK == CRL_TASK_CM ? col_word : p.init_hi;
+    out.hi = (TASK == CRL_TASK_CM ? col_word : p.init_hi) | (((episode + 1u) & 1u) ? kParBit : 0u);
     out.cd = make_uint2(0u, 0u);
     p.seed[e] = chosen + 1;                       // Engine.reset: self._seed += 1
     p.episode[e] = episode + 1u;
     p.origin[e] = make_float4(x0, y0, rot0, 0.f);
     if (p.goal) p.goal[e] = -1;                   // a new episode has no goal until set_goal
-    // hand the slot back to the prefetcher (release: our reads of it are done)
-    if (slot_flag) st_release_u32(slot_flag, kSlotEmpty);
+    // hand the slot back to the sampler: a plain store, the next round's scan is ordered after this
+    // kernel by the host (crl_prefetch_layouts is enqueued behind the steps it follows)
+    if (slot_flag) *slot_flag = kSlotEmpty;
   }
   const unsigned fm = __ballot_sync(kFull, mine && fast);
   if (lane == 0) {
@@ -477,7 +502,9 @@ __global__ void __launch_bounds__(256) prefetch_scan_kernel(const __grid_constan
     for (uint32_t ahead = 0; ahead < 2u; ++ahead) {
       const uint32_t slot = (episode + ahead) & 1u;
       uint32_t* flag = p.next_ready + (size_t)slot * p.B + e;
-      const bool want = in && ld_relaxed_u32(flag) == kSlotEmpty;
+      // claim with a compare-and-swap: two rounds that overlap (they should not: the host orders
+      // them) can then never list the same slot twice
+      const bool want = in && ld_relaxed_u32(flag) == kSlotEmpty && atomicCAS(flag, kSlotEmpty, kSlotClaimed) == kSlotEmpty;
       const unsigned m = __ballot_sync(kFull, want);
       if (m) {
         uint32_t base = 0u;
@@ -487,7 +514,6 @@ __global__ void __launch_bounds__(256) prefetch_scan_kernel(const __grid_constan
           WorkItem it;
           it.e = e; it.slot = slot; it.seed = choose_seed(p, e, episode, ahead);
           work[1u + base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = it;
-          *flag = kSlotClaimed;                 // not empty: a later scan must not list it again
         }
       }
     }
@@ -576,6 +602,11 @@ __global__ void __launch_bounds__(32) prefetch_layout_kernel(const __grid_consta
   }
 }
 
+// crl_prefetch_publish: the trusted epoch only grows (a late publish of an older round is a no-op)
+__global__ void publish_epoch_kernel(uint32_t* epoch, uint32_t round) {
+  if (*epoch < round) *epoch = round;
+}
+
 template <int TASK, int N>
 __global__ void __launch_bounds__(128) prefetch_task_kernel(const __grid_constant__ KParams p, const WorkItem* work) {
   const WorkHeader* hdr = reinterpret_cast<const WorkHeader*>(work);
@@ -613,7 +644,7 @@ __global__ void __launch_bounds__(128) prefetch_task_kernel(const __grid_constan
     }
     __threadfence();
     __syncwarp();
-    if (live && zone == 0) st_release_u32(p.next_ready + sb + it.e, kSlotReady);
+    if (live && zone == 0) st_release_u32(p.next_ready + sb + it.e, kSlotReady + p.round);
   }
 }
 
@@ -817,6 +848,19 @@ __global__ void __launch_bounds__(kThreads, min_blocks<N>()) step_kernel(const _
     asm volatile("griddepcontrol.wait;" ::: "memory");
   }
 
+  // CRL_STEP_ACTION_COUNTER: the step index of the in-kernel action draw is step_index + the number of
+  // such steps this group of 32 envs has taken (a device counter), so that a captured launch that
+  // is REPLAYED still draws fresh iid actions at every replay.  Plain read-modify-write by lane 0:
+  // steps of the same envs are ordered (whole-grid or chained wait above).
+  uint32_t act_base = 0u;
+  if (!p.actions && (p.flags & CRL_STEP_ACTION_COUNTER)) {
+    if (lane == 0 && warp_env0 < p.B) {
+      uint32_t* cnt = p.act_count + (warp_env0 >> 5);
+      act_base = ld_relaxed_u32(cnt);
+      *cnt = act_base + 1u;
+    }
+    act_base = __shfl_sync(kFull, act_base, 0);
+  }
   Env<N> env;
   float2 act = make_float2(0.f, 0.f);
   if (valid) {
@@ -825,7 +869,8 @@ __global__ void __launch_bounds__(kThreads, min_blocks<N>()) step_kernel(const _
       act = p.actions[e];
     } else {
       const unsigned ge = (unsigned)(p.env_offset + e);
-      U4 ctr{ge, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32), kTagAction};
+      const unsigned long long si = p.step_index + act_base;
+      U4 ctr{ge, (uint32_t)si, (uint32_t)(si >> 32), kTagAction};
       const U4 r = philox4x32(ctr, (uint32_t)p.action_seed, (uint32_t)(p.action_seed >> 32));
       act = make_float2(2.f * u01(r.x) - 1.f, 2.f * u01(r.y) - 1.f);
     }
@@ -842,6 +887,11 @@ __global__ void __launch_bounds__(kThreads, min_blocks<N>()) step_kernel(const _
   // (stored step count = sentinel); stepping it is a no-op that reports zeros and done.
   const bool parked = EXT && (p.flags & CRL_STEP_WAIT) && valid && env.steps == kParkedSteps;
   const bool live = valid && !parked;
+  // a parked env under an AUTO-RESET step (hier_base.py: step_no_reset for skill_len - 1 steps, then
+  // step): the worker's env.step is WaitWrapper's no-op (reward 0, done, info {}), and `if done:
+  // obs = env.reset()` (penv.py:7-10) then restarts it -- the call returns the new episode's first
+  // observation and counts nothing
+  const bool revive = EXT && parked && (p.flags & CRL_STEP_AUTO_RESET);
   // goal-conditioned variants: the goal zone and the distance to it BEFORE the physics, which
   // is the reference's last_dist_to_goal (set by set_goal or left by the previous step, both
   // at the position this step starts from)
@@ -912,9 +962,10 @@ __global__ void __launch_bounds__(kThreads, min_blocks<N>()) step_kernel(const _
     if (TASK == CRL_TASK_CM) {
       // goal_dist == 0 (colour_match_env.py:122-123)  <=>  all N zones share one colour
       constexpr uint32_t kOnes = ((1u << (2 * N)) - 1u) & 0x55555555u;
-      goal = env.hi == 0u || env.hi == kOnes || env.hi == 2u * kOnes;
+      const uint32_t col = env.hi & kHiMask;
+      goal = col == 0u || col == kOnes || col == 2u * kOnes;
     } else {
-      goal = env.hi == ((1u << N) - 1u);
+      goal = (env.hi & kHiMask) == ((1u << N) - 1u);
     }
     bool done = false;
     float reward = (float)event;
@@ -922,7 +973,9 @@ __global__ void __launch_bounds__(kThreads, min_blocks<N>()) step_kernel(const _
       reward = (float)((double)event + (double)(p.num_steps - env.steps) * p.bonus_per_step);
       done = true;
     }
-    env.steps += 1;
+    // a finished env that is stepped on without a reset (the reference asserts instead) must not
+    // run its 16-bit step count into the parked sentinel or the visited / colour bits
+    env.steps = min(env.steps + 1, kParkedSteps - 1);
     if (env.steps >= p.num_steps) done = true;
     if (TASK == CRL_TASK_TTSP && !done) {
       // TTSP_env.py:67: any unvisited zone with (zone_max_steps - steps) / max_steps <= 0
@@ -964,7 +1017,8 @@ __global__ void __launch_bounds__(kThreads, min_blocks<N>()) step_kernel(const _
       if (EXT && goals && live && need_next && goal_zone >= 0) p.goal[e] = -1;
     }
     const unsigned dm = __ballot_sync(kFull, done);
-    if (dm) {
+    const unsigned rm = EXT ? __ballot_sync(kFull, done || revive) : dm;   // envs to rebuild
+    if (rm) {
       float ret = done ? env.ep_return : 0.f;
       float len = done ? (float)env.steps : 0.f;
       const unsigned gm = __ballot_sync(kFull, goal);
@@ -973,7 +1027,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks<N>()) step_kernel(const _
         ret += __shfl_xor_sync(kFull, ret, o);
         len += __shfl_xor_sync(kFull, len, o);
       }
-      if (lane == 0) {
+      if (lane == 0 && dm) {
         atomicAdd(p.counters + 0, (double)ret);
         atomicAdd(p.counters + 1, (double)__popc(dm));
         atomicAdd(p.counters + 2, (double)__popc(gm));
@@ -984,9 +1038,9 @@ __global__ void __launch_bounds__(kThreads, min_blocks<N>()) step_kernel(const _
         // a copy crosses the (cold, out-of-line) call so that `env` itself is dead across it and
         // stays in registers everywhere else (keeping it live costs spills in the hot path)
         Env<N> next = env;
-        warp_reset<TASK, N, FIXED>(p, dm, lane, e, reinterpret_cast<float2*>(stage), next);
+        warp_reset<TASK, N, FIXED>(p, rm, lane, e, reinterpret_cast<float2*>(stage), env.hi >> 15, next);
         env = next;
-        fresh = done;
+        fresh = done || revive;
       }
     }
   }
@@ -1003,7 +1057,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks<N>()) step_kernel(const _
     }
     if (valid) store_state_obs<TASK, N>(p, env, e, c, s);
   } else {
-    zone_obs_send<TASK, N>(p, env, live, stage, lane, warp_env0, parked);
+    zone_obs_send<TASK, N>(p, env, live || revive, stage, lane, warp_env0, parked && !revive);
     // an env rebuilt by the auto-reset still integrates its OLD body: the shaped reward of the
     // episode's last step is measured at the post-physics position (TSP_next_city_env.py:57-67)
     Body pb = fresh ? old_b : env.b;
@@ -1023,8 +1077,8 @@ __global__ void __launch_bounds__(kThreads, min_blocks<N>()) step_kernel(const _
       }
       p.shaped[e] = (float)shaped;
     }
-    if (parked) {
-      if (goals) p.shaped[e] = 0.f;
+    if (parked && goals) p.shaped[e] = 0.f;
+    if (parked && !revive) {
       p.obs[2 * (size_t)e] = make_float4(0.f, 0.f, 0.f, 0.f);
       p.obs[2 * (size_t)e + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
     } else if (valid) {
@@ -1052,7 +1106,7 @@ __global__ void __launch_bounds__(kThreads) reset_kernel(const __grid_constant__
   if (valid) load_env<TASK, N>(p, e, env);
   const bool want = valid && (p.mask == nullptr || p.mask[e] != 0);
   const unsigned m = __ballot_sync(kFull, want);
-  if (m) warp_reset<TASK, N, true>(p, m, lane, e, reinterpret_cast<float2*>(stage), env);
+  if (m) warp_reset<TASK, N, true, true>(p, m, lane, e, reinterpret_cast<float2*>(stage), 0u, env);
   float c = 1.f, s = 0.f;
   if (valid) sincosf(env.b.phi, &s, &c);
   // the warp's 32 zone_obs rows leave as one bulk copy: rows of envs that were not reset are
@@ -1096,11 +1150,12 @@ __global__ void reset_from_layout_kernel(const KParams p, const LayoutParams L) 
 #pragma unroll
     for (int j = 0; j < (N + 1) / 2; ++j) p.zone_tmax[(size_t)j * p.B + e] = env.tmax[j];
   }
-  p.episode[e] += 1u;
+  const uint32_t episode = p.episode[e] + 1u;
+  p.episode[e] = episode;
   if (p.goal) p.goal[e] = -1;
   p.origin[e] = make_float4(env.b.X, env.b.Y, rot0, 0.f);
   p.pose[e] = make_float4(env.b.X, env.b.Y, env.b.phi, 0.f);
-  p.aux[e] = make_float4(0.f, 0.f, 0.f, __int_as_float((int)(env.hi << 16)));
+  p.aux[e] = make_float4(0.f, 0.f, 0.f, __int_as_float((int)((env.hi << 16) | ((episode & 1u) << 31))));
   if (TASK == CRL_TASK_CM) p.cooldown[e] = env.cd;
   float c, s;
   sincosf(env.b.phi, &s, &c);
@@ -1185,7 +1240,7 @@ __global__ void set_goal_kernel(const KParams p, const int32_t* goals, int N) {
   const int g = goals[e];
   if (g < 0) return;
   const uint32_t bits = (uint32_t)__float_as_int(p.aux[e].w);
-  const bool ok = g < N && (TASK == CRL_TASK_CM || !((bits >> 16 >> g) & 1u));
+  const bool ok = g < N && (TASK == CRL_TASK_CM || !((bits >> 16 >> g) & 1u));   // g < 15: never the parity bit
   if (ok) p.goal[e] = g; else atomicAdd(p.counters + 6, 1.0);
 }
 
@@ -1261,7 +1316,8 @@ __global__ void check_state_kernel(const KParams p, int task, int N, unsigned lo
   const float4 ps = p.pose[e], ax = p.aux[e];
   const uint32_t bits = (uint32_t)__float_as_int(ax.w);
   const int steps = (int)(bits & 0xffffu);
-  const uint32_t hi = bits >> 16;
+  const uint32_t hi = (bits >> 16) & 0x7fffu;
+  if ((bits >> 31) != (p.episode[e] & 1u)) atomicAdd(bad + 5, 1ull);   // slot parity out of step with the episode counter
   if (!(isfinite(ps.x) && isfinite(ps.y) && isfinite(ps.z) && isfinite(ps.w) && isfinite(ax.x) && isfinite(ax.y) &&
         isfinite(ax.z)))
     atomicAdd(bad + 0, 1ull);
@@ -1277,7 +1333,7 @@ __global__ void check_state_kernel(const KParams p, int task, int N, unsigned lo
   if (zone_bad) atomicAdd(bad + 3, 1ull);
   bool hi_bad = false;
   if (task == CRL_TASK_CM) {
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 7; ++i) {
       const uint32_t c = (hi >> (2 * i)) & 3u;
       hi_bad |= i < N ? c == 3u : c != 0u;
     }
@@ -1287,7 +1343,10 @@ __global__ void check_state_kernel(const KParams p, int task, int N, unsigned lo
     hi_bad = (hi >> N) != 0u;
   }
   if (hi_bad) atomicAdd(bad + 4, 1ull);
-  if (p.next_ready && (p.next_ready[e] > 3u || p.next_ready[(size_t)p.B + e] > 3u)) atomicAdd(bad + 5, 1ull);
+  if (p.next_ready) {                             // 0 empty, 2 layout parked, 3 claimed, >= 16 ready (round r)
+    const uint32_t f0 = p.next_ready[e], f1 = p.next_ready[(size_t)p.B + e];
+    if (f0 == 1u || (f0 > 3u && f0 < kSlotReady) || f1 == 1u || (f1 > 3u && f1 < kSlotReady)) atomicAdd(bad + 5, 1ull);
+  }
   if (p.goal && (p.goal[e] < -1 || p.goal[e] >= N)) atomicAdd(bad + 6, 1ull);
   if (task == CRL_TASK_TTSP) {
     bool t_bad = false;
@@ -1306,7 +1365,8 @@ static int check_config(const CrlConfig* c) {
   if (!c) return CRL_ERR_NULL;
   if (c->task < 0 || c->task > 2) return CRL_ERR_CONFIG;
   if (c->num_envs <= 0 || c->num_zones <= 0 || c->num_zones > CRL_MAX_ZONES) return CRL_ERR_CONFIG;
-  if (c->task == CRL_TASK_CM && c->num_zones > 8) return CRL_ERR_CONFIG;
+  // bits 16-30 of the state word hold the visited mask / colour codes, bit 31 the episode parity
+  if (c->task == CRL_TASK_CM ? c->num_zones > 7 : c->num_zones > 15) return CRL_ERR_CONFIG;
   if (c->num_steps <= 0 || c->num_steps > 65534) return CRL_ERR_CONFIG;   // 65535 = parked sentinel
   if (c->frameskip < 0 || c->max_cooldown < 0 || c->max_cooldown > 255) return CRL_ERR_CONFIG;
   if (c->seed_mode == CRL_SEED_FIXED_RANGE && c->max_seed < c->min_seed) return CRL_ERR_CONFIG;
@@ -1370,6 +1430,9 @@ static int fill_params(const CrlConfig* c, const CrlState* st, const CrlOut* out
   }
   p.init_hi = c->task == CRL_TASK_CM ? 0u : c->initial_visited;
   p.stamp = st->stamp;
+  p.act_count = st->stamp ? st->stamp + 2 * (size_t)((c->num_envs + 31) / 32) : nullptr;
+  p.epoch = st->prefetch_epoch;
+  if (p.next_ready && !p.epoch) return CRL_ERR_NULL;
   p.row_list = st->row_list;
   p.goal = st->goal;
   if (st->bank_zone_xy || st->bank_origin || st->bank_task) {
@@ -1466,11 +1529,12 @@ int crl_plane_bytes(const CrlConfig* c, int64_t* out_bytes, int32_t n) {
   o[10] = 2 * (c->task == CRL_TASK_TTSP ? 4 * ((N + 1) / 2) * B : (c->task == CRL_TASK_CM ? 4 * B : 0));
   o[11] = 2 * 16 * B; o[12] = 2 * 8 * B; o[13] = 2 * 4 * B;
   o[14] = 32 * B; o[15] = 4 * N * Z * B; o[16] = 8 * B;
-  o[17] = 2 * 4 * ((B + 31) / 32);
+  o[17] = 3 * 4 * ((B + 31) / 32);
   o[18] = 16 * (1 + 2 * B);
   o[19] = 4 * (4 + B);
   o[20] = 4 * B;   /* goal */
   o[21] = 4 * B;   /* shaped_reward */
+  o[22] = 16;      /* prefetch_epoch */
   for (int i = 0; i < n && i < CRL_NUM_PLANES; ++i) out_bytes[i] = o[i];
   return CRL_OK;
 }
@@ -1500,6 +1564,7 @@ int crl_step(const CrlConfig* c, const CrlState* st, const float* actions, const
   if (ticketed && !p.stamp) return CRL_ERR_NULL;
   if ((flags & CRL_STEP_TRACK_ROWS) && !p.row_list) return CRL_ERR_NULL;
   if ((flags & CRL_STEP_GOALS) && (!p.goal || !p.shaped)) return CRL_ERR_NULL;
+  if ((flags & CRL_STEP_ACTION_COUNTER) && !p.act_count) return CRL_ERR_NULL;
   const bool ext = (flags & (CRL_STEP_GOALS | CRL_STEP_WAIT)) != 0u;
   // Programmatic launch (this grid may start while its predecessor drains) is safe when the
   // kernel then waits for the whole predecessor (plain, chain start) or for its own previous
@@ -1571,11 +1636,13 @@ int crl_reset_from_layout(const CrlConfig* c, const CrlState* st, const CrlOut* 
   return launch_status();
 }
 
-int crl_prefetch_layouts(const CrlConfig* c, const CrlState* st, int32_t warps_per_sm, void* stream) {
+int crl_prefetch_layouts(const CrlConfig* c, const CrlState* st, int32_t warps_per_sm, uint32_t round, void* stream) {
   KParams p;
   int rc = fill_params(c, st, nullptr, p);
   if (rc) return rc;
-  if (!p.next_ready || !st->prefetch_work) return CRL_ERR_NULL;
+  if (!p.next_ready || !st->prefetch_work || !p.epoch) return CRL_ERR_NULL;
+  if (round > 0xffffff00u) return CRL_ERR_CONFIG;
+  p.round = round;
   if (!aligned16(st->prefetch_work)) return CRL_ERR_ALIGN;
   if (warps_per_sm <= 0) warps_per_sm = 2;
   if (warps_per_sm > 32) warps_per_sm = 32;
@@ -1588,7 +1655,7 @@ int crl_prefetch_layouts(const CrlConfig* c, const CrlState* st, int32_t warps_p
   CRL_DISPATCH(c->task, c->num_zones, CRL_CALL_PREFETCH_0);
   // (A) layouts: persistent lanes, one layout each; a few warps per SM share it with the steps
   const int blocks_a = min((2 * p.B + 31) / 32, 148 * warps_per_sm);
-  const uint32_t done_state = c->task == CRL_TASK_TSP ? kSlotReady : kSlotLayoutDone;
+  const uint32_t done_state = c->task == CRL_TASK_TSP ? kSlotReady + round : kSlotLayoutDone;
 #define CRL_CALL_PREFETCH_A(T, NN) { prefetch_layout_kernel<NN><<<blocks_a, 32, 0, s>>>(p, work, done_state); }
   CRL_DISPATCH(c->task, c->num_zones, CRL_CALL_PREFETCH_A);
   rc = launch_status();
@@ -1597,6 +1664,12 @@ int crl_prefetch_layouts(const CrlConfig* c, const CrlState* st, int32_t warps_p
   const int blocks_b = min((2 * p.B + 7) / 8, 148 * 2);
 #define CRL_CALL_PREFETCH_B(T, NN) { prefetch_task_kernel<T, NN><<<blocks_b, 128, 0, s>>>(p, work); }
   CRL_DISPATCH(c->task, c->num_zones, CRL_CALL_PREFETCH_B);
+  return launch_status();
+}
+
+int crl_prefetch_publish(const CrlState* st, uint32_t round, void* stream) {
+  if (!st || !st->prefetch_epoch) return CRL_ERR_NULL;
+  publish_epoch_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(st->prefetch_epoch, round);
   return launch_status();
 }
 

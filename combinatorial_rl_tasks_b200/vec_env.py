@@ -117,10 +117,17 @@ class ZoneVecEnv:
         self.next_seed = z(2, B, dtype=torch.int64)
         self.next_ready = z(2, B, dtype=torch.int32)
         self._prefetch_work = z(1 + 2 * B, 4, dtype=torch.int32)
+        # sampler rounds: numbered 1, 2, ...; a round's parked layouts become usable by the steps once it
+        # has been PUBLISHED on the stepping stream (crl_prefetch_publish), which tick() does two
+        # rounds later -- the stepping stream then waits for an event that fired long ago
+        self._prefetch_epoch = z(4, dtype=torch.int32)
+        self._round = 0
+        self._round_done = {}                     # round -> event recorded behind it on its stream
+        self._published = 0
         self._pf_found = torch.zeros(1, dtype=torch.int32).pin_memory()   # empty slots the last round found
         self._side = torch.cuda.Stream(device=dev)
         # per-warp completion stamps of crl_step (CRL_STEP_CHAINED)
-        self.stamp = z(2, (B + 31) // 32, dtype=torch.int32)
+        self.stamp = z(3, (B + 31) // 32, dtype=torch.int32)
         self._chain_ok = False                    # True: the last kernel enqueued for this state was a ticketed step
         # envs whose zone_obs row changed in the last step (CRL_STEP_TRACK_ROWS, step_host)
         self._row_list = z(4 + B, dtype=torch.int32)
@@ -141,7 +148,8 @@ class ZoneVecEnv:
                                    next_task=ptr(self.next_task), next_origin=ptr(self.next_origin),
                                    next_seed=ptr(self.next_seed), next_ready=ptr(self.next_ready),
                                    stamp=ptr(self.stamp), prefetch_work=ptr(self._prefetch_work),
-                                   row_list=ptr(self._row_list), goal=ptr(self.goal))
+                                   row_list=ptr(self._row_list), goal=ptr(self.goal),
+                                   prefetch_epoch=ptr(self._prefetch_epoch))
         fixed = spec.fixed_layout()               # hard instances: fixed robot / city placements
         if fixed is not None:
             self._fixed = torch.from_numpy(fixed).to(dev).contiguous()
@@ -248,28 +256,55 @@ class ZoneVecEnv:
             seeds = torch.arange(self.num_envs, dtype=torch.int64) + seeds
         self.seeds.copy_(self._as_dev(seeds, torch.int64))
         self.episode.zero_()
+        self.aux[:, 3] = (self.aux[:, 3].view(torch.int32) & 0x7fffffff).view(torch.float32)   # slot parity follows `episode`
         self.next_ready.zero_()          # parked layouts were drawn for the old seeds
         self._pf_interval = self._pf_due = max(self.prefetch_every, 1)
         self._chain_ok = False
         self._mirror_ok = False
 
     def prefetch(self, stream=None, warps_per_sm=0):
-        """Fill the empty next-layout slots in the background (crl_prefetch_layouts) on a
-        side stream.  Needs no ordering with step(): slots change hands through
-        acquire/release flags and an env that finishes before its slot is filled is
-        sampled inline with the identical result."""
-        if stream is None:
-            # not earlier than the work already queued on the stepping stream (the host may
-            # run far ahead of the device), but never blocking it
-            stream = self._side
-            stream.wait_stream(torch.cuda.current_stream(self.device))
+        """One sampler round (crl_prefetch_layouts): fill the empty next-layout slots.
+
+        ``stream=None``: in the background, on the side stream, ordered behind the work already queued on
+        the stepping stream but never blocking it.  Before launching round r the stepping stream
+        publishes round r - 2 (it waits for that round's event, which fired long ago: rounds are at least
+        ``prefetch_every`` steps apart), so a round's layouts reach the steps one to two intervals after
+        it was launched and the step's reset path needs no acquire / release.  An env that finishes before
+        its slot is usable samples inline with the identical result.
+        ``stream=<the stepping stream>``: in line (reset, load_state_dict); published at once."""
+        cur = torch.cuda.current_stream(self.device)
+        background = stream is None
+        if torch.cuda.is_current_stream_capturing():
+            return
         with self._guard():
+            if background:
+                stream = self._side
+                self._publish(self._round - 1, cur)
+                stream.wait_stream(cur)
+            else:
+                # rounds share one work list: not before a background round still running is over
+                stream.wait_stream(self._side)
+            self._round += 1
             _lib.check(self.lib.crl_prefetch_layouts(self.cfg, self.state, warps_per_sm or self.prefetch_warps,
-                                                     ctypes.c_void_p(stream.cuda_stream)))
-            if not torch.cuda.is_current_stream_capturing():
-                with torch.cuda.stream(stream):           # how much there was to do, read by tick() later
-                    self._pf_found.copy_(self._prefetch_work[0, :1], non_blocking=True)
+                                                     self._round, ctypes.c_void_p(stream.cuda_stream)))
+            with torch.cuda.stream(stream):               # how much there was to do, read by tick() later
+                self._pf_found.copy_(self._prefetch_work[0, :1], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            self._round_done[self._round] = ev
+            if not background:
+                self._publish(self._round, cur)
         self.gpu_launches += 2 if self.spec.task == _lib.TASK_TSP else 3
+
+    def _publish(self, rnd, cur):
+        """Make rounds <= rnd usable by the steps enqueued on ``cur`` from here on."""
+        if rnd <= self._published:
+            return
+        for r in [r for r in self._round_done if r <= rnd]:
+            cur.wait_event(self._round_done.pop(r))
+        _lib.check(self.lib.crl_prefetch_publish(self.state, rnd, ctypes.c_void_p(cur.cuda_stream)))
+        self._published = rnd
+        self.gpu_launches += 1
 
     def tick(self, steps=1):
         """Cadence of the background sampler, called once per step (step() does; a caller that
@@ -296,6 +331,8 @@ class ZoneVecEnv:
         with self._guard():
             if layout is None:
                 m = None if mask is None else self._as_dev(mask, torch.uint8)
+                if not torch.cuda.is_current_stream_capturing():
+                    self._publish(self._round, torch.cuda.current_stream(self.device))   # everything parked so far
                 if mask is None and self.state.bank_zone_xy is None and not torch.cuda.is_current_stream_capturing():
                     # a full reset: sample every layout with the one-lane-per-env sampler first
                     # (all SMs, nothing else is running), then crl_reset only copies
@@ -341,8 +378,9 @@ class ZoneVecEnv:
                     actions = self._as_dev(actions, torch.float32)
                 assert actions.shape == (self.num_envs, 2)
                 aptr = actions.data_ptr()
-            _lib.check(self.lib.crl_step(self.cfg, self.state, aptr, self.out, flags, action_seed,
-                                         self._step_index, self._stream()))
+            # replayable draws count their steps on the device; the host index then stays out of it
+            si = 0 if flags & _lib.STEP_ACTION_COUNTER else self._step_index
+            _lib.check(self.lib.crl_step(self.cfg, self.state, aptr, self.out, flags, action_seed, si, self._stream()))
         self._step_index += 1
         self.gpu_launches += 1
         self._chain_ok = bool(chained)
@@ -354,7 +392,9 @@ class ZoneVecEnv:
     def step(self, actions):
         """ParallelEnv.step (penv.py:52-59): finished envs restart inside the call; their
         returned observation is the new episode's first one, reward/done/info the old one's."""
-        return self._step(actions, _lib.STEP_AUTO_RESET if self.auto_reset else 0)
+        # with wait=True a parked env (finished under step_no_reset) is WaitWrapper's no-op followed by
+        # the worker's reset: (first obs of the new episode, 0, True, {}) -- wrappers.py:36-44, penv.py:7-10
+        return self._step(actions, (_lib.STEP_AUTO_RESET if self.auto_reset else 0) | (_lib.STEP_WAIT if self.wait else 0))
 
     def step_no_reset(self, actions):
         """ParallelEnv.step_no_reset (penv.py:61-66).  With ``wait=True`` (the reference wraps each
@@ -409,10 +449,13 @@ class ZoneVecEnv:
         a = self._available.view(torch.bool)
         return a if env_idx is None else a[env_idx]
 
-    def step_random(self, action_seed=1, auto_reset=True, chained=False):
+    def step_random(self, action_seed=1, auto_reset=True, chained=False, replayable=False):
         """A step with U(-1,1)^2 actions drawn in-kernel (Philox): action_space.sample().
-        ``chained=True`` for back-to-back rollout steps with nothing else enqueued in between."""
-        return self._step(None, _lib.STEP_AUTO_RESET if auto_reset else 0, action_seed, chained=chained)
+        ``chained=True`` for back-to-back rollout steps with nothing else enqueued in between.
+        ``replayable=True`` (CRL_STEP_ACTION_COUNTER): the draw's step index advances on the device, so a
+        CUDA graph that captured this call draws fresh iid actions at every replay."""
+        flags = (_lib.STEP_AUTO_RESET if auto_reset else 0) | (_lib.STEP_ACTION_COUNTER if replayable else 0)
+        return self._step(None, flags, action_seed, chained=chained)
 
     def step_host(self, actions, auto_reset=True, delta=True, wait=False, zero_copy=True):
         """The reference-facing call with HOST buffers: numpy actions in, numpy obs /
@@ -432,7 +475,7 @@ class ZoneVecEnv:
         if a is not h['np']['actions']:
             np.copyto(h['np']['actions'], a)
         flags = (_lib.STEP_AUTO_RESET if auto_reset else 0) | self._mode_flags
-        if wait and not auto_reset:
+        if wait:
             flags |= _lib.STEP_WAIT
         use_delta = delta and self._mirror_ok and self.spec.task != _lib.TASK_TTSP
         with self._guard():
@@ -490,11 +533,17 @@ class ZoneVecEnv:
     def steps(self):
         return self.aux[:, 3].view(torch.int32) & 0xffff
 
-    def counters(self):
-        """Episode statistics accumulated in-kernel since construction."""
+    def counters(self, allow_chain_timeouts=False):
+        """Episode statistics accumulated in-kernel since construction.  Raises if a chained step ever
+        gave up its wait (see CRL_STEP_CHAINED), unless ``allow_chain_timeouts``."""
         out = (ctypes.c_double * 8)()
         with self._guard():
             _lib.check(self.lib.crl_counters_read(self.state, out, self._stream()))
+        if out[7] != 0 and not allow_chain_timeouts:
+            # a chained step (CRL_STEP_CHAINED) gave up waiting for its own previous step and went on:
+            # the state may be corrupt.  Never seen; never to be ignored.
+            raise RuntimeError(f'{int(out[7])} chained step(s) stopped waiting for their predecessor '
+                               '(counters[7]); the env state is not trustworthy')
         return {'return_sum': out[0], 'episodes': out[1], 'successes': out[2], 'length_sum': out[3],
                 'resets_prefetched': out[4], 'resets_inline': out[5], 'goals_rejected': out[6],
                 'chain_wait_timeouts': out[7]}
@@ -505,7 +554,11 @@ class ZoneVecEnv:
         v = torch.zeros(8, dtype=torch.int64, device=self.device)
         with self._guard():
             _lib.check(self.lib.crl_check_state(self.cfg, self.state, v.data_ptr(), self._stream()))
-        return [int(x) for x in v.cpu()]
+        bad = [int(x) for x in v.cpu()]
+        if float(self.counters_dev[7].item()) != 0:
+            raise RuntimeError('a chained step stopped waiting for its predecessor (counters[7]); the env state is '
+                               'not trustworthy')
+        return bad
 
     _STATE_KEYS = ('pose', 'aux', 'zone_xy', 'zone_tmax', 'cooldown', 'seeds', 'episode', 'origin', 'counters_dev',
                    'goal', 'obs', 'zone_obs', 'result', 'shaped_reward')
@@ -517,6 +570,7 @@ class ZoneVecEnv:
         torch.cuda.current_stream(self.device).synchronize()
         d = {k: getattr(self, k).clone() for k in self._STATE_KEYS if getattr(self, k) is not None}
         d['step_index'] = self._step_index
+        d['action_count'] = self.stamp[2].clone()     # CRL_STEP_ACTION_COUNTER steps taken, per 32 envs
         d['env_id'], d['num_envs'], d['num_steps'] = self.env_id, self.num_envs, int(self.cfg.num_steps)
         return d
 
@@ -528,7 +582,9 @@ class ZoneVecEnv:
         self.cfg.num_steps = d['num_steps']
         self._step_index = d['step_index']
         self.next_ready.zero_()                   # parked layouts belong to the run that was interrupted
-        self.stamp.zero_()
+        self.stamp[:2].zero_()
+        if 'action_count' in d:
+            self.stamp[2].copy_(d['action_count'])
         self._chain_ok = False
         self._mirror_ok = False
         if self.prefetch_every and self.state.bank_zone_xy is None:

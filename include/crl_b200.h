@@ -26,9 +26,10 @@
  *    pose      float4[B]   (X, Y, phi, Vx)      world-frame position, heading in
  *                                                [-pi, pi], world-frame velocity
  *    aux       float4[B]   (Vy, omega, episode_return, bits)
- *                          bits (int32 reinterpret): steps in bits 0-15; bits 16-31 =
- *                          visited mask (TSP/TTSP) or 2-bit colour codes (ColourMatch:
- *                          0 Blue, 1 Green, 2 Red)
+ *                          bits (int32 reinterpret): steps in bits 0-15; bits 16-30 =
+ *                          visited mask (TSP/TTSP, N <= 15) or 2-bit colour codes (ColourMatch,
+ *                          N <= 7: 0 Blue, 1 Green, 2 Red); bit 31 = parity of `episode` (the
+ *                          next-layout slot the env's next reset takes, known without a load)
  *    zone_xy   float2[N][B]                      zone centres, plane-major
  *    zone_tmax uint32[ceil(N/2)][B]              TimedTSP only: zone_max_steps, two
  *                                                uint16 per word (zone 2j low half)
@@ -47,8 +48,9 @@
  *  rejection-sampling loop
  *    next_zone_xy float2[2][N][B], next_task uint32[2][ceil(N/2)][B] (TimedTSP timeouts) or
  *    uint32[2][B] (ColourMatch colour codes), next_origin float4[2][B], next_seed int64[2][B]
- *    (the seed the parked layout was drawn for), next_ready uint32[2][B] (0 = slot empty, 1 =
- *    ready, 2 = layout parked and task draws pending, 3 = claimed by a running prefetch)
+ *    (the seed the parked layout was drawn for), next_ready uint32[2][B] (0 = slot empty, 2 = layout
+ *    parked and task draws pending, 3 = claimed by a running prefetch, 16 + r = ready, filled by
+ *    sampler round r)
  *  optional stamp uint32[2][ceil(B/32)]: steps started / finished per group of 32 envs,
  *  see CRL_STEP_CHAINED
  *  optional row_list uint32[4 + B] (CRL_STEP_TRACK_ROWS, crl_step_host_delta) and goal int32[B]
@@ -68,7 +70,7 @@
 extern "C" {
 #endif
 
-#define CRL_ABI_VERSION 5
+#define CRL_ABI_VERSION 6
 #define CRL_MAX_ZONES 16
 
 /* task ids; reference classes: main/envs/TSP_env.py:11, TTSP_env.py:12, colour_match_env.py:11 */
@@ -116,6 +118,12 @@ enum CrlError {
  * ends in a step without CRL_STEP_AUTO_RESET is parked; further steps of a parked env change
  * nothing and report an all-zero observation, reward 0, done = 1, until it is reset. */
 #define CRL_STEP_WAIT 64u
+/* With actions == NULL: the step index of the in-kernel Philox action draw is `step_index` PLUS the
+ * number of CRL_STEP_ACTION_COUNTER steps the env's group of 32 has taken so far, kept on the device
+ * (third plane of CrlState.stamp).  A launch captured in a CUDA graph and replayed then draws fresh
+ * iid U(-1,1)^2 actions per (env, step) at every replay -- action_space.sample() of a random-action
+ * rollout -- with nothing coming from the host.  Needs CrlState.stamp. */
+#define CRL_STEP_ACTION_COUNTER 128u
 /* crl_step_host_delta only: no staging and no copy-engine transfers -- the step kernel reads the
  * actions from, and writes obs / result / shaped_reward straight to, the caller's host buffers,
  * which must be page-locked and device-mapped (cudaHostAlloc; CRL_ERR_CONFIG otherwise).  The
@@ -169,8 +177,9 @@ typedef struct CrlState {
   float* next_origin;   /* float4[2][B]; optional */
   int64_t* next_seed;   /* int64[2][B]; optional */
   uint32_t* next_ready; /* uint32[2][B]; optional.  Zero it whenever CrlState.seed is rewritten */
-  uint32_t* stamp;      /* uint32[2][ceil(B/32)]; optional, zero-initialised.  Steps started and
-                           steps finished for each group of 32 envs (CRL_STEP_CHAINED) */
+  uint32_t* stamp;      /* uint32[3][ceil(B/32)]; optional, zero-initialised.  Steps started and
+                           steps finished for each group of 32 envs (CRL_STEP_CHAINED), and the
+                           in-kernel-action steps taken (CRL_STEP_ACTION_COUNTER) */
   uint32_t* prefetch_work; /* 16 (1 + 2 B) bytes, 16-byte aligned: work list of crl_prefetch_layouts
                               (needed with next_*) */
   uint32_t* row_list;   /* uint32[4 + B]; optional (CRL_STEP_TRACK_ROWS): word 0 = number of envs
@@ -197,6 +206,9 @@ typedef struct CrlState {
    * every sampler (crl_reset, the auto-reset of crl_step, crl_prefetch_layouts); layout banks and
    * crl_reset_from_layout take their positions as given. */
   const float* fixed_layout;
+  /* uint32[4], zero-initialised; needed with next_*.  Word 0 = the last sampler round whose parked
+   * layouts crl_step / crl_reset may use (written by crl_prefetch_publish). */
+  uint32_t* prefetch_epoch;
 } CrlState;
 
 typedef struct CrlResult {
@@ -230,9 +242,9 @@ const char* crl_strerror(int code);
 /* Bytes the caller must allocate for each plane of CrlState / CrlOut, in the order
  * pose, aux, zone_xy, zone_tmax, cooldown, seed, episode, origin, counters, next_zone_xy,
  * next_task, next_origin, next_seed, next_ready, obs, zone_obs, result, stamp,
- * prefetch_work, row_list, goal, shaped_reward (CRL_NUM_PLANES entries; 0 = plane unused by
+ * prefetch_work, row_list, goal, shaped_reward, prefetch_epoch (CRL_NUM_PLANES entries; 0 = plane unused by
  * this task).  Writes the first min(n, CRL_NUM_PLANES) entries of out_bytes. */
-#define CRL_NUM_PLANES 22
+#define CRL_NUM_PLANES 23
 int crl_plane_bytes(const CrlConfig* cfg, int64_t* out_bytes, int32_t n);
 
 /* Algorithmic HBM bytes one env-step moves in this layout: read, written. */
@@ -248,14 +260,23 @@ int crl_reset(const CrlConfig* cfg, const CrlState* st, const CrlOut* out,
 
 /* Fill the empty next-layout slots (see CrlState.next_*): for each env whose slot is
  * empty, draw its NEXT reset now.  Meant to be launched every few steps on a stream other
- * than the stepping one; it needs no ordering with crl_step (slots are handed over with
- * acquire/release flags, and an env that finishes before its slot is filled is sampled
- * inline by crl_step with the identical result).  Hides Engine.build_layout's rejection
- * sampling, which the reference runs inside reset() (penv.py:9-10).  The sampler runs one
- * lane per env on `warps_per_sm` persistent warps per SM (0 = default 2: a background job
- * beside the steps; up to 32 before a full crl_reset, where nothing else is running). */
+ * than the stepping one.  Hides Engine.build_layout's rejection sampling, which the reference
+ * runs inside reset() (penv.py:9-10).  The sampler runs one lane per env on `warps_per_sm`
+ * persistent warps per SM (0 = default 2: a background job beside the steps; up to 32 before a
+ * full crl_reset, where nothing else is running).
+ * ORDERING (ABI 6: stream order instead of acquire/release flags, so that the step's reset path is
+ * one batch of plain loads).  `round` numbers the call, 1, 2, 3 ... per CrlState, increasing.
+ *  - the call must be ordered AFTER the steps whose finished envs it is to serve (enqueue it on a
+ *    stream that has waited for the stepping stream), and rounds of one CrlState must not overlap;
+ *  - slots it fills are marked "ready, round r" and crl_step ignores them (samples inline, with the
+ *    identical result) until crl_prefetch_publish(st, r, stepping_stream) has been enqueued on the
+ *    stepping stream AFTER that stream waited for round r to finish.  Steps enqueued behind the
+ *    publish see everything the round wrote by stream order.
+ * The step never waits for the sampler as long as the caller publishes a round a few steps after
+ * launching it (vec_env.ZoneVecEnv.tick publishes round r - 2 when it launches round r). */
 int crl_prefetch_layouts(const CrlConfig* cfg, const CrlState* st, int32_t warps_per_sm,
-                         void* stream);
+                         uint32_t round, void* stream);
+int crl_prefetch_publish(const CrlState* st, uint32_t round, void* stream);
 
 /* The same reset with the layout handed in (device arrays, see CrlLayoutIn) for
  * envs env_ids[0..n) (env_ids == NULL: envs 0..n). */

@@ -267,6 +267,71 @@ def test_wait_wrapper_semantics(crl):
     assert bool(d.all().item()) and bool((env2.steps == 0).all().item())
 
 
+def test_parked_env_under_auto_reset_step_is_noop_then_reset(crl):
+    """hier_base.py:180-183: step_no_reset for skill_len - 1 steps, then step().  An env parked
+    in between goes through WaitWrapper's no-op (wrappers.py:36-44: reward 0, done, info {}) and the
+    worker's `if done: obs = env.reset()` (penv.py:7-10): the call returns the NEW episode's first
+    observation, reward 0, done True, and counts no second episode."""
+    B = 8
+    kw = dict(seed_mode='fixed_range', min_seed=1, max_seed=50, wait=True)
+    for env_id in ('PointTSP-v0', 'PointTSP-v3', 'ColourMatch-v0'):
+        env, twin = crl.ZoneVecEnv(env_id, B, **kw), crl.ZoneVecEnv(env_id, B, **kw)
+        for v in (env, twin):
+            v.reset()
+            # envs 0-2 run into the step limit after 1 / 2 / 3 steps
+            st = torch.tensor([1999, 1998, 1997], dtype=torch.int32, device='cuda')
+            v.aux[:3, 3] = (v.aux[:3, 3].view(torch.int32) & ~0xffff | st).view(torch.float32)
+            if v.spec.task != 2:
+                # env 3 succeeds at its first step: every zone but the last visited, robot on the last one
+                bits = v.aux[3, 3].view(torch.int32)
+                v.aux[3, 3] = (bits & 0xffff | (((1 << 14) - 1) << 16)).view(torch.float32)
+                v.pose[3, :2] = v.zone_xy[14, 3, :]
+        n_done = 3 if env.spec.task == 2 else 4
+        rs = np.random.RandomState(3)
+        for t in range(4):
+            a = torch.from_numpy(rs.uniform(-1, 1, (B, 2)).astype(np.float32)).cuda()
+            o, r, d, info = env.step_no_reset(a)
+            twin.step_no_reset(a)
+        assert bool(d[:n_done].all().item()) and not bool(d[n_done:].any().item())
+        assert env.counters()['episodes'] == n_done
+        before = env.counters()
+        # what a reset of exactly the parked envs builds (same seeds, same episode numbers)
+        mask = torch.zeros(B, dtype=torch.uint8); mask[:n_done] = 1
+        first = twin.reset(mask=mask)
+        first_obs, first_zone = first['obs'].clone(), first['zone_obs'].clone()
+        a = torch.from_numpy(rs.uniform(-1, 1, (B, 2)).astype(np.float32)).cuda()
+        o, r, d, info = env.step(a)                           # the auto-reset step
+        o2, r2, d2, info2 = twin.step(a)
+        assert bool(d[:n_done].all().item()) and not bool(d[n_done:].any().item())
+        assert not r[:n_done].any() and not env.goal_met[:n_done].any() and not env.event[:n_done].any()
+        assert torch.equal(o['obs'][:n_done], first_obs[:n_done]) and torch.equal(o['zone_obs'][:n_done], first_zone[:n_done])
+        assert bool((o['obs'][:n_done, 0] == 1.0).all().item()) and bool(o['zone_obs'][:n_done].any().item())
+        assert bool((env.steps[:n_done] == 0).all().item())
+        # the envs that were never parked stepped as usual, identically in both replicas
+        assert torch.equal(o['obs'][n_done:], o2['obs'][n_done:]) and torch.equal(r[n_done:], r2[n_done:])
+        after = env.counters()
+        for k in ('episodes', 'successes', 'return_sum', 'length_sum'):
+            assert after[k] == before[k], k                   # nothing counted twice
+        if env.spec.goals:
+            assert not info['shaped_reward'][:n_done].any() and not info['need_next_goal'][:n_done].any()
+        # and the revived envs now run: the next step is an ordinary one
+        o, r, d, info = env.step(a)
+        assert not bool(d.any().item()) and bool((env.steps[:n_done] == 1).all().item())
+    # the reference's list / tuple protocol: info {} for the parked envs
+    pe = crl.ParallelEnv('PointTSP-v0', 4, num_training_tasks=5, hier=True)
+    pe.reset()
+    pe.vec.aux[:2, 3] = (pe.vec.aux[:2, 3].view(torch.int32) & ~0xffff | 1999).view(torch.float32)
+    acts = [np.zeros(2)] * 4
+    pe.step_no_reset(acts)
+    o, r, d, info = pe.step_no_reset(acts)
+    assert info[0] == {} and info[1] == {} and d[0] and not o[0]['obs'].any()
+    o, r, d, info = pe.step(acts)
+    assert info[0] == {} and info[1] == {} and d[0] and d[1] and r[0] == 0.0 and not d[2]
+    assert o[0]['obs'][0] == 1.0 and o[0]['zone_obs'].any() and info[2] == {'cost': 0}
+    o, r, d, info = pe.step(acts)
+    assert not any(d) and info[0] == {'cost': 0} and o[0]['obs'][0] == np.float32(1999 / 2000)
+
+
 def test_parallel_env_compat_has_the_reference_protocol(crl):
     """compat.ParallelEnv: the call and return types of penv.py:46-66 and zone-goals
     penv.py:75-99 (lists / tuples of per-env Python objects), values equal to the tensor API's."""

@@ -294,6 +294,81 @@ def test_full_size_properties(crl, env_id, B):
             assert np.array_equal(z[:, :, 6], want)
 
 
+@pytest.mark.parametrize('env_id,B', [('PointTSP-v0', 65536), ('PointTTSP-v0', 262144), ('ColourMatch-v0', 262144)])
+def test_full_size_sampled_envs_against_the_oracle(crl, env_id, B):
+    """BASELINE.json configs 2-4 at FULL size, checked against the oracle directly: 256 envs spread
+    over the batch (first and last warp, CTA boundaries, random ones) are stepped by the fp64 oracle
+    beside the kernel from identical positions -- events, visited / colour / cooldown state,
+    timeouts, done, goal_met and integer rewards bit-exact, rewards 1e-6, observations as in
+    test_gpu_parity -- while the whole batch steps in the same launches."""
+    from oracle import zone_env as ze
+    from tests.test_gpu_parity import REWARD_ATOL, check_obs
+    task = ze.TASK_OF_ENV_ID[env_id]
+    env = crl.ZoneVecEnv(env_id, B)
+    env.seed(4242)
+    env.reset()
+    N = env.spec.num_zones
+    rs = np.random.RandomState(11)
+    idx = np.unique(np.concatenate([np.arange(0, 40), np.arange(B - 40, B), np.arange(63, 4096, 64)[:48],
+                                    rs.randint(0, B, 160)]))[:256]
+    it = torch.from_numpy(idx).cuda()
+    # make things happen in the sampled envs: some close to the step limit, some sitting on a zone
+    bits = env.aux[:, 3].view(torch.int32)
+    near_end = it[::5]
+    bits[near_end] = (bits[near_end] & ~0xffff) | torch.randint(1960, 1999, (len(near_end),), device='cuda', dtype=torch.int32)
+    refs = []
+    zone32 = env.zone_xy[:, it, :].cpu().numpy().astype(np.float64)           # (N, n, 2)
+    b0 = bits_of(env)
+    tm = tmax_of(env) if task == ze.TTSP else None
+    for j, i in enumerate(idx):
+        r = ze.ZoneTaskEnv(task)
+        lay = {'xy0': np.zeros(2), 'rot0': 0.0, 'zone_xy': zone32[:, j, :]}
+        if task == ze.TTSP:
+            lay['zone_max_steps'] = tm[i]
+        if task == ze.CM:
+            lay['colours'] = np.array([(b0[i] >> 16 >> (2 * k)) & 3 for k in range(N)])
+        r.reset(layout=lay)
+        r.steps = int(b0[i] & 0xffff)
+        refs.append(r)
+    alive = np.ones(len(idx), dtype=bool)
+    n_events = n_done = 0
+    for t in range(48):
+        if t % 6 == 0:                                                       # teleport a third of them onto a zone
+            sel = it[(t // 6) % 3::3]
+            z = torch.randint(0, N, (len(sel),), device='cuda')
+            env.pose[sel, :2] = env.zone_xy[z, sel, :] + 0.05
+        a = torch.from_numpy(rs.uniform(-1, 1, (B, 2)).astype(np.float32)).cuda()
+        pose, aux = env.pose[it].cpu().numpy().astype(np.float64), env.aux[it].cpu().numpy().astype(np.float64)
+        obs, reward, done, info = env.step_no_reset(a)
+        res = env.result[it].cpu().numpy()
+        og, zg = obs['obs'][it].cpu().numpy(), obs['zone_obs'][it].cpu().numpy()
+        b1 = bits_of(env)[idx]
+        cd = cooldown_of(env)[idx] if task == ze.CM else None
+        a_np = a[it].cpu().numpy()
+        for j, r in enumerate(refs):
+            if not alive[j]:
+                continue                                                     # the reference asserts on a finished env
+            r.set_state([pose[j, 0], pose[j, 1], pose[j, 2]], [pose[j, 3], aux[j, 0], aux[j, 1]])
+            o_ref, r_ref, d_ref, i_ref = r.step(a_np[j])
+            where = (env_id, t, int(idx[j]))
+            assert bool(res[j, 4]) == d_ref and bool(res[j, 5]) == bool(i_ref.get('goal_met', False)), where
+            assert int(res[j, 6:7].view(np.int8)[0]) == r.event, where
+            assert abs(float(res[j, :4].view(np.float32)[0]) - r_ref) <= REWARD_ATOL, where
+            assert int(b1[j] & 0xffff) == r.steps, where
+            if task == ze.CM:
+                assert [(int(b1[j]) >> 16 >> (2 * k)) & 3 for k in range(N)] == list(r.colours), where
+                assert list(cd[j]) == list(r.cooldown), where
+            else:
+                assert [bool((int(b1[j]) >> 16 >> k) & 1) for k in range(N)] == list(r.visited), where
+            check_obs(task, og[j], zg[j], o_ref['obs'], o_ref['zone_obs'], where)
+            n_events += r.event != 0
+            if d_ref:
+                alive[j] = False
+                n_done += 1
+    assert n_events >= 20 and n_done >= 20, (n_events, n_done)
+    assert env.check_state()[:2] == [0, 0]
+
+
 @pytest.mark.parametrize('env_id', ['PointTTSP-v0', 'ColourMatch-v0'])
 def test_device_sampler_is_distribution_equivalent_to_reference_sampler(crl, env_id):
     """The Philox reset on the device vs Engine.sample_layout / beta / choice on numpy's
@@ -355,7 +430,8 @@ def test_prefetched_resets_equal_inline_resets(crl, env_id):
     torch.cuda.synchronize()
     # a full reset() parks the layouts of the next two resets and consumes the first; `a` then tops
     # its slots up again, `b` (never prefetching) is stripped of its parked layout: all inline
-    assert bool((a.next_ready == 1).all()) and bool((b.next_ready[0] == 0).all()) and bool((b.next_ready[1] == 1).all())
+    # (slot flags: 0 empty, 16 + r = ready, filled by sampler round r)
+    assert bool((a.next_ready >= 16).all()) and bool((b.next_ready[0] == 0).all()) and bool((b.next_ready[1] >= 16).all())
     b.next_ready.zero_()
     gen = torch.Generator(device='cuda'); gen.manual_seed(0)
     for rnd in range(3):

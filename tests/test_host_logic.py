@@ -48,7 +48,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.crl_abi_version() == 5
+    assert lib.crl_abi_version() == 6
     assert b'NULL' in lib.crl_strerror(-1)
 
 
@@ -57,14 +57,14 @@ def test_argument_errors_are_detected_on_the_host():
     lib = _lib.load()
     cfg = _lib.CrlConfig(task=0, num_envs=64, num_zones=15, num_steps=2000, frameskip=10, max_cooldown=150,
                          zone_size=0.2)
-    sizes = (ctypes.c_int64 * 22)()
-    assert lib.crl_plane_bytes(cfg, sizes, 22) == 0
+    sizes = (ctypes.c_int64 * 23)()
+    assert lib.crl_plane_bytes(cfg, sizes, 23) == 0
     assert list(sizes) == [1024, 1024, 7680, 0, 0, 512, 256, 1024, 64, 2 * 7680, 0, 2 * 1024, 2 * 512, 2 * 256,
-                           2048, 64 * 90 * 4, 512, 16, 16 * 129, 4 * 68, 256, 256]
+                           2048, 64 * 90 * 4, 512, 24, 16 * 129, 4 * 68, 256, 256, 16]
     rd, wr = ctypes.c_int64(), ctypes.c_int64()
     assert lib.crl_step_bytes(cfg, ctypes.byref(rd), ctypes.byref(wr)) == 0 and (rd.value, wr.value) == (160, 432)
     bad = _lib.CrlConfig(task=7, num_envs=64, num_zones=15, num_steps=2000, zone_size=0.2)
-    assert lib.crl_plane_bytes(bad, sizes, 22) == -2
+    assert lib.crl_plane_bytes(bad, sizes, 23) == -2
     st, out = _lib.CrlState(), _lib.CrlOut()
     assert lib.crl_step(cfg, st, None, out, 0, 0, 0, None) == -1          # NULL planes
     cfg2 = _lib.CrlConfig(task=0, num_envs=64, num_zones=9, num_steps=2000, frameskip=10, zone_size=0.2)
@@ -110,8 +110,8 @@ def test_hard_instance_specs_and_config_checks():
     ok = _lib.CrlConfig(task=0, num_envs=64, num_zones=15, num_steps=1000, zone_size=0.2, initial_visited=0x7fe0)
     assert lib.crl_plane_bytes(ok, sizes, 22) == 0
     bad = _lib.CrlConfig(task=0, num_envs=64, num_zones=15, num_steps=1000, zone_size=0.2, initial_visited=0x8000)
-    assert lib.crl_plane_bytes(bad, sizes, 22) == -2     # a bit beyond zone N - 1
-    assert ctypes.sizeof(_lib.CrlConfig) == 112 and ctypes.sizeof(_lib.CrlState) == 22 * 8
+    assert lib.crl_plane_bytes(bad, sizes, 23) == -2     # a bit beyond zone N - 1
+    assert ctypes.sizeof(_lib.CrlConfig) == 112 and ctypes.sizeof(_lib.CrlState) == 23 * 8
 
 
 def test_design_twin_honours_fixed_placements():
