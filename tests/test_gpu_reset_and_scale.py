@@ -560,7 +560,13 @@ def test_check_state_detects_corruption(crl):
     env.next_ready[1, 8] = 9
     env.goal[9] = 15
     env.zone_tmax[0, 10] = 2001
-    assert env.check_state() == [1] * 8
+    # (1 << 31 of the state word is the episode parity, no longer a visited bit: a wrong parity counts with
+    # the slot flags, index 5; every one of a 15-zone env's 15 visited bits is legal)
+    assert env.check_state() == [1, 1, 1, 1, 0, 2, 1, 1]
+    easy = crl.ZoneVecEnv('PointTSP-v1', 64)
+    easy.reset()
+    easy.aux[7, 3] = (easy.aux[7, 3].view(torch.int32) | (1 << 26)).view(torch.float32)   # "zone 10" of a 5-zone env
+    assert easy.check_state() == [0, 0, 0, 0, 1, 0, 0, 0]
     cm = crl.ZoneVecEnv('ColourMatch-v0', 64)
     cm.reset()
     assert cm.check_state() == [0] * 8
