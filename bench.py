@@ -171,9 +171,12 @@ class Ring:
         self.step_bytes = rd.value + wr.value - 8
         self.task = probe.spec.task
         del probe
-        self.R = R = max(2, -(-2 * L2_BYTES // (B * self.step_bytes)))
-        self.chained = (B <= 131072 and streams == 1) if chained is None else bool(chained)
-        self.S = S = max(1, min(streams, R))
+        self.R = R = max(2, getattr(args, 'min_replicas', 0), -(-2 * L2_BYTES // (B * self.step_bytes)))
+        # the replicas are independent batches: by default each is stepped on its own stream (up to 8), so that
+        # the tail of one replica's launch overlaps another's body; on ONE stream back-to-back steps of small
+        # batches chain warp by warp instead (CRL_STEP_CHAINED)
+        self.S = S = max(1, min(streams if streams > 0 else 8, R))
+        self.chained = (B <= 131072 and S == 1) if chained is None else bool(chained)
         bank_kw = self._bank(crl, args, dev) if args.bank else {}
         self.envs = []
         for r in range(R):
@@ -380,6 +383,7 @@ def run_ours(args):
     for k in ('ms_per_step', 'ms_per_step_best', 'ms_per_step_mean'):
         m[k] = rank_max(m[k])
     head = device_line(ring, m, world, peak)
+    head_R, head_S, head_chained = ring.R, ring.S, ring.chained
     head_stats = stats(ring)
     head_launches = m['timed_steps'] + ring.prefetch_launches
 
@@ -446,7 +450,7 @@ def run_ours(args):
             for k in ('ms_per_step', 'ms_per_step_best', 'ms_per_step_mean'):
                 m2[k] = rank_max(m2[k])
             d = device_line(r2, m2, world, peak)
-            d.update({'config': tag, 'env': env_id, 'envs_per_gpu_per_launch': b, 'ring_replicas': r2.R,
+            d.update({'config': tag, 'env': env_id, 'envs_per_gpu_per_launch': b, 'ring_replicas': r2.R, 'streams': r2.S,
                       'chained_steps': r2.chained, 'timed_steps': m2['timed_steps'], 'timed_region_s': m2['timed_region_s'],
                       'unit': UNIT, 'episode_stats': stats(r2), 'sampler_launches': r2.prefetch_launches})
             extra[f'{env_id}:{b}'] = d
@@ -474,8 +478,9 @@ def run_ours(args):
                    'envs_per_gpu_per_launch': B,
                    'l2': f'inputs larger than L2: ring of {head_ring_desc(sb, B)}',
                    'launch': 'CUDA graphs of whole ring cycles, replayed back to back; in-kernel actions advance on a device counter',
-                   'chained_steps': bool(chained) if chained is not None else B <= 131072 and args.streams == 1,
-                   'streams': args.streams, 'prefetch_every': args.prefetch_every, 'layout_bank': args.bank or None,
+                   'ring_replicas': head_R, 'streams': head_S, 'chained_steps': head_chained,
+                   'concurrency': 'the ring\'s replicas are independent env batches, each stepped on its own CUDA stream (launches of '
+                                  'different replicas overlap; steps of one replica are ordered by its stream)', 'prefetch_every': args.prefetch_every, 'layout_bank': args.bank or None,
                    'timing': f'{m["blocks"]} blocks of K={K} steps back to back ({m["timed_region_s"]:.2f} s of device time, CUDA events, '
                              f'barrier + synchronize on both sides), {m["segments"]} segments of {m["steps_per_segment"]} steps; '
                              f'ms_per_step / value = the MEDIAN segment, max over ranks'},
@@ -531,8 +536,10 @@ def main():
     ap.add_argument('--chained', type=int, default=-1,
                     help='1: back-to-back steps order themselves warp by warp (CRL_STEP_CHAINED); 0: whole-grid '
                          'wait; -1: chained when a launch is at most a wave or two (<= 131072 envs)')
-    ap.add_argument('--streams', type=int, default=1,
-                    help='the ring\'s replicas are independent: step them on this many streams (replica r on stream r %% S)')
+    ap.add_argument('--streams', type=int, default=0,
+                    help='the ring\'s replicas are independent batches: step them on this many streams (replica r on stream '
+                         'r %% S); 0 = one stream per replica, at most 8')
+    ap.add_argument('--min-replicas', type=int, default=0, help='at least this many ring replicas')
     ap.add_argument('--prefetch-every', type=int, default=32,
                     help='top up the next-layout slots every N steps of an env (0: resets sample inline)')
     ap.add_argument('--bank', type=int, default=0,

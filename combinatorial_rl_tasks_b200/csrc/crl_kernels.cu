@@ -89,18 +89,18 @@ constexpr uint32_t kParBit = 0x8000u, kHiMask = 0x7fffu;
 template <int TASK>
 struct ZoneDim { static constexpr int Z = (TASK == CRL_TASK_TSP) ? 6 : 7; };
 
-// Resident warps per SM the step kernel is compiled for (register cap = 64 K / 32 / this):
-// the zone_obs stage (32 rows per warp in shared memory) allows 16-19 warps at 15 zones
-// and 42 at 6, so registers are capped to match rather than left to ptxas.
-template <int N>
-struct Occupancy { static constexpr int kWarps = N > 8 ? 16 : 24; };
-#ifdef CRL_NO_MINBLOCKS
-template <int N>
-constexpr int min_blocks() { return 1; }
-#else
-template <int N>
-constexpr int min_blocks() { return Occupancy<N>::kWarps * 32 / kThreads; }
+// Registers per thread the step kernel is compiled for.  Occupancy is set by the zone_obs stage (32 rows
+// per warp in shared memory: 8 CTAs = 16 warps per SM at 15 zones, 12 CTAs = 24 warps at <= 8), and the
+// register cap is chosen to LEAVE ROOM beside those CTAs: 8 x 64 x 112 = 57,344 (12 x 64 x 80 = 61,440) of
+// the SM's 65,536 registers, so that four (two) 32-thread CTAs of the background layout sampler (64
+// registers) fit without displacing a step CTA.  At 128 registers the step kernel fills the register file exactly, every
+// sampler CTA costs the SM an eighth of its step warps for as long as it runs, and TimedTSP -- whose sampler
+// runs all the time -- loses a fifth of its throughput (profiles/r02_notes.md).
+#ifndef CRL_REGS_N15
+#define CRL_REGS_N15 112
 #endif
+template <int N>
+struct MaxRegs { static constexpr int v = N > 8 ? CRL_REGS_N15 : 80; };
 
 // Registers describing one env between load and store.
 template <int N>
@@ -324,6 +324,78 @@ __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
+// The hot way through an auto-reset, INLINE in the step kernel and lane-local: take the env's parked
+// next layout if the slot (parity in the state word) holds a trusted one drawn for the seed this
+// reset runs with.  Inline because a call would see the kernel parameters through a generic pointer
+// (every `p.x` a memory load and a dependent round trip: ~10 us per resetting warp under load,
+// profiles/r02_notes.md) where the kernel itself reads them from the constant bank; lean because it
+// writes the new layout straight into the env's own registers, which are dead once the episode is
+// over.  Returns false (env.zone / tmax clobbered, nothing stored) when the slot cannot be used: the
+// out-of-line warp_reset then rebuilds the env.
+template <int TASK, int N>
+__device__ __forceinline__ bool reset_from_slot(const KParams& p, int e, Env<N>& env) {
+  const int B = p.B;
+  const uint32_t par = env.hi >> 15;
+  uint32_t episode, col_word = 0u;
+  long long chosen;
+  float4 o;
+  uint32_t* slot_flag = nullptr;
+  if (p.bank_zone_xy) {
+    // fixed task set (make_train_env's num_training_tasks maps): the map of seed `chosen` is entry
+    // chosen - min_seed of the layout bank (a few KB, cache resident): copy it, nothing to sample
+    episode = p.episode[e];
+    chosen = choose_seed(p, e, episode);
+    if (chosen < p.min_seed || chosen > p.max_seed) return false;
+    const size_t k = (size_t)(chosen - p.min_seed);
+    o = p.bank_origin[k];
+#pragma unroll
+    for (int i = 0; i < N; ++i) env.zone[i] = p.bank_zone_xy[k * N + i];
+    if (TASK == CRL_TASK_TTSP) {
+#pragma unroll
+      for (int j = 0; j < (N + 1) / 2; ++j) env.tmax[j] = p.bank_task[k * ((N + 1) / 2) + j];
+    }
+    if (TASK == CRL_TASK_CM) col_word = p.bank_task[k];
+  } else {
+    if (!p.next_ready) return false;
+    const size_t sb = (size_t)par * (size_t)B;
+    slot_flag = p.next_ready + sb + e;
+    const float2* nz = p.next_zone_xy + sb * N + e;
+    const uint32_t flag = ld_relaxed_u32(slot_flag);
+    const uint32_t trusted = ld_relaxed_u32(p.epoch);
+    episode = p.episode[e];
+    const long long parked_for = __ldcg(p.next_seed + sb + e);
+    o = __ldcg(p.next_origin + sb + e);
+#pragma unroll
+    for (int i = 0; i < N; ++i) env.zone[i] = __ldcg(nz + (size_t)i * B);
+    if (TASK == CRL_TASK_TTSP) {
+      const uint32_t* nt = p.next_task + sb * ((N + 1) / 2) + e;
+#pragma unroll
+      for (int j = 0; j < (N + 1) / 2; ++j) env.tmax[j] = __ldcg(nt + (size_t)j * B);
+    }
+    if (TASK == CRL_TASK_CM) col_word = __ldcg(p.next_task + sb + e);
+    chosen = choose_seed(p, e, episode);
+    if (!(flag >= kSlotReady && flag - kSlotReady <= trusted && parked_for == chosen && (episode & 1u) == par)) return false;
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) p.zone_xy[(size_t)i * B + e] = env.zone[i];
+  if (TASK == CRL_TASK_TTSP) {
+#pragma unroll
+    for (int j = 0; j < (N + 1) / 2; ++j) p.zone_tmax[(size_t)j * B + e] = env.tmax[j];
+  }
+  env.b.X = o.x; env.b.Y = o.y; env.b.phi = wrap_pi(o.z);
+  env.b.vx = env.b.vy = env.b.w = 0.f;
+  env.ep_return = 0.f;
+  env.steps = 0;
+  env.hi = (TASK == CRL_TASK_CM ? col_word : p.init_hi) | (((episode + 1u) & 1u) ? kParBit : 0u);
+  env.cd = make_uint2(0u, 0u);
+  p.seed[e] = chosen + 1;                         // Engine.reset: self._seed += 1
+  p.episode[e] = episode + 1u;
+  p.origin[e] = make_float4(o.x, o.y, o.z, 0.f);
+  if (p.goal) p.goal[e] = -1;                     // a new episode has no goal until set_goal
+  if (slot_flag) *slot_flag = kSlotEmpty;         // plain store: the next sampler round is ordered after this kernel
+  return true;
+}
+
 // Engine.reset for the lanes in `dm` (each lane = one env).  A lane whose next layout
 // was prefetched (next_ready set for exactly the seed this reset runs with) only copies
 // it: no sampling latency on the step's critical path.  The others are rebuilt one at a
@@ -491,7 +563,7 @@ struct WorkItem { int e; uint32_t slot; long long seed; };   // 16 bytes; item 0
 struct WorkHeader { uint32_t count, cursor, pad0, pad1; };
 
 template <int N>
-__global__ void __launch_bounds__(256) prefetch_scan_kernel(const __grid_constant__ KParams p, WorkItem* work) {
+__global__ void __launch_bounds__(64) prefetch_scan_kernel(const __grid_constant__ KParams p, WorkItem* work) {
   WorkHeader* hdr = reinterpret_cast<WorkHeader*>(work);
   const int lane = threadIdx.x & 31;
   const int n_round = (p.B + 31) & ~31;
@@ -537,7 +609,6 @@ __global__ void __launch_bounds__(32) prefetch_layout_kernel(const __grid_consta
   int e = -1, k = 0, j = 0;
   uint32_t attempt = 0u, slot = 0u;
   long long layout_seed = 0;
-  U4 r{0u, 0u, 0u, 0u};
   for (;;) {
     const unsigned idle = __ballot_sync(kFull, !have);
     if (idle && !drained) {                       // one atomic refills every idle lane of the warp
@@ -554,7 +625,11 @@ __global__ void __launch_bounds__(32) prefetch_layout_kernel(const __grid_consta
     }
     if (__ballot_sync(kFull, have) == 0u) break;
     if (have) {
-      // one try of Engine.sample_layout's sequential procedure
+      // TWO tries of Engine.sample_layout's sequential procedure per iteration: tries j and j + 1 are
+      // the two halves of one Philox block, so the block is computed once per iteration by every lane
+      // (with one try per iteration the lanes' parities differ and the warp paid for the block every
+      // time), and the two distance tests are independent chains.  The first valid try in index
+      // order wins, exactly as before.
       const float keep = k == 0 ? rk : zk;
       float lo_x = -ext + keep, lo_y = lo_x, span = (ext - keep) - lo_x;
       bool pinned = false;                        // fixed location: a box of width 0, one try
@@ -562,25 +637,31 @@ __global__ void __launch_bounds__(32) prefetch_layout_kernel(const __grid_consta
         const float4 fx = p.fixed[min(k, N)];
         if (fx.w == 1.f || fx.w == 3.f) { lo_x = fx.x; lo_y = fx.y; span = 0.f; pinned = true; }
       }
-      if (!(j & 1)) r = draw(layout_seed, (uint32_t)(j >> 1), (uint32_t)k, attempt, kTagLayout);
-      const float x = __fadd_rn(lo_x, __fmul_rn(span, u01((j & 1) ? r.z : r.x)));
-      const float y = __fadd_rn(lo_y, __fmul_rn(span, u01((j & 1) ? r.w : r.y)));
+      const U4 r = draw(layout_seed, (uint32_t)(j >> 1), (uint32_t)k, attempt, kTagLayout);   // j is even
+      const float x0 = __fadd_rn(lo_x, __fmul_rn(span, u01(r.x))), y0 = __fadd_rn(lo_y, __fmul_rn(span, u01(r.y)));
+      const float x1 = __fadd_rn(lo_x, __fmul_rn(span, u01(r.z))), y1 = __fadd_rn(lo_y, __fmul_rn(span, u01(r.w)));
       const float need_r = __fadd_rn(rk, keep), need_z = __fadd_rn(zk, keep);
       const float need_r2 = __fmul_rn(need_r, need_r), need_z2 = __fmul_rn(need_z, need_z);
-      uint32_t bad = 0u;                          // bit q: too close to object q (no branches)
+      uint32_t bad0 = 0u, bad1 = 0u;              // bit q: too close to object q (no branches)
 #pragma unroll
       for (int q = 0; q < N; ++q) {
         const float2 o = placed[q];
-        const float dx = __fsub_rn(x, o.x), dy = __fsub_rn(y, o.y);
-        const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-        bad |= (d2 >= (q == 0 ? need_r2 : need_z2)) ? 0u : (1u << q);
+        const float lim = q == 0 ? need_r2 : need_z2;
+        const float dx0 = __fsub_rn(x0, o.x), dy0 = __fsub_rn(y0, o.y);
+        const float dx1 = __fsub_rn(x1, o.x), dy1 = __fsub_rn(y1, o.y);
+        const float d20 = __fadd_rn(__fmul_rn(dx0, dx0), __fmul_rn(dy0, dy0));
+        const float d21 = __fadd_rn(__fmul_rn(dx1, dx1), __fmul_rn(dy1, dy1));
+        bad0 |= (d20 >= lim) ? 0u : (1u << q);
+        bad1 |= (d21 >= lim) ? 0u : (1u << q);
       }
-      bad &= (1u << k) - 1u;                      // objects >= k hold stale values
-      if (bad == 0u) {
+      const uint32_t live = (1u << k) - 1u;       // objects >= k hold stale values
+      const bool ok0 = (bad0 & live) == 0u, ok1 = !pinned && (bad1 & live) == 0u;
+      if (ok0 || ok1) {
+        const float x = ok0 ? x0 : x1, y = ok0 ? y0 : y1;
 #pragma unroll
         for (int q = 0; q <= N; ++q) if (q == k) placed[q] = make_float2(x, y);
         ++k; j = 0;
-      } else if (++j >= (pinned ? 1 : 100)) {     // 100 misses abandon the layout
+      } else if ((j += 2) >= (pinned ? 1 : 100)) {   // 100 misses abandon the layout
         j = 0; k = 0;
         if (++attempt >= 10000u) k = N + 1;       // as the twin: give up with what there is
       }
@@ -608,7 +689,7 @@ __global__ void publish_epoch_kernel(uint32_t* epoch, uint32_t round) {
 }
 
 template <int TASK, int N>
-__global__ void __launch_bounds__(128) prefetch_task_kernel(const __grid_constant__ KParams p, const WorkItem* work) {
+__global__ void __maxnreg__(64) prefetch_task_kernel(const __grid_constant__ KParams p, const WorkItem* work) {
   const WorkHeader* hdr = reinterpret_cast<const WorkHeader*>(work);
   const uint32_t count = hdr->count;
   const int lane = threadIdx.x & 31;
@@ -692,11 +773,11 @@ __device__ __forceinline__ void zone_row(const KParams& p, const Env<N>& env, fl
 // the copy is issued early and drains while the warp integrates; zone_obs_wait() must
 // run before the CTA exits (the copy reads shared memory asynchronously).
 template <int TASK, int N>
-__device__ __forceinline__ void zone_obs_issue(const KParams& p, float* stage, int lane, int warp_env0) {
+__device__ __forceinline__ void zone_obs_issue(const KParams& p, float* stage, int lane, int env0, int max_rows) {
   constexpr int ROW = N * ZoneDim<TASK>::Z;
-  const int n_valid = min(32, p.B - warp_env0);
+  const int n_valid = max(0, min(max_rows, p.B - env0));
   const uint32_t bytes = (uint32_t)n_valid * ROW * 4u;
-  float* gdst = p.zone_obs + (size_t)warp_env0 * ROW;
+  float* gdst = p.zone_obs + (size_t)env0 * ROW;
   if ((bytes & 15u) == 0u) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
@@ -720,7 +801,7 @@ __device__ __forceinline__ void zone_obs_send(const KParams& p, const Env<N>& en
   if (zero_row) {                                  // WaitWrapper.noop_obs (wrappers.py:46-50)
     for (int k = 0; k < ROW; ++k) stage[lane * ROW + k] = 0.f;
   }
-  zone_obs_issue<TASK, N>(p, stage, lane, warp_env0);
+  zone_obs_issue<TASK, N>(p, stage, lane, warp_env0, 32);
 }
 
 __device__ __forceinline__ void zone_obs_wait(int lane) {
@@ -819,7 +900,7 @@ __device__ __forceinline__ void chain_release(const KParams& p, int w, int lane,
 // EXT = true: the variant that also serves the goal-conditioned tasks (CRL_STEP_GOALS) and
 // WaitWrapper semantics (CRL_STEP_WAIT); the plain rollout kernel carries none of it.
 template <int TASK, int N, bool EXT, bool FIXED = false>
-__global__ void __launch_bounds__(kThreads, min_blocks<N>()) step_kernel(const __grid_constant__ KParams p) {
+__global__ void __maxnreg__(MaxRegs<N>::v) step_kernel(const __grid_constant__ KParams p) {
   constexpr int ROW = N * ZoneDim<TASK>::Z;
   extern __shared__ __align__(128) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -851,20 +932,24 @@ __global__ void __launch_bounds__(kThreads, min_blocks<N>()) step_kernel(const _
   // CRL_STEP_ACTION_COUNTER: the step index of the in-kernel action draw is step_index + the number of
   // such steps this group of 32 envs has taken (a device counter), so that a captured launch that
   // is REPLAYED still draws fresh iid actions at every replay.  Plain read-modify-write by lane 0:
-  // steps of the same envs are ordered (whole-grid or chained wait above).
+  // steps of the same envs are ordered (whole-grid or chained wait above).  The load is ISSUED first
+  // (the previous step wrote the word: an L2 hit) and CONSUMED behind the state loads: issued behind
+  // them it returns behind them, and the shuffle then holds the warp until the last plane is in
+  // (+19 % per launch at 65,536 PointTSP envs, profiles/r02_notes.md).
   uint32_t act_base = 0u;
-  if (!p.actions && (p.flags & CRL_STEP_ACTION_COUNTER)) {
-    if (lane == 0 && warp_env0 < p.B) {
-      uint32_t* cnt = p.act_count + (warp_env0 >> 5);
-      act_base = ld_relaxed_u32(cnt);
-      *cnt = act_base + 1u;
-    }
-    act_base = __shfl_sync(kFull, act_base, 0);
+  uint32_t* act_cnt = nullptr;
+  if (!p.actions && (p.flags & CRL_STEP_ACTION_COUNTER) && lane == 0 && warp_env0 < p.B) {
+    act_cnt = p.act_count + (warp_env0 >> 5);
+    act_base = ld_relaxed_u32(act_cnt);
   }
   Env<N> env;
   float2 act = make_float2(0.f, 0.f);
+  if (valid) load_env<TASK, N>(p, e, env);
+  if (!p.actions && (p.flags & CRL_STEP_ACTION_COUNTER)) {
+    if (act_cnt) *act_cnt = act_base + 1u;
+    act_base = __shfl_sync(kFull, act_base, 0);
+  }
   if (valid) {
-    load_env<TASK, N>(p, e, env);
     if (p.actions) {
       act = p.actions[e];
     } else {
@@ -1035,12 +1120,22 @@ __global__ void __launch_bounds__(kThreads, min_blocks<N>()) step_kernel(const _
       }
       // (5) auto-reset, penv.py:9-10: only the finished envs are rebuilt
       if (p.flags & CRL_STEP_AUTO_RESET) {
-        // a copy crosses the (cold, out-of-line) call so that `env` itself is dead across it and
-        // stays in registers everywhere else (keeping it live costs spills in the hot path)
-        Env<N> next = env;
-        warp_reset<TASK, N, FIXED>(p, rm, lane, e, reinterpret_cast<float2*>(stage), env.hi >> 15, next);
-        env = next;
         fresh = done || revive;
+        // hot way: the parked layout, lane-local and inline (reset_from_slot)
+        const uint32_t par_in = env.hi >> 15;
+        bool served = false;
+        if (fresh) served = reset_from_slot<TASK, N>(p, e, env);
+        const unsigned sm = __ballot_sync(kFull, served);
+        if (lane == 0 && sm) atomicAdd(p.counters + 4, (double)__popc(sm));
+        // cold way (layout bank, slot not usable: inline sampling by the whole warp), out of line.
+        // A copy crosses the call so that `env` itself is dead across it and stays in registers
+        // everywhere else (keeping it live costs spills in the hot path)
+        const unsigned left = rm & ~sm;
+        if (left) {
+          Env<N> next = env;
+          warp_reset<TASK, N, FIXED>(p, left, lane, e, reinterpret_cast<float2*>(stage), par_in, next);
+          env = next;
+        }
       }
     }
   }
@@ -1650,8 +1745,10 @@ int crl_prefetch_layouts(const CrlConfig* c, const CrlState* st, int32_t warps_p
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (cudaMemsetAsync(work, 0, sizeof(WorkHeader), s) != cudaSuccess) return CRL_ERR_DEVICE;
   // (0) empty slots -> dense work list
-  const int blocks_0 = min((p.B + 255) / 256, 148 * 4);
-#define CRL_CALL_PREFETCH_0(T, NN) { prefetch_scan_kernel<NN><<<blocks_0, 256, 0, s>>>(p, work); }
+  // every sampler kernel runs in small CTAs (<= 64 registers x 32 or 64 threads): they fit into the registers
+  // the step kernel leaves free on each SM (MaxRegs) instead of displacing one of its CTAs
+  const int blocks_0 = min((p.B + 63) / 64, 148 * 8);
+#define CRL_CALL_PREFETCH_0(T, NN) { prefetch_scan_kernel<NN><<<blocks_0, 64, 0, s>>>(p, work); }
   CRL_DISPATCH(c->task, c->num_zones, CRL_CALL_PREFETCH_0);
   // (A) layouts: persistent lanes, one layout each; a few warps per SM share it with the steps
   const int blocks_a = min((2 * p.B + 31) / 32, 148 * warps_per_sm);
@@ -1661,8 +1758,8 @@ int crl_prefetch_layouts(const CrlConfig* c, const CrlState* st, int32_t warps_p
   rc = launch_status();
   if (rc || c->task == CRL_TASK_TSP) return rc;
   // (B) task draws for the same work list
-  const int blocks_b = min((2 * p.B + 7) / 8, 148 * 2);
-#define CRL_CALL_PREFETCH_B(T, NN) { prefetch_task_kernel<T, NN><<<blocks_b, 128, 0, s>>>(p, work); }
+  const int blocks_b = min((2 * p.B + 1) / 2, 148 * 4);
+#define CRL_CALL_PREFETCH_B(T, NN) { prefetch_task_kernel<T, NN><<<blocks_b, 32, 0, s>>>(p, work); }
   CRL_DISPATCH(c->task, c->num_zones, CRL_CALL_PREFETCH_B);
   return launch_status();
 }

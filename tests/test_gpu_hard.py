@@ -47,7 +47,7 @@ def test_device_reset_with_fixed_placements_equals_design_twin(crl, env_id):
     torch.cuda.synchronize()
     zxy, origin = env.zone_xy.cpu().numpy(), env.origin.cpu().numpy()
     bits = env.aux[:, 3].view(torch.int32).cpu().numpy()
-    assert np.all((bits >> 16) & 0xffff == spec.initial_visited) and np.all(bits & 0xffff == 0)
+    assert np.all((bits >> 16) & 0x7fff == spec.initial_visited) and np.all(bits & 0xffff == 0)   # bit 31 = episode parity
     assert np.all(origin[:, :2] == np.float32(h['robot_locations'][0]))
     for k in range(n_fixed):
         assert np.all(zxy[k] == np.array(h['zones_locations'][k], dtype=np.float32)), k
@@ -93,7 +93,7 @@ def test_auto_reset_of_hard_instance_prefetched_and_inline(crl):
         assert n_done == B and bool(done.all())            # the 250-step limit (num_steps of the config)
         assert torch.all(env.episode == 2) and torch.all(env.steps == 0)
         bits = env.aux[:, 3].view(torch.int32).cpu().numpy()
-        assert np.all((bits >> 16) & 0xffff == spec.initial_visited)
+        assert np.all((bits >> 16) & 0x7fff == spec.initial_visited)
         zxy, origin = env.zone_xy.cpu().numpy(), env.origin.cpu().numpy()
         for i in range(0, B, 41):
             tw = co.philox_reset('PointTSP-v5', 777000 + i + 1, fixed=table)     # second episode: seed + 1

@@ -3,7 +3,8 @@
 Ring / measure, no e2e, no CPU baseline): one JSON line per case.  Tuning tool; bench.py is the record.
 
     python tools/sweep.py PointTSP-v0:65536:c1:s1 PointTTSP-v0:262144:c0:s2 ... [--seconds 1.0] [--steps 200]
-    case = env:envs[:cX][:sY][:pZ][:bK]   c = chained (0/1, default auto), s = streams, p = prefetch_every, b = layout bank size
+    case = env:envs[:cX][:sY][:pZ][:bK][:wW][:rR]   c = chained (0/1, default auto), s = streams, p = prefetch_every, b = layout bank size,
+           w = sampler warps per SM, r = minimum number of ring replicas
 """
 import argparse
 import json
@@ -35,9 +36,9 @@ def main():
         env_id, B = parts[0], int(parts[1])
         opt = {p[0]: int(p[1:]) for p in parts[2:]}
         args = argparse.Namespace(bank=opt.get('b', 0), prefetch_every=opt.get('p', 32), prefetch_warps=opt.get('w', 0),
-                                  cfg=a.cfg, no_auto_reset=a.no_auto_reset, env=env_id)
+                                  cfg=a.cfg, no_auto_reset=a.no_auto_reset, env=env_id, min_replicas=opt.get('r', 0))
         ring = bench.Ring(crl, _lib, args, env_id, B, dev, 0, chained=(None if 'c' not in opt else bool(opt['c'])),
-                          streams=opt.get('s', 1))
+                          streams=opt.get('s', 0))
         m = bench.measure(ring, a.steps, a.warmup, a.seconds, 1, None)
         d = bench.device_line(ring, m, 1, peak)
         c = ring.counters().cpu().numpy()
