@@ -390,9 +390,13 @@ def run_ours(args):
     # ---- e2e: host numpy in, host numpy out, through the public API --------------------------------------
     env = ring.envs[0]
     N, Z = env.spec.num_zones, env.spec.zone_dim
-    host_actions = [np.random.RandomState(7 + i + 100 * rank).uniform(-1, 1, (B, 2)).astype(np.float32) for i in range(8)]
+    pageable = [np.random.RandomState(7 + i + 100 * rank).uniform(-1, 1, (B, 2)).astype(np.float32) for i in range(8)]
+    pinned = env.pinned_actions(8)                                     # the caller's own page-locked action buffers
+    for a, b in zip(pinned, pageable):
+        np.copyto(a, b)
+    host_actions = pinned
 
-    def timed_host_steps(delta, seconds):
+    def timed_host_steps(delta, seconds, host_actions=pinned):
         for i in range(3):
             env.step_host(host_actions[i % 8], delta=delta)
         torch.cuda.synchronize()
@@ -400,34 +404,39 @@ def run_ours(args):
             dist.barrier()
         rows = calls = 0
         per_call = []
+        env.host_rows_moved(reset=True)
         t_start = time.perf_counter()
         while True:
             t0 = time.perf_counter()
             for i in range(25):
                 obs, rew, done, info = env.step_host(host_actions[(calls + i) % 8], delta=delta)
-                rows += env.delta_rows
+                rows += max(env.delta_rows, 0)
             torch.cuda.synchronize()
             t1 = time.perf_counter()
             per_call.append((t1 - t0) / 25)
             calls += 25
             if t1 - t_start >= seconds or calls >= args.e2e_max_calls:
                 break
+        rows += env.host_rows_moved(reset=True)                      # the zero-copy path counts its rows on the device
         per_call.sort()
         med = rank_max(per_call[len(per_call) // 2])
         return world * B / med, rows / calls, calls, world * B / rank_max(per_call[0])
 
     full_rate, _, _, _ = timed_host_steps(False, args.e2e_seconds / 3)
+    pageable_rate, _, _, _ = timed_host_steps(True, args.e2e_seconds / 3, pageable)
     rate, rows_per_step, e2e_calls, best_rate = timed_host_steps(True, args.e2e_seconds)
     is_delta = rows_per_step < B
     e2e = {'value': rate, 'unit': UNIT, 'h2d_bytes_per_step': 8 * B,
-           'd2h_bytes_per_step': int((32 + 8) * B + rows_per_step * (4 * N * Z + (4 if is_delta else 0)) + (16 if is_delta else 0)),
+           'd2h_bytes_per_step': int((32 + 8) * B + rows_per_step * 4 * N * Z),
            'calls': e2e_calls, 'timing': 'median over groups of 25 calls (host clock, synchronize on both sides)',
            'best_group_value': best_rate,
-           'api': 'ZoneVecEnv.step_host: host numpy actions in, host numpy obs/zone_obs/reward/done out, pinned '
-                  'staging, copies + stream sync inside every call'
-                  + ('; crl_step_host_delta, zero-copy: the step kernel reads the actions from and writes obs and result to the '
-                     'pinned host buffers itself; of zone_obs only the rows that changed cross PCIe (mean %.1f of %d '
-                     'rows per step); host buffers byte-identical to a full copy' % (rows_per_step, B) if is_delta
+           'pageable_actions_value': pageable_rate,
+           'api': 'ZoneVecEnv.step_host: host numpy actions in (page-locked arrays from env.pinned_actions(), one of 8 per call; '
+                  '`pageable_actions_value` = the same with ordinary numpy arrays, staged through a pinned buffer inside the '
+                  'call), host numpy obs/zone_obs/reward/done out, transfers + stream sync inside every call'
+                  + ('; crl_step_host_delta, zero-copy: ONE kernel per call -- the step kernel reads the actions from, and writes '
+                     'obs, result and the zone_obs rows that changed (mean %.1f of %d rows per step) to, the pinned host '
+                     'buffers itself; host buffers byte-identical to a full copy' % (rows_per_step, B) if is_delta
                      else '; crl_step_host: everything copied whole'),
            'full_copy_value': full_rate,
            'full_copy_d2h_bytes_per_step': (32 + 4 * N * Z + 8) * B}

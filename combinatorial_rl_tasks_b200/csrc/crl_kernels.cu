@@ -69,6 +69,7 @@ struct KParams {
   const uint32_t* epoch;        // CrlState.prefetch_epoch: last sampler round whose slots the step may trust
   uint32_t round;               // crl_prefetch_layouts: the round being run
   uint32_t* row_list;
+  float* zone_obs_host;         // CRL_STEP_HOST_ZERO_COPY: the caller's host zone_obs (device-mapped); changed rows go there
   int32_t* goal;
   const float2* bank_zone_xy;
   const float4* bank_origin;
@@ -804,6 +805,22 @@ __device__ __forceinline__ void zone_obs_send(const KParams& p, const Env<N>& en
   zone_obs_issue<TASK, N>(p, stage, lane, warp_env0, 32);
 }
 
+// CRL_STEP_HOST_ZERO_COPY: the rows of `mask`'s lanes (the envs whose zone_obs row this step changed) from the
+// warp's stage straight into the caller's host mirror of zone_obs (pinned, device-mapped), each row by the whole
+// warp with coalesced stores.  A handful of rows per launch: the host buffer stays a byte-exact copy of the device
+// one with no list, no gather kernel and no host-side scatter.
+template <int TASK, int N>
+__device__ __noinline__ void rows_to_host(const KParams& p, const float* stage, unsigned mask, int lane, int warp_env0) {
+  constexpr int ROW = N * ZoneDim<TASK>::Z;
+  while (mask) {
+    const int src = __ffs(mask) - 1;
+    mask &= mask - 1u;
+    float* dst = p.zone_obs_host + (size_t)(warp_env0 + src) * ROW;
+    const float* row = stage + src * ROW;
+    for (int i = lane; i < ROW; i += 32) dst[i] = row[i];
+  }
+}
+
 __device__ __forceinline__ void zone_obs_wait(int lane) {
   if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
@@ -816,6 +833,8 @@ __device__ __forceinline__ void zone_obs_wait(int lane) {
 // `park`: the stored step count becomes the parked sentinel (CRL_STEP_WAIT); the observation
 // still shows the real count.
 constexpr int kParkedSteps = 0xffff;
+__device__ void obs_rows_bulk(float4* obs, int B, float4 row0, float4 row1, bool valid, float* stage, int lane, int warp_env0);
+
 template <int TASK, int N>
 __device__ __forceinline__ void store_state_obs(const KParams& p, const Env<N>& env, int e, float c, float s,
                                                 bool park = false) {
@@ -827,6 +846,45 @@ __device__ __forceinline__ void store_state_obs(const KParams& p, const Env<N>& 
   p.obs[2 * (size_t)e] = make_float4(remaining, env.b.X * (1.0f / 3.0f), env.b.Y * (1.0f / 3.0f), c);
   p.obs[2 * (size_t)e + 1] = make_float4(s, env.b.vx * (1.0f / 1.5f), env.b.vy * (1.0f / 1.5f),
                                          env.b.w * (1.0f / 3.0f));
+}
+
+// the same with the obs rows leaving through obs_rows_bulk (host-direct steps); every lane of the warp calls it
+template <int TASK, int N>
+__device__ __forceinline__ void store_state_obs_host(const KParams& p, const Env<N>& env, bool valid, int e, float c, float s,
+                                                     float* stage, int lane, int warp_env0) {
+  if (valid) {
+    p.pose[e] = make_float4(env.b.X, env.b.Y, env.b.phi, env.b.vx);
+    p.aux[e] = make_float4(env.b.vy, env.b.w, env.ep_return, __int_as_float((int)((uint32_t)env.steps | (env.hi << 16))));
+    if (TASK == CRL_TASK_CM) p.cooldown[e] = env.cd;
+  }
+  const float remaining = div_const((float)(p.num_steps - env.steps), p.div_steps);
+  obs_rows_bulk(p.obs, p.B, make_float4(remaining, env.b.X * (1.0f / 3.0f), env.b.Y * (1.0f / 3.0f), c),
+                make_float4(s, env.b.vx * (1.0f / 1.5f), env.b.vy * (1.0f / 1.5f), env.b.w * (1.0f / 3.0f)), valid, stage, lane,
+                warp_env0);
+}
+
+// CRL_STEP_HOST_ZERO_COPY: p.obs is host memory.  The warp's 32 obs rows (1 KB, contiguous) leave as ONE bulk
+// copy through the zone_obs stage (long drained by now) instead of 64 half-line stores: full-size PCIe writes.
+// Takes the row by value: a reference to the caller's Env would put the whole Env into local memory.
+__device__ __noinline__ void obs_rows_bulk(float4* obs, int B, float4 row0, float4 row1, bool valid, float* stage, int lane,
+                                           int warp_env0) {
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the zone_obs copy has read the stage
+  __syncwarp();
+  if (valid) {
+    float4* row = reinterpret_cast<float4*>(stage) + 2 * lane;
+    row[0] = row0;
+    row[1] = row1;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  const int n_valid = max(0, min(32, B - warp_env0));
+  if (lane == 0 && n_valid > 0) {
+    const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(stage);
+    float4* gdst = obs + 2 * (size_t)warp_env0;
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"(saddr), "r"((uint32_t)n_valid * 32u) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
 }
 
 template <int TASK, int N>
@@ -995,6 +1053,10 @@ __global__ void __maxnreg__(MaxRegs<N>::v) step_kernel(const __grid_constant__ K
     }
   }
   int fired_out = -1;
+  // lanes whose zone_obs row changed, when the rows go straight to the host (zone_obs_host): parked in shared
+  // memory, not in a register that would be live across the whole task logic of the ordinary step
+  __shared__ unsigned s_rows_mask[kThreads / 32];
+  if (p.zone_obs_host && lane == 0) s_rows_mask[warp] = 0u;
   bool fresh = false;   // true: this env was rebuilt by the auto-reset, no physics this call
   if (!(p.flags & CRL_STEP_PHYSICS_ONLY)) {
     // does this step rewrite the env's zone_obs row with different bytes? (CRL_STEP_TRACK_ROWS)
@@ -1086,8 +1148,12 @@ __global__ void __maxnreg__(MaxRegs<N>::v) step_kernel(const __grid_constant__ K
       if (cm) {
         uint32_t base = 0u;
         if (lane == 0) base = atomicAdd(p.row_list, (uint32_t)__popc(cm));
-        base = __shfl_sync(kFull, base, 0);
-        if (ch) p.row_list[4u + base + (uint32_t)__popc(cm & ((1u << lane) - 1u))] = (uint32_t)e;
+        if (p.zone_obs_host) {
+          if (lane == 0) s_rows_mask[warp] = cm;   // the rows themselves go straight to the host mirror, below
+        } else {
+          base = __shfl_sync(kFull, base, 0);
+          if (ch) p.row_list[4u + base + (uint32_t)__popc(cm & ((1u << lane) - 1u))] = (uint32_t)e;
+        }
       }
     }
     // (4) result word and episode statistics
@@ -1143,6 +1209,7 @@ __global__ void __maxnreg__(MaxRegs<N>::v) step_kernel(const __grid_constant__ K
   if (!EXT) {
     // (6) zone_obs leaves now and drains under the physics
     zone_obs_send<TASK, N>(p, env, live, stage, lane, warp_env0, false);
+    if (p.zone_obs_host) rows_to_host<TASK, N>(p, stage, s_rows_mask[warp], lane, warp_env0);
     // (7) physics: all frameskip substeps in registers
     if (fresh) {
       sincosf(env.b.phi, &s, &c);
@@ -1150,9 +1217,15 @@ __global__ void __maxnreg__(MaxRegs<N>::v) step_kernel(const __grid_constant__ K
       substeps(env.b, act.x, act.y, p.frameskip, c, s);
       env.b.phi = wrap_pi(env.b.phi);
     }
-    if (valid) store_state_obs<TASK, N>(p, env, e, c, s);
+    if (p.zone_obs_host) {
+      // CRL_STEP_HOST_ZERO_COPY: p.obs is host memory; the warp's 32 obs rows leave as one bulk copy
+      store_state_obs_host<TASK, N>(p, env, valid, e, c, s, stage, lane, warp_env0);
+    } else if (valid) {
+      store_state_obs<TASK, N>(p, env, e, c, s);
+    }
   } else {
     zone_obs_send<TASK, N>(p, env, live || revive, stage, lane, warp_env0, parked && !revive);
+    if (p.zone_obs_host) rows_to_host<TASK, N>(p, stage, s_rows_mask[warp], lane, warp_env0);
     // an env rebuilt by the auto-reset still integrates its OLD body: the shaped reward of the
     // episode's last step is measured at the post-physics position (TSP_next_city_env.py:57-67)
     Body pb = fresh ? old_b : env.b;
@@ -1646,12 +1719,13 @@ int crl_step_bytes(const CrlConfig* c, int64_t* rd, int64_t* wr) {
   return CRL_OK;
 }
 
-int crl_step(const CrlConfig* c, const CrlState* st, const float* actions, const CrlOut* out,
-             uint32_t flags, uint64_t action_seed, uint64_t step_index, void* stream) {
+static int step_launch(const CrlConfig* c, const CrlState* st, const float* actions, const CrlOut* out,
+                       uint32_t flags, uint64_t action_seed, uint64_t step_index, float* zone_obs_host, void* stream) {
   KParams p;
   if (!out) return CRL_ERR_NULL;
   int rc = fill_params(c, st, out, p);
   if (rc) return rc;
+  p.zone_obs_host = zone_obs_host;
   if (actions && (reinterpret_cast<uintptr_t>(actions) & 7u)) return CRL_ERR_ALIGN;
   p.actions = reinterpret_cast<const float2*>(actions);
   p.flags = flags; p.action_seed = action_seed; p.step_index = step_index;
@@ -1693,6 +1767,11 @@ int crl_step(const CrlConfig* c, const CrlState* st, const float* actions, const
   }
   CRL_DISPATCH(c->task, c->num_zones, CRL_CALL_STEP);
   return launch_status();
+}
+
+int crl_step(const CrlConfig* c, const CrlState* st, const float* actions, const CrlOut* out,
+             uint32_t flags, uint64_t action_seed, uint64_t step_index, void* stream) {
+  return step_launch(c, st, actions, out, flags, action_seed, step_index, nullptr, stream);
 }
 
 int crl_reset(const CrlConfig* c, const CrlState* st, const CrlOut* out, const uint8_t* mask, void* stream) {
@@ -1847,12 +1926,49 @@ int crl_step_host(const CrlConfig* c, const CrlState* st, const float* actions_h
 int crl_step_host_delta(const CrlConfig* c, const CrlState* st, const float* actions_host, float* actions_dev,
                         const CrlOut* out, const CrlOut* host_out, void* host_delta, int64_t host_delta_bytes,
                         uint32_t flags, int32_t* delta_rows, void* stream) {
-  if (!c || !st || !actions_host || !actions_dev || !out || !host_out || !host_out->obs || !host_out->zone_obs ||
-      !host_out->result || !host_delta || !st->row_list)
+  if (!c || !st || !actions_host || !out || !host_out || !host_out->obs || !host_out->zone_obs ||
+      !host_out->result || !st->row_list)
     return CRL_ERR_NULL;
   int rc = check_config(c);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool zero_copy = (flags & CRL_STEP_HOST_ZERO_COPY) != 0u;
+  flags &= ~CRL_STEP_HOST_ZERO_COPY;
+  if (zero_copy) {
+    // ONE kernel and a stream synchronisation.  The step kernel itself reads the actions from, and writes
+    // obs / result (/ shaped_reward) and every zone_obs row it changed to, the caller's pinned device-mapped
+    // host buffers: no copy-engine transfers, no staging, no row list, no gather, no host-side scatter
+    // (host_delta and actions_dev are not used).  row_list[0] counts the rows (cumulative).
+    struct Mapped { const void* host; void* dev; };
+    static thread_local Mapped cache[8] = {};
+    static thread_local int next = 0;
+    auto mapped = [&](const void* h) -> void* {
+      if (!h) return nullptr;
+      for (auto& m : cache) if (m.host == h) return m.dev;
+      cudaPointerAttributes a;
+      if (cudaPointerGetAttributes(&a, h) != cudaSuccess || a.type != cudaMemoryTypeHost || !a.devicePointer) {
+        (void)cudaGetLastError();
+        return nullptr;
+      }
+      cache[next] = Mapped{h, a.devicePointer};
+      next = (next + 1) % 8;
+      return a.devicePointer;
+    };
+    CrlOut direct = *out;
+    direct.obs = static_cast<float*>(mapped(host_out->obs));
+    direct.result = static_cast<CrlResult*>(mapped(host_out->result));
+    const float* act = static_cast<const float*>(mapped(actions_host));
+    float* zhost = static_cast<float*>(mapped(host_out->zone_obs));
+    if ((flags & CRL_STEP_GOALS) && host_out->shaped_reward)
+      direct.shaped_reward = static_cast<float*>(mapped(host_out->shaped_reward));
+    if (!direct.obs || !direct.result || !act || !zhost || ((flags & CRL_STEP_GOALS) && !direct.shaped_reward)) return CRL_ERR_CONFIG;
+    rc = step_launch(c, st, act, &direct, flags | CRL_STEP_TRACK_ROWS, 0, 0, zhost, stream);
+    if (rc) return rc;
+    if (cudaStreamSynchronize(s) != cudaSuccess) return CRL_ERR_DEVICE;
+    if (delta_rows) *delta_rows = -1;              // not known to the host: row_list[0] counts them on the device
+    return CRL_OK;
+  }
+  if (!host_delta || !actions_dev) return CRL_ERR_NULL;
   const size_t B = c->num_envs, N = c->num_zones, Z = zone_dim(c->task), row = N * Z;
   const size_t rows_off = (16 + 4 * B + 15) & ~(size_t)15;
   if (!aligned16(host_delta) || (size_t)host_delta_bytes < rows_off + B * row * 4) return CRL_ERR_CONFIG;
@@ -1866,33 +1982,8 @@ int crl_step_host_delta(const CrlConfig* c, const CrlState* st, const float* act
   float* host_rows = reinterpret_cast<float*>(static_cast<char*>(host_delta) + rows_off);
   uint32_t* dev_host_list = static_cast<uint32_t*>(pa.devicePointer);
   float* dev_host_rows = reinterpret_cast<float*>(static_cast<char*>(pa.devicePointer) + rows_off);
-  if (cudaMemsetAsync(st->row_list, 0, 16, s) != cudaSuccess) return CRL_ERR_DEVICE;
-  const bool zero_copy = (flags & CRL_STEP_HOST_ZERO_COPY) != 0u;
-  flags &= ~CRL_STEP_HOST_ZERO_COPY;
-  if (zero_copy) {
-    // the step kernel itself reads the actions from, and writes obs / result (/ shaped_reward) to,
-    // the caller's pinned device-mapped host buffers: no copy-engine transfers, no staging
-    auto mapped = [](const void* h) -> void* {
-      cudaPointerAttributes a;
-      if (!h || cudaPointerGetAttributes(&a, h) != cudaSuccess || a.type != cudaMemoryTypeHost) {
-        (void)cudaGetLastError();
-        return nullptr;
-      }
-      return a.devicePointer;
-    };
-    CrlOut direct = *out;
-    direct.obs = static_cast<float*>(mapped(host_out->obs));
-    direct.result = static_cast<CrlResult*>(mapped(host_out->result));
-    const float* act = static_cast<const float*>(mapped(actions_host));
-    if ((flags & CRL_STEP_GOALS) && host_out->shaped_reward)
-      direct.shaped_reward = static_cast<float*>(mapped(host_out->shaped_reward));
-    if (!direct.obs || !direct.result || !act || !direct.shaped_reward) return CRL_ERR_CONFIG;
-    rc = crl_step(c, st, act, &direct, flags | CRL_STEP_TRACK_ROWS, 0, 0, stream);
-    if (rc) return rc;
-    gather_rows_kernel<<<148, 256, 0, s>>>(st->row_list, out->zone_obs, dev_host_list, dev_host_rows, (int)row, (int)B);
-    rc = launch_status();
-    if (rc) return rc;
-  } else {
+  {
+    if (cudaMemsetAsync(st->row_list, 0, 16, s) != cudaSuccess) return CRL_ERR_DEVICE;
     if (cudaMemcpyAsync(actions_dev, actions_host, B * 8, cudaMemcpyHostToDevice, s) != cudaSuccess) return CRL_ERR_DEVICE;
     rc = crl_step(c, st, actions_dev, out, flags | CRL_STEP_TRACK_ROWS, 0, 0, stream);
     if (rc) return rc;

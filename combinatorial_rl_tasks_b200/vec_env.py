@@ -159,6 +159,7 @@ class ZoneVecEnv:
         self.bind_outputs(z(B, 8), z(B, N, Z), z(B, 8, dtype=torch.uint8), z(B))
         self._actions_dev = z(B, 2)
         self._host = None
+        self._pinned = {}                         # id(numpy array) -> (pinned tensor, pointer, array): pinned_actions()
         self._step_index = 0
         self.gpu_launches = 0
         # spaces: wrappers.py:144-153 (Box(-inf, inf)), Engine action space Box(-1, 1, (2,))
@@ -463,51 +464,61 @@ class ZoneVecEnv:
         arrays are persistent host buffers overwritten by the next call, as the device ones are.
 
         ``delta=True`` (PointTSP, ColourMatch): once the host zone_obs buffer mirrors the device
-        one, later calls move only the rows that changed (crl_step_host_delta); the arrays
-        returned are byte-identical to a full copy.  TimedTSP's time-left column moves every
-        step, so it always copies whole.  ``zero_copy=True`` (with the delta path): the step kernel
-        reads the actions from, and writes obs / result / shaped_reward to, the pinned host buffers
-        itself -- no staging copies; the DEVICE tensors ``env.obs`` / ``env.result`` are then not
-        updated by the call (``env.zone_obs`` is)."""
-        B, N, Z = self.num_envs, self.spec.num_zones, self.spec.zone_dim
-        h = self._host_buffers()
-        a = np.asarray(actions, dtype=np.float32).reshape(B, 2)
-        if a is not h['np']['actions']:
-            np.copyto(h['np']['actions'], a)
+        one, later calls move only the rows that changed; the arrays returned are byte-identical to
+        a full copy.  TimedTSP's time-left column moves every step, so it always copies whole.
+        ``zero_copy=True`` (with the delta path): ONE kernel and a stream synchronisation -- the step
+        kernel reads the actions from, and writes obs / result / shaped_reward and the changed zone_obs
+        rows to, the pinned host buffers itself; the DEVICE tensors ``env.obs`` / ``env.result`` are then
+        not updated by the call (``env.zone_obs`` is).  ``env.delta_rows`` = rows the call moved (B = all;
+        -1 = counted on the device only, see ``host_rows_moved()``)."""
+        h = self._host or self._host_buffers()
+        hn = h['np']
+        aptr = h['actions_ptr']
+        if actions is not hn['actions']:
+            pin = self._pinned.get(id(actions))
+            if pin is not None:                       # one of pinned_actions(): read where it lies
+                aptr = pin[1]
+            else:
+                np.copyto(hn['actions'], np.asarray(actions, dtype=np.float32).reshape(self.num_envs, 2))
         flags = (_lib.STEP_AUTO_RESET if auto_reset else 0) | self._mode_flags
         if wait:
             flags |= _lib.STEP_WAIT
         use_delta = delta and self._mirror_ok and self.spec.task != _lib.TASK_TTSP
         with self._guard():
-            if use_delta:
+            if use_delta and zero_copy:
+                _lib.check(self.lib.crl_step_host_delta(self.cfg, self.state, aptr, None, self.out, h['out'],
+                                                        None, 0, flags | _lib.STEP_HOST_ZERO_COPY, None, self._stream()))
+                self.delta_rows = -1
+            elif use_delta:
                 if h['delta'] is None:
+                    B, N, Z = self.num_envs, self.spec.num_zones, self.spec.zone_dim
                     nbytes = ((16 + 4 * B + 15) & ~15) + 4 * B * N * Z
                     h['delta'] = torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
                 n = ctypes.c_int32(0)
-                if zero_copy:                         # the kernel reads / writes the pinned host buffers itself
-                    flags |= _lib.STEP_HOST_ZERO_COPY
-                _lib.check(self.lib.crl_step_host_delta(self.cfg, self.state, h['actions'].data_ptr(),
+                _lib.check(self.lib.crl_step_host_delta(self.cfg, self.state, aptr,
                                                         self._actions_dev.data_ptr(), self.out, h['out'],
                                                         h['delta'].data_ptr(), h['delta'].numel(), flags,
                                                         ctypes.byref(n), self._stream()))
                 self.delta_rows = n.value
                 self.gpu_launches += 1                # the gather kernel
             else:
-                _lib.check(self.lib.crl_step_host(self.cfg, self.state, h['actions'].data_ptr(),
+                _lib.check(self.lib.crl_step_host(self.cfg, self.state, aptr,
                                                   self._actions_dev.data_ptr(), self.out, h['out'],
                                                   flags, self._stream()))
-                self.delta_rows = B
+                self.delta_rows = self.num_envs
         self._step_index += 1
         self.gpu_launches += 1
         self._chain_ok = False                    # memcpys follow the step kernel on the stream
         self._mirror_ok = True
-        res = h['np']['result']
-        info = {'goal_met': res[:, 5].view(np.bool_), 'event': res[:, 6].view(np.int8)}
-        if self.spec.goals:
-            info['shaped_reward'] = h['np']['shaped']
-            info['need_next_goal'] = res[:, 7].view(np.bool_)
-        return ({'zone_obs': h['np']['zone_obs'], 'obs': h['np']['obs']}, res.view(np.float32)[:, 0],
-                res[:, 4].view(np.bool_), info)
+        return h['ret']
+
+    def host_rows_moved(self, reset=False):
+        """zone_obs rows the zero-copy step_host calls have written to the host mirror since the count was last
+        reset (the kernel counts them in CrlState.row_list[0])."""
+        n = int(self._row_list[0].item())
+        if reset:
+            self._row_list[:1].zero_()
+        return n
 
     def _host_buffers(self):
         if self._host is None:
@@ -520,8 +531,29 @@ class ZoneVecEnv:
                                    result=h['result'].data_ptr(), shaped_reward=h['shaped'].data_ptr())
             h['np'] = {k: h[k].numpy() for k in ('actions', 'obs', 'zone_obs', 'result', 'shaped')}
             h['delta'] = None
+            h['actions_ptr'] = h['actions'].data_ptr()
+            # what every step_host call returns: views of the persistent host buffers, built once
+            res = h['np']['result']
+            info = {'goal_met': res[:, 5].view(np.bool_), 'event': res[:, 6].view(np.int8)}
+            if self.spec.goals:
+                info['shaped_reward'] = h['np']['shaped']
+                info['need_next_goal'] = res[:, 7].view(np.bool_)
+            h['ret'] = ({'zone_obs': h['np']['zone_obs'], 'obs': h['np']['obs']}, res.view(np.float32)[:, 0],
+                        res[:, 4].view(np.bool_), info)
             self._host = h
         return self._host
+
+    def pinned_actions(self, n=1):
+        """``n`` page-locked (B,2) float32 numpy arrays for the caller to fill with actions: step_host reads an
+        array of this pool where it lies (no staging copy).  Any other array is first copied into the env's own
+        pinned buffer."""
+        out = []
+        for _ in range(n):
+            t = torch.zeros(self.num_envs, 2, dtype=torch.float32).pin_memory()
+            a = t.numpy()
+            self._pinned[id(a)] = (t, t.data_ptr(), a)
+            out.append(a)
+        return out
 
     def host_actions(self):
         """The pinned (B,2) float32 action buffer step_host stages from; filling it in place and

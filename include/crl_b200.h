@@ -124,10 +124,13 @@ enum CrlError {
  * iid U(-1,1)^2 actions per (env, step) at every replay -- action_space.sample() of a random-action
  * rollout -- with nothing coming from the host.  Needs CrlState.stamp. */
 #define CRL_STEP_ACTION_COUNTER 128u
-/* crl_step_host_delta only: no staging and no copy-engine transfers -- the step kernel reads the
- * actions from, and writes obs / result / shaped_reward straight to, the caller's host buffers,
- * which must be page-locked and device-mapped (cudaHostAlloc; CRL_ERR_CONFIG otherwise).  The
- * device copies CrlOut.obs / result / shaped_reward are NOT updated by such a call. */
+/* crl_step_host_delta only: ONE kernel and a stream synchronisation per call.  No staging, no
+ * copy-engine transfers, no row list, no gather kernel, no host-side scatter -- the step kernel reads
+ * the actions from, and writes obs / result / shaped_reward AND every zone_obs row it changed straight
+ * to, the caller's host buffers (actions_host and all of host_out), which must be page-locked and
+ * device-mapped (cudaHostAlloc; CRL_ERR_CONFIG otherwise).  host_delta and actions_dev are not used
+ * (may be NULL); *delta_rows is set to -1 and CrlState.row_list[0] counts the rows moved, cumulatively.
+ * The device copies CrlOut.obs / result / shaped_reward are NOT updated by such a call (zone_obs is). */
 #define CRL_STEP_HOST_ZERO_COPY 256u
 
 /* how a reset chooses the episode's seed; wrappers.py:10-23 and Engine.seed/reset */

@@ -190,11 +190,14 @@ def test_step_host_equals_device_step(crl):
         assert np.array_equal(rew_h, rew_d.cpu().numpy()) and np.array_equal(done_h, done_d.cpu().numpy())
 
 
+@pytest.mark.parametrize('zero_copy', [True, False], ids=['zero_copy', 'staged'])
 @pytest.mark.parametrize('env_id', TASKS)
-def test_step_host_delta_is_byte_identical_to_full_copy(crl, env_id):
+def test_step_host_delta_is_byte_identical_to_full_copy(crl, env_id, zero_copy):
     """crl_step_host_delta moves only the zone_obs rows that changed; what the caller sees in its
     host buffers must be byte for byte what crl_step_host (full copy) delivers -- across zone
-    events, cooldown ticks, timeouts and auto-resets (episodes cut short to force many)."""
+    events, cooldown ticks, timeouts and auto-resets (episodes cut short to force many).  Both flavours:
+    zero-copy (one kernel; the step writes obs / result / changed rows into the pinned host buffers itself)
+    and staged (row list + gather kernel + copy-engine transfers)."""
     B = 1000
     envs = []
     for _ in range(2):
@@ -212,15 +215,16 @@ def test_step_host_delta_is_byte_identical_to_full_copy(crl, env_id):
             for e in envs:
                 e.pose[:200, :2] = e.zone_xy[3, :200, :]
         of, rf, df, inf_ = full.step_host(a, delta=False)
-        od, rd, dd, ind = delta.step_host(a, delta=True)
+        od, rd, dd, ind = delta.step_host(a, delta=True, zero_copy=zero_copy)
+        rows = delta.delta_rows if delta.delta_rows >= 0 else delta.host_rows_moved(reset=True)   # -1: counted on the device
         if t == 20:
-            assert delta.delta_rows >= 200 and (env_id == 'ColourMatch-v0' or int((ind['event'] != 0).sum()) >= 200)
+            assert rows >= 200 and (env_id == 'ColourMatch-v0' or int((ind['event'] != 0).sum()) >= 200)
         assert np.array_equal(of['zone_obs'].view(np.uint32), od['zone_obs'].view(np.uint32)), t
         assert np.array_equal(of['obs'].view(np.uint32), od['obs'].view(np.uint32)), t
         assert np.array_equal(rf.view(np.uint32), rd.view(np.uint32)) and np.array_equal(df, dd), t
         assert np.array_equal(inf_['event'], ind['event']) and np.array_equal(inf_['goal_met'], ind['goal_met'])
         assert np.array_equal(od['zone_obs'], delta.zone_obs.cpu().numpy()), t
-        moved.append(delta.delta_rows)
+        moved.append(rows)
     assert moved[0] == B and moved[70] == B           # first call and the call after device-side work: full copy
     if env_id == 'PointTTSP-v0':
         assert all(m == B for m in moved)             # the time-left column moves every step

@@ -14,8 +14,8 @@ def t(f, n=200):
     for _ in range(n): f()
     torch.cuda.synchronize(); return (time.perf_counter() - t0) / n * 1e6
 h = env._host_buffers()
-print('step_host(delta) total      %.1f us' % t(lambda: env.step_host(a)))
-print('step_host(delta), pinned in %.1f us' % t(lambda: env.step_host(h['np']['actions'])))
+print('step_host(delta, staged) total %.1f us' % t(lambda: env.step_host(a, zero_copy=False)))
+print('step_host(delta, staged), pinned in %.1f us' % t(lambda: env.step_host(h['np']['actions'], zero_copy=False)))
 print('step_host(full)             %.1f us' % t(lambda: env.step_host(a, delta=False), 50))
 env.step_host(a)
 print('np.copyto actions           %.1f us' % t(lambda: np.copyto(h['np']['actions'], a)))
