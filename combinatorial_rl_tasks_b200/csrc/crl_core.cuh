@@ -46,12 +46,37 @@ struct Body {
   float vx, vy, w;   // world velocity and yaw rate
 };
 
+// ---- the contact term, isolated (twin of oracle/mj_point.py::constraint_force) ----------------
+// Model 0 (canonical): the sphere/floor contact sits at signed distance exactly 0.0 == margin: MuJoCo lists it
+// and excludes it, no constraint force.  Model 1: the alternative reading (contact active, pyramidal cone whose
+// normal row vanishes for these DOFs): every DOF loses the fraction d of (its smooth acceleration + b x its
+// velocity), d = 0.9 (solimp at zero penetration), b = 2 / (0.95 x 0.02) (solref).  A compile-time switch
+// (-DCRL_CONTACT_MODEL=1), so that a correction -- should a MuJoCo 2.0 trace ever pin the question -- is this one
+// function; tests/test_contact_hypothesis.py measures what the switch changes (the robot's terminal speed falls
+// from 1.5 m/s, the reference's own velocity normaliser, ZoneEnvBase.py:223, to 3 mm/s).
+#ifndef CRL_CONTACT_MODEL
+#define CRL_CONTACT_MODEL 0
+#endif
+constexpr double kContactImpedance = 0.9;
+constexpr double kContactB = 2.0 / (0.95 * 0.02);
+
+template <int MODEL>
+CRL_HD void constraint_acc(float& ax, float& ay, float& ath, float vx, float vy, float w) {
+  if (MODEL == 1) {
+    const float d = (float)kContactImpedance, b = (float)kContactB;
+    ax = (1.f - d) * ax - d * b * vx;
+    ay = (1.f - d) * ay - d * b * vy;
+    ath = (1.f - d) * ath - d * b * w;
+  }
+}
+
 CRL_HD float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 
 // n MuJoCo substeps with constant ctrl.  (c, s) = (cos phi, sin phi) is carried in
 // registers and advanced by the exact rotation of h*w each substep (|h w| < 0.01, so
 // a 5th-order series is exact to fp32), instead of n full-range sincosf calls.
 // Returns the final (c, s), renormalised, for the observation.
+template <int CONTACT = CRL_CONTACT_MODEL>
 CRL_HD void substeps(Body& b, float a0, float a1, int n, float& c_out, float& s_out) {
   const float h = (float)kH;
   const float bl = (float)kDampLin, bt = (float)kDampYaw, g = (float)kGear;
@@ -71,11 +96,13 @@ CRL_HD void substeps(Body& b, float a0, float a1, int n, float& c_out, float& s_
     const float tau_x = drive * c - bl * vx;
     const float tau_y = drive * s - bl * vy;
     const float ka = k * a_th;
-    const float ax = (tau_x + ka * s) * inv_m;
-    const float ay = (tau_y - ka * c) * inv_m;
+    float ax = (tau_x + ka * s) * inv_m;
+    float ay = (tau_y - ka * c) * inv_m;
+    float a_th_c = a_th;
+    constraint_acc<CONTACT>(ax, ay, a_th_c, vx, vy, w);   // model 0: nothing (compiled out)
     vx += h * ax;
     vy += h * ay;
-    w += h * a_th;
+    w += h * a_th_c;
     X += h * vx;
     Y += h * vy;
     const float d = h * w;

@@ -128,9 +128,32 @@ def actuator_force(theta, qvel, ctrl):
                      GEAR_VELOCITY * f_servo])
 
 
-def constraint_force(qpos, qvel, qfrc_smooth):
-    """Sphere-on-plane contact: listed, excluded (dist == margin) -> no force."""
-    return np.zeros(3)
+# Which reading of the sphere/floor contact the hook below implements.  'excluded' is the canonical
+# one; 'active' exists to put a NUMBER on what the unpinned question could change (tests/test_contact_hypothesis.py)
+# and has its compile-time twin in csrc/crl_core.cuh (CRL_CONTACT_MODEL 1).
+CONTACT_MODEL = 'excluded'
+# MuJoCo defaults the active reading would run with: solimp d0 = 0.9 at zero penetration, solref (timeconst 0.02,
+# dampratio 1) -> velocity gain b = 2 / (dmax * timeconst) with dmax = 0.95
+CONTACT_IMPEDANCE = 0.9
+CONTACT_B = 2.0 / (0.95 * 0.02)
+
+
+def constraint_force(qpos, qvel, qfrc_smooth, h=TIMESTEP):
+    """qfrc_constraint, the ONE isolated place where a contact enters the step.
+
+    'excluded' (canonical): the sphere/floor contact has signed distance exactly 0.0 == margin; MuJoCo lists it and
+    excludes it (``dist < includemargin`` is false) -> no force.
+    'active' (the alternative of SURVEY A.3, simplified): a pyramidal friction cone whose normal row has a zero
+    Jacobian for these three DOFs leaves opposing pairs of unilateral edges +-mu J_i per direction i (x, y, torsion).
+    For a pair the regularised dual has the closed form f = -J_i^T d (J_i a_smooth + b J_i v) / A_ii with
+    R = (1 - d) / d * mu^2 A_ii (mu cancels), i.e. every DOF loses the fraction d of (its smooth acceleration + b times
+    its velocity): a = (1 - d) a_smooth - d b v.  (Decoupled A_ii; MuJoCo's diagApprox / impratio details cannot be
+    checked here -- this is an order-of-magnitude model of that reading, not a restatement of the solver.)"""
+    if CONTACT_MODEL == 'excluded':
+        return np.zeros(3)
+    A = mass_matrix(qpos[2]) + h * np.diag(DAMPING)
+    a_smooth = np.linalg.solve(A, qfrc_smooth)
+    return A @ (-CONTACT_IMPEDANCE * (a_smooth + CONTACT_B * qvel))
 
 
 def substep(qpos, qvel, ctrl, h=TIMESTEP):
