@@ -13,7 +13,7 @@ c_void_p, c_int32, c_int64, c_uint32, c_uint64, c_double = (
 TASK_TSP, TASK_TTSP, TASK_CM = 0, 1, 2
 SEED_INCREMENT, SEED_FIXED_RANGE = 0, 1
 STEP_AUTO_RESET, STEP_PHYSICS_ONLY, STEP_CHAINED, STEP_CHAIN_START, STEP_TRACK_ROWS = 1, 2, 4, 8, 16
-STEP_GOALS, STEP_WAIT, STEP_ACTION_COUNTER, STEP_HOST_ZERO_COPY = 32, 64, 128, 256
+STEP_GOALS, STEP_WAIT, STEP_ACTION_COUNTER, STEP_HOST_ZERO_COPY, STEP_NO_ZONE_OBS = 32, 64, 128, 256, 512
 ABI_VERSION = 6
 NUM_PLANES = 23
 
@@ -22,7 +22,8 @@ SYMBOLS = ['crl_abi_version', 'crl_strerror', 'crl_plane_bytes', 'crl_step_bytes
            'crl_prefetch_layouts', 'crl_prefetch_publish', 'crl_reset_from_layout', 'crl_step', 'crl_step_host', 'crl_step_host_delta',
            'crl_set_goal', 'crl_goal_query', 'crl_set_qpos_qvel',
            'crl_get_qpos_qvel', 'crl_gae', 'crl_check_state', 'crl_counters_read',
-           'crl_encoder_packed_bytes', 'crl_encoder_pack', 'crl_zone_encode']
+           'crl_encoder_packed_bytes', 'crl_encoder_pack', 'crl_zone_encode', 'crl_zone_encode_state',
+           'crl_encoder_head_packed_bytes', 'crl_encoder_pack_head', 'crl_encoder_head']
 
 
 class CrlConfig(ctypes.Structure):
@@ -97,6 +98,12 @@ def load():
     lib.crl_encoder_pack.argtypes = [P(CrlEncoderShape)] + [c_void_p] * 6
     lib.crl_zone_encode.argtypes = [P(CrlEncoderShape), c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p]
+    lib.crl_zone_encode_state.argtypes = [P(CrlEncoderShape), P(CrlConfig), P(CrlState), c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_void_p]
+    lib.crl_encoder_head_packed_bytes.argtypes = [P(CrlEncoderShape), P(c_int64)]
+    lib.crl_encoder_pack_head.argtypes = [P(CrlEncoderShape)] + [c_void_p] * 4
+    lib.crl_encoder_head.argtypes = [P(CrlEncoderShape), c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p]
     for name in SYMBOLS:
         getattr(lib, name)
     if lib.crl_abi_version() != ABI_VERSION:

@@ -53,6 +53,7 @@
 #include <stdint.h>
 
 #include "../../include/crl_b200.h"
+#include "crl_core.cuh"
 
 namespace crl_enc {
 
@@ -206,24 +207,74 @@ struct EncArgs {
   float* out;              // [B][h]: pooled hidden activation
   int* status;             // device int: set to 1 if a tensor-core wait expired
   int B, N, Z, obs_dim, h, n_tiles, S;   // S = slots_per_env(N)
+  // crl_zone_encode_state: the zone part of the input rows is built from the STATE planes instead of being read
+  // from a materialised zone_obs (aux != nullptr selects it; zone_obs is then not touched)
+  const float4* aux;           // float4[B]: .w = steps | visited mask / colour codes << 16
+  const float2* zone_xy;       // float2[N][B]
+  const uint32_t* zone_tmax;   // uint32[ceil(N/2)][B] (TimedTSP)
+  const uint2* cooldown;       // uint2[B] (ColourMatch)
+  int task, num_steps;
+  crl::DivConst div_steps, div_cd;
 };
 
+// Feature f of zone `slot` of env e from the state planes: EXACTLY what step_kernel's zone_row writes to
+// zone_obs[e][slot][f] (crl_kernels.cu; tests/test_gpu_encode.py compares the two paths bit for bit):
+// x/3, y/3, r, g, b, 0.25 [, time left | cooldown / max_cooldown]
+__device__ __forceinline__ void zone_features_from_state(const EncArgs& a, int e, int slot, float (&z)[7]) {
+  const float2 c = __ldg(a.zone_xy + (size_t)slot * a.B + e);
+  const uint32_t bits = (uint32_t)__float_as_int(__ldg(reinterpret_cast<const float*>(a.aux + e) + 3));
+  const int steps = (int)(bits & 0xffffu);
+  const uint32_t hi = bits >> 16;
+  const float third = 1.0f / 3.0f;
+  z[0] = c.x * third; z[1] = c.y * third; z[5] = 0.25f; z[6] = 0.f;
+  if (a.task == CRL_TASK_CM) {
+    const uint32_t col = (hi >> (2 * slot)) & 3u;               // 0 B, 1 G, 2 R
+    z[2] = col == 2u ? 1.f : 0.f; z[3] = col == 1u ? 1.f : 0.f; z[4] = col == 0u ? 1.f : 0.f;
+    const uint2 cd = __ldg(a.cooldown + e);
+    const uint32_t w = slot < 4 ? cd.x : cd.y;
+    z[6] = crl::div_const((float)((w >> (8 * (slot & 3))) & 0xffu), a.div_cd);
+  } else {
+    const bool v = (hi >> slot) & 1u;                          // Yellow (1,1,0) visited / Cyan (0,1,1)
+    z[2] = v ? 1.f : 0.f; z[3] = 1.f; z[4] = v ? 0.f : 1.f;
+    if (a.task == CRL_TASK_TTSP) {
+      const uint32_t w = __ldg(a.zone_tmax + (size_t)(slot >> 1) * a.B + e);
+      const int tm = (int)((w >> (16 * (slot & 1))) & 0xffffu);
+      z[6] = v ? 1.0f : crl::div_const((float)(tm - steps), a.div_steps);
+    }
+  }
+}
+
 // eight consecutive values (k = 8 kc .. 8 kc + 7) of row (e, slot) of the layer-1 input
-// [obs[e], zone_obs[e][slot], 1, 1, 0...]; all zeros -- the ones included -- for a padding row
+// [obs[e], zone_obs[e][slot], 1, 1, 0...]; all zeros -- the ones included -- for a padding row.
+// STATE: the zone part comes from the state planes (obs_dim == 8, so chunk 1 is exactly the zone features + ones);
+// a template parameter so that the materialised path compiles exactly as it did without the feature.
+template <bool STATE>
 __device__ __forceinline__ void load_half_row(const EncArgs& a, int tile, int m, int kc, float (&x)[8]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) x[j] = 0.f;
   const int e = tile * (kRows / a.S) + m / a.S, slot = m % a.S;
   if (tile < a.n_tiles && e < a.B && slot < a.N) {
     const float* ob = a.obs + (size_t)e * a.obs_dim;
-    const float* zo = a.zone_obs + ((size_t)e * a.N + slot) * a.Z;
-    const int in_dim = a.obs_dim + a.Z;
+    if (STATE) {
+      if (kc == 0) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = 8 * kc + j;
-      if (k < a.obs_dim) x[j] = __ldg(ob + k);
-      else if (k < in_dim) x[j] = __ldg(zo + (k - a.obs_dim));
-      else if (k <= in_dim + 1) x[j] = 1.f;
+        for (int j = 0; j < 8; ++j) x[j] = __ldg(ob + j);
+      } else {
+        float z[7];
+        zone_features_from_state(a, e, slot, z);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = j < 7 && j < a.Z ? z[j < 7 ? j : 0] : (j <= a.Z + 1 ? 1.f : 0.f);
+      }
+    } else {
+      const float* zo = a.zone_obs + ((size_t)e * a.N + slot) * a.Z;
+      const int in_dim = a.obs_dim + a.Z;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = 8 * kc + j;
+        if (k < a.obs_dim) x[j] = __ldg(ob + k);
+        else if (k < in_dim) x[j] = __ldg(zo + (k - a.obs_dim));
+        else if (k <= in_dim + 1) x[j] = 1.f;
+      }
     }
   }
 }
@@ -261,6 +312,7 @@ __device__ __forceinline__ void relu_pool_store(const uint32_t (&v)[32], const E
   }
 }
 
+template <bool STATE>
 __global__ void __launch_bounds__(kGroupThreads * kGroups, 1) zone_encode_kernel(const EncArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const Offsets o = offsets(a.h, a.obs_dim + a.Z);
@@ -318,8 +370,8 @@ __global__ void __launch_bounds__(kGroupThreads * kGroups, 1) zone_encode_kernel
   const int tile_stride = kGroups * gridDim.x;
   int tile = kGroups * blockIdx.x + group;
   float x[8], x2[8];                                         // 16-byte units `half` and, for 32-wide inputs, `half + 2`
-  load_half_row(a, tile, m, half, x);
-  if (kK1 == 32) load_half_row(a, tile, m, half + 2, x2);
+  load_half_row<STATE>(a, tile, m, half, x);
+  if (!STATE && kK1 == 32) load_half_row<STATE>(a, tile, m, half + 2, x2);
   for (; tile < a.n_tiles; tile += tile_stride) {
     // ---- layer-1 B operand (the tile's 128 input rows) from the prefetched registers ----------
     *reinterpret_cast<uint4*>(xbuf + x_off) =
@@ -339,8 +391,8 @@ __global__ void __launch_bounds__(kGroupThreads * kGroups, 1) zone_encode_kernel
                    smem_desc(x_addr + 256u * s, 128u, 16 * kK1), idesc1, s > 0);
       mma_commit(bar_addr);
     }
-    load_half_row(a, tile + tile_stride, m, half, x);         // prefetch: in flight for the rest of the tile
-    if (kK1 == 32) load_half_row(a, tile + tile_stride, m, half + 2, x2);
+    load_half_row<STATE>(a, tile + tile_stride, m, half, x);  // prefetch: in flight for the rest of the tile
+    if (!STATE && kK1 == 32) load_half_row<STATE>(a, tile + tile_stride, m, half + 2, x2);
     healthy = mbar_wait(bar_addr, parity) && healthy;
     parity ^= 1u;
     tc_fence_after();
@@ -407,6 +459,183 @@ __global__ void __launch_bounds__(kGroupThreads * kGroups, 1) zone_encode_kernel
   }
 }
 
+// ---- the head: forward() = combine_net_([obs, L3(pooled)]) (env_model.py:79) as ONE more tcgen05 GEMM ----------
+// Both Linears are affine, so  out[e] = Wc [obs[e], W3 pooled[e] + b3] + bc = W' [obs[e], pooled[e], 1, 1]  with
+// W' = [Wc_obs | Wc_emb W3 | bias hi | bias lo] folded once on the host side (encoder.py).  The same transposed
+// formulation as above: out^T[j][e] = W'[j][:] X^T, the folded weights resident in shared memory as the A operand
+// (M = output units in blocks of 128 = TMEM lanes), a tile of 128 ENVS the N dimension, K = obs_dim + h + 2 padded to
+// 16.  After tcgen05.ld lane j holds unit j of 32 consecutive envs: 32 coalesced 128-byte stores per load.  4.7 GFLOP
+// at 65,536 envs and h = 185: the kernel is bound by reading (obs, pooled) and writing out once (~100 MB), not by the
+// tensor pipe -- the library fp32 GEMM it replaces took longer than the whole fused zone kernel (profiles/r01_notes.md).
+__host__ __device__ inline int head_k(int obs_dim, int h) { return (obs_dim + h + 2 + 15) & ~15; }
+
+struct HeadOffsets { uint32_t w, packed_end, group0, xbuf, bar, group_bytes, tmem_slot, smem_end; };
+__host__ __device__ inline HeadOffsets head_offsets(int obs_dim, int h) {
+  const int KH = head_k(obs_dim, h), MP = padded_m(h);
+  HeadOffsets o;
+  o.w = 0;
+  o.packed_end = (uint32_t)MP * KH * 2;
+  o.group0 = (o.packed_end + 127u) & ~127u;
+  o.xbuf = 0;
+  o.bar = (uint32_t)kRows * KH * 2;
+  o.group_bytes = (o.bar + 8 + 127u) & ~127u;
+  o.tmem_slot = o.group0 + kGroups * o.group_bytes;
+  o.smem_end = o.tmem_slot + 16;
+  return o;
+}
+
+struct HeadPackArgs { const float *w, *b; uint8_t* out; int obs_dim, h; };
+
+// W' rows n < h: [w[n][0 .. obs_dim + h), bf16(b[n]), b[n] - bf16(b[n]), 0...]; rows >= h: zeros
+__global__ void head_pack_kernel(const HeadPackArgs a) {
+  const int KH = head_k(a.obs_dim, a.h), MP = padded_m(a.h), in = a.obs_dim + a.h;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < MP * KH; i += gridDim.x * blockDim.x) {
+    const int n = i / KH, k = i % KH;
+    float v = 0.f;
+    if (n < a.h) {
+      if (k < in) v = a.w[(size_t)n * in + k];
+      else if (k == in) v = __bfloat162float(__float2bfloat16_rn(a.b[n]));
+      else if (k == in + 1) v = a.b[n] - __bfloat162float(__float2bfloat16_rn(a.b[n]));
+    }
+    *reinterpret_cast<__nv_bfloat16*>(a.out + canon(n, k, KH)) = __float2bfloat16_rn(v);
+  }
+}
+
+struct HeadArgs {
+  const float* obs;      // [B][obs_dim]
+  const float* pooled;   // [B][h]
+  const uint8_t* packed;
+  float* out;            // [B][h]
+  int* status;
+  int B, obs_dim, h, n_tiles;
+};
+
+__global__ void __launch_bounds__(kGroupThreads * kGroups, 1) encoder_head_kernel(const HeadArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const HeadOffsets o = head_offsets(a.obs_dim, a.h);
+  const int KH = head_k(a.obs_dim, a.h), MP = padded_m(a.h), in = a.obs_dim + a.h;
+  const int n_mblocks = MP / 128, chunks = KH / 8;
+  const int group = threadIdx.x / kGroupThreads, t = threadIdx.x % kGroupThreads;
+  const int warp = t >> 5, lane = t & 31, mblock = warp >> 2, quad = warp & 3;
+  const int j = mblock * 128 + quad * 32 + lane;              // output unit (accumulator row) of this thread
+  uint8_t* gbase = smem + o.group0 + (uint32_t)group * o.group_bytes;
+  uint8_t* xbuf = gbase + o.xbuf;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(gbase + o.bar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + o.tmem_slot);
+  const uint32_t bar_addr = smem_u32(bar);
+  if (t == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_addr) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 32) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 :: "r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.packed);
+    uint4* dst = reinterpret_cast<uint4*>(smem);
+    for (uint32_t i = threadIdx.x; i < o.packed_end / 16; i += kGroupThreads * kGroups) dst[i] = __ldg(src + i);
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc = tmem_base + (uint32_t)group * 256u;
+  const uint32_t my_acc = acc + (uint32_t)(mblock * 128) + ((uint32_t)(quad * 32) << 16);
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kRows >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint32_t x_addr = smem_u32(xbuf), w_addr = smem_u32(smem + o.w);
+  const bool drains = mblock < n_mblocks && mblock * 128 + quad * 32 < a.h;
+  uint32_t parity = 0u;
+  bool healthy = true;
+  for (int tile = kGroups * blockIdx.x + group; tile < a.n_tiles; tile += kGroups * gridDim.x) {
+    // ---- B operand: the tile's 128 rows [obs, pooled, 1, 1, 0..] as bf16, K-major; consecutive threads take
+    // consecutive 8-value chunks of one env (coalesced reads); a row beyond the batch is all zeros.  Four chunks
+    // per iteration with UNCONDITIONAL loads from clamped addresses (the selects come after), so that 32 loads
+    // are in flight per thread: this kernel is bound by how fast it reads (obs, pooled), not by the tensor pipe.
+    for (int u0 = t; u0 < kRows * chunks; u0 += 4 * kGroupThreads) {
+      float x[4][8];
+      int mm[4], cc[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int u = u0 + i * kGroupThreads;
+        const int m = u / chunks, c = u - m * chunks, e = tile * kRows + m;
+        mm[i] = m; cc[i] = u < kRows * chunks ? c : -1;
+        const size_t e_ok = (size_t)(e < a.B ? e : 0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int k = 8 * c + q;
+          const float* src = k < a.obs_dim ? a.obs + e_ok * a.obs_dim + k
+                                           : a.pooled + e_ok * a.h + (k < in ? k - a.obs_dim : 0);
+          x[i][q] = __ldg(src);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (cc[i] < 0) continue;
+        const int e = tile * kRows + mm[i];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int k = 8 * cc[i] + q;
+          x[i][q] = e < a.B ? (k < in ? x[i][q] : (k <= in + 1 ? 1.f : 0.f)) : 0.f;
+        }
+        *reinterpret_cast<uint4*>(xbuf + (uint32_t)((mm[i] & 7) * 16 + (mm[i] >> 3) * (16 * KH) + cc[i] * 128)) =
+            make_uint4(pack_bf16(x[i][0], x[i][1]), pack_bf16(x[i][2], x[i][3]), pack_bf16(x[i][4], x[i][5]),
+                       pack_bf16(x[i][6], x[i][7]));
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    group_sync(group);
+    if (t == 0) {
+      tc_fence_after();
+      for (int b = 0; b < n_mblocks; ++b)
+        for (int s = 0; s < KH / 16; ++s)
+          mma_bf16(acc + (uint32_t)(b * 128), smem_desc(w_addr + (uint32_t)(b * 16 * 16 * KH) + 256u * s, 128u, 16 * KH),
+                   smem_desc(x_addr + 256u * s, 128u, 16 * KH), idesc, s > 0);
+      mma_commit(bar_addr);
+    }
+    healthy = mbar_wait(bar_addr, parity) && healthy;
+    parity ^= 1u;
+    tc_fence_after();
+    if (drains) {
+#pragma unroll 1
+      for (int c = 0; c < kRows / 32; c += 2) {               // two TMEM loads in flight
+        uint32_t v0[32], v1[32];
+        tmem_ld32(my_acc + (uint32_t)(c * 32), v0);
+        tmem_ld32(my_acc + (uint32_t)(c * 32 + 32), v1);
+        tmem_ld_wait(v0);
+        if (j < a.h) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int e = tile * kRows + c * 32 + i;
+            if (e < a.B) a.out[(size_t)e * a.h + j] = __uint_as_float(v0[i]);
+          }
+        }
+        tmem_ld_wait(v1);
+        if (j < a.h) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int e = tile * kRows + (c + 1) * 32 + i;
+            if (e < a.B) a.out[(size_t)e * a.h + j] = __uint_as_float(v1[i]);
+          }
+        }
+      }
+    }
+    // the next tile's MMAs overwrite the accumulators and the operand buffer: ordered after these loads by the
+    // fence and the group barrier that precede them
+    tc_fence_before();
+  }
+  if (!healthy && a.status) atomicExch(a.status, 1);
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
 static int check_shape(const CrlEncoderShape* s) {
   if (!s) return CRL_ERR_NULL;
   if (s->obs_dim <= 0 || s->zone_dim <= 0 || s->obs_dim + s->zone_dim + 1 > 32) return CRL_ERR_CONFIG;   // + a ones column
@@ -441,11 +670,12 @@ int crl_encoder_pack(const CrlEncoderShape* s, const float* w1, const float* b1,
   return cudaGetLastError() == cudaSuccess ? CRL_OK : CRL_ERR_LAUNCH;
 }
 
-int crl_zone_encode(const CrlEncoderShape* s, int32_t num_envs, const float* obs, const float* zone_obs,
-                    const void* packed, float* pooled, int32_t* status, void* stream) {
+static int zone_encode_launch(const CrlEncoderShape* s, int32_t num_envs, const float* obs, const float* zone_obs,
+                              const CrlConfig* cfg, const CrlState* st, const void* packed, float* pooled, int32_t* status,
+                              void* stream) {
   const int rc = check_shape(s);
   if (rc) return rc;
-  if (!obs || !zone_obs || !packed || !pooled) return CRL_ERR_NULL;
+  if (!obs || (!zone_obs && !st) || !packed || !pooled) return CRL_ERR_NULL;
   if (num_envs <= 0) return CRL_ERR_CONFIG;
   if (reinterpret_cast<uintptr_t>(packed) & 15u) return CRL_ERR_ALIGN;
   const Offsets o = offsets(s->hidden, s->obs_dim + s->zone_dim);
@@ -453,17 +683,108 @@ int crl_zone_encode(const CrlEncoderShape* s, int32_t num_envs, const float* obs
   if (cudaGetDevice(&dev) != cudaSuccess) return CRL_ERR_DEVICE;
   static bool attr_set[64] = {false};                       // per device: opt in to > 48 KB of dynamic shared memory
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    if (cudaFuncSetAttribute(zone_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(zone_encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(zone_encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return CRL_ERR_DEVICE;
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
-  EncArgs a{obs, zone_obs, static_cast<const uint8_t*>(packed), pooled, status, num_envs, s->num_zones, s->zone_dim,
-            s->obs_dim, s->hidden, 0, slots_per_env(s->num_zones)};
+  EncArgs a{};
+  a.obs = obs; a.zone_obs = zone_obs; a.packed = static_cast<const uint8_t*>(packed); a.out = pooled; a.status = status;
+  a.B = num_envs; a.N = s->num_zones; a.Z = s->zone_dim; a.obs_dim = s->obs_dim; a.h = s->hidden;
+  a.S = slots_per_env(s->num_zones);
   a.n_tiles = (num_envs + kRows / a.S - 1) / (kRows / a.S);
+  if (st) {
+    // the zone features come from the state planes: the shapes must be the env's own
+    if (!cfg || !st->aux || !st->zone_xy) return CRL_ERR_NULL;
+    if (s->obs_dim != 8 || cfg->num_envs != num_envs || cfg->num_zones != s->num_zones || cfg->task < 0 || cfg->task > 2 ||
+        s->zone_dim != (cfg->task == CRL_TASK_TSP ? 6 : 7) || cfg->num_steps <= 0 || cfg->num_steps > 65534 ||
+        cfg->max_cooldown < 0 || cfg->max_cooldown > 255)
+      return CRL_ERR_CONFIG;
+    if (cfg->task == CRL_TASK_TTSP && !st->zone_tmax) return CRL_ERR_NULL;
+    if (cfg->task == CRL_TASK_CM && !st->cooldown) return CRL_ERR_NULL;
+    a.aux = reinterpret_cast<const float4*>(st->aux);
+    a.zone_xy = reinterpret_cast<const float2*>(st->zone_xy);
+    a.zone_tmax = st->zone_tmax;
+    a.cooldown = reinterpret_cast<const uint2*>(st->cooldown);
+    a.task = cfg->task; a.num_steps = cfg->num_steps;
+    // the same exact-division constants the step kernel uses (proven on the host once per divisor)
+    static struct { int d, lo, hi; crl::DivConst k; } cache[8];
+    static int used = 0;
+    auto div_for = [&](int d, int lo, int hi) {
+      for (int i = 0; i < used; ++i)
+        if (cache[i].d == d && cache[i].lo == lo && cache[i].hi == hi) return cache[i].k;
+      const crl::DivConst k = crl::make_div_const(d, lo, hi);
+      if (used < 8) { cache[used].d = d; cache[used].lo = lo; cache[used].hi = hi; cache[used].k = k; ++used; }
+      return k;
+    };
+    a.div_steps = div_for(cfg->num_steps, -65535, 65535);
+    a.div_cd = div_for(cfg->max_cooldown > 0 ? cfg->max_cooldown : 1, 0, 255);
+    if (!a.div_steps.exact || !a.div_cd.exact) return CRL_ERR_CONFIG;
+  }
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int want = (a.n_tiles + kGroups - 1) / kGroups;
   const int grid = want < sms ? want : sms;                   // persistent: one CTA per SM, weights loaded once
-  zone_encode_kernel<<<grid, kGroupThreads * kGroups, o.smem_end, static_cast<cudaStream_t>(stream)>>>(a);
+  if (st) zone_encode_kernel<true><<<grid, kGroupThreads * kGroups, o.smem_end, static_cast<cudaStream_t>(stream)>>>(a);
+  else zone_encode_kernel<false><<<grid, kGroupThreads * kGroups, o.smem_end, static_cast<cudaStream_t>(stream)>>>(a);
+  return cudaGetLastError() == cudaSuccess ? CRL_OK : CRL_ERR_LAUNCH;
+}
+
+int crl_zone_encode(const CrlEncoderShape* s, int32_t num_envs, const float* obs, const float* zone_obs,
+                    const void* packed, float* pooled, int32_t* status, void* stream) {
+  if (!zone_obs) return CRL_ERR_NULL;
+  return zone_encode_launch(s, num_envs, obs, zone_obs, nullptr, nullptr, packed, pooled, status, stream);
+}
+
+int crl_zone_encode_state(const CrlEncoderShape* s, const CrlConfig* cfg, const CrlState* st, const float* obs,
+                          const void* packed, float* pooled, int32_t* status, void* stream) {
+  if (!cfg || !st) return CRL_ERR_NULL;
+  return zone_encode_launch(s, cfg->num_envs, obs, nullptr, cfg, st, packed, pooled, status, stream);
+}
+
+int crl_encoder_head_packed_bytes(const CrlEncoderShape* s, int64_t* bytes) {
+  const int rc = check_shape(s);
+  if (rc) return rc;
+  if (!bytes) return CRL_ERR_NULL;
+  const HeadOffsets o = head_offsets(s->obs_dim, s->hidden);
+  if (o.smem_end > 227u * 1024u) return CRL_ERR_UNSUPPORTED;
+  *bytes = (int64_t)o.packed_end;
+  return CRL_OK;
+}
+
+int crl_encoder_pack_head(const CrlEncoderShape* s, const float* w, const float* b, void* packed, void* stream) {
+  const int rc = check_shape(s);
+  if (rc) return rc;
+  if (!w || !b || !packed) return CRL_ERR_NULL;
+  if (reinterpret_cast<uintptr_t>(packed) & 15u) return CRL_ERR_ALIGN;
+  if (head_offsets(s->obs_dim, s->hidden).smem_end > 227u * 1024u) return CRL_ERR_UNSUPPORTED;
+  HeadPackArgs a{w, b, static_cast<uint8_t*>(packed), s->obs_dim, s->hidden};
+  head_pack_kernel<<<148, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  return cudaGetLastError() == cudaSuccess ? CRL_OK : CRL_ERR_LAUNCH;
+}
+
+int crl_encoder_head(const CrlEncoderShape* s, int32_t num_envs, const float* obs, const float* pooled,
+                     const void* packed_head, float* out, int32_t* status, void* stream) {
+  const int rc = check_shape(s);
+  if (rc) return rc;
+  if (!obs || !pooled || !packed_head || !out) return CRL_ERR_NULL;
+  if (num_envs <= 0) return CRL_ERR_CONFIG;
+  if (reinterpret_cast<uintptr_t>(packed_head) & 15u) return CRL_ERR_ALIGN;
+  const HeadOffsets o = head_offsets(s->obs_dim, s->hidden);
+  if (o.smem_end > 227u * 1024u) return CRL_ERR_UNSUPPORTED;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess) return CRL_ERR_DEVICE;
+  static bool attr_set[64] = {false};
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    if (cudaFuncSetAttribute(encoder_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return CRL_ERR_DEVICE;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  HeadArgs a{obs, pooled, static_cast<const uint8_t*>(packed_head), out, status, num_envs, s->obs_dim, s->hidden, 0};
+  a.n_tiles = (num_envs + kRows - 1) / kRows;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int want = (a.n_tiles + kGroups - 1) / kGroups;
+  const int grid = want < sms ? want : sms;
+  encoder_head_kernel<<<grid, kGroupThreads * kGroups, o.smem_end, static_cast<cudaStream_t>(stream)>>>(a);
   return cudaGetLastError() == cudaSuccess ? CRL_OK : CRL_ERR_LAUNCH;
 }
 

@@ -1208,7 +1208,9 @@ __global__ void __maxnreg__(MaxRegs<N>::v) step_kernel(const __grid_constant__ K
   float c, s;
   if (!EXT) {
     // (6) zone_obs leaves now and drains under the physics
-    zone_obs_send<TASK, N>(p, env, live, stage, lane, warp_env0, false);
+    // (CRL_STEP_NO_ZONE_OBS: a consumer that builds the zone rows from the state planes itself --
+    // crl_zone_encode_state -- needs neither the rows nor their 360 / 420 / 168 bytes per env-step)
+    if (!(p.flags & CRL_STEP_NO_ZONE_OBS)) zone_obs_send<TASK, N>(p, env, live, stage, lane, warp_env0, false);
     if (p.zone_obs_host) rows_to_host<TASK, N>(p, stage, s_rows_mask[warp], lane, warp_env0);
     // (7) physics: all frameskip substeps in registers
     if (fresh) {
@@ -1224,7 +1226,8 @@ __global__ void __maxnreg__(MaxRegs<N>::v) step_kernel(const __grid_constant__ K
       store_state_obs<TASK, N>(p, env, e, c, s);
     }
   } else {
-    zone_obs_send<TASK, N>(p, env, live || revive, stage, lane, warp_env0, parked && !revive);
+    if (!(p.flags & CRL_STEP_NO_ZONE_OBS))
+      zone_obs_send<TASK, N>(p, env, live || revive, stage, lane, warp_env0, parked && !revive);
     if (p.zone_obs_host) rows_to_host<TASK, N>(p, stage, s_rows_mask[warp], lane, warp_env0);
     // an env rebuilt by the auto-reset still integrates its OLD body: the shaped reward of the
     // episode's last step is measured at the post-physics position (TSP_next_city_env.py:57-67)
@@ -1612,7 +1615,7 @@ static int fill_params(const CrlConfig* c, const CrlState* st, const CrlOut* out
     p.bank_task = st->bank_task;
   }
   if (out) {
-    if (!out->obs || !out->zone_obs || !out->result) return CRL_ERR_NULL;
+    if (!out->obs || !out->result) return CRL_ERR_NULL;     // zone_obs: checked by the callers that write it
     if (!aligned16(out->obs) || !aligned16(out->zone_obs)) return CRL_ERR_ALIGN;
     p.obs = reinterpret_cast<float4*>(out->obs); p.zone_obs = out->zone_obs;
     p.result = reinterpret_cast<unsigned long long*>(out->result);
@@ -1734,6 +1737,8 @@ static int step_launch(const CrlConfig* c, const CrlState* st, const float* acti
   if ((flags & CRL_STEP_TRACK_ROWS) && !p.row_list) return CRL_ERR_NULL;
   if ((flags & CRL_STEP_GOALS) && (!p.goal || !p.shaped)) return CRL_ERR_NULL;
   if ((flags & CRL_STEP_ACTION_COUNTER) && !p.act_count) return CRL_ERR_NULL;
+  if (!(flags & CRL_STEP_NO_ZONE_OBS) && !p.zone_obs) return CRL_ERR_NULL;
+  if ((flags & CRL_STEP_NO_ZONE_OBS) && (zone_obs_host || (flags & CRL_STEP_TRACK_ROWS))) return CRL_ERR_CONFIG;
   const bool ext = (flags & (CRL_STEP_GOALS | CRL_STEP_WAIT)) != 0u;
   // Programmatic launch (this grid may start while its predecessor drains) is safe when the
   // kernel then waits for the whole predecessor (plain, chain start) or for its own previous
@@ -1776,7 +1781,7 @@ int crl_step(const CrlConfig* c, const CrlState* st, const float* actions, const
 
 int crl_reset(const CrlConfig* c, const CrlState* st, const CrlOut* out, const uint8_t* mask, void* stream) {
   KParams p;
-  if (!out) return CRL_ERR_NULL;
+  if (!out || !out->zone_obs) return CRL_ERR_NULL;
   int rc = fill_params(c, st, out, p);
   if (rc) return rc;
   p.mask = mask;
@@ -1796,7 +1801,7 @@ int crl_reset(const CrlConfig* c, const CrlState* st, const CrlOut* out, const u
 int crl_reset_from_layout(const CrlConfig* c, const CrlState* st, const CrlOut* out, const CrlLayoutIn* lay,
                           const int32_t* env_ids, int32_t n, void* stream) {
   KParams p;
-  if (!out || !lay || !lay->xy0 || !lay->rot0 || !lay->zone_xy) return CRL_ERR_NULL;
+  if (!out || !out->zone_obs || !lay || !lay->xy0 || !lay->rot0 || !lay->zone_xy) return CRL_ERR_NULL;
   int rc = fill_params(c, st, out, p);
   if (rc) return rc;
   if (c->task == CRL_TASK_TTSP && !lay->zone_max_steps) return CRL_ERR_NULL;

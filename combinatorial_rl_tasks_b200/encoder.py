@@ -1,16 +1,17 @@
 """ZoneEncoder: the reference's ``ZoneEnvModel`` (main/src/env_model.py:48-79) for the rollout-time
 forward, with the wide part of its per-zone network and the mean-pool fused into one tensor-core kernel
 (include/crl_b200.h: crl_zone_encode; csrc/crl_encode.cu).  The last Linear of ``zone_net_`` is affine, so
-the mean over zones is taken before it: the kernel returns ``pooled = mean_z relu(L2(relu(L1(.))))`` and
-``zone_emb = L3(pooled)`` is a (B, h) library GEMM.
+the mean over zones is taken before it: the kernel returns ``pooled = mean_z relu(L2(relu(L1(.))))``; the rest
+of the forward, ``combine_net_([obs, L3(pooled)])``, is one affine map of ``[obs, pooled]`` and runs as a second
+tensor-core kernel of the same library (crl_encoder_head).  No library GEMM is called.
 
     model = ZoneEnvModel(obs_space, h_dim)                  # the reference's module, trained as usual
     enc = ZoneEncoder(model.state_dict(), num_zones=15)     # packs zone_net_ once (repack after an update)
     emb = enc(env.obs, env.zone_obs)                        # == model(DictList(obs=..., zone_obs=...))
 
-The first two layers run with bf16 operands and fp32 accumulation (the reference: fp32); the third
-layer and ``combine_net_`` are plain ``torch.nn.functional.linear`` calls in fp32.  Inference only -- no autograd graph is built.  There is
-no CPU path: the constructor raises without CUDA.
+All GEMMs run with bf16 operands and fp32 accumulation (the reference: fp32; biases ride in the GEMMs as bf16
+hi + lo pairs).  Inference only -- no autograd graph is built.  There is no CPU path: the constructor raises
+without CUDA.
 """
 import ctypes
 
@@ -52,7 +53,17 @@ class ZoneEncoder:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.crl_encoder_pack(self.shape, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
                                                  self.packed.data_ptr(), self._stream()))
-        self._keep = (w1, b1, w2, b2)               # alive until the pack kernel has run
+        # the two heads: forward() = fold_w [obs, pooled] + fold_b, zone_embedding() = [0 | W3] [obs, pooled] + b3
+        l3_w = torch.cat([torch.zeros(h, self.obs_dim, device=self.device), self.w3], dim=1).contiguous()
+        _lib.check(self.lib.crl_encoder_head_packed_bytes(self.shape, ctypes.byref(n)))
+        self.packed_head = torch.zeros(n.value, dtype=torch.uint8, device=self.device)
+        self.packed_l3 = torch.zeros(n.value, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.crl_encoder_pack_head(self.shape, self.fold_w.data_ptr(), self.fold_b.data_ptr(),
+                                                      self.packed_head.data_ptr(), self._stream()))
+            _lib.check(self.lib.crl_encoder_pack_head(self.shape, l3_w.data_ptr(), self.b3.data_ptr(),
+                                                      self.packed_l3.data_ptr(), self._stream()))
+        self._keep = (w1, b1, w2, b2, l3_w)         # alive until the pack kernels have run
 
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -72,9 +83,38 @@ class ZoneEncoder:
                                                 self._stream()))
         return out
 
-    def zone_embedding(self, obs, zone_obs):
+    def pooled_from_state(self, env, out=None):
+        """``pooled`` with the zone part of the input rows built from the env's STATE planes (crl_zone_encode_state)
+        instead of read from ``env.zone_obs``: bit-identical to ``pooled(env.obs, env.zone_obs)`` after a step that
+        wrote zone_obs, and the way to consume steps taken with ``env.write_zone_obs = False``."""
+        B = env.num_envs
+        assert env.spec.num_zones == self.num_zones and env.spec.zone_dim == self.zone_dim and self.obs_dim == 8
+        if out is None:
+            out = torch.empty(B, self.hidden, dtype=torch.float32, device=self.device)
+        assert out.shape == (B, self.hidden) and out.dtype == torch.float32 and out.is_contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.crl_zone_encode_state(self.shape, env.cfg, env.state, env.obs.data_ptr(),
+                                                      self.packed.data_ptr(), out.data_ptr(), self._status.data_ptr(),
+                                                      self._stream()))
+        return out
+
+    def forward_from_state(self, env):
+        """ZoneEnvModel.forward on the env's current observation without touching ``env.zone_obs``."""
+        return self._head(self.packed_head, env.obs, self.pooled_from_state(env))
+
+    def _head(self, packed, obs, pooled, out=None):
+        B = obs.shape[0]
+        if out is None:
+            out = torch.empty(B, self.hidden, dtype=torch.float32, device=self.device)
+        assert out.shape == (B, self.hidden) and out.dtype == torch.float32 and out.is_contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.crl_encoder_head(self.shape, B, obs.data_ptr(), pooled.data_ptr(), packed.data_ptr(),
+                                                 out.data_ptr(), self._status.data_ptr(), self._stream()))
+        return out
+
+    def zone_embedding(self, obs, zone_obs, out=None):
         """mean_z zone_net_([obs, zone_obs[:, z]]) (env_model.py:73) = L3(pooled)."""
-        return torch.nn.functional.linear(self.pooled(obs, zone_obs), self.w3, self.b3)
+        return self._head(self.packed_l3, obs, self.pooled(obs, zone_obs), out)
 
     def healthy(self):
         """False if a tensor-core completion wait ever expired (synchronises)."""
@@ -84,4 +124,4 @@ class ZoneEncoder:
         """ZoneEnvModel.forward: accepts the env's obs dict or the two tensors."""
         if zone_obs is None:
             obs, zone_obs = obs['obs'], obs['zone_obs']
-        return torch.nn.functional.linear(torch.cat([obs, self.pooled(obs, zone_obs)], dim=-1), self.fold_w, self.fold_b)
+        return self._head(self.packed_head, obs, self.pooled(obs, zone_obs))

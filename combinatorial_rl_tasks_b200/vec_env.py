@@ -83,6 +83,7 @@ class ZoneVecEnv:
         # step_no_reset an env whose episode ended is parked until it is reset
         self.wait = bool(wait)
         self._mode_flags = (_lib.STEP_GOALS if spec.goals else 0)
+        self._write_zone_obs = True
         N, Z = spec.num_zones, spec.zone_dim
         self.cfg = _lib.CrlConfig(
             task=spec.task, num_envs=B, num_zones=N, num_steps=spec.num_steps, frameskip=spec.frameskip,
@@ -230,6 +231,19 @@ class ZoneVecEnv:
         self._mirror_ok = False
         self._chain_ok = False
 
+    @property
+    def write_zone_obs(self):
+        """False: step() / step_no_reset() / step_random() neither build nor write ``zone_obs`` (CRL_STEP_NO_ZONE_OBS)
+        -- for rollouts whose only consumer is ``ZoneEncoder.forward_from_state(env)``, which derives the zone rows
+        from the state planes.  ``env.zone_obs`` then keeps what the last reset / full step wrote.  step_host always
+        writes it."""
+        return self._write_zone_obs
+
+    @write_zone_obs.setter
+    def write_zone_obs(self, on):
+        self._write_zone_obs = bool(on)
+        self._mirror_ok = False
+
     def _guard(self):
         """Make this env's device current for the call; free when it already is (the usual case)."""
         return _NO_GUARD if torch.cuda.current_device() == self._dev_index else torch.cuda.device(self.device)
@@ -370,6 +384,8 @@ class ZoneVecEnv:
             flags |= _lib.STEP_CHAINED if self._chain_ok else _lib.STEP_CHAIN_START
         if not flags & _lib.STEP_PHYSICS_ONLY:
             flags |= self._mode_flags
+        if not self._write_zone_obs:
+            flags |= _lib.STEP_NO_ZONE_OBS
         with self._guard():
             if actions is None:
                 aptr = None

@@ -132,6 +132,11 @@ enum CrlError {
  * (may be NULL); *delta_rows is set to -1 and CrlState.row_list[0] counts the rows moved, cumulatively.
  * The device copies CrlOut.obs / result / shaped_reward are NOT updated by such a call (zone_obs is). */
 #define CRL_STEP_HOST_ZERO_COPY 256u
+/* The step does not build or write zone_obs (CrlOut.zone_obs may be NULL): for a consumer that derives the zone
+ * rows from the state planes itself -- crl_zone_encode_state, the fused ZoneEnvModel encoder -- a rollout that only
+ * needs the embedding never materialises 360 / 420 / 168 of the 584 / 676 / 336 bytes an env-step moves.  Not with
+ * CRL_STEP_TRACK_ROWS / CRL_STEP_HOST_ZERO_COPY (they ship zone_obs rows). */
+#define CRL_STEP_NO_ZONE_OBS 512u
 
 /* how a reset chooses the episode's seed; wrappers.py:10-23 and Engine.seed/reset */
 enum CrlSeedMode {
@@ -393,6 +398,25 @@ int crl_encoder_pack(const CrlEncoderShape* shape, const float* w1, const float*
  * (results then undefined); the kernel never hangs. */
 int crl_zone_encode(const CrlEncoderShape* shape, int32_t num_envs, const float* obs, const float* zone_obs,
                     const void* packed, float* pooled, int32_t* status, void* stream);
+/* The same with the zone part of every input row BUILT FROM THE STATE PLANES (CrlState.aux, zone_xy, zone_tmax /
+ * cooldown; cfg gives task, sizes, num_steps, max_cooldown) instead of read from a materialised zone_obs: bit for bit
+ * the rows the step writes (main/envs obs_zones: x/3, y/3, r, g, b, 0.25 [, time left | cooldown / 150]), so
+ * `pooled` is bit-identical to crl_zone_encode on the step's own zone_obs.  Reads 32 + 8 N (+ 4 ceil(N/2) | 8) + 4
+ * bytes per env instead of 32 + 4 N Z; with CRL_STEP_NO_ZONE_OBS the step does not write zone_obs at all.
+ * obs: the step's CrlOut.obs, float[B][obs_dim = 8]. */
+int crl_zone_encode_state(const CrlEncoderShape* shape, const CrlConfig* cfg, const CrlState* st, const float* obs,
+                          const void* packed, float* pooled, int32_t* status, void* stream);
+
+/* The rest of ZoneEnvModel.forward (env_model.py:76-79): out = combine_net_([obs, L3(pooled)]).  Both Linears are
+ * affine, so this is ONE GEMM  out[e] = W' [obs[e], pooled[e], 1]  with W' = [Wc_obs | Wc_emb W3], b' = Wc_emb b3 + bc
+ * folded by the caller; crl_encoder_head runs it on the tensor cores as well (tcgen05, bf16 operands, fp32
+ * accumulation, folded weights resident in shared memory; bound by reading (obs, pooled) and writing out once), so
+ * the whole forward is two kernels of this library and no library GEMM.  With w = [0 | W3], b = b3 the same call
+ * yields zone_emb = L3(pooled).  w: float[h][obs_dim + h] (torch layout), b: float[h], all device pointers. */
+int crl_encoder_head_packed_bytes(const CrlEncoderShape* shape, int64_t* bytes);
+int crl_encoder_pack_head(const CrlEncoderShape* shape, const float* w, const float* b, void* packed, void* stream);
+int crl_encoder_head(const CrlEncoderShape* shape, int32_t num_envs, const float* obs, const float* pooled,
+                     const void* packed_head, float* out, int32_t* status, void* stream);
 
 /* Copies the eight counters to the host (synchronises `stream`).  The first four (sum of
  * returns, episodes, successes, sum of lengths) are what ranks all-reduce. */

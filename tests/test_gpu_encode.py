@@ -31,7 +31,7 @@ def crl():
     return m
 
 
-def bf16_twin(sd, obs, zone_obs):
+def bf16_twin(sd, obs, zone_obs, head=True):
     """The kernel's arithmetic in torch: operands rounded to bf16, products and sums in fp32 (fp64 here)."""
     r = lambda t: t.to(torch.bfloat16).to(torch.float64)
     B, N, _ = zone_obs.shape
@@ -43,8 +43,11 @@ def bf16_twin(sd, obs, zone_obs):
     h, in_dim = sd['zone_net_.0.weight'].shape
     x = r(torch.relu(x @ r(sd['zone_net_.0.weight']).T + bias(sd['zone_net_.0.bias'], in_dim + 1 not in (16, 32))).to(torch.float32))
     x = torch.relu(x @ r(sd['zone_net_.2.weight']).T + bias(sd['zone_net_.2.bias'], True))
-    pooled = x.sum(dim=1) / N                        # the kernel's output; the third Linear is fp32 on (B, h)
-    return (pooled @ sd['zone_net_.4.weight'].to(torch.float64).T + sd['zone_net_.4.bias'].to(torch.float64)).to(torch.float32)
+    pooled = x.sum(dim=1) / N                        # the fused kernel's output (fp32)
+    if not head:                                     # the third Linear in fp32 on (B, h): what the pooled kernel is tested with
+        return (pooled @ sd['zone_net_.4.weight'].to(torch.float64).T + sd['zone_net_.4.bias'].to(torch.float64)).to(torch.float32)
+    # crl_encoder_head: [obs, pooled] and the weights rounded to bf16, the bias as hi + lo
+    return (r(pooled.to(torch.float32)) @ r(sd['zone_net_.4.weight']).T + bias(sd['zone_net_.4.bias'], True)).to(torch.float32)
 
 
 def fp32_ref(sd, obs, zone_obs):
@@ -98,11 +101,24 @@ def test_random_batches_against_torch(crl, B, N, Z, h, D):
     emb = torch.nn.functional.linear(pooled, sd['zone_net_.4.weight'], sd['zone_net_.4.bias'])
     torch.cuda.synchronize()
     assert enc.healthy() and bool((out[B:] == 7.0).all()) and bool((pooled >= 0).all())
-    twin, ref = bf16_twin(sd, obs, zobs), fp32_ref(sd, obs, zobs)
+    twin, ref = bf16_twin(sd, obs, zobs, head=False), fp32_ref(sd, obs, zobs)
     e_twin, e_ref = float((emb - twin).abs().max()), float((emb - ref).abs().max())
     print(f'B={B} N={N} Z={Z} h={h} D={D}: vs bf16 twin {e_twin:.2e}, vs fp32 {e_ref:.2e}, |ref| max {float(ref.abs().max()):.2f}')
     scale = max(1.0, float(ref.abs().max()))
     assert e_twin <= BF16_TWIN_RTOL * scale and e_ref <= FP32_RTOL * scale
+    # the head kernel (crl_encoder_head): zone_embedding = L3(pooled), forward = combine_net_([obs, zone_emb]); guard rows
+    out2 = torch.full((B + 3, h), 7.0, device='cuda')
+    emb_k = enc.zone_embedding(obs, zobs, out=out2[:B])
+    fwd_k = enc(obs, zobs)
+    fwd_ref = torch.nn.functional.linear(torch.cat([obs, ref], -1).double(), sd['combine_net_.weight'].double(),
+                                         sd['combine_net_.bias'].double()).float()
+    torch.cuda.synchronize()
+    e_head_twin, e_head = float((emb_k - bf16_twin(sd, obs, zobs)).abs().max()), float((emb_k - ref).abs().max())
+    e_fwd = float((fwd_k - fwd_ref).abs().max())
+    print(f'   head: zone_emb vs bf16 twin {e_head_twin:.2e}, vs fp32 {e_head:.2e}; forward vs fp32 {e_fwd:.2e}')
+    assert enc.healthy() and bool((out2[B:] == 7.0).all())
+    assert e_head_twin <= BF16_TWIN_RTOL * scale and e_head <= FP32_RTOL * scale
+    assert e_fwd <= FP32_RTOL * max(1.0, float(fwd_ref.abs().max()))
     # second call on the same encoder (barrier phases, TMEM re-allocation) gives the same bits
     assert torch.equal(enc.pooled(obs, zobs), pooled)
 
@@ -124,6 +140,50 @@ def test_encoder_on_the_env_outputs(crl):
     assert float((y - ref).abs().max()) <= FP32_RTOL * max(1.0, float(ref.abs().max()))
 
 
+@pytest.mark.parametrize('env_id', ['PointTSP-v0', 'PointTTSP-v0', 'ColourMatch-v0', 'PointTSP-v1'])
+def test_rows_built_from_the_state_planes_are_the_rows_the_step_writes(crl, env_id):
+    """crl_zone_encode_state builds the zone part of the encoder's input from the state planes (zone centres,
+    visited / colour bits, timeouts, cooldowns, step count).  It must see bit for bit the rows the step writes to
+    zone_obs -- so `pooled` is bit-identical between the two paths -- also for envs that have visited zones, run
+    cooldowns, been reset; and a rollout with env.write_zone_obs = False (CRL_STEP_NO_ZONE_OBS: the step neither
+    builds nor writes zone_obs) gives the same embeddings as one that materialises them."""
+    B, h = 3000, 96
+    N, Z = crl.ENV_SPECS[env_id].num_zones, crl.ENV_SPECS[env_id].zone_dim
+    gen = torch.Generator(device='cuda').manual_seed(5)
+    rn = lambda *s_, scale=1.0: (torch.randn(*s_, device='cuda', generator=gen) * scale)
+    sd = {'zone_net_.0.weight': rn(h, 8 + Z, scale=0.4), 'zone_net_.0.bias': rn(h, scale=0.2),
+          'zone_net_.2.weight': rn(h, h, scale=0.15), 'zone_net_.2.bias': rn(h, scale=0.2),
+          'zone_net_.4.weight': rn(h, h, scale=0.15), 'zone_net_.4.bias': rn(h, scale=0.2),
+          'combine_net_.weight': rn(h, 8 + h, scale=0.1), 'combine_net_.bias': rn(h, scale=0.1)}
+    enc = crl.ZoneEncoder(sd, num_zones=N)
+    full, lean = crl.ZoneVecEnv(env_id, B), crl.ZoneVecEnv(env_id, B)
+    for e in (full, lean):
+        e.seed(77)
+        e.cfg.num_steps = 60                                   # short episodes: auto-resets inside the test
+        e.reset()
+    lean.write_zone_obs = False
+    frozen = lean.zone_obs.clone()
+    rs = np.random.RandomState(2)
+    for t in range(90):
+        a = torch.from_numpy(rs.uniform(-1, 1, (B, 2)).astype(np.float32)).cuda()
+        if t % 7 == 3:                                         # zone events: visited bits / colour cycles / cooldowns
+            z = int(rs.randint(N))
+            for e in (full, lean):
+                e.pose[t % 5::5, :2] = e.zone_xy[z, t % 5::5, :]
+        full.step(a)
+        lean.step(a)
+        if t % 9 == 0 or t > 84:
+            want = enc.pooled(full.obs, full.zone_obs)
+            assert torch.equal(enc.pooled_from_state(full), want), (env_id, t)      # same env, both paths
+            assert torch.equal(enc.pooled_from_state(lean), want), (env_id, t)      # the env that never wrote zone_obs
+            assert torch.equal(enc.forward_from_state(lean), enc(full.obs, full.zone_obs)), (env_id, t)
+    torch.cuda.synchronize()
+    assert enc.healthy()
+    assert torch.equal(lean.zone_obs, frozen)                  # CRL_STEP_NO_ZONE_OBS: untouched since the reset
+    assert torch.equal(lean.obs, full.obs) and torch.equal(lean.result, full.result) and torch.equal(lean.aux, full.aux)
+    assert full.counters()['episodes'] == lean.counters()['episodes'] >= B
+
+
 def test_unsupported_shapes_are_refused(crl):
     from combinatorial_rl_tasks_b200 import _lib
     import ctypes
@@ -132,3 +192,4 @@ def test_unsupported_shapes_are_refused(crl):
     assert lib.crl_encoder_packed_bytes(_lib.CrlEncoderShape(8, 6, 185, 15), ctypes.byref(n)) == 0 and n.value == 256 * 192 * 2 + 256 * 32
     assert lib.crl_encoder_packed_bytes(_lib.CrlEncoderShape(8, 6, 256, 15), ctypes.byref(n)) == -4    # two resident weights do not fit
     assert lib.crl_encoder_packed_bytes(_lib.CrlEncoderShape(20, 12, 64, 15), ctypes.byref(n)) == -2     # no room for the ones column in the 32-wide input
+    assert lib.crl_encoder_head_packed_bytes(_lib.CrlEncoderShape(8, 6, 185, 15), ctypes.byref(n)) == 0 and n.value == 256 * 208 * 2

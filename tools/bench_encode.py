@@ -65,10 +65,29 @@ def main():
 
     torch.backends.cuda.matmul.allow_tf32 = False
     t_fused = time_it(lambda i: enc.pooled(obs_r[i], zobs_r[i], out=out), args.iters)
-    t_emb = time_it(lambda i: enc.zone_embedding(obs_r[i], zobs_r[i]), args.iters)      # + the (B, h) third Linear
+    t_emb = time_it(lambda i: enc.zone_embedding(obs_r[i], zobs_r[i]), args.iters)      # + the head kernel with [0 | W3]
+    t_fwd = time_it(lambda i: enc(obs_r[i], zobs_r[i]), args.iters)                      # ZoneEnvModel.forward: pooled + folded head
+    pooled0 = enc.pooled(obs_r[0], zobs_r[0])
+    t_head = time_it(lambda i: enc._head(enc.packed_head, obs_r[i], pooled0), args.iters)
+
+    def torch_fwd(i, dtype=None):
+        with torch.no_grad(), torch.autocast('cuda', dtype=dtype, enabled=dtype is not None):
+            return comb(torch.cat([obs_r[i], torch_ref(i, dtype)], dim=-1))
     ok = enc.healthy()
     t_fp32 = time_it(lambda i: torch_ref(i), max(3, args.iters // 10))
     t_bf16 = time_it(lambda i: torch_ref(i, torch.bfloat16), max(3, args.iters // 5))
+    # the rows built from the state planes instead of read from zone_obs (crl_zone_encode_state); replicas of the env
+    envs = [env] + [crl.ZoneVecEnv(args.env, B, env_offset=(k + 1) * B) for k in range(min(reps, 6) - 1)]
+    for e in envs[1:]:
+        e.seed(1 + e.cfg.env_offset)
+        e.reset()
+        for _ in range(8):
+            e.step_random(action_seed=4)
+    t_state = time_it(lambda i: enc.pooled_from_state(envs[i % len(envs)], out=out), args.iters)
+    same = bool(torch.equal(enc.pooled_from_state(env), enc.pooled(env.obs, env.zone_obs)))
+    t_fwd_fp32 = time_it(lambda i: torch_fwd(i), max(3, args.iters // 10))
+    t_fwd_bf16 = time_it(lambda i: torch_fwd(i, torch.bfloat16), max(3, args.iters // 5))
+    err_fwd = float((enc(obs_r[0], zobs_r[0]) - torch_fwd(0)).abs().max())
     err = float((enc.zone_embedding(obs_r[0], zobs_r[0]) - torch_ref(0)).abs().max())
     useful = B * N * 2 * ((8 + Z) * h + h * h)           # the kernel's two layers; the third runs on (B, h) in cuBLAS
     HP = (h + 31) // 32 * 32
@@ -78,7 +97,11 @@ def main():
     peak = peaks.get('bf16_tflops', 2250.0)
     print(json.dumps({
         'op': 'ZoneEnvModel.zone_net_ + mean over zones (env_model.py:56-78)', 'workload': f'{args.env}, {B} envs, N={N}, Z={Z}, h={h}',
-        'healthy': ok, 'fused_us': t_fused * 1e6, 'zone_embedding_us': t_emb * 1e6, 'torch_fp32_us': t_fp32 * 1e6, 'torch_bf16_autocast_us': t_bf16 * 1e6,
+        'healthy': ok, 'fused_us': t_fused * 1e6, 'fused_from_state_us': t_state * 1e6, 'from_state_bit_identical': same, 'head_us': t_head * 1e6, 'zone_embedding_us': t_emb * 1e6, 'forward_us': t_fwd * 1e6,
+        'torch_fp32_us': t_fp32 * 1e6, 'torch_bf16_autocast_us': t_bf16 * 1e6,
+        'torch_forward_fp32_us': t_fwd_fp32 * 1e6, 'torch_forward_bf16_autocast_us': t_fwd_bf16 * 1e6,
+        'forward_speedup_vs_torch_fp32': t_fwd_fp32 / t_fwd, 'forward_speedup_vs_torch_bf16_autocast': t_fwd_bf16 / t_fwd,
+        'max_abs_err_forward_vs_torch_fp32': err_fwd,
         'envs_per_s': B / t_emb, 'speedup_vs_torch_fp32': t_fp32 / t_emb, 'speedup_vs_torch_bf16': t_bf16 / t_emb,
         'max_abs_err_vs_torch_fp32': err,
         'roofline': {'bound': 'tensor', 'achieved': useful / t_fused / 1e12, 'issued': issued / t_fused / 1e12, 'peak': peak,
