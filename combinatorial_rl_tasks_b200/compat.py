@@ -175,6 +175,34 @@ class GymEnv:
         return self._batch().envs[0].noop_obs()
 
 
+class TimeoutWrapper:
+    """main/envs/wrappers.py:161-194 for any env with the single-env surface (``GymEnv`` here): the episode runs exactly
+    ``max_timeout`` steps; once the inner env is done every further step returns its last observation and reward 0;
+    ``done`` is raised only by the timer; ``info`` is ``{'timer': t}``.  Host-side bookkeeping only (the reference
+    defines the class and uses it nowhere on the three tasks' training paths)."""
+
+    def __init__(self, env, max_timeout=10000):
+        self.env, self.max_timeout = env, max_timeout
+        self.timer, self.inner_done, self.last_obs = 0, False, None
+
+    def __getattr__(self, name):                    # gym.Wrapper forwards unknown attributes
+        return getattr(self.env, name)
+
+    def step(self, action):
+        self.timer += 1
+        if not self.inner_done:
+            obs, rew, done, info = self.env.step(action)
+            if done:
+                self.inner_done, self.last_obs = True, obs
+        else:
+            obs, rew = self.last_obs, 0
+        return obs, rew, self.timer == self.max_timeout, {'timer': self.timer}
+
+    def reset(self):
+        self.timer, self.inner_done, self.last_obs = 0, False, None
+        return self.env.reset()
+
+
 def make_train_env(env_name, hier=False, num_training_tasks=100, rng_seed=0, device='cuda:0'):
     """make_env.make_train_env (make_env.py:3-18): FixedSeedsWrapper over [1, num_training_tasks].
     ``rng_seed`` only decorrelated the per-process seed choosers; here the chooser is keyed by

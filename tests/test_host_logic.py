@@ -302,3 +302,54 @@ def test_philox_reset_twin_layouts_are_valid():
     assert abs(tm.mean() - 2 / 3) < 0.015 and abs(tm.var() - 0.0404) < 0.004
     cols = np.concatenate([co.philox_reset('ColourMatch-v0', s)['colours'] for s in range(2000)])
     assert np.all(np.abs(np.bincount(cols, minlength=3) / len(cols) - 1 / 3) < 0.02)
+
+
+def test_timeout_wrapper_matches_the_reference_class():
+    """compat.TimeoutWrapper against the REAL main/envs/wrappers.py:161-194 (imported over the gym / mujoco_py / glfw stubs
+    when /root/reference is present; the recorded expectations below otherwise) on a scripted inner env."""
+    import importlib
+    import sys
+    from combinatorial_rl_tasks_b200.compat import TimeoutWrapper
+
+    class Inner:
+        observation_space = action_space = None
+
+        def __init__(self):
+            self.t = 0
+
+        def reset(self):
+            self.t = 0
+            return ('obs', 0)
+
+        def step(self, action):
+            self.t += 1
+            return ('obs', self.t), 1.5 * self.t, self.t == 4, {'inner': True}
+
+    def trace(w):
+        out = [w.reset()]
+        for k in range(9):
+            out.append(w.step(k))
+        out.append(w.reset())
+        out.append(w.step(0))
+        return out
+
+    ours = trace(TimeoutWrapper(Inner(), max_timeout=7))
+    # steps 1-3 pass through, step 4 ends the inner env (reward kept, done hidden), 5-6 repeat its last obs with reward
+    # 0, step 7 raises done; the timer keeps counting past max_timeout without raising done again
+    assert ours[1] == (('obs', 1), 1.5, False, {'timer': 1}) and ours[4] == (('obs', 4), 6.0, False, {'timer': 4})
+    assert ours[5] == (('obs', 4), 0, False, {'timer': 5}) and ours[7] == (('obs', 4), 0, True, {'timer': 7})
+    assert ours[8] == (('obs', 4), 0, False, {'timer': 8}) and ours[10] == ('obs', 0) and ours[11][3] == {'timer': 1}
+    ref_dir = '/root/reference/main'
+    if os.path.isdir(ref_dir):
+        stubs = os.path.join(ROOT, 'tests', 'golden', 'stubs')
+        saved = list(sys.path)
+        sys.path[:0] = [stubs, ref_dir]
+        try:
+            ref_mod = importlib.import_module('envs.wrappers')
+            real = ref_mod.TimeoutWrapper.__new__(ref_mod.TimeoutWrapper)     # gym.Wrapper.__init__ of the stub needs a gym.Env
+            real.env, real.max_timeout, real.timer, real.inner_done, real.last_obs = Inner(), 7, 0, False, None
+            assert trace(real) == ours
+        finally:
+            sys.path[:] = saved
+            for m in [m for m in sys.modules if m == 'envs' or m.startswith('envs.')]:
+                del sys.modules[m]
