@@ -422,6 +422,31 @@ def run_ours(args):
         med = rank_max(per_call[len(per_call) // 2])
         return world * B / med, rows / calls, calls, world * B / rank_max(per_call[0])
 
+    def e2e_of(env_, seconds):
+        """step_host end to end for one env batch (page-locked action arrays): env-steps/s, median group of 25 calls."""
+        acts = env_.pinned_actions(4)
+        rs_ = np.random.RandomState(11 + rank)
+        for a_ in acts:
+            np.copyto(a_, rs_.uniform(-1, 1, a_.shape).astype(np.float32))
+        for i in range(3):
+            env_.step_host(acts[i % 4])
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        per, n, t_start = [], 0, time.perf_counter()
+        while True:
+            t0 = time.perf_counter()
+            for i in range(10):
+                env_.step_host(acts[(n + i) % 4])
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            per.append((t1 - t0) / 10)
+            n += 10
+            if t1 - t_start >= seconds or n >= 2000:
+                break
+        per.sort()
+        return world * env_.num_envs / rank_max(per[len(per) // 2])
+
     full_rate, _, _, _ = timed_host_steps(False, args.e2e_seconds / 3)
     pageable_rate, _, _, _ = timed_host_steps(True, args.e2e_seconds / 3, pageable)
     rate, rows_per_step, e2e_calls, best_rate = timed_host_steps(True, args.e2e_seconds)
@@ -459,6 +484,8 @@ def run_ours(args):
             for k in ('ms_per_step', 'ms_per_step_best', 'ms_per_step_mean'):
                 m2[k] = rank_max(m2[k])
             d = device_line(r2, m2, world, peak)
+            if world == 1:
+                d['e2e_value'] = e2e_of(r2.envs[0], 0.4)        # ZoneVecEnv.step_host, host numpy in / out
             d.update({'config': tag, 'env': env_id, 'envs_per_gpu_per_launch': b, 'ring_replicas': r2.R, 'streams': r2.S,
                       'chained_steps': r2.chained, 'timed_steps': m2['timed_steps'], 'timed_region_s': m2['timed_region_s'],
                       'unit': UNIT, 'episode_stats': stats(r2), 'sampler_launches': r2.prefetch_launches})

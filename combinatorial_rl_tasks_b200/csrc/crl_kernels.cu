@@ -809,9 +809,27 @@ __device__ __forceinline__ void zone_obs_send(const KParams& p, const Env<N>& en
 // warp's stage straight into the caller's host mirror of zone_obs (pinned, device-mapped), each row by the whole
 // warp with coalesced stores.  A handful of rows per launch: the host buffer stays a byte-exact copy of the device
 // one with no list, no gather kernel and no host-side scatter.
+// CRL_STEP_HOST_PLANES (TimedTSP): the host mirror is PLANE-major, float[Z][B][N] (the caller views it as (B, N, Z)
+// through strides), so that the one column that moves every step -- time left, plane 6 -- is a contiguous
+// [B][N] array: the warp writes its 32 x N values of it with fully coalesced stores, every step; a changed row
+// (a visit, a reset) is N values in each of the other planes.
 template <int TASK, int N>
 __device__ __noinline__ void rows_to_host(const KParams& p, const float* stage, unsigned mask, int lane, int warp_env0) {
-  constexpr int ROW = N * ZoneDim<TASK>::Z;
+  constexpr int Z = ZoneDim<TASK>::Z, ROW = N * Z;
+  if (TASK == CRL_TASK_TTSP && (p.flags & CRL_STEP_HOST_PLANES)) {
+    const size_t plane = (size_t)p.B * N;
+    const int n_valid = max(0, min(32, p.B - warp_env0));
+    float* tl = p.zone_obs_host + 6 * plane + (size_t)warp_env0 * N;
+    for (int i = lane; i < n_valid * N; i += 32) tl[i] = stage[(i / N) * ROW + (i % N) * Z + 6];
+    while (mask) {
+      const int src = __ffs(mask) - 1;
+      mask &= mask - 1u;
+      const float* row = stage + src * ROW;
+      float* dst = p.zone_obs_host + (size_t)(warp_env0 + src) * N;
+      for (int i = lane; i < 6 * N; i += 32) dst[(size_t)(i / N) * plane + (i % N)] = row[(i % N) * Z + (i / N)];
+    }
+    return;
+  }
   while (mask) {
     const int src = __ffs(mask) - 1;
     mask &= mask - 1u;
@@ -1060,7 +1078,9 @@ __global__ void __maxnreg__(MaxRegs<N>::v) step_kernel(const __grid_constant__ K
   bool fresh = false;   // true: this env was rebuilt by the auto-reset, no physics this call
   if (!(p.flags & CRL_STEP_PHYSICS_ONLY)) {
     // does this step rewrite the env's zone_obs row with different bytes? (CRL_STEP_TRACK_ROWS)
-    bool row_changed = TASK == CRL_TASK_TTSP;                       // the time-left column moves
+    // TimedTSP's time-left column moves every step: the whole row counts as changed -- unless the host mirror is
+    // plane-major (CRL_STEP_HOST_PLANES), where that column is shipped as its own contiguous plane every step
+    bool row_changed = TASK == CRL_TASK_TTSP && !(p.flags & CRL_STEP_HOST_PLANES);
     // (1) ColourMatch cooldowns tick before anything else (colour_match_env.py:98-100)
     if (TASK == CRL_TASK_CM) {
       row_changed = (env.cd.x | env.cd.y) != 0u;
@@ -1739,6 +1759,7 @@ static int step_launch(const CrlConfig* c, const CrlState* st, const float* acti
   if ((flags & CRL_STEP_ACTION_COUNTER) && !p.act_count) return CRL_ERR_NULL;
   if (!(flags & CRL_STEP_NO_ZONE_OBS) && !p.zone_obs) return CRL_ERR_NULL;
   if ((flags & CRL_STEP_NO_ZONE_OBS) && (zone_obs_host || (flags & CRL_STEP_TRACK_ROWS))) return CRL_ERR_CONFIG;
+  if ((flags & CRL_STEP_HOST_PLANES) && (!zone_obs_host || c->task != CRL_TASK_TTSP)) return CRL_ERR_CONFIG;
   const bool ext = (flags & (CRL_STEP_GOALS | CRL_STEP_WAIT)) != 0u;
   // Programmatic launch (this grid may start while its predecessor drains) is safe when the
   // kernel then waits for the whole predecessor (plain, chain start) or for its own previous

@@ -499,11 +499,14 @@ class ZoneVecEnv:
         flags = (_lib.STEP_AUTO_RESET if auto_reset else 0) | self._mode_flags
         if wait:
             flags |= _lib.STEP_WAIT
-        use_delta = delta and self._mirror_ok and self.spec.task != _lib.TASK_TTSP
+        ttsp = self.spec.task == _lib.TASK_TTSP
+        use_delta = delta and self._mirror_ok and (zero_copy or not ttsp)
         with self._guard():
             if use_delta and zero_copy:
+                # TimedTSP: the host mirror is plane-major (see _host_buffers), the time-left plane crosses every step
+                zc = _lib.STEP_HOST_ZERO_COPY | (_lib.STEP_HOST_PLANES if ttsp else 0)
                 _lib.check(self.lib.crl_step_host_delta(self.cfg, self.state, aptr, None, self.out, h['out'],
-                                                        None, 0, flags | _lib.STEP_HOST_ZERO_COPY, None, self._stream()))
+                                                        None, 0, flags | zc, None, self._stream()))
                 self.delta_rows = -1
             elif use_delta:
                 if h['delta'] is None:
@@ -517,6 +520,20 @@ class ZoneVecEnv:
                                                         ctypes.byref(n), self._stream()))
                 self.delta_rows = n.value
                 self.gpu_launches += 1                # the gather kernel
+            elif ttsp:
+                # full copy into the plane-major mirror: step on the device, then everything crosses (the device
+                # transposes zone_obs to [Z][B][N] first)
+                src = h['actions'] if aptr == h['actions_ptr'] else self._pinned[id(actions)][0]
+                self._actions_dev.copy_(src, non_blocking=True)
+                _lib.check(self.lib.crl_step(self.cfg, self.state, self._actions_dev.data_ptr(), self.out, flags, 0,
+                                             self._step_index, self._stream()))
+                h['zone_obs'].copy_(self.zone_obs.permute(2, 0, 1), non_blocking=True)
+                h['obs'].copy_(self.obs, non_blocking=True)
+                h['result'].copy_(self.result, non_blocking=True)
+                if self.spec.goals:
+                    h['shaped'].copy_(self.shaped_reward, non_blocking=True)
+                torch.cuda.current_stream(self.device).synchronize()
+                self.delta_rows = self.num_envs
             else:
                 _lib.check(self.lib.crl_step_host(self.cfg, self.state, aptr,
                                                   self._actions_dev.data_ptr(), self.out, h['out'],
@@ -526,6 +543,8 @@ class ZoneVecEnv:
         self.gpu_launches += 1
         self._chain_ok = False                    # memcpys follow the step kernel on the stream
         self._mirror_ok = True
+        if self.prefetch_every:
+            self.tick()                           # the background sampler's cadence, as in _step
         return h['ret']
 
     def host_rows_moved(self, reset=False):
@@ -540,12 +559,17 @@ class ZoneVecEnv:
         if self._host is None:
             B, N, Z = self.num_envs, self.spec.num_zones, self.spec.zone_dim
             pin = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype).pin_memory()
+            # TimedTSP: the host mirror of zone_obs is PLANE-major, [Z][B][N], handed out as a (B, N, Z) strided view:
+            # the time-left column, which moves every step, is then one contiguous plane (CRL_STEP_HOST_PLANES)
+            zshape = (Z, B, N) if self.spec.task == _lib.TASK_TTSP else (B, N, Z)
             h = {'actions': pin(B, 2, dtype=torch.float32), 'obs': pin(B, 8, dtype=torch.float32),
-                 'zone_obs': pin(B, N, Z, dtype=torch.float32), 'result': pin(B, 8, dtype=torch.uint8),
+                 'zone_obs': pin(*zshape, dtype=torch.float32), 'result': pin(B, 8, dtype=torch.uint8),
                  'shaped': pin(B, dtype=torch.float32)}
             h['out'] = _lib.CrlOut(obs=h['obs'].data_ptr(), zone_obs=h['zone_obs'].data_ptr(),
                                    result=h['result'].data_ptr(), shaped_reward=h['shaped'].data_ptr())
             h['np'] = {k: h[k].numpy() for k in ('actions', 'obs', 'zone_obs', 'result', 'shaped')}
+            if self.spec.task == _lib.TASK_TTSP:
+                h['np']['zone_obs'] = h['np']['zone_obs'].transpose(1, 2, 0)
             h['delta'] = None
             h['actions_ptr'] = h['actions'].data_ptr()
             # what every step_host call returns: views of the persistent host buffers, built once

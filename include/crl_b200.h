@@ -137,6 +137,11 @@ enum CrlError {
  * needs the embedding never materialises 360 / 420 / 168 of the 584 / 676 / 336 bytes an env-step moves.  Not with
  * CRL_STEP_TRACK_ROWS / CRL_STEP_HOST_ZERO_COPY (they ship zone_obs rows). */
 #define CRL_STEP_NO_ZONE_OBS 512u
+/* With CRL_STEP_HOST_ZERO_COPY, TimedTSP only: host_out->zone_obs is PLANE-major, float[Z][B][N] (the caller views it
+ * as (B, N, Z) through strides).  TimedTSP's time-left column moves every step, so with a row-major mirror every row
+ * would cross PCIe every step (420 B per env); plane-major, that column is one contiguous [B][N] plane the step
+ * writes with coalesced stores (60 B per env), and only the rows of visits and resets touch the other six planes. */
+#define CRL_STEP_HOST_PLANES 1024u
 
 /* how a reset chooses the episode's seed; wrappers.py:10-23 and Engine.seed/reset */
 enum CrlSeedMode {

@@ -226,11 +226,13 @@ def test_step_host_delta_is_byte_identical_to_full_copy(crl, env_id, zero_copy):
         assert np.array_equal(od['zone_obs'], delta.zone_obs.cpu().numpy()), t
         moved.append(rows)
     assert moved[0] == B and moved[70] == B           # first call and the call after device-side work: full copy
-    if env_id == 'PointTTSP-v0':
-        assert all(m == B for m in moved)             # the time-left column moves every step
-    else:
-        assert max(moved[1:39]) < B // 4              # between resets only a few rows move
-        assert B in moved[39:42] or max(moved[38:42]) >= B // 2   # the step-limit reset rewrites every row
+    if env_id == 'PointTTSP-v0' and not zero_copy:
+        assert all(m == B for m in moved)             # the time-left column moves every step: staged = full copies
+    else:                                             # (zero-copy TimedTSP: plane-major mirror, that column is its own plane)
+        # between the step-limit resets only a few rows move (TimedTSP: its 40-step episodes also end on timeouts)
+        assert max(moved[1:39]) < (B // 2 if env_id == 'PointTTSP-v0' else B // 4)
+        if env_id != 'PointTTSP-v0':                  # (TimedTSP's episodes are desynchronised by their timeouts long before)
+            assert B in moved[39:42] or max(moved[38:42]) >= B // 2   # the step-limit reset rewrites every row
 
 
 @pytest.mark.parametrize('env_id,B', [('PointTSP-v0', 65536), ('PointTTSP-v0', 262144), ('ColourMatch-v0', 262144)])
