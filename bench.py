@@ -352,6 +352,11 @@ def run_ours(args):
             os.close(saved)
     dev = torch.device(f'cuda:{local}')
     torch.cuda.set_device(dev)
+    # each rank next to its own GPU: its pinned host buffers (the e2e path moves tens of GB/s per GPU) then live on
+    # that GPU's NUMA node instead of wherever torchrun happened to start the process
+    from combinatorial_rl_tasks_b200.hostbind import bind_to_gpu_numa_node
+    all_cores = os.sched_getaffinity(0)
+    numa = {'bound': False, 'why': '--no-numa-bind'} if args.no_numa_bind else bind_to_gpu_numa_node(local)
     peak, peak_src = measured_peaks()
     B, K, W = args.envs, max(1, args.steps), max(3, args.warmup)
     chained = None if args.chained < 0 else bool(args.chained)
@@ -463,6 +468,7 @@ def run_ours(args):
                      'obs, result and the zone_obs rows that changed (mean %.1f of %d rows per step) to, the pinned host '
                      'buffers itself; host buffers byte-identical to a full copy' % (rows_per_step, B) if is_delta
                      else '; crl_step_host: everything copied whole'),
+           'host_placement': numa,
            'full_copy_value': full_rate,
            'full_copy_d2h_bytes_per_step': (32 + 4 * N * Z + 8) * B}
     del ring, env
@@ -538,6 +544,7 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         try:
+            os.sched_setaffinity(0, all_cores)                        # the CPU baseline gets ALL host cores back
             out['cpu_baseline'] = cpu_baselines(args.env, args.cpu_seconds)
         except Exception as ex:  # the baseline is a reported number, never the product path
             out['cpu_baseline'] = {'error': repr(ex)}
@@ -566,6 +573,7 @@ def main():
     ap.add_argument('--e2e-max-calls', type=int, default=20000)
     ap.add_argument('--cpu-seconds', type=float, default=9.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-numa-bind', action='store_true', help='leave the process where the launcher put it')
     ap.add_argument('--no-extra', action='store_true', help='skip the configs[2] / [3] / [4] legs')
     ap.add_argument('--configs4', action='store_true', help='run the 1,048,576-env legs of configs[4] also on one GPU')
     ap.add_argument('--no-auto-reset', action='store_true', help='diagnostic: finished envs keep stepping')

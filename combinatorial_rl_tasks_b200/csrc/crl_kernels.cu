@@ -249,7 +249,7 @@ __device__ void warp_layout(const KParams& p, long long seed, float2* placed, in
           const float oy = (q & 1) ? pl[q >> 1].w : pl[q >> 1].y;
           const float need = __fadd_rn(q == 0 ? p.robot_keepout : p.zone_keepout, keep);
           const float dx = __fsub_rn(x, ox), dy = __fsub_rn(y, oy);
-          const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+          const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));   // the form of the packed test in prefetch_layout_kernel
           valid = valid && (q >= k || d2 >= __fmul_rn(need, need));
         }
         const unsigned m = __ballot_sync(kFull, valid);
@@ -539,6 +539,31 @@ __device__ __noinline__ void warp_reset(const KParams& p, unsigned dm, int lane,
   __syncwarp();
 }
 
+// packed fp32 pairs (Blackwell: add / sub / mul / fma .f32x2), IEEE round-to-nearest per half
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long sub_f32x2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long mul_f32x2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
 // ---- background prefetch of next layouts -------------------------------------------
 // Every env has TWO next-layout slots: reset number n takes slot n & 1, so the layouts of
 // its next two resets can be parked at once and an env that finishes again before the
@@ -643,15 +668,18 @@ __global__ void __launch_bounds__(32) prefetch_layout_kernel(const __grid_consta
       const float x1 = __fadd_rn(lo_x, __fmul_rn(span, u01(r.z))), y1 = __fadd_rn(lo_y, __fmul_rn(span, u01(r.w)));
       const float need_r = __fadd_rn(rk, keep), need_z = __fadd_rn(zk, keep);
       const float need_r2 = __fmul_rn(need_r, need_r), need_z2 = __fmul_rn(need_z, need_z);
+      // both tries against object q with PACKED fp32 arithmetic (sub / mul / fma .f32x2: FADD2, FMUL2, FFMA2 in SASS,
+      // the object's coordinate broadcast): 4 floating-point instructions per object for the two tries instead of 10;
+      // d2 = fma(dy, dy, fl(dx dx)) per try -- the design twin (oracle/crl_oracle.c) forms it the same way
+      const unsigned long long X2 = pack_f32x2(x0, x1), Y2 = pack_f32x2(y0, y1);
       uint32_t bad0 = 0u, bad1 = 0u;              // bit q: too close to object q (no branches)
 #pragma unroll
       for (int q = 0; q < N; ++q) {
         const float2 o = placed[q];
         const float lim = q == 0 ? need_r2 : need_z2;
-        const float dx0 = __fsub_rn(x0, o.x), dy0 = __fsub_rn(y0, o.y);
-        const float dx1 = __fsub_rn(x1, o.x), dy1 = __fsub_rn(y1, o.y);
-        const float d20 = __fadd_rn(__fmul_rn(dx0, dx0), __fmul_rn(dy0, dy0));
-        const float d21 = __fadd_rn(__fmul_rn(dx1, dx1), __fmul_rn(dy1, dy1));
+        const unsigned long long dx = sub_f32x2(X2, pack_f32x2(o.x, o.x)), dy = sub_f32x2(Y2, pack_f32x2(o.y, o.y));
+        float d20, d21;
+        unpack_f32x2(fma_f32x2(dy, dy, mul_f32x2(dx, dx)), d20, d21);
         bad0 |= (d20 >= lim) ? 0u : (1u << q);
         bad1 |= (d21 >= lim) ? 0u : (1u << q);
       }

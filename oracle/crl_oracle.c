@@ -628,8 +628,10 @@ void ph_reset(int task, int N, int num_steps, int seed_mode, int64_t min_seed, i
         for (int q = 0; q < k; ++q) {
           const float need = (q == 0 ? robot_keepout : zone_keepout) + keep;
           const float dx = x - px[q], dy = y - py[q];
-          volatile float xx = dx * dx, yy = dy * dy, nn = need * need;
-          const float d2 = xx + yy;
+          /* as the device forms it: d2 = fma(dy, dy, fl(dx * dx)), one rounding for the second product and the sum
+             (packed FFMA2 in the background sampler, __fmaf_rn in the warp-cooperative one) */
+          volatile float xx = dx * dx, nn = need * need;
+          const float d2 = fmaf(dy, dy, xx);
           valid = valid && (d2 >= nn);
         }
         if (valid) { px[k] = x; py[k] = y; found = 1; }
