@@ -1994,7 +1994,7 @@ int crl_step_host_delta(const CrlConfig* c, const CrlState* st, const float* act
     // host buffers: no copy-engine transfers, no staging, no row list, no gather, no host-side scatter
     // (host_delta and actions_dev are not used).  row_list[0] counts the rows (cumulative).
     struct Mapped { const void* host; void* dev; };
-    static thread_local Mapped cache[8] = {};
+    static thread_local Mapped cache[64] = {};   // a caller rotating a few action buffers must not evict the fixed ones
     static thread_local int next = 0;
     auto mapped = [&](const void* h) -> void* {
       if (!h) return nullptr;
@@ -2005,7 +2005,7 @@ int crl_step_host_delta(const CrlConfig* c, const CrlState* st, const float* act
         return nullptr;
       }
       cache[next] = Mapped{h, a.devicePointer};
-      next = (next + 1) % 8;
+      next = (next + 1) % 64;
       return a.devicePointer;
     };
     CrlOut direct = *out;

@@ -479,9 +479,10 @@ class ZoneVecEnv:
         reward / done out (pinned staging; host<->device copies inside the call).  The returned
         arrays are persistent host buffers overwritten by the next call, as the device ones are.
 
-        ``delta=True`` (PointTSP, ColourMatch): once the host zone_obs buffer mirrors the device
-        one, later calls move only the rows that changed; the arrays returned are byte-identical to
-        a full copy.  TimedTSP's time-left column moves every step, so it always copies whole.
+        ``delta=True``: once the host zone_obs buffer mirrors the device one, later calls move only
+        the rows that changed; the arrays returned are byte-identical to a full copy.  TimedTSP's
+        time-left column moves every step: its host mirror is plane-major (``zone_obs`` is then a
+        (B, N, Z) strided view of a [Z][B][N] buffer) and that column crosses as one contiguous plane.
         ``zero_copy=True`` (with the delta path): ONE kernel and a stream synchronisation -- the step
         kernel reads the actions from, and writes obs / result / shaped_reward and the changed zone_obs
         rows to, the pinned host buffers itself; the DEVICE tensors ``env.obs`` / ``env.result`` are then

@@ -140,7 +140,7 @@ def test_encoder_on_the_env_outputs(crl):
     assert float((y - ref).abs().max()) <= FP32_RTOL * max(1.0, float(ref.abs().max()))
 
 
-@pytest.mark.parametrize('env_id', ['PointTSP-v0', 'PointTTSP-v0', 'ColourMatch-v0', 'PointTSP-v1'])
+@pytest.mark.parametrize('env_id', ['PointTSP-v0', 'PointTTSP-v0', 'ColourMatch-v0', 'PointTSP-v1', 'PointTTSP-v3'])
 def test_rows_built_from_the_state_planes_are_the_rows_the_step_writes(crl, env_id):
     """crl_zone_encode_state builds the zone part of the encoder's input from the state planes (zone centres,
     visited / colour bits, timeouts, cooldowns, step count).  It must see bit for bit the rows the step writes to

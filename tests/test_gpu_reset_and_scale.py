@@ -191,7 +191,7 @@ def test_step_host_equals_device_step(crl):
 
 
 @pytest.mark.parametrize('zero_copy', [True, False], ids=['zero_copy', 'staged'])
-@pytest.mark.parametrize('env_id', TASKS)
+@pytest.mark.parametrize('env_id', TASKS + ['PointTTSP-v3', 'ColourMatch-v3'])     # -v3: the EXT kernels (shaped_reward too)
 def test_step_host_delta_is_byte_identical_to_full_copy(crl, env_id, zero_copy):
     """crl_step_host_delta moves only the zone_obs rows that changed; what the caller sees in its
     host buffers must be byte for byte what crl_step_host (full copy) delivers -- across zone
@@ -218,20 +218,22 @@ def test_step_host_delta_is_byte_identical_to_full_copy(crl, env_id, zero_copy):
         od, rd, dd, ind = delta.step_host(a, delta=True, zero_copy=zero_copy)
         rows = delta.delta_rows if delta.delta_rows >= 0 else delta.host_rows_moved(reset=True)   # -1: counted on the device
         if t == 20:
-            assert rows >= 200 and (env_id == 'ColourMatch-v0' or int((ind['event'] != 0).sum()) >= 200)
+            assert rows >= 200 and (env_id.startswith('ColourMatch') or int((ind['event'] != 0).sum()) >= 200)
         assert np.array_equal(of['zone_obs'].view(np.uint32), od['zone_obs'].view(np.uint32)), t
         assert np.array_equal(of['obs'].view(np.uint32), od['obs'].view(np.uint32)), t
         assert np.array_equal(rf.view(np.uint32), rd.view(np.uint32)) and np.array_equal(df, dd), t
         assert np.array_equal(inf_['event'], ind['event']) and np.array_equal(inf_['goal_met'], ind['goal_met'])
+        if 'shaped_reward' in ind:
+            assert np.array_equal(inf_['shaped_reward'], ind['shaped_reward']) and np.array_equal(inf_['need_next_goal'], ind['need_next_goal'])
         assert np.array_equal(od['zone_obs'], delta.zone_obs.cpu().numpy()), t
         moved.append(rows)
     assert moved[0] == B and moved[70] == B           # first call and the call after device-side work: full copy
-    if env_id == 'PointTTSP-v0' and not zero_copy:
+    if env_id.startswith('PointTTSP') and not zero_copy:
         assert all(m == B for m in moved)             # the time-left column moves every step: staged = full copies
     else:                                             # (zero-copy TimedTSP: plane-major mirror, that column is its own plane)
         # between the step-limit resets only a few rows move (TimedTSP: its 40-step episodes also end on timeouts)
-        assert max(moved[1:39]) < (B // 2 if env_id == 'PointTTSP-v0' else B // 4)
-        if env_id != 'PointTTSP-v0':                  # (TimedTSP's episodes are desynchronised by their timeouts long before)
+        assert max(moved[1:39]) < (B // 2 if env_id.startswith('PointTTSP') else B // 4)
+        if not env_id.startswith('PointTTSP'):                  # (TimedTSP's episodes are desynchronised by their timeouts long before)
             assert B in moved[39:42] or max(moved[38:42]) >= B // 2   # the step-limit reset rewrites every row
 
 
