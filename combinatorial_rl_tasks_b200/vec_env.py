@@ -269,6 +269,8 @@ class ZoneVecEnv:
         """Engine.seed for every env: an int (env i gets seed + i) or a (B,) tensor."""
         if isinstance(seeds, int):
             seeds = torch.arange(self.num_envs, dtype=torch.int64) + seeds
+        # a sampler round still running on the side stream writes slot flags: it must be over before they are zeroed
+        torch.cuda.current_stream(self.device).wait_stream(self._side)
         self.seeds.copy_(self._as_dev(seeds, torch.int64))
         self.episode.zero_()
         self.aux[:, 3] = (self.aux[:, 3].view(torch.int32) & 0x7fffffff).view(torch.float32)   # slot parity follows `episode`
@@ -649,6 +651,7 @@ class ZoneVecEnv:
 
     def load_state_dict(self, d):
         assert d['env_id'] == self.env_id and d['num_envs'] == self.num_envs
+        torch.cuda.current_stream(self.device).wait_stream(self._side)      # no sampler round in flight while slots are dropped
         for k in self._STATE_KEYS:
             if getattr(self, k) is not None:
                 getattr(self, k).copy_(d[k])
