@@ -92,7 +92,7 @@ __host__ __device__ inline Offsets offsets(int h, int in_dim) {
   o.h1 = 0;                                              // relative to the group's base
   o.xbuf = o.h1 + (uint32_t)KP * kRows * 2;
   o.bar = o.xbuf + (uint32_t)kRows * kK1 * 2;
-  o.group_bytes = (o.bar + 8 + 127u) & ~127u;
+  o.group_bytes = (o.bar + 40 + 127u) & ~127u;           // five mbarriers per slot (kBarBytes)
   o.tmem_slot = o.group0 + kGroups * o.group_bytes;
   o.smem_end = o.tmem_slot + 16;
   return o;
@@ -161,6 +161,9 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     if (ok) return true;
+#ifdef CRL_ENC_DIAG_SLEEP                                       // timing diagnostic: how much do the polling warps cost the MMAs' operand reads
+    __nanosleep(CRL_ENC_DIAG_SLEEP);
+#endif
   }
   return false;
 }
@@ -252,7 +255,8 @@ template <bool STATE>
 __device__ __forceinline__ void load_half_row(const EncArgs& a, int tile, int m, int kc, float (&x)[8]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) x[j] = 0.f;
-  const int e = tile * (kRows / a.S) + m / a.S, slot = m % a.S;
+  const int sh = a.S == 16 ? 4 : 3;                          // S is 8 or 16: no runtime division on this path
+  const int e = (tile << (7 - sh)) + (m >> sh), slot = m & (a.S - 1);
   if (tile < a.n_tiles && e < a.B && slot < a.N) {
     const float* ob = a.obs + (size_t)e * a.obs_dim;
     if (STATE) {
@@ -280,7 +284,11 @@ __device__ __forceinline__ void load_half_row(const EncArgs& a, int tile, int m,
 }
 
 // relu of 32 consecutive rows m of this thread's hidden unit -> bf16 -> four 16-byte units of H1
-__device__ __forceinline__ void relu_to_h1(const uint32_t (&v)[32], uint8_t* h1_row, int c) {
+__device__ __forceinline__ void relu_to_h1(const uint32_t (&v)[32], uint8_t* h1_row, int c, bool in_range) {
+#ifdef CRL_ENC_DIAG_NO_H1_STORE                                 // timing diagnostic (wrong results): epilogue 1 without its shared-memory stores
+  if (v[0] != 0x7fc12345u) return;
+#endif
+  if (!in_range) return;                                     // hidden rows >= KP do not exist in H1 (the X buffer follows it)
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     *reinterpret_cast<uint4*>(h1_row + (uint32_t)((c * 4 + q) * 128)) =
@@ -289,8 +297,11 @@ __device__ __forceinline__ void relu_to_h1(const uint32_t (&v)[32], uint8_t* h1_
   }
 }
 
-// 32 consecutive rows m = the zone slots of envs e0 .. e0 + 32 / S - 1: relu, sum in registers, store column j
-__device__ __forceinline__ void relu_pool_store(const uint32_t (&v)[32], const EncArgs& a, int e0, int j, float inv_n) {
+// 32 consecutive rows m = the zone slots of envs e0 .. e0 + 32 / S - 1: relu, sum in registers, store column j.
+// `col` = out + j (this thread's column of the output); `full`: every env of the tile exists and j < h, so the stores
+// need no predicates (their address chains were a third of epilogue 2's time).
+__device__ __forceinline__ void relu_pool_store(const uint32_t (&v)[32], float* col, int h, int B, int S, int e0, bool full,
+                                                bool j_ok, float inv_n) {
   float q[4];                                                 // sums of 8 consecutive rows
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -300,38 +311,99 @@ __device__ __forceinline__ void relu_pool_store(const uint32_t (&v)[32], const E
       s[i] = fmaxf(__uint_as_float(v[8 * g + 2 * i]), 0.f) + fmaxf(__uint_as_float(v[8 * g + 2 * i + 1]), 0.f);
     q[g] = (s[0] + s[1]) + (s[2] + s[3]);
   }
-  if (j < a.h) {
-    if (a.S == 16) {
-      if (e0 < a.B) a.out[(size_t)e0 * a.h + j] = (q[0] + q[1]) * inv_n;
-      if (e0 + 1 < a.B) a.out[(size_t)(e0 + 1) * a.h + j] = (q[2] + q[3]) * inv_n;
-    } else {
+  float* p = col + (size_t)e0 * (size_t)h;
+  if (S == 16) {
+    const float r0 = (q[0] + q[1]) * inv_n, r1 = (q[2] + q[3]) * inv_n;
+    if (full) { p[0] = r0; p[h] = r1; }
+    else if (j_ok) {
+      if (e0 < B) p[0] = r0;
+      if (e0 + 1 < B) p[h] = r1;
+    }
+  } else {
+    if (full) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) p[(size_t)g * h] = q[g] * inv_n;
+    } else if (j_ok) {
 #pragma unroll
       for (int g = 0; g < 4; ++g)
-        if (e0 + g < a.B) a.out[(size_t)(e0 + g) * a.h + j] = q[g] * inv_n;
+        if (e0 + g < B) p[(size_t)g * h] = q[g] * inv_n;
     }
   }
 }
 
+// The pipeline (round 2).  17 warps: two GROUPS of 8 epilogue warps, each owning one tile slot (256 TMEM columns = two
+// M-blocks of accumulators, an H1 buffer, an X buffer), and ONE issuing warp whose lane 0 issues every tcgen05.mma of
+// both slots.  Nothing meets at a CTA / group barrier any more; five mbarriers per slot carry the dependencies:
+//   full_x   (8 warp arrivals)  the slot's next input rows are staged AND its accumulators have been drained  -> L1 may go
+//   full_h1  (8 warp arrivals)  epilogue 1 has written H1 (and read the layer-1 accumulators)                 -> L2 may go
+//   l1_done  (tcgen05.commit)   layer 1 has completed                                                         -> epilogue 1
+//   l2_done[b] (commit)         M-block b of layer 2 has completed                                            -> epilogue 2 of b
+// Tensor-pipe order in steady state: L2 of slot g (24 MMAs) with the OTHER slot's next L1 inserted after the first few
+// of them -- by then that slot's epilogue 2 (which started when ITS L2 completed, i.e. when this one began) has freed
+// its accumulators -- so that slot's epilogue 1 runs under the rest of this L2 and its own L2 is ready to issue the
+// moment this one ends: the pipe always has queued work, and each epilogue has a whole L2 (~1,500 cycles) to hide in.
+constexpr int kIssuerThreads = 32;
+constexpr int kEncThreads = kGroupThreads * kGroups + kIssuerThreads;
+#ifndef CRL_ENC_INSERT_AFTER
+#define CRL_ENC_INSERT_AFTER 6     // MMAs of an L2 issued before the issuer BLOCKS for the other slot's L1 (earlier if ready)
+#endif
+enum { kBarFullX = 0, kBarFullH1 = 8, kBarL1Done = 16, kBarL2Done = 24 /* + 8 b */, kBarBytes = 40 };
+
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0u;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0u;
+}
+
+#ifdef CRL_ENC_TIMELINE   // diagnostic build: clock64 stamps of the first 64 tiles of every slot (tools/enc_timeline.py)
+__device__ long long g_timeline[148 * 2 * 64 * 16];
+#define CRL_TL(g, k, i) do { if ((k) < 64 && blockIdx.x < 148) g_timeline[((blockIdx.x * 2 + (g)) * 64 + (k)) * 16 + (i)] = clock64(); } while (0)
+#else
+#define CRL_TL(g, k, i) do { } while (0)
+#endif
+
 template <bool STATE>
-__global__ void __launch_bounds__(kGroupThreads * kGroups, 1) zone_encode_kernel(const EncArgs a) {
+__global__ void __launch_bounds__(kEncThreads, 1) zone_encode_kernel(const EncArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const Offsets o = offsets(a.h, a.obs_dim + a.Z);
   const int KP = padded_k(a.h), MP = padded_m(a.h), kK1 = padded_k1(a.obs_dim + a.Z);
   const int n_mblocks = MP / 128;
-  const int group = threadIdx.x / kGroupThreads;              // 0 / 1
+  const int warp_idx = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform, and the compiler knows it
+  const bool issuer = warp_idx >= kGroupThreads * kGroups / 32;
+  const int group = issuer ? 0 : warp_idx / (kGroupThreads / 32);   // 0 / 1
   const int t = threadIdx.x % kGroupThreads;
   const int m = t & (kRows - 1), half = t >> 7;               // input row / half of it this thread stages
   const int warp = t >> 5, lane = t & 31;
   const int mblock = warp >> 2, quad = warp & 3;              // accumulator rows this warp drains
   const int j = mblock * 128 + quad * 32 + lane;              // hidden unit (accumulator row) of this thread
   uint8_t* gbase = smem + o.group0 + (uint32_t)group * o.group_bytes;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(gbase + o.bar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + o.tmem_slot);
-  const uint32_t bar_addr = smem_u32(bar);
+  const uint32_t bar0 = smem_u32(smem + o.group0 + o.bar);    // slot g's barriers at bar0 + g * group_bytes
 
   // ---- one-time setup: barriers, TMEM, resident weights ------------------------------------
-  if (t == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_addr) : "memory");
+  if (threadIdx.x == 0) {
+    for (int g = 0; g < kGroups; ++g) {
+      const uint32_t b = bar0 + (uint32_t)g * o.group_bytes;
+      mbar_init(b + kBarFullX, kGroupThreads / 32);
+      mbar_init(b + kBarFullH1, kGroupThreads / 32);
+      mbar_init(b + kBarL1Done, 1);
+      mbar_init(b + kBarL2Done, 1);
+      mbar_init(b + kBarL2Done + 8, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < 32) {
@@ -343,113 +415,187 @@ __global__ void __launch_bounds__(kGroupThreads * kGroups, 1) zone_encode_kernel
   {
     const uint4* src = reinterpret_cast<const uint4*>(a.packed);
     uint4* dst = reinterpret_cast<uint4*>(smem);
-    for (uint32_t i = threadIdx.x; i < o.packed_end / 16; i += kGroupThreads * kGroups) dst[i] = __ldg(src + i);
+    for (uint32_t i = threadIdx.x; i < o.packed_end / 16; i += kEncThreads) dst[i] = __ldg(src + i);
   }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t acc = tmem_base + (uint32_t)group * 256u;    // this group's accumulators: M-block b at + 128 b
-  const uint32_t my_acc = acc + (uint32_t)(mblock * 128) + ((uint32_t)(quad * 32) << 16);
   // instruction descriptors: D fp32, A and B bf16, M = 128, N = 128; layer 1: both K-major; layer 2: B MN-major
   const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kRows >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   const uint32_t idesc2 = idesc1 | (1u << 16);
-  uint8_t* h1buf = gbase + o.h1;
-  uint8_t* xbuf = gbase + o.xbuf;
-  const uint32_t h1_addr = smem_u32(h1buf), x_addr = smem_u32(xbuf);
-  const uint32_t w1_addr = smem_u32(smem + o.w1), w2_addr = smem_u32(smem + o.w2);
-  const uint32_t x_off = (uint32_t)((m & 7) * 16 + (m >> 3) * (16 * kK1) + half * 128);
-  const uint32_t h1_off = (uint32_t)((j & 7) * 16 + (j >> 3) * 2048);
-  const bool drains1 = mblock < n_mblocks && mblock * 128 + quad * 32 < KP;     // layer 2 reads hidden rows < KP
-  const bool drains2 = mblock < n_mblocks && mblock * 128 + quad * 32 < a.h;    // the output has h columns
-  const float inv_n = 1.0f / (float)a.N;
-  uint32_t parity = 0u;
+  const int tile_stride = kGroups * gridDim.x;
   bool healthy = true;
 
-  const int tile_stride = kGroups * gridDim.x;
-  int tile = kGroups * blockIdx.x + group;
-  float x[8], x2[8];                                         // 16-byte units `half` and, for 32-wide inputs, `half + 2`
-  load_half_row<STATE>(a, tile, m, half, x);
-  if (!STATE && kK1 == 32) load_half_row<STATE>(a, tile, m, half + 2, x2);
-  for (; tile < a.n_tiles; tile += tile_stride) {
-    // ---- layer-1 B operand (the tile's 128 input rows) from the prefetched registers ----------
-    *reinterpret_cast<uint4*>(xbuf + x_off) =
-        make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
-    if (kK1 == 32)
-      *reinterpret_cast<uint4*>(xbuf + x_off + 256) =
-          make_uint4(pack_bf16(x2[0], x2[1]), pack_bf16(x2[2], x2[3]), pack_bf16(x2[4], x2[5]), pack_bf16(x2[6], x2[7]));
-    fence_async_smem();
-    tc_fence_before();
-    group_sync(group);
-    // ---- layer 1: H1^T[128 b ..][m] = W1[128 b ..][16] X^T -------------------------------------
-    if (t == 0) {
+  if (issuer) {
+    // ================= the issuing warp feeds the tensor pipe for both slots =================
+    // All 32 lanes run this code CONVERGED and every value in it is warp-uniform (kernel parameters, blockIdx, vote
+    // results), so the descriptors live in uniform registers; only the tcgen05 instructions themselves are executed by
+    // one elected lane.  (The first version ran the loop in a single thread: ptxas then keeps everything in vector
+    // registers, and each MMA cost six R2UR moves, a waterfall loop and ~100 instructions -- 300 cycles per MMA against
+    // the 64 the tensor pipe needs; profiles/r02_notes.md.)
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t w1_addr = smem_u32(smem + o.w1), w2_addr = smem_u32(smem + o.w2);
+    const uint32_t slot0 = smem_u32(smem + o.group0);
+    const int n_s = KP / 16;
+    const bool leader = elect_one();                          // the same lane issues every MMA and commit
+    int n[kGroups], l1i[kGroups] = {0, 0}, l2i[kGroups] = {0, 0};
+    for (int g = 0; g < kGroups; ++g) {
+      const int first = kGroups * (int)blockIdx.x + g;
+      n[g] = first < a.n_tiles ? (a.n_tiles - first + tile_stride - 1) / tile_stride : 0;
+    }
+    // descriptors differ between MMAs only in their start-address field (bits 0..13, in 16-byte units)
+    const uint64_t a1_desc = smem_desc(w1_addr, 128u, 16 * kK1), a2_desc = smem_desc(w2_addr, 128u, 16 * KP);
+    const uint64_t x_desc = smem_desc(slot0 + o.xbuf, 128u, 16 * kK1), h1_desc = smem_desc(slot0 + o.h1, 2048u, 128u);
+    const uint32_t slot_units = o.group_bytes >> 4;
+    auto ready = [&](uint32_t bar, uint32_t parity) {          // warp-uniform poll
+      return __shfl_sync(0xffffffffu, (int)mbar_test(bar, parity), 0) != 0;
+    };
+    // layer 1 of slot g's next tile: H1^T[128 b ..][m] = W1[128 b ..][kK1] X^T
+    auto issue_l1 = [&](int g) {
+      const uint32_t bars = bar0 + (uint32_t)g * o.group_bytes;
+      healthy = mbar_wait(bars + kBarFullX, (uint32_t)l1i[g] & 1u) && healthy;
+      __syncwarp();
       tc_fence_after();
       for (int b = 0; b < n_mblocks; ++b)
-        for (int s = 0; s < kK1 / 16; ++s)
-          mma_bf16(acc + (uint32_t)(b * 128), smem_desc(w1_addr + (uint32_t)(b * 16 * 16 * kK1) + 256u * s, 128u, 16 * kK1),
-                   smem_desc(x_addr + 256u * s, 128u, 16 * kK1), idesc1, s > 0);
-      mma_commit(bar_addr);
+        for (int s2 = 0; s2 < kK1 / 16; ++s2) {
+          const uint64_t ad = a1_desc + (uint64_t)(uint32_t)(b * 16 * kK1 + 16 * s2);
+          const uint64_t bd = x_desc + (uint64_t)((uint32_t)g * slot_units + 16u * (uint32_t)s2);
+          if (leader) mma_bf16(tm + (uint32_t)(g * 256 + b * 128), ad, bd, idesc1, s2 > 0);
+        }
+      if (leader) mma_commit(bars + kBarL1Done);
+      CRL_TL(g, l1i[g], 0);                                    // layer 1 issued
+      ++l1i[g];
+    };
+    // K steps [s_from, s_to) of M-block b of slot g's layer 2: H2^T[128 b ..][m] = W2[128 b ..][KP] H1^T
+    auto issue_l2 = [&](int g, int b, int s_from, int s_to) {
+      const uint32_t acc = tm + (uint32_t)(g * 256 + b * 128);
+      uint64_t ad = a2_desc + (uint64_t)(uint32_t)(b * 16 * KP + 16 * s_from);
+      uint64_t bd = h1_desc + (uint64_t)((uint32_t)g * slot_units + 256u * (uint32_t)s_from);
+#pragma unroll 4
+      for (int s2 = s_from; s2 < s_to; ++s2, ad += 16u, bd += 256u)
+        if (leader) mma_bf16(acc, ad, bd, idesc2, s2 > 0);
+      if (s_from < s_to && s_to == n_s && leader) mma_commit(bar0 + (uint32_t)g * o.group_bytes + kBarL2Done + 8u * (uint32_t)b);
+    };
+    for (int k = 0; k < n[0]; ++k) {
+      for (int g = 0; g < kGroups; ++g) {
+        if (k >= n[g]) continue;
+        if (l1i[g] <= k) issue_l1(g);                         // the first tile; a CTA whose other slot has no tiles
+        const int og = g ^ 1;
+        const uint32_t bars = bar0 + (uint32_t)g * o.group_bytes, obars = bar0 + (uint32_t)og * o.group_bytes;
+        // the other slot's next L1 rides inside this L2 -- unless that slot still owes the L2 before it
+        bool need = l1i[og] < n[og] && l1i[og] <= l2i[og];
+        for (uint32_t it = 0;; ++it) {                         // wait for H1 of (g, k); meanwhile serve the other slot
+          if (need && ready(obars + kBarFullX, (uint32_t)l1i[og] & 1u)) { issue_l1(og); need = false; }
+          if (ready(bars + kBarFullH1, (uint32_t)k & 1u)) break;
+          if (it >= kSpinLimit) { healthy = false; break; }
+        }
+        tc_fence_after();
+        CRL_TL(g, k, 1);                                       // H1 seen by the issuer
+        int done = 0;
+        if (need) {                                            // the insert point: inside M-block 0
+          done = n_s < CRL_ENC_INSERT_AFTER ? n_s : CRL_ENC_INSERT_AFTER;
+          issue_l2(g, 0, 0, done);
+          issue_l1(og);                                        // blocks until that slot's epilogue 2 is over
+        }
+        issue_l2(g, 0, done, n_s);
+        for (int b = 1; b < n_mblocks; ++b) issue_l2(g, b, 0, n_s);
+        CRL_TL(g, k, 2);                                       // layer 2 issued
+        ++l2i[g];
+      }
     }
-    load_half_row<STATE>(a, tile + tile_stride, m, half, x);  // prefetch: in flight for the rest of the tile
-    if (!STATE && kK1 == 32) load_half_row<STATE>(a, tile + tile_stride, m, half + 2, x2);
-    healthy = mbar_wait(bar_addr, parity) && healthy;
-    parity ^= 1u;
-    tc_fence_after();
-    if (drains1) {
-      // this thread: hidden unit j, rows m = 32 c .. 32 c + 31 -> relu -> bf16 -> four 16-byte units of H1
+  } else {
+    // ================= the two groups: stage X, epilogue 1 (-> H1), epilogue 2 (-> pooled) =================
+    const uint32_t bars = bar0 + (uint32_t)group * o.group_bytes;
+    const uint32_t my_acc = tmem_base + (uint32_t)group * 256u + (uint32_t)(mblock * 128) + ((uint32_t)(quad * 32) << 16);
+    uint8_t* h1buf = gbase + o.h1;
+    uint8_t* xbuf = gbase + o.xbuf;
+    const uint32_t x_off = (uint32_t)((m & 7) * 16 + (m >> 3) * (16 * kK1) + half * 128);
+    const uint32_t h1_off = (uint32_t)((j & 7) * 16 + (j >> 3) * 2048);
+    const bool drains1 = mblock < n_mblocks && mblock * 128 + quad * 32 < KP;     // layer 2 reads hidden rows < KP
+    const bool drains2 = mblock < n_mblocks && mblock * 128 + quad * 32 < a.h;    // the output has h columns
+    const uint32_t l2_bar = bars + kBarL2Done + 8u * (uint32_t)(mblock < n_mblocks ? mblock : n_mblocks - 1);
+    const float inv_n = 1.0f / (float)a.N;
+    float* const out_col = a.out + j;
+    const int log2_s = a.S == 16 ? 4 : 3, per_chunk = 32 >> log2_s;   // envs per 32 accumulator columns (a runtime
+    int tile = kGroups * blockIdx.x + group;                           // division here cost epilogue 2 ~800 cycles per tile)
+    float x[8], x2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // 16-byte units `half` and, for 32-wide inputs, `half + 2`
+    auto stage_x = [&]() {                                     // this thread's part of the slot's layer-1 B operand
+      *reinterpret_cast<uint4*>(xbuf + x_off) =
+          make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+      if (kK1 == 32)
+        *reinterpret_cast<uint4*>(xbuf + x_off + 256) =
+            make_uint4(pack_bf16(x2[0], x2[1]), pack_bf16(x2[2], x2[3]), pack_bf16(x2[4], x2[5]), pack_bf16(x2[6], x2[7]));
+      fence_async_smem();
+    };
+    auto fetch_x = [&](int tl) {
+      load_half_row<STATE>(a, tl, m, half, x);
+      if (!STATE && kK1 == 32) load_half_row<STATE>(a, tl, m, half + 2, x2);
+    };
+    fetch_x(tile);
+    stage_x();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bars + kBarFullX);
+    fetch_x(tile + tile_stride);                               // in flight until the first epilogue 1 is over
+    uint32_t parity = 0u;
+    for (int k = 0; tile < a.n_tiles; tile += tile_stride, parity ^= 1u, ++k) {
+      // ---- epilogue 1: hidden unit j, rows m = 32 c .. 32 c + 31 -> relu -> bf16 -> four 16-byte units of H1 ----
+      healthy = mbar_wait(bars + kBarL1Done, parity) && healthy;
+      tc_fence_after();
+      if (t == 0) CRL_TL(group, k, 3);                         // layer 1 done, seen by warp 0
+      if (drains1) {
 #ifdef CRL_ENC_DIAG_HALF_DRAIN                                // timing diagnostic (wrong results): half of epilogue 1's TMEM reads
-      const int c_stop = kRows / 64;
+        const int c_stop = kRows / 64;
 #else
-      const int c_stop = kRows / 32;
+        const int c_stop = kRows / 32;
 #endif
 #pragma unroll 1
-      for (int c = 0; c < c_stop; c += 2) {                   // two TMEM loads in flight
-        uint32_t v0[32], v1[32];
-        tmem_ld32(my_acc + (uint32_t)(c * 32), v0);
-        tmem_ld32(my_acc + (uint32_t)(c * 32 + 32), v1);
-        tmem_ld_wait(v0);
-        relu_to_h1(v0, h1buf + h1_off, c);
-        tmem_ld_wait(v1);
-        relu_to_h1(v1, h1buf + h1_off, c + 1);
+        for (int c = 0; c < c_stop; c += 2) {                 // two TMEM loads in flight
+          uint32_t v0[32], v1[32];
+          tmem_ld32(my_acc + (uint32_t)(c * 32), v0);
+          tmem_ld32(my_acc + (uint32_t)(c * 32 + 32), v1);
+          tmem_ld_wait(v0);
+          relu_to_h1(v0, h1buf + h1_off, c, j < KP);
+          tmem_ld_wait(v1);
+          relu_to_h1(v1, h1buf + h1_off, c + 1, j < KP);
+        }
       }
-    }
-    fence_async_smem();
-    tc_fence_before();
-    group_sync(group);
-    // ---- layer 2: H2^T[128 b ..][m] = W2[128 b ..][KP] H1^T (layer 1's values have been read) ---
-    if (t == 0) {
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + kBarFullH1);
+      if (t == 0) CRL_TL(group, k, 4);                         // epilogue 1 over (warp 0)
+      // ---- the next tile's input rows (layer 1 of this tile has completed: the X buffer is free) ----
+      stage_x();
+      fetch_x(tile + 2 * tile_stride);
+      // ---- epilogue 2: ReLU, mean over each env's zone slots (register adds), coalesced stores ----
+      if (t == 0) CRL_TL(group, k, 5);                         // next rows staged (warp 0)
+      healthy = mbar_wait(l2_bar, parity) && healthy;
       tc_fence_after();
-#ifdef CRL_ENC_DIAG_HALF_MMA                                  // timing diagnostic (wrong results): half of layer 2's K steps
-      const int s_stop = KP / 32;
-#else
-      const int s_stop = KP / 16;
-#endif
-      for (int b = 0; b < n_mblocks; ++b)
-        for (int s = 0; s < s_stop; ++s)
-          mma_bf16(acc + (uint32_t)(b * 128), smem_desc(w2_addr + (uint32_t)(b * 16 * 16 * KP) + 256u * s, 128u, 16 * KP),
-                   smem_desc(h1_addr + 4096u * s, 2048u, 128u), idesc2, s > 0);
-      mma_commit(bar_addr);
-    }
-    healthy = mbar_wait(bar_addr, parity) && healthy;
-    parity ^= 1u;
-    tc_fence_after();
-    // ---- ReLU, mean over each env's 16 zone slots (register adds), coalesced stores -----------
-    if (drains2) {
+      if (t == 0) CRL_TL(group, k, 6);                         // layer 2 (M-block 0) done, seen by warp 0
+      if (drains2) {
+        const bool full = j < a.h && ((tile + 1) << (7 - log2_s)) <= a.B;
 #pragma unroll 1
-      for (int c = 0; c < kRows / 32; c += 2) {               // two TMEM loads in flight
-        uint32_t v0[32], v1[32];
-        tmem_ld32(my_acc + (uint32_t)(c * 32), v0);
-        tmem_ld32(my_acc + (uint32_t)(c * 32 + 32), v1);
-        tmem_ld_wait(v0);
-        const int per_chunk = 32 / a.S, e0 = tile * (kRows / a.S) + c * per_chunk;
-        relu_pool_store(v0, a, e0, j, inv_n);
-        tmem_ld_wait(v1);
-        relu_pool_store(v1, a, e0 + per_chunk, j, inv_n);
+        for (int c = 0; c < kRows / 32; c += 2) {             // two TMEM loads in flight
+          uint32_t v0[32], v1[32];
+          tmem_ld32(my_acc + (uint32_t)(c * 32), v0);
+          tmem_ld32(my_acc + (uint32_t)(c * 32 + 32), v1);
+          tmem_ld_wait(v0);
+          if (t == 0) CRL_TL(group, k, 8 + 2 * c);               // 8 / 12: a pair of TMEM loads has arrived
+          const int e0 = (tile << (7 - log2_s)) + c * per_chunk;
+          relu_pool_store(v0, out_col, a.h, a.B, a.S, e0, full, j < a.h, inv_n);
+          tmem_ld_wait(v1);
+          relu_pool_store(v1, out_col, a.h, a.B, a.S, e0 + per_chunk, full, j < a.h, inv_n);
+          if (t == 0) CRL_TL(group, k, 9 + 2 * c);               // 9 / 13: pooled and stored
+        }
       }
+      // accumulators drained + next rows staged: the issuer may overwrite both with the slot's next layer 1
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + kBarFullX);
+      if (t == 0) CRL_TL(group, k, 7);                         // epilogue 2 over (warp 0)
     }
-    // the next tile's layer-1 MMA overwrites the accumulators: ordered after these loads by the fence
-    // and the group barrier that precede it
   }
   if (!healthy && a.status) atomicExch(a.status, 1);
   tc_fence_before();
@@ -651,6 +797,12 @@ using namespace crl_enc;
 
 extern "C" {
 
+#ifdef CRL_ENC_TIMELINE
+int crl_debug_enc_timeline(long long* host, int64_t bytes) {
+  return cudaMemcpyFromSymbol(host, g_timeline, (size_t)bytes < sizeof(g_timeline) ? (size_t)bytes : sizeof(g_timeline)) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 int crl_encoder_packed_bytes(const CrlEncoderShape* s, int64_t* bytes) {
   const int rc = check_shape(s);
   if (rc) return rc;
@@ -724,8 +876,8 @@ static int zone_encode_launch(const CrlEncoderShape* s, int32_t num_envs, const 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int want = (a.n_tiles + kGroups - 1) / kGroups;
   const int grid = want < sms ? want : sms;                   // persistent: one CTA per SM, weights loaded once
-  if (st) zone_encode_kernel<true><<<grid, kGroupThreads * kGroups, o.smem_end, static_cast<cudaStream_t>(stream)>>>(a);
-  else zone_encode_kernel<false><<<grid, kGroupThreads * kGroups, o.smem_end, static_cast<cudaStream_t>(stream)>>>(a);
+  if (st) zone_encode_kernel<true><<<grid, kEncThreads, o.smem_end, static_cast<cudaStream_t>(stream)>>>(a);
+  else zone_encode_kernel<false><<<grid, kEncThreads, o.smem_end, static_cast<cudaStream_t>(stream)>>>(a);
   return cudaGetLastError() == cudaSuccess ? CRL_OK : CRL_ERR_LAUNCH;
 }
 
