@@ -542,6 +542,12 @@ def run_ours(args):
         'episode_stats': head_stats,
         'configs': extra,
     }
+    if world == 1 and not args.no_extra:
+        try:
+            out['encoder'] = encoder_leg(crl, torch, dev)
+            out['gpu_launches_detail']['encoder leg (zone + head kernels, not in gpu_launches)'] = 'see encoder.timing'
+        except Exception as ex:
+            out['encoder'] = {'error': repr(ex)}
     if world == 1 and not args.no_cpu_baseline:
         try:
             os.sched_setaffinity(0, all_cores)                        # the CPU baseline gets ALL host cores back
@@ -551,6 +557,72 @@ def run_ours(args):
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def encoder_leg(crl, torch, dev, envs=65536, hidden=185, seconds=0.3):
+    """the rollout-time ZoneEnvModel.forward (main/src/env_model.py:48-79, h = 185:
+    scripts/train_ppo.py:66) on the observations of `envs` PointTSP envs through ZoneEncoder (two tcgen05 kernels of this
+    library: zone_net_ + mean-pool fused, then combine_net_([obs, L3(pooled)]) as one folded GEMM).  Device time, CUDA
+    events, input replicas larger than 2 x L2 cycled, random-init weights.  Tensor roofline: useful flops of the fused zone
+    kernel's two layers against the measured bf16 peak."""
+    spec = crl.ENV_SPECS['PointTSP-v0']
+    N, Z, h, B = spec.num_zones, spec.zone_dim, hidden, envs
+    g = torch.Generator(device=dev).manual_seed(7)
+    rn = lambda *sh, scale=1.0: torch.randn(*sh, device=dev, generator=g) * scale
+    sd = {'zone_net_.0.weight': rn(h, 8 + Z, scale=0.3), 'zone_net_.0.bias': rn(h, scale=0.1),
+          'zone_net_.2.weight': rn(h, h, scale=0.1), 'zone_net_.2.bias': rn(h, scale=0.1),
+          'zone_net_.4.weight': rn(h, h, scale=0.1), 'zone_net_.4.bias': rn(h, scale=0.1),
+          'combine_net_.weight': rn(h, 8 + h, scale=0.1), 'combine_net_.bias': rn(h, scale=0.1)}
+    enc = crl.ZoneEncoder(sd, num_zones=N, device=dev)
+    env = crl.ZoneVecEnv('PointTSP-v0', B, device=dev)
+    env.seed(3)
+    obs = env.reset()
+    for _ in range(4):
+        obs, *_ = env.step_random(action_seed=9)
+    in_bytes = B * (8 + N * Z) * 4
+    reps = max(2, -(-2 * L2_BYTES // in_bytes))
+    o_r = [obs['obs'].clone() for _ in range(reps)]
+    z_r = [obs['zone_obs'].clone() for _ in range(reps)]
+    pooled = torch.empty(B, h, device=dev)
+
+    def timed(fn):
+        for i in range(5):
+            fn(i % reps)
+        torch.cuda.synchronize()
+        per, n = [], 0
+        t_end = time.perf_counter() + seconds
+        while time.perf_counter() < t_end or len(per) < 3:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(20):
+                fn((n + i) % reps)
+            e1.record()
+            torch.cuda.synchronize()
+            per.append(e0.elapsed_time(e1) / 20 * 1e-3)
+            n += 20
+        per.sort()
+        return per[len(per) // 2]
+
+    t_zone = timed(lambda i: enc.pooled(o_r[i], z_r[i], out=pooled))
+    t_fwd = timed(lambda i: enc(o_r[i], z_r[i]))
+    t_state = timed(lambda i: enc.forward_from_state(env))
+    ok = enc.healthy()
+    useful = B * N * 2 * ((8 + Z) * h + h * h)
+    pk = 2250.0
+    pp = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(pp):
+        with open(pp) as f:
+            pk = json.load(f).get('bf16_tflops', pk)
+    del env
+    return {'op': 'ZoneEnvModel.forward (env_model.py:48-79), rollout time, bf16 operands / fp32 accumulation',
+            'workload': f'PointTSP-v0 observations of {B} envs, N={N}, Z={Z}, h={h}, random-init weights',
+            'healthy': ok, 'forward_us': t_fwd * 1e6, 'zone_kernel_us': t_zone * 1e6,
+            'forward_from_state_us': t_state * 1e6, 'envs_per_s': B / t_fwd,
+            'launches_per_forward': 2,
+            'roofline': {'bound': 'tensor', 'kernel': 'zone_encode_kernel', 'achieved': useful / t_zone / 1e12, 'peak': pk,
+                         'unit': 'TFLOP/s', 'frac': useful / t_zone / 1e12 / pk},
+            'l2': f'{reps} input replicas ({reps * in_bytes >> 20} MB) cycled; forward_from_state reads one env\'s state planes',
+            'timing': 'median group of 20 calls, CUDA events'}
 
 
 def head_ring_desc(step_bytes, B):

@@ -14,7 +14,7 @@ TASK_TSP, TASK_TTSP, TASK_CM = 0, 1, 2
 SEED_INCREMENT, SEED_FIXED_RANGE = 0, 1
 STEP_AUTO_RESET, STEP_PHYSICS_ONLY, STEP_CHAINED, STEP_CHAIN_START, STEP_TRACK_ROWS = 1, 2, 4, 8, 16
 STEP_GOALS, STEP_WAIT, STEP_ACTION_COUNTER, STEP_HOST_ZERO_COPY, STEP_NO_ZONE_OBS, STEP_HOST_PLANES = 32, 64, 128, 256, 512, 1024
-ABI_VERSION = 6
+ABI_VERSION = 7
 NUM_PLANES = 23
 
 # every symbol include/crl_b200.h declares
@@ -32,7 +32,7 @@ class CrlConfig(ctypes.Structure):
                 ('env_offset', c_int32), ('min_seed', c_int64), ('max_seed', c_int64),
                 ('zone_size', c_double), ('time_saved_reward', c_double), ('beta_a', c_double),
                 ('beta_b', c_double), ('robot_keepout', c_double), ('zone_keepout', c_double),
-                ('extent', c_double), ('initial_visited', c_uint32), ('reserved_', c_uint32)]
+                ('extent', c_double), ('initial_visited', c_uint32), ('walled', c_uint32)]
 
 
 class CrlState(ctypes.Structure):

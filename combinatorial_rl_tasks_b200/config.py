@@ -20,6 +20,7 @@ class TaskSpec:
     zone_keepout: float = 0.55     # ZoneEnvBase.py:50
     extent: float = 3.0            # ZoneEnvBase.py:41
     goals: bool = False            # goal-conditioned "next city" variant (zone-goals/envs/*_next_city_env.py)
+    walled: bool = False           # `walled=True` (ZoneEnvBase.py:39,55-62): wall boxes around the arena; no registration sets it
     # hard instances (TSP_hard_env.py over main/envs/__init__.py:52-81): Engine's robot_locations[0],
     # robot_rot, zones_locations (the first len() zones) and zones_colours (5 = Yellow = starts visited,
     # 6 = Cyan = a city; zone enum ZoneEnvBase.py:13-21)
@@ -91,3 +92,9 @@ ENV_SPECS.update({
     'zone-goals/PointTSP-v5': TaskSpec(_lib.TASK_TSP, 15, 300, 6, goals=True, robot_location=(0.8, 0.8),
                                        zones_locations=_ZONES_2, zones_colours=(6,) * 3 + (5,) * 12),
 })
+# `walled=True` (main/envs/zone_envs/ZoneEnvBase.py:39,55-62): no registration of the reference sets it
+# (main/envs/__init__.py:7-50), so there is no gym id; 'walled/<id>' names the env the reference's class builds
+# from <id>'s config with walled=True (tests/golden/gen_golden_walls.py builds exactly that).
+import dataclasses as _dc
+ENV_SPECS.update({'walled/' + k: _dc.replace(ENV_SPECS[k], walled=True)
+                  for k in ('PointTSP-v0', 'PointTSP-v1', 'PointTTSP-v0', 'PointTTSP-v1', 'ColourMatch-v0')})

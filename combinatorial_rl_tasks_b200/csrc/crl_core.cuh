@@ -15,8 +15,10 @@
 
 #if defined(__CUDACC__)
 #define CRL_HD __host__ __device__ __forceinline__
+#define CRL_HD_COLD inline __host__ __device__ __noinline__        /* rare paths: keep them out of the callers' register allocation */
 #else
 #define CRL_HD inline
+#define CRL_HD_COLD inline
 #endif
 
 namespace crl {
@@ -72,12 +74,109 @@ CRL_HD void constraint_acc(float& ax, float& ay, float& ath, float vx, float vy,
 
 CRL_HD float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 
+// ---- walls (`walled=True`, ZoneEnvBase.py:55-62): twin of oracle/mj_point.py::wall_force -------------------------
+// 244 box geoms of half-size 0.1 centred on the square of half-width `extent` = 3 at every multiple of 0.1 (both rows and
+// both columns list their corner box: the corners hold two boxes, as in the reference's list).  The robot's sphere
+// (radius 0.1, centre at the boxes' centre height, so the geometry is planar) touches a box when the distance from its
+// centre to the nearest point of the box is below the radius.  MuJoCo's soft contact as recalled (default solref 0.02 / 1,
+// solimp 0.9 / 0.95 / 0.001 / 0.5 / 2), NORMAL rows only -- frictionless, the pointarrow box ignored, R_ii = (1 - d) / d
+// A_ii: PARITY UNPINNED and simplified, see the oracle's header.  Contacts with the same normal and depth (the face
+// contacts of one wall: two or three overlapping boxes) are one row with a multiplicity.  Returns the generalised
+// constraint force (Fx, Fy) in the world frame; it has no yaw component (the contact normal passes through the hinge).
+constexpr double kWallHalf = 0.1, kSphereR = 0.1, kWallPitch = 0.1;
+constexpr double kSolTc = 0.02, kSolD0 = 0.9, kSolDmax = 0.95, kSolWidth = 0.001;
+constexpr double kD0 = kIHinge - kK * kK / kMass;             // I - k^2 / m of the bare mass matrix
+constexpr int kMaxWallRows = 12;
+
+CRL_HD float wall_impedance(float dist) {
+  const float x = fminf(fabsf(dist) * (float)(1.0 / kSolWidth), 1.f);
+  const float y = x <= 0.5f ? 2.f * x * x : 1.f - 2.f * (1.f - x) * (1.f - x);     // midpoint 0.5, power 2
+  return (float)kSolD0 + y * (float)(kSolDmax - kSolD0);
+}
+
+struct WallForce { float fx, fy; };
+
+// (X, Y): sphere centre; (c, s) = (cos, sin) of the heading; (vx, vy): velocity; (tx, ty, tth): the smooth generalised
+// force (actuators + centrifugal bias + damping) of this substep.  By value on purpose (see profiles/r02_notes.md on
+// what a by-reference Env does to the step kernel's stack frame).
+CRL_HD_COLD WallForce wall_force(float X, float Y, float c, float s, float vx, float vy, float tx, float ty, float tth,
+                            float extent) {
+  float nx[kMaxWallRows], ny[kMaxWallRows], dist[kMaxWallRows], mult[kMaxWallRows];
+  int rows = 0;
+  const float half = (float)kWallHalf, R = (float)kSphereR, pitch = (float)kWallPitch;
+  const int jmax = (int)(extent / pitch + 0.5f);
+#pragma unroll 1
+  for (int wall = 0; wall < 4; ++wall) {
+    // wall 0 / 1: boxes at (+-extent, j pitch); wall 2 / 3: boxes at (j pitch, +-extent)
+    const float sign = (wall & 1) ? -1.f : 1.f;
+    const float across = wall < 2 ? X : Y, along = wall < 2 ? Y : X;
+    if (sign * across <= extent - half - R - 1e-3f) continue;              // this wall's inner face is out of reach
+    const int jc = (int)rintf(along / pitch);
+#pragma unroll 1
+    for (int dj = -2; dj <= 2; ++dj) {
+      const int j = jc + dj;
+      if (j < -jmax || j > jmax) continue;
+      const float bc_across = sign * extent, bc_along = (float)j * pitch;
+      const float da = across - clampf(across, bc_across - half, bc_across + half);
+      const float dl = along - clampf(along, bc_along - half, bc_along + half);
+      const float len = sqrtf(da * da + dl * dl);
+      if (len <= 0.f || len >= R) continue;
+      const float n_across = da / len, n_along = dl / len;
+      const float ex = wall < 2 ? n_across : n_along, ey = wall < 2 ? n_along : n_across;
+      const float d = len - R;
+      int hit = -1;
+      for (int r = 0; r < rows; ++r)
+        if (nx[r] == ex && ny[r] == ey && dist[r] == d) hit = r;
+      if (hit >= 0) { mult[hit] += 1.f; continue; }
+      if (rows < kMaxWallRows) { nx[rows] = ex; ny[rows] = ey; dist[rows] = d; mult[rows] = 1.f; ++rows; }
+    }
+  }
+  WallForce out{0.f, 0.f};
+  if (rows == 0) return out;
+  // u_r = M^-1 (nx, ny, 0) with the bare mass matrix (closed form); A_rq = n_r . u_q; a0_r = u_r . tau
+  const float k = (float)kK, inv_m = (float)(1.0 / kMass), inv_mD0 = (float)(1.0 / (kMass * kD0));
+  float ux[kMaxWallRows], uy[kMaxWallRows], rhs[kMaxWallRows], reg[kMaxWallRows], f[kMaxWallRows];
+  const float b = (float)(2.0 / (kSolDmax * kSolTc));
+  for (int r = 0; r < rows; ++r) {
+    const float ut = k * (s * nx[r] - c * ny[r]) * inv_mD0;
+    ux[r] = (nx[r] + k * s * ut) * inv_m;
+    uy[r] = (ny[r] - k * c * ut) * inv_m;
+    const float a0 = ux[r] * tx + uy[r] * ty + ut * tth;
+    const float d = wall_impedance(dist[r]);
+    const float kk = d * (float)(1.0 / (kSolDmax * kSolDmax * kSolTc * kSolTc));
+    const float aref = -b * (nx[r] * vx + ny[r] * vy) - kk * dist[r];
+    rhs[r] = aref - a0;
+    reg[r] = (1.f - d) / d * (nx[r] * ux[r] + ny[r] * uy[r]);
+    f[r] = 0.f;
+  }
+  // projected Gauss-Seidel on  sum_q mult_q A_rq f_q + reg_r f_r = rhs_r,  f >= 0  (f = the force of ONE contact of row r)
+#pragma unroll 1
+  for (int it = 0; it < 200; ++it) {
+    float delta = 0.f, scale = 0.f;
+    for (int r = 0; r < rows; ++r) {
+      float acc = reg[r] * f[r] - rhs[r];
+      for (int q = 0; q < rows; ++q) acc += mult[q] * (nx[r] * ux[q] + ny[r] * uy[q]) * f[q];
+      const float arr = mult[r] * (nx[r] * ux[r] + ny[r] * uy[r]) + reg[r];
+      const float fr = fmaxf(0.f, f[r] - acc / arr);
+      delta = fmaxf(delta, fabsf(fr - f[r]));
+      scale = fmaxf(scale, fr);
+      f[r] = fr;
+    }
+    if (delta <= 1e-7f * scale) break;
+  }
+  for (int r = 0; r < rows; ++r) {
+    out.fx += mult[r] * f[r] * nx[r];
+    out.fy += mult[r] * f[r] * ny[r];
+  }
+  return out;
+}
+
 // n MuJoCo substeps with constant ctrl.  (c, s) = (cos phi, sin phi) is carried in
 // registers and advanced by the exact rotation of h*w each substep (|h w| < 0.01, so
 // a 5th-order series is exact to fp32), instead of n full-range sincosf calls.
 // Returns the final (c, s), renormalised, for the observation.
-template <int CONTACT = CRL_CONTACT_MODEL>
-CRL_HD void substeps(Body& b, float a0, float a1, int n, float& c_out, float& s_out) {
+template <int CONTACT = CRL_CONTACT_MODEL, bool WALLS = false>
+CRL_HD void substeps(Body& b, float a0, float a1, int n, float& c_out, float& s_out, float extent = 3.f) {
   const float h = (float)kH;
   const float bl = (float)kDampLin, bt = (float)kDampYaw, g = (float)kGear;
   const float k = (float)kK, inv_m = (float)(1.0 / kMp), inv_D = (float)(1.0 / kD);
@@ -100,6 +199,17 @@ CRL_HD void substeps(Body& b, float a0, float a1, int n, float& c_out, float& s_
     float ay = (tau_y - ka * c) * inv_m;
     float a_th_c = a_th;
     constraint_acc<CONTACT>(ax, ay, a_th_c, vx, vy, w);   // model 0: nothing (compiled out)
+    if (WALLS) {
+      // a wall can only be touched from within one radius of its inner face
+      if (fmaxf(fabsf(X), fabsf(Y)) > extent - (float)(kWallHalf + kSphereR)) {
+        const WallForce wf = wall_force(X, Y, c, s, vx, vy, tau_x, tau_y, tau_th, extent);
+        // a += (M + hB)^-1 (Fx, Fy, 0), the same closed form as above
+        const float ut = k * (s * wf.fx - c * wf.fy) * inv_m * inv_D;
+        ax += (wf.fx + k * s * ut) * inv_m;
+        ay += (wf.fy - k * c * ut) * inv_m;
+        a_th_c += ut;
+      }
+    }
     vx += h * ax;
     vy += h * ay;
     w += h * a_th_c;

@@ -76,6 +76,7 @@ struct KParams {
   const uint32_t* bank_task;
   const float4* fixed;          // fixed placements (CrlState.fixed_layout), or nullptr
   uint32_t init_hi;             // visited mask an episode starts with (CrlConfig.initial_visited)
+  uint32_t walled;              // CrlConfig.walled: the arena's wall boxes exist (EXT kernels only)
   // io
   const float2* actions;
   float4* obs;
@@ -1280,7 +1281,8 @@ __global__ void __maxnreg__(MaxRegs<N>::v) step_kernel(const __grid_constant__ K
     // an env rebuilt by the auto-reset still integrates its OLD body: the shaped reward of the
     // episode's last step is measured at the post-physics position (TSP_next_city_env.py:57-67)
     Body pb = fresh ? old_b : env.b;
-    substeps(pb, act.x, act.y, p.frameskip, c, s);
+    if (p.walled) substeps<CRL_CONTACT_MODEL, true>(pb, act.x, act.y, p.frameskip, c, s, p.extent);   // ZoneEnvBase.py:55-62
+    else substeps(pb, act.x, act.y, p.frameskip, c, s);
     if (fresh) {
       sincosf(env.b.phi, &s, &c);
     } else {
@@ -1591,6 +1593,9 @@ static int check_config(const CrlConfig* c) {
   if (c->seed_mode == CRL_SEED_FIXED_RANGE && c->max_seed < c->min_seed) return CRL_ERR_CONFIG;
   if (!(c->zone_size > 0.0)) return CRL_ERR_CONFIG;
   if (c->task != CRL_TASK_CM && (c->initial_visited >> c->num_zones) != 0u) return CRL_ERR_CONFIG;
+  if (c->walled > 1u) return CRL_ERR_CONFIG;
+  // walled: every placement stays keepout (>= 0.4) inside the extents, i.e. clear of the wall boxes of half-size 0.1
+  if (c->walled && (c->robot_keepout < 0.2 || c->zone_keepout < 0.1)) return CRL_ERR_CONFIG;
   return CRL_OK;
 }
 
@@ -1648,6 +1653,7 @@ static int fill_params(const CrlConfig* c, const CrlState* st, const CrlOut* out
     p.fixed = reinterpret_cast<const float4*>(st->fixed_layout);
   }
   p.init_hi = c->task == CRL_TASK_CM ? 0u : c->initial_visited;
+  p.walled = c->walled;
   p.stamp = st->stamp;
   p.act_count = st->stamp ? st->stamp + 2 * (size_t)((c->num_envs + 31) / 32) : nullptr;
   p.epoch = st->prefetch_epoch;
@@ -1788,7 +1794,8 @@ static int step_launch(const CrlConfig* c, const CrlState* st, const float* acti
   if (!(flags & CRL_STEP_NO_ZONE_OBS) && !p.zone_obs) return CRL_ERR_NULL;
   if ((flags & CRL_STEP_NO_ZONE_OBS) && (zone_obs_host || (flags & CRL_STEP_TRACK_ROWS))) return CRL_ERR_CONFIG;
   if ((flags & CRL_STEP_HOST_PLANES) && (!zone_obs_host || c->task != CRL_TASK_TTSP)) return CRL_ERR_CONFIG;
-  const bool ext = (flags & (CRL_STEP_GOALS | CRL_STEP_WAIT)) != 0u;
+  // the walls live in the EXT kernels only (the plain rollout kernels keep their register allocation)
+  const bool ext = (flags & (CRL_STEP_GOALS | CRL_STEP_WAIT)) != 0u || c->walled != 0u;
   // Programmatic launch (this grid may start while its predecessor drains) is safe when the
   // kernel then waits for the whole predecessor (plain, chain start) or for its own previous
   // step (chained).  After a CHAINED launch, though, "the predecessor is complete" no longer

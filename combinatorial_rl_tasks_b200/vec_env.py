@@ -92,7 +92,7 @@ class ZoneVecEnv:
             env_offset=env_offset, min_seed=min_seed, max_seed=max_seed, zone_size=spec.zone_size,
             time_saved_reward=spec.time_saved_reward, beta_a=spec.beta_a, beta_b=spec.beta_b,
             robot_keepout=spec.robot_keepout, zone_keepout=spec.zone_keepout, extent=spec.extent,
-            initial_visited=spec.initial_visited)
+            initial_visited=spec.initial_visited, walled=1 if spec.walled else 0)
         dev = self.device
         z = lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype, device=dev)
         # state planes (layout documented in include/crl_b200.h)

@@ -70,7 +70,7 @@
 extern "C" {
 #endif
 
-#define CRL_ABI_VERSION 6
+#define CRL_ABI_VERSION 7
 #define CRL_MAX_ZONES 16
 
 /* task ids; reference classes: main/envs/TSP_env.py:11, TTSP_env.py:12, colour_match_env.py:11 */
@@ -172,7 +172,11 @@ typedef struct CrlConfig {
    * main/envs/__init__.py:52-81: Cyan = a city, Yellow = a distractor that counts as visited).
    * 0 for every other registration.  Ignored by ColourMatch. */
   uint32_t initial_visited;
-  uint32_t reserved_;    /* keep 0 */
+  /* 1: `walled=True` (main/envs/zone_envs/ZoneEnvBase.py:39,55-62): 244 box geoms of half-size 0.1 centred on the
+   * square of half-width `extent` at every multiple of 0.1; the robot's sphere collides with them (soft contact,
+   * normal rows only: PARITY UNPINNED and simplified -- DESIGN.md 4.9).  No registration of the reference sets it
+   * (main/envs/__init__.py:7-50); 0 everywhere else.  A walled env steps through the EXT kernels. */
+  uint32_t walled;
 } CrlConfig;
 
 typedef struct CrlState {

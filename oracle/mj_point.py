@@ -156,13 +156,86 @@ def constraint_force(qpos, qvel, qfrc_smooth, h=TIMESTEP):
     return A @ (-CONTACT_IMPEDANCE * (a_smooth + CONTACT_B * qvel))
 
 
-def substep(qpos, qvel, ctrl, h=TIMESTEP):
+# ---- walls (ZoneEnvBase.py:55-62, `walled=True`): box geoms the robot's sphere can touch ------------------------
+# PARITY UNPINNED, and SIMPLIFIED: MuJoCo's soft-contact model as recalled from its documentation ("Computation /
+# Solver parameters"), default solref = (timeconst 0.02, dampratio 1) and solimp = (0.9, 0.95, 0.001, 0.5, 2), for the
+# NORMAL row of each sphere-box contact only: no friction rows (pyramidal cone edges), no contacts of the `pointarrow`
+# box geom, regulariser R_ii = (1 - d) / d x the exact A_ii instead of MuJoCo's diagApprox.  What is restated: contact
+# detection (sphere centre to the nearest point of each box, dist < 0), impedance d(|dist|), reference acceleration
+# a_ref = -b v - k dist with b = 2 / (dmax tc), k = d / (dmax^2 tc^2 dr^2), and the constrained minimisation
+# f >= 0,  (A + R) f + J a_smooth - a_ref >= 0, complementary -- solved by projected Gauss-Seidel to convergence.
+SOLREF_TC, SOLREF_DR = 0.02, 1.0
+SOLIMP_D0, SOLIMP_DMAX, SOLIMP_WIDTH, SOLIMP_MID, SOLIMP_POWER = 0.9, 0.95, 0.001, 0.5, 2.0
+
+
+def impedance(dist):
+    """d(r) of solimp for penetration r = |dist| (MuJoCo 2.0's five-parameter sigmoid)."""
+    x = min(abs(dist) / SOLIMP_WIDTH, 1.0)
+    if x <= SOLIMP_MID:
+        y = x ** SOLIMP_POWER / SOLIMP_MID ** (SOLIMP_POWER - 1.0)
+    else:
+        y = 1.0 - (1.0 - x) ** SOLIMP_POWER / (1.0 - SOLIMP_MID) ** (SOLIMP_POWER - 1.0)
+    return SOLIMP_D0 + y * (SOLIMP_DMAX - SOLIMP_D0)
+
+
+def sphere_box_contacts(centre_xy, boxes_xy, half):
+    """Contacts of the robot's sphere (radius SPHERE_R, centre height == box centre height, so the geometry is planar)
+    with axis-aligned boxes of half-size `half`: list of (normal (2,), dist < 0), normal from the box to the sphere."""
+    out = []
+    c = np.asarray(centre_xy, dtype=np.float64)
+    near = np.abs(boxes_xy - c).max(axis=1) < half + SPHERE_R
+    for b in boxes_xy[near]:
+        nearest = np.minimum(np.maximum(c, b - half), b + half)
+        d = c - nearest
+        ln = math.sqrt(float(d @ d))
+        if ln == 0.0:          # centre inside a box: never reached with these stiffnesses
+            continue
+        dist = ln - SPHERE_R
+        if dist < 0.0:
+            out.append((d / ln, dist))
+    return out
+
+
+def wall_force(qpos, qvel, qfrc_smooth, walls):
+    """qfrc_constraint of the sphere-wall contacts.  `walls` = dict(p0 (2,), rot0, boxes (K, 2), half)."""
+    c0, s0 = math.cos(walls['rot0']), math.sin(walls['rot0'])
+    ax_x, ax_y = np.array([c0, s0]), np.array([-s0, c0])       # the slides' axes in the world
+    centre = walls['p0'] + ax_x * qpos[0] + ax_y * qpos[1]
+    contacts = sphere_box_contacts(centre, walls['boxes'], walls['half'])
+    if not contacts:
+        return np.zeros(3)
+    J = np.array([[n @ ax_x, n @ ax_y, 0.0] for n, _ in contacts])    # the contact point is on the hinge axis' normal
+    Minv = np.linalg.inv(mass_matrix(qpos[2]))
+    A = J @ Minv @ J.T
+    a0 = J @ (Minv @ qfrc_smooth)
+    vel = J @ qvel
+    d = np.array([impedance(dist) for _, dist in contacts])
+    b = 2.0 / (SOLIMP_DMAX * SOLREF_TC)
+    k = d / (SOLIMP_DMAX ** 2 * SOLREF_TC ** 2 * SOLREF_DR ** 2)
+    aref = -b * vel - k * np.array([dist for _, dist in contacts])
+    R = (1.0 - d) / d * np.diag(A)
+    f = np.zeros(len(contacts))
+    for _ in range(10000):                                      # projected Gauss-Seidel
+        delta = 0.0
+        for i in range(len(f)):
+            resid = A[i] @ f + R[i] * f[i] + a0[i] - aref[i]
+            fi = max(0.0, f[i] - resid / (A[i, i] + R[i]))
+            delta = max(delta, abs(fi - f[i]))
+            f[i] = fi
+        if delta < 1e-15:
+            break
+    return J.T @ f
+
+
+def substep(qpos, qvel, ctrl, h=TIMESTEP, walls=None):
     """One mj_step.  Returns new (qpos, qvel); inputs are not modified."""
     theta = qpos[2]
     M = mass_matrix(theta)
     passive = -DAMPING * qvel
     smooth = passive - bias_force(theta, qvel) + actuator_force(theta, qvel, ctrl)
     total = smooth + constraint_force(qpos, qvel, smooth)
+    if walls is not None:
+        total = total + wall_force(qpos, qvel, smooth, walls)
     qacc = np.linalg.solve(M + h * np.diag(DAMPING), total)
     qvel_new = qvel + h * qacc
     qpos_new = qpos + h * qvel_new
@@ -211,7 +284,11 @@ class PointSim:
     contype = conaffinity = 0, so they never collide).
     """
 
-    def __init__(self, robot_xy, robot_rot, static_bodies=None, geom_rgba=None):
+    def __init__(self, robot_xy, robot_rot, static_bodies=None, geom_rgba=None, wall_boxes=None, wall_half=0.1):
+        # wall_boxes: (K, 2) centres of the `walled=True` box geoms (ZoneEnvBase.py:55-62); None = no walls
+        self.walls = None if wall_boxes is None or not len(wall_boxes) else {
+            'p0': np.array([robot_xy[0], robot_xy[1]], dtype=np.float64), 'rot0': float(robot_rot),
+            'boxes': np.asarray(wall_boxes, dtype=np.float64).reshape(-1, 2), 'half': float(wall_half)}
         self.robot_p0 = np.array([robot_xy[0], robot_xy[1], BODY_Z], dtype=np.float64)
         q0 = np.array([math.cos(robot_rot / 2.0), 0.0, 0.0, math.sin(robot_rot / 2.0)])
         self.robot_q0 = q0 / math.sqrt(float(q0 @ q0))
@@ -226,7 +303,7 @@ class PointSim:
         self.forward()
 
     def step(self):
-        self.data.qpos, self.data.qvel = substep(self.data.qpos, self.data.qvel, self.data.ctrl)
+        self.data.qpos, self.data.qvel = substep(self.data.qpos, self.data.qvel, self.data.ctrl, walls=self.walls)
         self.data.time += TIMESTEP
 
     def forward(self):

@@ -70,7 +70,12 @@ class _World:
         geoms = config.get('geoms', {})
         static = {name: np.asarray(g['pos'], dtype=np.float64) for name, g in geoms.items()}
         rgba = {name: np.asarray(g['rgba'], dtype=np.float64) for name, g in geoms.items()}
-        self.sim = mj_point.PointSim(config['robot_xy'], config['robot_rot'], static, rgba)
+        # box geoms with collisions on = the walls (Engine.build_world_config [upstream]: size = walls_size in all three
+        # dimensions, centre height = walls_size -- the height of the robot's sphere centre for walls_size 0.1)
+        boxes = [g for g in geoms.values() if g.get('type') == 'box' and g.get('group') == GROUP_WALL]
+        self.sim = mj_point.PointSim(config['robot_xy'], config['robot_rot'], static, rgba,
+                                     wall_boxes=[g['pos'][:2] for g in boxes] if boxes else None,
+                                     wall_half=float(boxes[0]['size'][0]) if boxes else 0.1)
         self.model = self.sim.model
         self.data = self.sim.data
 
@@ -311,7 +316,12 @@ class Engine(Env):
             world_config['robot_rot'] = float(self.robot_rot)
         world_config['objects'] = {}
         world_config['geoms'] = {}
-        assert self.walls_num == 0, 'walls are outside the oracle'
+        for i in range(self.walls_num):                            # Engine.build_world_config [upstream]
+            name = f'wall{i}'
+            assert self.walls_size == mj_point.BODY_Z, 'the oracle\'s planar sphere-box contact needs walls_size == 0.1'
+            world_config['geoms'][name] = {'name': name, 'size': np.ones(3) * self.walls_size,
+                                           'pos': np.r_[self.layout[name], self.walls_size], 'rot': 0, 'type': 'box',
+                                           'group': GROUP_WALL, 'rgba': np.array([.5, .5, .5, 1.0])}
         return world_config
 
     def build(self):

@@ -63,6 +63,8 @@ HARD = {
 HARD['zone-goals/PointTSP-v4'] = dict(HARD['PointTSP-v4'])
 HARD['zone-goals/PointTSP-v5'] = dict(HARD['PointTSP-v5'], num_steps=300)
 TASK_OF_ENV_ID.update({k: TSP for k in HARD})
+# `walled=True` builds of the registered configs (make_task_env; tests/golden/gen_golden_walls.py)
+TASK_OF_ENV_ID.update({'walled/' + k: v for k, v in list(TASK_OF_ENV_ID.items()) if k in ('PointTSP-v0', 'PointTTSP-v0', 'ColourMatch-v0')})
 
 NUM_STEPS = 2000            # envs/__init__.py:13, :49
 NUM_ZONES = {TSP: 15, TTSP: 15, CM: 6}   # envs/__init__.py:9, :45
@@ -92,7 +94,19 @@ def hamming_to_goal(colours):
     return min(2 * ng + nr, 2 * nr + nb, 2 * nb + ng)
 
 
-def sample_layout(rs, num_zones, robot_locations=(), zones_locations=(), robot_rot=None):
+def wall_locations(extent=3):
+    """The box centres of a `walled=True` env, in the reference's order (ZoneEnvBase.py:55-57): the two rows y = -+extent
+    point by point in x (steps of 0.1), then the two columns x = -+extent point by point in y."""
+    w = [(i / 10, j) for i in range(int(-extent * 10), int(extent * 10 + 1), 1) for j in [-extent, extent]]
+    w += [(i, j / 10) for i in [-extent, extent] for j in range(int(-extent * 10), int(extent * 10 + 1), 1)]
+    return w
+
+
+WALLS_SIZE = 0.1          # ZoneEnvBase.py:61
+WALLS_KEEPOUT = 0.0       # Engine default [upstream]
+
+
+def sample_layout(rs, num_zones, robot_locations=(), zones_locations=(), robot_rot=None, walls=(), walls_out=None):
     """Engine.build_layout / sample_layout / build_world_config [upstream],
     specialised to: robot (keepout .4) then ``num_zones`` zones (keepout .55),
     extents +-3.  Consumes ``rs`` exactly as upstream does
@@ -102,8 +116,10 @@ def sample_layout(rs, num_zones, robot_locations=(), zones_locations=(), robot_r
     -- still consuming two uniforms -- from the box of half-width keepout + 1e-9 around it
     shrunk by keepout, i.e. within 1e-9 of the location, and must pass the same keepout
     test.  A fixed ``robot_rot`` draws nothing.  Returns xy0, rot0, zone_xy."""
-    keepouts = [ROBOT_KEEPOUT] + [ZONE_KEEPOUT] * num_zones
-    locations = [robot_locations[0] if len(robot_locations) else None]
+    # build_placements_dict order [upstream]: robot, walls (fixed locations, keepout 0: they never reject anything but
+    # each consumes two uniforms per layout attempt), then the zones (ZoneEnvBase.py:118-122)
+    keepouts = [ROBOT_KEEPOUT] + [WALLS_KEEPOUT] * len(walls) + [ZONE_KEEPOUT] * num_zones
+    locations = [robot_locations[0] if len(robot_locations) else None] + list(walls)
     locations += [zones_locations[i] if i < len(zones_locations) else None for i in range(num_zones)]
     for _ in range(10000):
         placed = []
@@ -132,7 +148,9 @@ def sample_layout(rs, num_zones, robot_locations=(), zones_locations=(), robot_r
     rot0 = rs.uniform(0, 2 * np.pi) if robot_rot is None else float(robot_rot)
     for _ in range(num_zones):
         rs.uniform(0, 2 * np.pi)
-    return placed[0][0], rot0, np.array([p for p, _ in placed[1:]])
+    if walls_out is not None:        # where the boxes really are: each drawn within 1e-9 of its location
+        walls_out[:] = [p for p, _ in placed[1:1 + len(walls)]]
+    return placed[0][0], rot0, np.array([p for p, _ in placed[1 + len(walls):]])
 
 
 class ZoneTaskEnv:
@@ -143,8 +161,10 @@ class ZoneTaskEnv:
     xy0 (2,), rot0, zone_xy (N,2) and, per task, zone_max_steps (N,) / colours (N,).
     """
 
-    def __init__(self, task, num_zones=None, num_steps=NUM_STEPS, goals=False, hard=None):
+    def __init__(self, task, num_zones=None, num_steps=NUM_STEPS, goals=False, hard=None, walled=False):
         self.task = task
+        self.walls = wall_locations(EXTENT) if walled else []   # `walled=True` (ZoneEnvBase.py:39,55-62)
+        self.wall_xy = list(self.walls)                         # as placed by the last sampled layout
         # hard instance: dict with zones_locations, zones_colours, robot_locations, robot_rot
         self.hard = hard
         self.goals = goals          # the *_next_city_env.py variants
@@ -175,7 +195,8 @@ class ZoneTaskEnv:
             self.rs = np.random.RandomState(self._seed)
             h = self.hard or {}
             xy0, rot0, zone_xy = sample_layout(self.rs, N, h.get('robot_locations', ()),
-                                               h.get('zones_locations', ()), h.get('robot_rot'))
+                                               h.get('zones_locations', ()), h.get('robot_rot'), walls=self.walls,
+                                               walls_out=self.wall_xy)
         else:
             xy0, rot0, zone_xy = layout['xy0'], layout['rot0'], layout['zone_xy']
             if self.task == TTSP:
@@ -192,7 +213,7 @@ class ZoneTaskEnv:
         if self.task == CM:
             self.cooldown = np.zeros(N, dtype=np.int64)
             self.goal_dist = hamming_to_goal(self.colours)
-        self.sim = mj_point.PointSim(self.xy0, self.rot0)
+        self.sim = mj_point.PointSim(self.xy0, self.rot0, wall_boxes=self.wall_xy or None, wall_half=WALLS_SIZE)
         self.steps = 0
         self.done = False
         self.event = 0
@@ -392,6 +413,10 @@ def make_task_env(env_id):
         h = HARD[env_id]
         return ZoneTaskEnv(TSP, num_zones=h['num_zones'], num_steps=h['num_steps'], goals=env_id in GOAL_ENV_IDS,
                            hard=h)
+    if env_id.startswith('walled/'):
+        # no registration of the reference says walled=True (main/envs/__init__.py:7-50); 'walled/<id>' names the env
+        # the real class builds from that id's config with walled=True (tests/golden/gen_golden_walls.py)
+        return ZoneTaskEnv(TASK_OF_ENV_ID[env_id[len('walled/'):]], walled=True)
     return ZoneTaskEnv(TASK_OF_ENV_ID[env_id], goals=env_id in GOAL_ENV_IDS)
 
 

@@ -17,6 +17,12 @@ void hc_substeps_contact_active(float* st, float a0, float a1, int n, float* cs)
   crl::substeps<1>(b, a0, a1, n, cs[0], cs[1]);
   st[0] = b.X; st[1] = b.Y; st[2] = b.phi; st[3] = b.vx; st[4] = b.vy; st[5] = b.w;
 }
+// substeps with the walls of a `walled=True` env (crl_core.cuh::wall_force), extent 3
+void hc_substeps_walled(float* st, float a0, float a1, int n, float* cs) {
+  crl::Body b{st[0], st[1], st[2], st[3], st[4], st[5]};
+  crl::substeps<CRL_CONTACT_MODEL, true>(b, a0, a1, n, cs[0], cs[1], 3.f);
+  st[0] = b.X; st[1] = b.Y; st[2] = b.phi; st[3] = b.vx; st[4] = b.vy; st[5] = b.w;
+}
 float hc_wrap_pi(float phi) { return crl::wrap_pi(phi); }
 double hc_sqrt_threshold(double r) { return crl::sqrt_threshold(r); }
 int hc_inside_zone(float X, float Y, float zx, float zy, double t2) { return crl::inside_zone(X, Y, zx, zy, t2); }

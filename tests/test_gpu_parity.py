@@ -21,7 +21,7 @@ from tests._driver import policy  # noqa: E402
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 EPISODES = sorted(f for f in glob.glob(os.path.join(GOLDEN, '*.npz'))
-                  if not f.endswith('_vector.npz') and not os.path.basename(f).startswith(('goals_', 'gae_', 'model_', 'hardgoals_', 'hardvec_')))   # incl. hard_*: PointTSP-v4 / v5
+                  if not f.endswith('_vector.npz') and not os.path.basename(f).startswith(('goals_', 'gae_', 'model_', 'hardgoals_', 'hardvec_', 'walls_')))   # incl. hard_*: PointTSP-v4 / v5; walls_*: test_gpu_walls.py
 
 PHYS_RTOL = 1e-5       # per substep, from identical inputs (the north-star bar)
 REWARD_ATOL = 1e-6
@@ -83,7 +83,7 @@ def check_obs(task, obs_gpu, zobs_gpu, obs_ref, zobs_ref, where):
 def test_library_is_the_cuda_one(crl):
     from combinatorial_rl_tasks_b200 import _lib
     lib = _lib.load()
-    assert lib.crl_abi_version() == _lib.ABI_VERSION == 6
+    assert lib.crl_abi_version() == _lib.ABI_VERSION == 7
     with open('/proc/self/maps') as f:
         assert 'libcrl_b200.so' in f.read()
 

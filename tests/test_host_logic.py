@@ -48,7 +48,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.crl_abi_version() == 6
+    assert lib.crl_abi_version() == 7
     assert b'NULL' in lib.crl_strerror(-1)
 
 
