@@ -93,7 +93,7 @@ __host__ __device__ inline Offsets offsets(int h, int in_dim) {
   o.xbuf = o.h1 + (uint32_t)KP * kRows * 2;
   o.bar = o.xbuf + (uint32_t)kRows * kK1 * 2;
   o.group_bytes = (o.bar + 40 + 127u) & ~127u;           // five mbarriers per slot (kBarBytes)
-  o.tmem_slot = o.group0 + kGroups * o.group_bytes;
+  o.tmem_slot = o.group0 + kGroups * o.group_bytes;    // + 8: the mbarrier of the weights' bulk copy
   o.smem_end = o.tmem_slot + 16;
   return o;
 }
@@ -358,6 +358,17 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0u;
 }
+// Resident weights: global -> shared memory by the bulk-copy engine (cp.async.bulk, UBLKCP in SASS), completion counted
+// in bytes on an mbarrier.  One thread issues it; nobody waits until the first MMA needs the image, so the copy runs
+// under the first tiles' input staging (the register round trip it replaces took 13 passes of the whole CTA).
+__device__ __forceinline__ void bulk_load_weights(uint32_t bar, uint32_t smem_dst, const uint8_t* src, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+  for (uint32_t off = 0; off < bytes; off += 32768u) {
+    const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_dst + off), "l"(src + off), "r"(n), "r"(bar) : "memory");
+  }
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
 }
@@ -409,7 +420,9 @@ __global__ void __launch_bounds__(kEncThreads, 1) zone_encode_kernel(const EncAr
       mbar_init(b + kBarL2Done, 1);
       mbar_init(b + kBarL2Done + 8, 1);
     }
+    mbar_init(smem_u32(tmem_slot) + 8u, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    bulk_load_weights(smem_u32(tmem_slot) + 8u, smem_u32(smem), a.packed, o.packed_end);
   }
   if (threadIdx.x < 32) {
     __syncwarp();
@@ -417,12 +430,6 @@ __global__ void __launch_bounds__(kEncThreads, 1) zone_encode_kernel(const EncAr
                  :: "r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(a.packed);
-    uint4* dst = reinterpret_cast<uint4*>(smem);
-    for (uint32_t i = threadIdx.x; i < o.packed_end / 16; i += kEncThreads) dst[i] = __ldg(src + i);
-  }
-  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -450,6 +457,8 @@ __global__ void __launch_bounds__(kEncThreads, 1) zone_encode_kernel(const EncAr
       const int first = kGroups * (int)blockIdx.x + g;
       n[g] = first < a.n_tiles ? (a.n_tiles - first + tile_stride - 1) / tile_stride : 0;
     }
+    healthy = mbar_wait(smem_u32(tmem_slot) + 8u, 0u) && healthy;     // the resident weights have landed
+    __syncwarp();
     // descriptors differ between MMAs only in their start-address field (bits 0..13, in 16-byte units)
     const uint64_t a1_desc = smem_desc(w1_addr, 128u, 16 * kK1), a2_desc = smem_desc(w2_addr, 128u, 16 * KP);
     const uint64_t x_desc = smem_desc(slot0 + o.xbuf, 128u, 16 * kK1), h1_desc = smem_desc(slot0 + o.h1, 2048u, 128u);
@@ -661,6 +670,20 @@ struct HeadArgs {
   int B, obs_dim, h, n_tiles;
 };
 
+// unit j of 32 consecutive envs e0 ..: one base pointer, constant strides; predicates only on the batch's last tile
+__device__ __forceinline__ void head_store(const uint32_t (&v)[32], float* col, int h, int B, int e0, bool j_ok) {
+  if (!j_ok) return;
+  float* p = col + (size_t)e0 * (size_t)h;
+  if (e0 + 32 <= B) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) p[(size_t)i * h] = __uint_as_float(v[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (e0 + i < B) p[(size_t)i * h] = __uint_as_float(v[i]);
+  }
+}
+
 __global__ void __launch_bounds__(kGroupThreads * kGroups, 1) encoder_head_kernel(const HeadArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const HeadOffsets o = head_offsets(a.obs_dim, a.h);
@@ -676,7 +699,9 @@ __global__ void __launch_bounds__(kGroupThreads * kGroups, 1) encoder_head_kerne
   const uint32_t bar_addr = smem_u32(bar);
   if (t == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_addr) : "memory");
+    if (group == 0) mbar_init(smem_u32(tmem_slot) + 8u, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (group == 0) bulk_load_weights(smem_u32(tmem_slot) + 8u, smem_u32(smem), a.packed, o.packed_end);
   }
   if (threadIdx.x < 32) {
     __syncwarp();
@@ -684,12 +709,6 @@ __global__ void __launch_bounds__(kGroupThreads * kGroups, 1) encoder_head_kerne
                  :: "r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(a.packed);
-    uint4* dst = reinterpret_cast<uint4*>(smem);
-    for (uint32_t i = threadIdx.x; i < o.packed_end / 16; i += kGroupThreads * kGroups) dst[i] = __ldg(src + i);
-  }
-  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -697,12 +716,58 @@ __global__ void __launch_bounds__(kGroupThreads * kGroups, 1) encoder_head_kerne
   const uint32_t acc = tmem_base + (uint32_t)group * 256u;
   const uint32_t my_acc = acc + (uint32_t)(mblock * 128) + ((uint32_t)(quad * 32) << 16);
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kRows >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  bool weights_in = false;
   const uint32_t x_addr = smem_u32(xbuf), w_addr = smem_u32(smem + o.w);
   const bool drains = mblock < n_mblocks && mblock * 128 + quad * 32 < a.h;
   uint32_t parity = 0u;
   bool healthy = true;
   for (int tile = kGroups * blockIdx.x + group; tile < a.n_tiles; tile += kGroups * gridDim.x) {
-    // ---- B operand: the tile's 128 rows [obs, pooled, 1, 1, 0..] as bf16, K-major; consecutive threads take
+    // ---- B operand: the tile's 128 rows [obs, pooled, 1, 1, 0..] as bf16, K-major.
+    if (a.obs_dim == 8 && chunks <= 32) {
+      // ZoneEnvModel's shape: chunk 0 of a row is exactly obs[e] (two 16-byte loads), chunk c >= 1 is
+      // pooled[e][8 (c - 1) ..].  A warp takes a row at a time, lane c its chunk c -- no index arithmetic, no address
+      // selects (the general loop below spends ~10 instructions per element on them) -- four rows per iteration so that
+      // 32 loads per lane are in flight.
+#pragma unroll 1
+      for (int m0 = warp; m0 < kRows; m0 += 4 * (kGroupThreads / 32)) {
+        float x[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int m = m0 + i * (kGroupThreads / 32), e = tile * kRows + m;
+          const size_t e_ok = (size_t)(e < a.B ? e : 0);
+          if (lane == 0) {
+            const float4 lo = __ldg(reinterpret_cast<const float4*>(a.obs + e_ok * 8));
+            const float4 hi = __ldg(reinterpret_cast<const float4*>(a.obs + e_ok * 8) + 1);
+            x[i][0] = lo.x; x[i][1] = lo.y; x[i][2] = lo.z; x[i][3] = lo.w;
+            x[i][4] = hi.x; x[i][5] = hi.y; x[i][6] = hi.z; x[i][7] = hi.w;
+          } else {
+            const float* src = a.pooled + e_ok * a.h;
+            const int k0 = 8 * (lane - 1);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) x[i][q] = __ldg(src + (k0 + q < a.h ? k0 + q : 0));
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int m = m0 + i * (kGroupThreads / 32), e = tile * kRows + m;
+          if (lane >= chunks) continue;
+          if (lane > 0) {
+            const int k0 = 8 * (lane - 1);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) x[i][q] = k0 + q < a.h ? x[i][q] : (k0 + q <= a.h + 1 ? 1.f : 0.f);
+          }
+          if (e >= a.B) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) x[i][q] = 0.f;
+          }
+          *reinterpret_cast<uint4*>(xbuf + (uint32_t)((m & 7) * 16 + (m >> 3) * (16 * KH) + lane * 128)) =
+              make_uint4(pack_bf16(x[i][0], x[i][1]), pack_bf16(x[i][2], x[i][3]), pack_bf16(x[i][4], x[i][5]),
+                         pack_bf16(x[i][6], x[i][7]));
+        }
+      }
+    } else
+    // the general shape (per-env features wider than 8: ZoneEnvGoalModel / ZoneEnvSkillModel): consecutive threads take
+
     // consecutive 8-value chunks of one env (coalesced reads); a row beyond the batch is all zeros.  Four chunks
     // per iteration with UNCONDITIONAL loads from clamped addresses (the selects come after), so that 32 loads
     // are in flight per thread: this kernel is bound by how fast it reads (obs, pooled), not by the tensor pipe.
@@ -741,6 +806,7 @@ __global__ void __launch_bounds__(kGroupThreads * kGroups, 1) encoder_head_kerne
     tc_fence_before();
     group_sync(group);
     if (t == 0) {
+      if (!weights_in) { weights_in = true; healthy = mbar_wait(smem_u32(tmem_slot) + 8u, 0u) && healthy; }
       tc_fence_after();
       for (int b = 0; b < n_mblocks; ++b)
         for (int s = 0; s < KH / 16; ++s)
@@ -758,21 +824,9 @@ __global__ void __launch_bounds__(kGroupThreads * kGroups, 1) encoder_head_kerne
         tmem_ld32(my_acc + (uint32_t)(c * 32), v0);
         tmem_ld32(my_acc + (uint32_t)(c * 32 + 32), v1);
         tmem_ld_wait(v0);
-        if (j < a.h) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int e = tile * kRows + c * 32 + i;
-            if (e < a.B) a.out[(size_t)e * a.h + j] = __uint_as_float(v0[i]);
-          }
-        }
+        head_store(v0, a.out + j, a.h, a.B, tile * kRows + c * 32, j < a.h);
         tmem_ld_wait(v1);
-        if (j < a.h) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int e = tile * kRows + (c + 1) * 32 + i;
-            if (e < a.B) a.out[(size_t)e * a.h + j] = __uint_as_float(v1[i]);
-          }
-        }
+        head_store(v1, a.out + j, a.h, a.B, tile * kRows + (c + 1) * 32, j < a.h);
       }
     }
     // the next tile's MMAs overwrite the accumulators and the operand buffer: ordered after these loads by the
