@@ -23,7 +23,8 @@ SYMBOLS = ['crl_abi_version', 'crl_strerror', 'crl_plane_bytes', 'crl_step_bytes
            'crl_set_goal', 'crl_goal_query', 'crl_set_qpos_qvel',
            'crl_get_qpos_qvel', 'crl_gae', 'crl_check_state', 'crl_counters_read',
            'crl_encoder_packed_bytes', 'crl_encoder_pack', 'crl_zone_encode', 'crl_zone_encode_state',
-           'crl_encoder_head_packed_bytes', 'crl_encoder_pack_head', 'crl_encoder_head']
+           'crl_encoder_head_packed_bytes', 'crl_encoder_pack_head', 'crl_encoder_head',
+           'crl_encoder_workspace_bytes', 'crl_encoder_forward']
 
 
 class CrlConfig(ctypes.Structure):
@@ -104,6 +105,8 @@ def load():
     lib.crl_encoder_pack_head.argtypes = [P(CrlEncoderShape)] + [c_void_p] * 4
     lib.crl_encoder_head.argtypes = [P(CrlEncoderShape), c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p]
+    lib.crl_encoder_workspace_bytes.argtypes = [P(CrlEncoderShape), c_int32, P(c_int64)]
+    lib.crl_encoder_forward.argtypes = [P(CrlEncoderShape), P(CrlConfig), P(CrlState), c_int32] + [c_void_p] * 8
     for name in SYMBOLS:
         getattr(lib, name)
     if lib.crl_abi_version() != ABI_VERSION:

@@ -211,6 +211,11 @@ struct EncArgs {
   const float* zone_obs;   // [B][N][Z]
   const uint8_t* packed;
   float* out;              // [B][h]: pooled hidden activation
+  // crl_encoder_forward: instead of `out`, the kernel writes the head kernel's layer-input image directly -- per tile of
+  // 128 envs the canonical K-major bf16 operand [obs, pooled, 1, 1, 0..] (head_k columns) -- so that the head's staging is
+  // one bulk copy per tile and `pooled` never exists in fp32 (the head rounds it to bf16 anyway: identical results)
+  uint8_t* xhead;
+  int KH;                  // head_k(obs_dim, h)
   int* status;             // device int: set to 1 if a tensor-core wait expired
   int B, N, Z, obs_dim, h, n_tiles, S;   // S = slots_per_env(N)
   // crl_zone_encode_state: the zone part of the input rows is built from the STATE planes instead of being read
@@ -303,8 +308,16 @@ __device__ __forceinline__ void relu_to_h1(const uint32_t (&v)[32], uint8_t* h1_
 // 32 consecutive rows m = the zone slots of envs e0 .. e0 + 32 / S - 1: relu, sum in registers, store column j.
 // `col` = out + j (this thread's column of the output); `full`: every env of the tile exists and j < h, so the stores
 // need no predicates (their address chains were a third of epilogue 2's time).
+// bf16 `val` = pooled unit of env e into the head operand image (xh_unit: image base + the unit's offset in a row)
+__device__ __forceinline__ void xhead_store(uint8_t* xh_unit, int KH, int e, float val) {
+  const int m = e & (kRows - 1);
+  *reinterpret_cast<__nv_bfloat16*>(xh_unit + (size_t)(e >> 7) * (size_t)(kRows * KH * 2) + (uint32_t)((m & 7) * 16 + (m >> 3) * (16 * KH))) =
+      __float2bfloat16_rn(val);
+}
+
+template <bool XHEAD = false>
 __device__ __forceinline__ void relu_pool_store(const uint32_t (&v)[32], float* col, int h, int B, int S, int e0, bool full,
-                                                bool j_ok, float inv_n) {
+                                                bool j_ok, float inv_n, uint8_t* xh_unit = nullptr, int KH = 0) {
   float q[4];                                                 // sums of 8 consecutive rows
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -313,6 +326,18 @@ __device__ __forceinline__ void relu_pool_store(const uint32_t (&v)[32], float* 
     for (int i = 0; i < 4; ++i)
       s[i] = fmaxf(__uint_as_float(v[8 * g + 2 * i]), 0.f) + fmaxf(__uint_as_float(v[8 * g + 2 * i + 1]), 0.f);
     q[g] = (s[0] + s[1]) + (s[2] + s[3]);
+  }
+  if (XHEAD) {                                               // crl_encoder_forward: bf16 into the head's operand image
+    if (!j_ok) return;
+    if (S == 16) {
+      if (e0 < B) xhead_store(xh_unit, KH, e0, (q[0] + q[1]) * inv_n);
+      if (e0 + 1 < B) xhead_store(xh_unit, KH, e0 + 1, (q[2] + q[3]) * inv_n);
+    } else {
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if (e0 + g < B) xhead_store(xh_unit, KH, e0 + g, q[g] * inv_n);
+    }
+    return;
   }
   float* p = col + (size_t)e0 * (size_t)h;
   if (S == 16) {
@@ -390,7 +415,9 @@ __device__ long long g_timeline[148 * 2 * 64 * 16];
 #define CRL_TL(g, k, i) do { } while (0)
 #endif
 
-template <bool STATE>
+// XHEAD: the output goes into the head kernel's operand image (crl_encoder_forward) instead of `out`; a template
+// parameter so that the plain kernels carry none of it (with a run-time test they lost 8 % to register pressure)
+template <bool STATE, bool XHEAD>
 __global__ void __launch_bounds__(kEncThreads, 1) zone_encode_kernel(const EncArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const Offsets o = offsets(a.h, a.obs_dim + a.Z);
@@ -532,12 +559,30 @@ __global__ void __launch_bounds__(kEncThreads, 1) zone_encode_kernel(const EncAr
     const uint32_t l2_bar = bars + kBarL2Done + 8u * (uint32_t)(mblock < n_mblocks ? mblock : n_mblocks - 1);
     const float inv_n = 1.0f / (float)a.N;
     float* const out_col = a.out + j;
+    // this thread's unit in a row of the head operand image: column obs_dim + j = 8 + j (the fused path needs obs_dim 8)
+    uint8_t* const xh_unit = XHEAD ? a.xhead + (uint32_t)(((8 + j) >> 3) * 128 + ((8 + j) & 7) * 2) : nullptr;
     const int log2_s = a.S == 16 ? 4 : 3, per_chunk = 32 >> log2_s;   // envs per 32 accumulator columns (a runtime
     int tile = kGroups * blockIdx.x + group;                           // division here cost epilogue 2 ~800 cycles per tile)
     float x[8], x2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // 16-byte units `half` and, for 32-wide inputs, `half + 2`
-    auto stage_x = [&]() {                                     // this thread's part of the slot's layer-1 B operand
-      *reinterpret_cast<uint4*>(xbuf + x_off) =
-          make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+    auto stage_x = [&](int tl) {                               // this thread's part of the slot's layer-1 B operand
+      const uint4 xv = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+      *reinterpret_cast<uint4*>(xbuf + x_off) = xv;
+      if (XHEAD && (m & (a.S - 1)) == 0) {
+        // the env's first row: its obs chunk (half 0: the same eight bf16 values) and its ones / zero padding behind
+        // the pooled units (half 1) go into the head operand image
+        const int e = (tl << (7 - (a.S == 16 ? 4 : 3))) + (m >> (a.S == 16 ? 4 : 3));
+        if (tl < a.n_tiles && e < a.B) {
+          const int mh = e & (kRows - 1);
+          uint8_t* row = a.xhead + (size_t)(e >> 7) * (size_t)(kRows * a.KH * 2) + (uint32_t)((mh & 7) * 16 + (mh >> 3) * (16 * a.KH));
+          if (half == 0) {
+            *reinterpret_cast<uint4*>(row) = xv;
+          } else {
+            for (int k = 8 + a.h; k < a.KH; ++k)
+              *reinterpret_cast<__nv_bfloat16*>(row + (uint32_t)((k >> 3) * 128 + (k & 7) * 2)) =
+                  __float2bfloat16_rn(k <= 8 + a.h + 1 ? 1.f : 0.f);
+          }
+        }
+      }
       if (kK1 == 32)
         *reinterpret_cast<uint4*>(xbuf + x_off + 256) =
             make_uint4(pack_bf16(x2[0], x2[1]), pack_bf16(x2[2], x2[3]), pack_bf16(x2[4], x2[5]), pack_bf16(x2[6], x2[7]));
@@ -548,7 +593,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) zone_encode_kernel(const EncAr
       if (!STATE && kK1 == 32) load_half_row<STATE>(a, tl, m, half + 2, x2);
     };
     fetch_x(tile);
-    stage_x();
+    stage_x(tile);
     __syncwarp();
     if (lane == 0) mbar_arrive(bars + kBarFullX);
     fetch_x(tile + tile_stride);                               // in flight until the first epilogue 1 is over
@@ -581,7 +626,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) zone_encode_kernel(const EncAr
       if (lane == 0) mbar_arrive(bars + kBarFullH1);
       if (t == 0) CRL_TL(group, k, 4);                         // epilogue 1 over (warp 0)
       // ---- the next tile's input rows (layer 1 of this tile has completed: the X buffer is free) ----
-      stage_x();
+      stage_x(tile + tile_stride);
       fetch_x(tile + 2 * tile_stride);
       // ---- epilogue 2: ReLU, mean over each env's zone slots (register adds), coalesced stores ----
       if (t == 0) CRL_TL(group, k, 5);                         // next rows staged (warp 0)
@@ -598,9 +643,9 @@ __global__ void __launch_bounds__(kEncThreads, 1) zone_encode_kernel(const EncAr
           tmem_ld_wait(v0);
           if (t == 0) CRL_TL(group, k, 8 + 2 * c);               // 8 / 12: a pair of TMEM loads has arrived
           const int e0 = (tile << (7 - log2_s)) + c * per_chunk;
-          relu_pool_store(v0, out_col, a.h, a.B, a.S, e0, full, j < a.h, inv_n);
+          relu_pool_store<XHEAD>(v0, out_col, a.h, a.B, a.S, e0, full, j < a.h, inv_n, xh_unit, a.KH);
           tmem_ld_wait(v1);
-          relu_pool_store(v1, out_col, a.h, a.B, a.S, e0 + per_chunk, full, j < a.h, inv_n);
+          relu_pool_store<XHEAD>(v1, out_col, a.h, a.B, a.S, e0 + per_chunk, full, j < a.h, inv_n, xh_unit, a.KH);
           if (t == 0) CRL_TL(group, k, 9 + 2 * c);               // 9 / 13: pooled and stored
         }
       }
@@ -637,8 +682,8 @@ __host__ __device__ inline HeadOffsets head_offsets(int obs_dim, int h) {
   o.packed_end = (uint32_t)MP * KH * 2;
   o.group0 = (o.packed_end + 127u) & ~127u;
   o.xbuf = 0;
-  o.bar = (uint32_t)kRows * KH * 2;
-  o.group_bytes = (o.bar + 8 + 127u) & ~127u;
+  o.bar = (uint32_t)kRows * KH * 2;                      // + 8: the mbarrier of the tile's bulk copy (PACKED)
+  o.group_bytes = (o.bar + 16 + 127u) & ~127u;
   o.tmem_slot = o.group0 + kGroups * o.group_bytes;
   o.smem_end = o.tmem_slot + 16;
   return o;
@@ -668,6 +713,7 @@ struct HeadArgs {
   float* out;            // [B][h]
   int* status;
   int B, obs_dim, h, n_tiles;
+  const uint8_t* xhead;  // PACKED: the operand images the zone kernel wrote (crl_encoder_forward); obs / pooled unused
 };
 
 // unit j of 32 consecutive envs e0 ..: one base pointer, constant strides; predicates only on the batch's last tile
@@ -684,6 +730,7 @@ __device__ __forceinline__ void head_store(const uint32_t (&v)[32], float* col, 
   }
 }
 
+template <bool PACKED>
 __global__ void __launch_bounds__(kGroupThreads * kGroups, 1) encoder_head_kernel(const HeadArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const HeadOffsets o = head_offsets(a.obs_dim, a.h);
@@ -699,6 +746,7 @@ __global__ void __launch_bounds__(kGroupThreads * kGroups, 1) encoder_head_kerne
   const uint32_t bar_addr = smem_u32(bar);
   if (t == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_addr) : "memory");
+    mbar_init(bar_addr + 8u, 1);
     if (group == 0) mbar_init(smem_u32(tmem_slot) + 8u, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (group == 0) bulk_load_weights(smem_u32(tmem_slot) + 8u, smem_u32(smem), a.packed, o.packed_end);
@@ -717,13 +765,21 @@ __global__ void __launch_bounds__(kGroupThreads * kGroups, 1) encoder_head_kerne
   const uint32_t my_acc = acc + (uint32_t)(mblock * 128) + ((uint32_t)(quad * 32) << 16);
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kRows >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   bool weights_in = false;
+  const uint32_t tile_bytes = (uint32_t)(kRows * KH * 2);
+  uint32_t xparity = 0u;
+  if (PACKED && t == 0) {                                      // the first tile's operand image: one bulk copy
+    const int tile0 = kGroups * blockIdx.x + group;
+    if (tile0 < a.n_tiles) bulk_load_weights(bar_addr + 8u, smem_u32(xbuf), a.xhead + (size_t)tile0 * tile_bytes, tile_bytes);
+  }
   const uint32_t x_addr = smem_u32(xbuf), w_addr = smem_u32(smem + o.w);
   const bool drains = mblock < n_mblocks && mblock * 128 + quad * 32 < a.h;
   uint32_t parity = 0u;
   bool healthy = true;
   for (int tile = kGroups * blockIdx.x + group; tile < a.n_tiles; tile += kGroups * gridDim.x) {
     // ---- B operand: the tile's 128 rows [obs, pooled, 1, 1, 0..] as bf16, K-major.
-    if (a.obs_dim == 8 && chunks <= 32) {
+    if (PACKED) {
+      // already in shared memory, or on its way (issued a tile ago); only the MMA-issuing thread waits for it
+    } else if (a.obs_dim == 8 && chunks <= 32) {
       // ZoneEnvModel's shape: chunk 0 of a row is exactly obs[e] (two 16-byte loads), chunk c >= 1 is
       // pooled[e][8 (c - 1) ..].  A warp takes a row at a time, lane c its chunk c -- no index arithmetic, no address
       // selects (the general loop below spends ~10 instructions per element on them) -- four rows per iteration so that
@@ -807,6 +863,7 @@ __global__ void __launch_bounds__(kGroupThreads * kGroups, 1) encoder_head_kerne
     group_sync(group);
     if (t == 0) {
       if (!weights_in) { weights_in = true; healthy = mbar_wait(smem_u32(tmem_slot) + 8u, 0u) && healthy; }
+      if (PACKED) { healthy = mbar_wait(bar_addr + 8u, xparity) && healthy; xparity ^= 1u; }
       tc_fence_after();
       for (int b = 0; b < n_mblocks; ++b)
         for (int s = 0; s < KH / 16; ++s)
@@ -817,6 +874,10 @@ __global__ void __launch_bounds__(kGroupThreads * kGroups, 1) encoder_head_kerne
     healthy = mbar_wait(bar_addr, parity) && healthy;
     parity ^= 1u;
     tc_fence_after();
+    if (PACKED && t == 0) {                                    // the MMAs have read the operand buffer: fetch the next image
+      const int next = tile + kGroups * (int)gridDim.x;       // under this tile's epilogue
+      if (next < a.n_tiles) bulk_load_weights(bar_addr + 8u, smem_u32(xbuf), a.xhead + (size_t)next * tile_bytes, tile_bytes);
+    }
     if (drains) {
 #pragma unroll 1
       for (int c = 0; c < kRows / 32; c += 2) {               // two TMEM loads in flight
@@ -883,10 +944,10 @@ int crl_encoder_pack(const CrlEncoderShape* s, const float* w1, const float* b1,
 
 static int zone_encode_launch(const CrlEncoderShape* s, int32_t num_envs, const float* obs, const float* zone_obs,
                               const CrlConfig* cfg, const CrlState* st, const void* packed, float* pooled, int32_t* status,
-                              void* stream) {
+                              void* stream, void* xhead = nullptr) {
   const int rc = check_shape(s);
   if (rc) return rc;
-  if (!obs || (!zone_obs && !st) || !packed || !pooled) return CRL_ERR_NULL;
+  if (!obs || (!zone_obs && !st) || !packed || (!pooled && !xhead)) return CRL_ERR_NULL;
   if (num_envs <= 0) return CRL_ERR_CONFIG;
   if (reinterpret_cast<uintptr_t>(packed) & 15u) return CRL_ERR_ALIGN;
   const Offsets o = offsets(s->hidden, s->obs_dim + s->zone_dim);
@@ -894,13 +955,16 @@ static int zone_encode_launch(const CrlEncoderShape* s, int32_t num_envs, const 
   if (cudaGetDevice(&dev) != cudaSuccess) return CRL_ERR_DEVICE;
   static bool attr_set[64] = {false};                       // per device: opt in to > 48 KB of dynamic shared memory
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    if (cudaFuncSetAttribute(zone_encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(zone_encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(zone_encode_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(zone_encode_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(zone_encode_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(zone_encode_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return CRL_ERR_DEVICE;
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   EncArgs a{};
   a.obs = obs; a.zone_obs = zone_obs; a.packed = static_cast<const uint8_t*>(packed); a.out = pooled; a.status = status;
+  a.xhead = static_cast<uint8_t*>(xhead); a.KH = head_k(s->obs_dim, s->hidden);
   a.B = num_envs; a.N = s->num_zones; a.Z = s->zone_dim; a.obs_dim = s->obs_dim; a.h = s->hidden;
   a.S = slots_per_env(s->num_zones);
   a.n_tiles = (num_envs + kRows / a.S - 1) / (kRows / a.S);
@@ -935,8 +999,11 @@ static int zone_encode_launch(const CrlEncoderShape* s, int32_t num_envs, const 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int want = (a.n_tiles + kGroups - 1) / kGroups;
   const int grid = want < sms ? want : sms;                   // persistent: one CTA per SM, weights loaded once
-  if (st) zone_encode_kernel<true><<<grid, kEncThreads, o.smem_end, static_cast<cudaStream_t>(stream)>>>(a);
-  else zone_encode_kernel<false><<<grid, kEncThreads, o.smem_end, static_cast<cudaStream_t>(stream)>>>(a);
+  const cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  if (st && xhead) zone_encode_kernel<true, true><<<grid, kEncThreads, o.smem_end, cs>>>(a);
+  else if (st) zone_encode_kernel<true, false><<<grid, kEncThreads, o.smem_end, cs>>>(a);
+  else if (xhead) zone_encode_kernel<false, true><<<grid, kEncThreads, o.smem_end, cs>>>(a);
+  else zone_encode_kernel<false, false><<<grid, kEncThreads, o.smem_end, cs>>>(a);
   return cudaGetLastError() == cudaSuccess ? CRL_OK : CRL_ERR_LAUNCH;
 }
 
@@ -973,11 +1040,11 @@ int crl_encoder_pack_head(const CrlEncoderShape* s, const float* w, const float*
   return cudaGetLastError() == cudaSuccess ? CRL_OK : CRL_ERR_LAUNCH;
 }
 
-int crl_encoder_head(const CrlEncoderShape* s, int32_t num_envs, const float* obs, const float* pooled,
-                     const void* packed_head, float* out, int32_t* status, void* stream) {
+static int head_launch(const CrlEncoderShape* s, int32_t num_envs, const float* obs, const float* pooled, const void* xhead,
+                       const void* packed_head, float* out, int32_t* status, void* stream) {
   const int rc = check_shape(s);
   if (rc) return rc;
-  if (!obs || !pooled || !packed_head || !out) return CRL_ERR_NULL;
+  if ((!xhead && (!obs || !pooled)) || !packed_head || !out) return CRL_ERR_NULL;
   if (num_envs <= 0) return CRL_ERR_CONFIG;
   if (reinterpret_cast<uintptr_t>(packed_head) & 15u) return CRL_ERR_ALIGN;
   const HeadOffsets o = head_offsets(s->obs_dim, s->hidden);
@@ -986,17 +1053,51 @@ int crl_encoder_head(const CrlEncoderShape* s, int32_t num_envs, const float* ob
   if (cudaGetDevice(&dev) != cudaSuccess) return CRL_ERR_DEVICE;
   static bool attr_set[64] = {false};
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    if (cudaFuncSetAttribute(encoder_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(encoder_head_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(encoder_head_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return CRL_ERR_DEVICE;
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
-  HeadArgs a{obs, pooled, static_cast<const uint8_t*>(packed_head), out, status, num_envs, s->obs_dim, s->hidden, 0};
+  HeadArgs a{obs, pooled, static_cast<const uint8_t*>(packed_head), out, status, num_envs, s->obs_dim, s->hidden, 0,
+             static_cast<const uint8_t*>(xhead)};
   a.n_tiles = (num_envs + kRows - 1) / kRows;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int want = (a.n_tiles + kGroups - 1) / kGroups;
   const int grid = want < sms ? want : sms;
-  encoder_head_kernel<<<grid, kGroupThreads * kGroups, o.smem_end, static_cast<cudaStream_t>(stream)>>>(a);
+  if (xhead) encoder_head_kernel<true><<<grid, kGroupThreads * kGroups, o.smem_end, static_cast<cudaStream_t>(stream)>>>(a);
+  else encoder_head_kernel<false><<<grid, kGroupThreads * kGroups, o.smem_end, static_cast<cudaStream_t>(stream)>>>(a);
   return cudaGetLastError() == cudaSuccess ? CRL_OK : CRL_ERR_LAUNCH;
+}
+
+int crl_encoder_head(const CrlEncoderShape* s, int32_t num_envs, const float* obs, const float* pooled,
+                     const void* packed_head, float* out, int32_t* status, void* stream) {
+  if (!obs || !pooled) return CRL_ERR_NULL;
+  return head_launch(s, num_envs, obs, pooled, nullptr, packed_head, out, status, stream);
+}
+
+int crl_encoder_workspace_bytes(const CrlEncoderShape* s, int32_t num_envs, int64_t* bytes) {
+  const int rc = check_shape(s);
+  if (rc) return rc;
+  if (!bytes) return CRL_ERR_NULL;
+  if (num_envs <= 0) return CRL_ERR_CONFIG;
+  if (s->obs_dim != 8 || padded_k1(s->obs_dim + s->zone_dim) != 16) return CRL_ERR_UNSUPPORTED;   // ZoneEnvModel's own shape
+  *bytes = (int64_t)((num_envs + kRows - 1) / kRows) * kRows * head_k(s->obs_dim, s->hidden) * 2;
+  return CRL_OK;
+}
+
+int crl_encoder_forward(const CrlEncoderShape* s, const CrlConfig* cfg, const CrlState* st, int32_t num_envs, const float* obs,
+                        const float* zone_obs, const void* packed, const void* packed_head, void* workspace, float* out,
+                        int32_t* status, void* stream) {
+  int64_t need = 0;
+  const int rc = crl_encoder_workspace_bytes(s, num_envs, &need);
+  if (rc) return rc;
+  if (!workspace || !out || !packed_head) return CRL_ERR_NULL;
+  if (reinterpret_cast<uintptr_t>(workspace) & 15u) return CRL_ERR_ALIGN;
+  if (st ? (!cfg || cfg->num_envs != num_envs) : !zone_obs) return st ? CRL_ERR_CONFIG : CRL_ERR_NULL;
+  const int rz = zone_encode_launch(s, num_envs, obs, st ? nullptr : zone_obs, st ? cfg : nullptr, st, packed, nullptr, status, stream,
+                                    workspace);
+  if (rz) return rz;
+  return head_launch(s, num_envs, nullptr, nullptr, workspace, packed_head, out, status, stream);
 }
 
 }  // extern "C"

@@ -3,7 +3,9 @@ forward, with the wide part of its per-zone network and the mean-pool fused into
 (include/crl_b200.h: crl_zone_encode; csrc/crl_encode.cu).  The last Linear of ``zone_net_`` is affine, so
 the mean over zones is taken before it: the kernel returns ``pooled = mean_z relu(L2(relu(L1(.))))``; the rest
 of the forward, ``combine_net_([obs, L3(pooled)])``, is one affine map of ``[obs, pooled]`` and runs as a second
-tensor-core kernel of the same library (crl_encoder_head).  No library GEMM is called.
+tensor-core kernel of the same library (crl_encoder_head).  No library GEMM is called.  ``enc(obs, zone_obs)`` /
+``enc.forward_from_state(env)`` run both through crl_encoder_forward: the first kernel writes the second one's bf16
+operand image directly (no fp32 ``pooled`` in between), the second fetches it with one bulk copy per 128 envs.
 
     model = ZoneEnvModel(obs_space, h_dim)                  # the reference's module, trained as usual
     enc = ZoneEncoder(model.state_dict(), num_zones=15)     # packs zone_net_ once (repack after an update)
@@ -28,6 +30,7 @@ class ZoneEncoder:
         self.device = torch.device(device)
         self.num_zones = int(num_zones)
         self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._ws = {}
         self.load_state_dict(state_dict)
 
     def load_state_dict(self, state_dict):
@@ -98,9 +101,44 @@ class ZoneEncoder:
                                                       self._stream()))
         return out
 
-    def forward_from_state(self, env):
+    def _workspace(self, B):
+        """Scratch of crl_encoder_forward: the head kernel's bf16 operand images, one per 128 envs; None if the shape is
+        not ZoneEnvModel's own (then the forward runs as two calls with an fp32 ``pooled`` in between)."""
+        ws = self._ws.get(B)
+        if ws is None:
+            n = ctypes.c_int64()
+            rc = self.lib.crl_encoder_workspace_bytes(self.shape, B, ctypes.byref(n))
+            if rc == -4:                                   # CRL_ERR_UNSUPPORTED: not ZoneEnvModel's own shape
+                ws = False
+            else:
+                _lib.check(rc)
+                ws = torch.empty(n.value, dtype=torch.uint8, device=self.device)
+            self._ws = {B: ws}                      # one batch size at a time
+        return ws if ws is not False else None
+
+    def _forward(self, obs, zone_obs=None, env=None, out=None):
+        B = obs.shape[0]
+        ws = self._workspace(B)
+        if ws is None:
+            pooled = self.pooled(obs, zone_obs) if env is None else self.pooled_from_state(env)
+            return self._head(self.packed_head, obs, pooled, out)
+        if out is None:
+            out = torch.empty(B, self.hidden, dtype=torch.float32, device=self.device)
+        assert out.shape == (B, self.hidden) and out.dtype == torch.float32 and out.is_contiguous()
+        assert obs.shape == (B, self.obs_dim) and obs.dtype == torch.float32 and obs.is_contiguous()
+        if env is None:
+            assert zone_obs.shape == (B, self.num_zones, self.zone_dim) and zone_obs.dtype == torch.float32 and zone_obs.is_contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.crl_encoder_forward(
+                self.shape, env.cfg if env is not None else None, env.state if env is not None else None, B, obs.data_ptr(),
+                None if env is not None else zone_obs.data_ptr(), self.packed.data_ptr(), self.packed_head.data_ptr(),
+                ws.data_ptr(), out.data_ptr(), self._status.data_ptr(), self._stream()))
+        return out
+
+    def forward_from_state(self, env, out=None):
         """ZoneEnvModel.forward on the env's current observation without touching ``env.zone_obs``."""
-        return self._head(self.packed_head, env.obs, self.pooled_from_state(env))
+        assert env.spec.num_zones == self.num_zones and env.spec.zone_dim == self.zone_dim and self.obs_dim == 8
+        return self._forward(env.obs, env=env, out=out)
 
     def _head(self, packed, obs, pooled, out=None):
         B = obs.shape[0]
@@ -124,4 +162,4 @@ class ZoneEncoder:
         """ZoneEnvModel.forward: accepts the env's obs dict or the two tensors."""
         if zone_obs is None:
             obs, zone_obs = obs['obs'], obs['zone_obs']
-        return self._head(self.packed_head, obs, self.pooled(obs, zone_obs))
+        return self._forward(obs, zone_obs)

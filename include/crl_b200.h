@@ -427,6 +427,18 @@ int crl_encoder_pack_head(const CrlEncoderShape* shape, const float* w, const fl
 int crl_encoder_head(const CrlEncoderShape* shape, int32_t num_envs, const float* obs, const float* pooled,
                      const void* packed_head, float* out, int32_t* status, void* stream);
 
+/* The whole ZoneEnvModel.forward (env_model.py:66-79) in two launches with NO fp32 `pooled` in between: the zone kernel
+ * writes the head kernel's input -- per tile of 128 envs the bf16 operand image [obs, pooled, 1, 1, 0..] -- into
+ * `workspace` (crl_encoder_workspace_bytes; contents are scratch), and the head kernel fetches each tile with one bulk
+ * copy.  Same result as crl_zone_encode + crl_encoder_head (the head rounds `pooled` to bf16 either way).  `st` != NULL:
+ * the zone rows are built from the state planes (as crl_zone_encode_state; `cfg` is the env's, `zone_obs` unused);
+ * `st` == NULL: from the materialised `zone_obs`.  Needs obs_dim == 8 and zone_dim <= 7 (ZoneEnvModel's own shape),
+ * otherwise CRL_ERR_UNSUPPORTED: use the two calls. */
+int crl_encoder_workspace_bytes(const CrlEncoderShape* shape, int32_t num_envs, int64_t* bytes);
+int crl_encoder_forward(const CrlEncoderShape* shape, const CrlConfig* cfg, const CrlState* st, int32_t num_envs,
+                        const float* obs, const float* zone_obs, const void* packed, const void* packed_head,
+                        void* workspace, float* out, int32_t* status, void* stream);
+
 /* Copies the eight counters to the host (synchronises `stream`).  The first four (sum of
  * returns, episodes, successes, sum of lengths) are what ranks all-reduce. */
 int crl_counters_read(const CrlState* st, double out[8], void* stream);

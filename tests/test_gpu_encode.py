@@ -193,3 +193,31 @@ def test_unsupported_shapes_are_refused(crl):
     assert lib.crl_encoder_packed_bytes(_lib.CrlEncoderShape(8, 6, 256, 15), ctypes.byref(n)) == -4    # two resident weights do not fit
     assert lib.crl_encoder_packed_bytes(_lib.CrlEncoderShape(20, 12, 64, 15), ctypes.byref(n)) == -2     # no room for the ones column in the 32-wide input
     assert lib.crl_encoder_head_packed_bytes(_lib.CrlEncoderShape(8, 6, 185, 15), ctypes.byref(n)) == 0 and n.value == 256 * 208 * 2
+
+
+@pytest.mark.parametrize('env_id,B', [('PointTSP-v0', 4099), ('ColourMatch-v0', 1000), ('PointTTSP-v0', 129), ('PointTSP-v1', 77)])
+def test_fused_forward_is_the_two_call_forward(crl, env_id, B):
+    """crl_encoder_forward (the zone kernel writes the head kernel's bf16 operand image, no fp32 pooled in between, one
+    bulk copy per 128 envs in the head) gives bit for bit what crl_zone_encode + crl_encoder_head give -- the head rounds
+    pooled to bf16 either way -- from the materialised zone_obs and from the state planes; ragged batches."""
+    N, Z, h = crl.ENV_SPECS[env_id].num_zones, crl.ENV_SPECS[env_id].zone_dim, 185
+    gen = torch.Generator(device='cuda').manual_seed(B)
+    rn = lambda *s_, scale=1.0: (torch.randn(*s_, device='cuda', generator=gen) * scale)
+    sd = {'zone_net_.0.weight': rn(h, 8 + Z, scale=0.4), 'zone_net_.0.bias': rn(h, scale=0.2),
+          'zone_net_.2.weight': rn(h, h, scale=0.1), 'zone_net_.2.bias': rn(h, scale=0.2),
+          'zone_net_.4.weight': rn(h, h, scale=0.1), 'zone_net_.4.bias': rn(h, scale=0.2),
+          'combine_net_.weight': rn(h, 8 + h, scale=0.1), 'combine_net_.bias': rn(h, scale=0.1)}
+    enc = crl.ZoneEncoder(sd, num_zones=N)
+    env = crl.ZoneVecEnv(env_id, B)
+    env.seed(5)
+    obs = env.reset()
+    for _ in range(30):
+        obs, *_ = env.step_random(action_seed=2)
+    two = enc._head(enc.packed_head, obs['obs'], enc.pooled(obs['obs'], obs['zone_obs']))
+    guard = torch.full((B + 2, h), 7.0, device='cuda')
+    fused = enc._forward(obs['obs'], obs['zone_obs'], out=guard[:B])
+    from_state = enc.forward_from_state(env)
+    torch.cuda.synchronize()
+    assert enc.healthy() and enc._workspace(B) is not None
+    assert torch.equal(fused, two) and torch.equal(from_state, two)
+    assert bool((guard[B:] == 7.0).all()) and bool(torch.isfinite(fused).all())

@@ -67,6 +67,7 @@ def main():
     t_fused = time_it(lambda i: enc.pooled(obs_r[i], zobs_r[i], out=out), args.iters)
     t_emb = time_it(lambda i: enc.zone_embedding(obs_r[i], zobs_r[i]), args.iters)      # + the head kernel with [0 | W3]
     t_fwd = time_it(lambda i: enc(obs_r[i], zobs_r[i]), args.iters)                      # ZoneEnvModel.forward: pooled + folded head
+    t_fwd2 = time_it(lambda i: enc._head(enc.packed_head, obs_r[i], enc.pooled(obs_r[i], zobs_r[i], out=out)), args.iters)   # the two-call forward (fp32 pooled in between)
     pooled0 = enc.pooled(obs_r[0], zobs_r[0])
     t_head = time_it(lambda i: enc._head(enc.packed_head, obs_r[i], pooled0), args.iters)
 
@@ -97,7 +98,7 @@ def main():
     peak = peaks.get('bf16_tflops', 2250.0)
     print(json.dumps({
         'op': 'ZoneEnvModel.zone_net_ + mean over zones (env_model.py:56-78)', 'workload': f'{args.env}, {B} envs, N={N}, Z={Z}, h={h}',
-        'healthy': ok, 'fused_us': t_fused * 1e6, 'fused_from_state_us': t_state * 1e6, 'from_state_bit_identical': same, 'head_us': t_head * 1e6, 'zone_embedding_us': t_emb * 1e6, 'forward_us': t_fwd * 1e6,
+        'healthy': ok, 'fused_us': t_fused * 1e6, 'fused_from_state_us': t_state * 1e6, 'from_state_bit_identical': same, 'head_us': t_head * 1e6, 'zone_embedding_us': t_emb * 1e6, 'forward_us': t_fwd * 1e6, 'forward_two_calls_us': t_fwd2 * 1e6,
         'torch_fp32_us': t_fp32 * 1e6, 'torch_bf16_autocast_us': t_bf16 * 1e6,
         'torch_forward_fp32_us': t_fwd_fp32 * 1e6, 'torch_forward_bf16_autocast_us': t_fwd_bf16 * 1e6,
         'forward_speedup_vs_torch_fp32': t_fwd_fp32 / t_fwd, 'forward_speedup_vs_torch_bf16_autocast': t_fwd_bf16 / t_fwd,
