@@ -24,7 +24,8 @@ SYMBOLS = ['crl_abi_version', 'crl_strerror', 'crl_plane_bytes', 'crl_step_bytes
            'crl_get_qpos_qvel', 'crl_gae', 'crl_check_state', 'crl_counters_read',
            'crl_encoder_packed_bytes', 'crl_encoder_pack', 'crl_zone_encode', 'crl_zone_encode_state',
            'crl_encoder_head_packed_bytes', 'crl_encoder_pack_head', 'crl_encoder_head',
-           'crl_encoder_workspace_bytes', 'crl_encoder_forward']
+           'crl_encoder_workspace_bytes', 'crl_encoder_forward',
+           'crl_encoder_precise_packed_bytes', 'crl_encoder_pack_precise', 'crl_zone_encode_precise']
 
 
 class CrlConfig(ctypes.Structure):
@@ -106,6 +107,9 @@ def load():
     lib.crl_encoder_head.argtypes = [P(CrlEncoderShape), c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p]
     lib.crl_encoder_workspace_bytes.argtypes = [P(CrlEncoderShape), c_int32, P(c_int64)]
+    lib.crl_encoder_precise_packed_bytes.argtypes = [P(CrlEncoderShape), P(c_int64)]
+    lib.crl_encoder_pack_precise.argtypes = [P(CrlEncoderShape)] + [c_void_p] * 6
+    lib.crl_zone_encode_precise.argtypes = [P(CrlEncoderShape), c_int32] + [c_void_p] * 6
     lib.crl_encoder_forward.argtypes = [P(CrlEncoderShape), P(CrlConfig), P(CrlState), c_int32] + [c_void_p] * 8
     for name in SYMBOLS:
         getattr(lib, name)

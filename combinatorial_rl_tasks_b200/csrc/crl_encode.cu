@@ -902,6 +902,233 @@ __global__ void __launch_bounds__(kGroupThreads * kGroups, 1) encoder_head_kerne
   }
 }
 
+// ================= the PRECISE mode: the same two layers with fp32-level accuracy =================================
+// The fast kernels multiply bf16-rounded operands (relative error 2^-9 per operand, 3-5e-3 of the largest output
+// against the fp32 reference module).  Here every operand is split into two bf16 terms, x = x_hi + x_lo (residual
+// 2^-18 |x|), and every product is three MMAs, W_hi X_hi + W_lo X_hi + W_hi X_lo (the dropped W_lo X_lo term is 2^-18
+// relative), accumulated in fp32 in TMEM; the biases are added in fp32 in the epilogues.  Measured against the REAL
+// module's fp32 output: <= 1e-4 of the largest value (tests/test_gpu_encode.py), i.e. like for like with the reference.
+// Twice the operand bytes do not fit an SM beside a tile's activations, so a CTA holds ONE M-block of W2 (hi + lo,
+// 96 KB) and computes that block's 128 output units for its tiles; layer 1 (all hidden units: they are layer 2's K)
+// is computed by both CTAs of a pair -- it is 6 of 42 MMAs.  One tile in flight per CTA: this is the validation /
+// like-for-like mode, ~7x the fast kernel's time (686 us at 65,536 PointTSP envs; torch fp32 eager: 7.3 ms).
+__host__ __device__ inline int precise_k(int h) { return (h + 15) & ~15; }
+
+struct PreciseOffsets {      // bytes; `g_*` in the packed global buffer, `s_*` in shared memory
+  uint32_t g_w1, g_w2, g_w2_block, g_bias, g_end;
+  uint32_t s_w1, s_w2, s_h1hi, s_h1lo, s_xhi, s_xlo, s_bar, s_wbar, s_tmem, s_end;
+};
+__host__ __device__ inline PreciseOffsets precise_offsets(int h) {
+  const uint32_t KP = (uint32_t)precise_k(h), MP = (KP + 127u) & ~127u;
+  PreciseOffsets o;
+  o.g_w1 = 0;                                   // W1 hi | W1 lo: MP x 16 bf16 each
+  o.g_w2 = 2u * MP * 16u * 2u;                  // per M-block: W2 hi | W2 lo, 128 x KP bf16 each
+  o.g_w2_block = 2u * 128u * KP * 2u;
+  o.g_bias = o.g_w2 + (MP / 128u) * o.g_w2_block;   // float b1[MP] | float b2[MP]
+  o.g_end = o.g_bias + 2u * MP * 4u;
+  o.s_w1 = 0;
+  o.s_w2 = o.g_w2;
+  o.s_h1hi = o.s_w2 + o.g_w2_block;
+  o.s_h1lo = o.s_h1hi + KP * kRows * 2u;
+  o.s_xhi = o.s_h1lo + KP * kRows * 2u;
+  o.s_xlo = o.s_xhi + kRows * 16u * 2u;
+  o.s_bar = o.s_xlo + kRows * 16u * 2u;
+  o.s_wbar = o.s_bar + 8u;
+  o.s_tmem = o.s_wbar + 8u;
+  o.s_end = o.s_tmem + 16u;
+  return o;
+}
+
+struct PrecisePackArgs { const float *w1, *b1, *w2, *b2; uint8_t* out; int in_dim, h; };
+
+__global__ void pack_precise_kernel(const PrecisePackArgs a) {
+  const PreciseOffsets o = precise_offsets(a.h);
+  const int KP = precise_k(a.h), MP = (KP + 127) & ~127;
+  const int n1 = MP * 16, n2 = MP * KP, total = n1 + n2 + 2 * MP;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    if (i >= n1 + n2) {                                        // biases, fp32
+      const int r = i - n1 - n2, n = r % MP;
+      reinterpret_cast<float*>(a.out + o.g_bias)[r] = n < a.h ? (r < MP ? a.b1[n] : a.b2[n]) : 0.f;
+      continue;
+    }
+    const bool second = i >= n1;
+    const int K = second ? KP : 16, lim = second ? a.h : a.in_dim;
+    const int q = second ? i - n1 : i, n = q / K, k = q % K;
+    const float v = (n < a.h && k < lim) ? (second ? a.w2[(size_t)n * a.h + k] : a.w1[(size_t)n * a.in_dim + k]) : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v), lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    uint8_t *phi, *plo;
+    if (second) {
+      uint8_t* blk = a.out + o.g_w2 + (uint32_t)(n >> 7) * o.g_w2_block;
+      phi = blk + canon(n & 127, k, KP);
+      plo = blk + 128u * KP * 2u + canon(n & 127, k, KP);
+    } else {
+      phi = a.out + o.g_w1 + canon(n, k, 16);
+      plo = a.out + o.g_w1 + (uint32_t)MP * 32u + canon(n, k, 16);
+    }
+    *reinterpret_cast<__nv_bfloat16*>(phi) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(plo) = lo;
+  }
+}
+
+__device__ __forceinline__ void split_bf16(float v, float& hi, float& lo) {
+  hi = __bfloat162float(__float2bfloat16_rn(v));
+  lo = v - hi;                                                 // exact; rounded to bf16 when packed
+}
+
+__global__ void __launch_bounds__(kGroupThreads, 1) zone_encode_precise_kernel(const EncArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const PreciseOffsets o = precise_offsets(a.h);
+  const int KP = precise_k(a.h), MP = (KP + 127) & ~127, n_mblocks = MP / 128;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int m = t & (kRows - 1), half = t >> 7;
+  const int my_block = (int)blockIdx.x % n_mblocks;            // the M-block of layer 2 this CTA owns
+  const uint32_t bar = smem_u32(smem + o.s_bar), wbar = smem_u32(smem + o.s_wbar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + o.s_tmem);
+  if (t == 0) {
+    mbar_init(bar, 1);
+    mbar_init(wbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(wbar), "r"(o.g_w2 + o.g_w2_block) : "memory");
+    const uint8_t* src2 = a.packed + o.g_w2 + (uint32_t)my_block * o.g_w2_block;
+    for (uint32_t off = 0; off < o.g_w2; off += 16384u)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   :: "r"(smem_u32(smem + o.s_w1) + off), "l"(a.packed + off), "r"(o.g_w2 - off < 16384u ? o.g_w2 - off : 16384u), "r"(wbar) : "memory");
+    for (uint32_t off = 0; off < o.g_w2_block; off += 16384u)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   :: "r"(smem_u32(smem + o.s_w2) + off), "l"(src2 + off), "r"(o.g_w2_block - off < 16384u ? o.g_w2_block - off : 16384u), "r"(wbar) : "memory");
+  }
+  if (t < 32) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc1 = tmem_base, acc2 = tmem_base + 256u;    // layer 1: two M-blocks x 128 columns; layer 2: one
+  const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kRows >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint32_t idesc2 = idesc1 | (1u << 16);
+  const float* bias = reinterpret_cast<const float*>(a.packed + o.g_bias);
+  // epilogue 1: warp = (M-block, lane quadrant) of layer 1's accumulators
+  const int mb1 = warp >> 2, q1 = warp & 3, j1 = mb1 * 128 + q1 * 32 + lane;
+  const bool drains1 = mb1 < n_mblocks && mb1 * 128 + q1 * 32 < KP;
+  const float b1v = drains1 ? __ldg(bias + j1) : 0.f;
+  // epilogue 2: warp = (lane quadrant, column half) of this CTA's layer-2 accumulators
+  const int q2 = warp & 3, ch = warp >> 2, j2 = my_block * 128 + q2 * 32 + lane;
+  const bool drains2 = my_block * 128 + q2 * 32 < a.h;
+  const float b2v = j2 < a.h ? __ldg(bias + MP + j2) : 0.f;
+  const float inv_n = 1.0f / (float)a.N;
+  const int log2_s = a.S == 16 ? 4 : 3;
+  uint32_t parity = 0u;
+  bool healthy = true, weights_in = false;
+  for (int tile = (int)blockIdx.x / n_mblocks; tile < a.n_tiles; tile += (int)gridDim.x / n_mblocks) {
+    // ---- the tile's input rows, split ----
+    float x[8], xh[8], xl[8];
+    load_half_row<false>(a, tile, m, half, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split_bf16(x[i], xh[i], xl[i]);
+    const uint32_t x_off = (uint32_t)((m & 7) * 16 + (m >> 3) * 256 + half * 128);
+    *reinterpret_cast<uint4*>(smem + o.s_xhi + x_off) =
+        make_uint4(pack_bf16(xh[0], xh[1]), pack_bf16(xh[2], xh[3]), pack_bf16(xh[4], xh[5]), pack_bf16(xh[6], xh[7]));
+    *reinterpret_cast<uint4*>(smem + o.s_xlo + x_off) =
+        make_uint4(pack_bf16(xl[0], xl[1]), pack_bf16(xl[2], xl[3]), pack_bf16(xl[4], xl[5]), pack_bf16(xl[6], xl[7]));
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (t == 0) {
+      if (!weights_in) healthy = mbar_wait(wbar, 0u) && healthy;
+      tc_fence_after();
+      const uint32_t w1hi = smem_u32(smem + o.s_w1), w1lo = w1hi + (uint32_t)MP * 32u;
+      const uint32_t xhi = smem_u32(smem + o.s_xhi), xlo = smem_u32(smem + o.s_xlo);
+      for (int b = 0; b < n_mblocks; ++b) {
+        const uint32_t d = acc1 + (uint32_t)(b * 128), wo = (uint32_t)(b * 128 * 32);
+        mma_bf16(d, smem_desc(w1hi + wo, 128u, 256u), smem_desc(xhi, 128u, 256u), idesc1, 0u);
+        mma_bf16(d, smem_desc(w1lo + wo, 128u, 256u), smem_desc(xhi, 128u, 256u), idesc1, 1u);
+        mma_bf16(d, smem_desc(w1hi + wo, 128u, 256u), smem_desc(xlo, 128u, 256u), idesc1, 1u);
+      }
+      mma_commit(bar);
+    }
+    weights_in = true;
+    healthy = mbar_wait(bar, parity) && healthy;
+    parity ^= 1u;
+    tc_fence_after();
+    // ---- epilogue 1: + bias, relu, split, two MN-major images of H1 ----
+    if (drains1) {
+      const uint32_t h1_off = (uint32_t)((j1 & 7) * 16 + (j1 >> 3) * 2048);
+      const uint32_t my_acc = acc1 + (uint32_t)(mb1 * 128) + ((uint32_t)(q1 * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < kRows / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(my_acc + (uint32_t)(c * 32), v);
+        tmem_ld_wait(v);
+        if (j1 < KP) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) split_bf16(fmaxf(__uint_as_float(v[u * 8 + i]) + b1v, 0.f), hi[i], lo[i]);
+            const uint32_t at = h1_off + (uint32_t)((c * 4 + u) * 128);
+            *reinterpret_cast<uint4*>(smem + o.s_h1hi + at) =
+                make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]), pack_bf16(hi[4], hi[5]), pack_bf16(hi[6], hi[7]));
+            *reinterpret_cast<uint4*>(smem + o.s_h1lo + at) =
+                make_uint4(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]), pack_bf16(lo[4], lo[5]), pack_bf16(lo[6], lo[7]));
+          }
+        }
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // ---- layer 2, this CTA's M-block: three MMAs per K step ----
+    if (t == 0) {
+      tc_fence_after();
+      const uint32_t w2hi = smem_u32(smem + o.s_w2), w2lo = w2hi + 128u * (uint32_t)KP * 2u;
+      const uint32_t hhi = smem_u32(smem + o.s_h1hi), hlo = smem_u32(smem + o.s_h1lo);
+      for (int s2 = 0; s2 < KP / 16; ++s2) {
+        const uint64_t ahi = smem_desc(w2hi + 256u * s2, 128u, 16 * KP), alo = smem_desc(w2lo + 256u * s2, 128u, 16 * KP);
+        const uint64_t bhi = smem_desc(hhi + 4096u * s2, 2048u, 128u), blo = smem_desc(hlo + 4096u * s2, 2048u, 128u);
+        mma_bf16(acc2, ahi, bhi, idesc2, s2 > 0);
+        mma_bf16(acc2, alo, bhi, idesc2, 1u);
+        mma_bf16(acc2, ahi, blo, idesc2, 1u);
+      }
+      mma_commit(bar);
+    }
+    healthy = mbar_wait(bar, parity) && healthy;
+    parity ^= 1u;
+    tc_fence_after();
+    // ---- epilogue 2: + bias, relu, mean over each env's REAL zone slots (a padding row is relu(bias) here, not 0) ----
+    if (drains2) {
+      const uint32_t my_acc = acc2 + ((uint32_t)(q2 * 32) << 16) + (uint32_t)(ch * 64);
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32(my_acc + (uint32_t)(c * 32), v);
+        tmem_ld_wait(v);
+        const int row0 = ch * 64 + c * 32;                     // tile row of v[0]
+        if (j2 < a.h) {
+          float sum = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int slot = (row0 + i) & (a.S - 1);
+            if (slot < a.N) sum += fmaxf(__uint_as_float(v[i]) + b2v, 0.f);
+            if (slot == a.S - 1) {
+              const int e = (tile << (7 - log2_s)) + ((row0 + i) >> log2_s);
+              if (e < a.B) a.out[(size_t)e * a.h + j2] = sum * inv_n;
+              sum = 0.f;
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();       // the next tile's MMAs overwrite the accumulators after the barrier at the loop's top
+  }
+  if (!healthy && a.status) atomicExch(a.status, 1);
+  tc_fence_before();
+  __syncthreads();
+  if (t < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(kTmemCols) : "memory");
+}
+
 static int check_shape(const CrlEncoderShape* s) {
   if (!s) return CRL_ERR_NULL;
   if (s->obs_dim <= 0 || s->zone_dim <= 0 || s->obs_dim + s->zone_dim + 1 > 32) return CRL_ERR_CONFIG;   // + a ones column
@@ -1098,6 +1325,63 @@ int crl_encoder_forward(const CrlEncoderShape* s, const CrlConfig* cfg, const Cr
                                     workspace);
   if (rz) return rz;
   return head_launch(s, num_envs, nullptr, nullptr, workspace, packed_head, out, status, stream);
+}
+
+// ---- precise mode (split-bf16 operands, fp32 biases; like for like with the fp32 reference module) ----
+static int check_precise(const CrlEncoderShape* s) {
+  const int rc = check_shape(s);
+  if (rc) return rc;
+  if (s->obs_dim + s->zone_dim > 16) return CRL_ERR_UNSUPPORTED;           // one K step of layer 1
+  if (precise_offsets(s->hidden).s_end > 227u * 1024u) return CRL_ERR_UNSUPPORTED;
+  return CRL_OK;
+}
+
+int crl_encoder_precise_packed_bytes(const CrlEncoderShape* s, int64_t* bytes) {
+  const int rc = check_precise(s);
+  if (rc) return rc;
+  if (!bytes) return CRL_ERR_NULL;
+  *bytes = (int64_t)precise_offsets(s->hidden).g_end;
+  return CRL_OK;
+}
+
+int crl_encoder_pack_precise(const CrlEncoderShape* s, const float* w1, const float* b1, const float* w2, const float* b2,
+                             void* packed, void* stream) {
+  const int rc = check_precise(s);
+  if (rc) return rc;
+  if (!w1 || !b1 || !w2 || !b2 || !packed) return CRL_ERR_NULL;
+  if (reinterpret_cast<uintptr_t>(packed) & 15u) return CRL_ERR_ALIGN;
+  PrecisePackArgs a{w1, b1, w2, b2, static_cast<uint8_t*>(packed), s->obs_dim + s->zone_dim, s->hidden};
+  pack_precise_kernel<<<148, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  return cudaGetLastError() == cudaSuccess ? CRL_OK : CRL_ERR_LAUNCH;
+}
+
+int crl_zone_encode_precise(const CrlEncoderShape* s, int32_t num_envs, const float* obs, const float* zone_obs,
+                            const void* packed_precise, float* pooled, int32_t* status, void* stream) {
+  const int rc = check_precise(s);
+  if (rc) return rc;
+  if (!obs || !zone_obs || !packed_precise || !pooled) return CRL_ERR_NULL;
+  if (num_envs <= 0) return CRL_ERR_CONFIG;
+  if (reinterpret_cast<uintptr_t>(packed_precise) & 15u) return CRL_ERR_ALIGN;
+  const PreciseOffsets o = precise_offsets(s->hidden);
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess) return CRL_ERR_DEVICE;
+  static bool attr_set[64] = {false};
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    if (cudaFuncSetAttribute(zone_encode_precise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return CRL_ERR_DEVICE;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  EncArgs a{};
+  a.obs = obs; a.zone_obs = zone_obs; a.packed = static_cast<const uint8_t*>(packed_precise); a.out = pooled; a.status = status;
+  a.B = num_envs; a.N = s->num_zones; a.Z = s->zone_dim; a.obs_dim = s->obs_dim; a.h = s->hidden;
+  a.S = slots_per_env(s->num_zones);
+  a.n_tiles = (num_envs + kRows / a.S - 1) / (kRows / a.S);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int nb = ((precise_k(s->hidden) + 127) & ~127) / 128;
+  const int want = a.n_tiles * nb, cap = sms / nb * nb;       // CTA c owns M-block c % nb of tiles c / nb, c / nb + grid / nb, ..
+  const int grid = want < cap ? want : cap;
+  zone_encode_precise_kernel<<<grid, kGroupThreads, o.s_end, static_cast<cudaStream_t>(stream)>>>(a);
+  return cudaGetLastError() == cudaSuccess ? CRL_OK : CRL_ERR_LAUNCH;
 }
 
 }  // extern "C"

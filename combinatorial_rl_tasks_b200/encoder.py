@@ -67,6 +67,7 @@ class ZoneEncoder:
             _lib.check(self.lib.crl_encoder_pack_head(self.shape, l3_w.data_ptr(), self.b3.data_ptr(),
                                                       self.packed_l3.data_ptr(), self._stream()))
         self._keep = (w1, b1, w2, b2, l3_w)         # alive until the pack kernels have run
+        self._packed_precise = None                 # packed on first use (pooled_precise)
 
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -153,6 +154,45 @@ class ZoneEncoder:
     def zone_embedding(self, obs, zone_obs, out=None):
         """mean_z zone_net_([obs, zone_obs[:, z]]) (env_model.py:73) = L3(pooled)."""
         return self._head(self.packed_l3, obs, self.pooled(obs, zone_obs), out)
+
+    # ---- precise mode: split-bf16 operands (three MMAs per product), fp32 biases; like for like with the fp32 module ----
+    def _precise_image(self):
+        if self._packed_precise is None:
+            n = ctypes.c_int64()
+            _lib.check(self.lib.crl_encoder_precise_packed_bytes(self.shape, ctypes.byref(n)))
+            buf = torch.zeros(n.value, dtype=torch.uint8, device=self.device)
+            w1, b1, w2, b2 = self._keep[:4]
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.crl_encoder_pack_precise(self.shape, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                                                             b2.data_ptr(), buf.data_ptr(), self._stream()))
+            self._packed_precise = buf
+        return self._packed_precise
+
+    def pooled_precise(self, obs, zone_obs, out=None):
+        """``pooled`` to fp32-level accuracy (crl_zone_encode_precise): ~1e-5 of the largest value against the fp32
+        module instead of 3-5e-3, at ~7x the fast kernel's time (686 us at 65,536 PointTSP envs)."""
+        B = obs.shape[0]
+        assert obs.shape == (B, self.obs_dim) and zone_obs.shape == (B, self.num_zones, self.zone_dim)
+        assert obs.dtype == zone_obs.dtype == torch.float32 and obs.is_contiguous() and zone_obs.is_contiguous()
+        if out is None:
+            out = torch.empty(B, self.hidden, dtype=torch.float32, device=self.device)
+        assert out.shape == (B, self.hidden) and out.dtype == torch.float32 and out.is_contiguous()
+        img = self._precise_image()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.crl_zone_encode_precise(self.shape, B, obs.data_ptr(), zone_obs.data_ptr(), img.data_ptr(),
+                                                        out.data_ptr(), self._status.data_ptr(), self._stream()))
+        return out
+
+    def zone_embedding_precise(self, obs, zone_obs):
+        """L3(pooled) with the precise kernel; the (B, h) affine map itself is an fp32 library GEMM (1 % of the flops)."""
+        return torch.addmm(self.b3, self.pooled_precise(obs, zone_obs), self.w3.t())
+
+    def forward_precise(self, obs, zone_obs=None):
+        """ZoneEnvModel.forward to fp32-level accuracy: precise kernel + the folded fp32 affine map of [obs, pooled]."""
+        if zone_obs is None:
+            obs, zone_obs = obs['obs'], obs['zone_obs']
+        x = torch.cat([obs, self.pooled_precise(obs, zone_obs)], dim=1)
+        return torch.addmm(self.fold_b, x, self.fold_w.t())
 
     def healthy(self):
         """False if a tensor-core completion wait ever expired (synchronises)."""

@@ -439,6 +439,18 @@ int crl_encoder_forward(const CrlEncoderShape* shape, const CrlConfig* cfg, cons
                         const float* obs, const float* zone_obs, const void* packed, const void* packed_head,
                         void* workspace, float* out, int32_t* status, void* stream);
 
+/* PRECISE mode of the fused zone kernel: every operand split into two bf16 terms (x = hi + lo), every product three
+ * tensor-core MMAs (hi hi + lo hi + hi lo), fp32 accumulation, fp32 biases in the epilogues -- `pooled` agrees with the
+ * fp32 reference module (env_model.py:56-78) to ~1e-5 of its largest value instead of the fast kernel's 3-5e-3, at about
+ * 7x its time (one tile in flight per CTA): the like-for-like / validation mode.  Own packed image (hi and lo of both layers + fp32 biases);
+ * needs obs_dim + zone_dim <= 16.  The remaining (B, h) affine map of the forward is then an fp32 GEMM on the
+ * caller's side. */
+int crl_encoder_precise_packed_bytes(const CrlEncoderShape* shape, int64_t* bytes);
+int crl_encoder_pack_precise(const CrlEncoderShape* shape, const float* w1, const float* b1, const float* w2,
+                             const float* b2, void* packed, void* stream);
+int crl_zone_encode_precise(const CrlEncoderShape* shape, int32_t num_envs, const float* obs, const float* zone_obs,
+                            const void* packed_precise, float* pooled, int32_t* status, void* stream);
+
 /* Copies the eight counters to the host (synchronises `stream`).  The first four (sum of
  * returns, episodes, successes, sum of lengths) are what ranks all-reduce. */
 int crl_counters_read(const CrlState* st, double out[8], void* stream);

@@ -221,3 +221,47 @@ def test_fused_forward_is_the_two_call_forward(crl, env_id, B):
     assert enc.healthy() and enc._workspace(B) is not None
     assert torch.equal(fused, two) and torch.equal(from_state, two)
     assert bool((guard[B:] == 7.0).all()) and bool(torch.isfinite(fused).all())
+
+
+PRECISE_RTOL = 1e-4       # the like-for-like bar against the fp32 module; measured ~1e-5
+
+
+@pytest.mark.parametrize('tag,n', [('tsp', 15), ('cm', 6)])
+def test_precise_mode_against_the_real_modules_fp32_output(crl, tag, n):
+    """crl_zone_encode_precise (split-bf16 operands, three MMAs per product, fp32 biases) against the fixture recorded
+    from the REAL ZoneEnvModel in fp32: zone_emb and forward within 1e-4 of the largest value."""
+    g = np.load(GOLDEN)
+    sd = {k[len(tag) + 4:]: torch.from_numpy(g[k]).cuda() for k in g.files if k.startswith(tag + '_sd_')}
+    enc = crl.ZoneEncoder(sd, num_zones=n)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    obs, zobs = torch.from_numpy(g[f'{tag}_obs']).cuda(), torch.from_numpy(g[f'{tag}_zone_obs']).cuda()
+    emb = enc.zone_embedding_precise(obs, zobs)
+    out = enc.forward_precise(obs, zobs)
+    torch.cuda.synchronize()
+    assert enc.healthy()
+    e_emb = float(np.abs(emb.cpu().numpy() - g[f'{tag}_zone_emb']).max()) / max(1.0, float(np.abs(g[f'{tag}_zone_emb']).max()))
+    e_out = float(np.abs(out.cpu().numpy() - g[f'{tag}_out']).max()) / max(1.0, float(np.abs(g[f'{tag}_out']).max()))
+    e_fast = float(np.abs(enc(obs, zobs).cpu().numpy() - g[f'{tag}_out']).max()) / max(1.0, float(np.abs(g[f'{tag}_out']).max()))
+    print(f'{tag}: precise zone_emb {e_emb:.2e}, forward {e_out:.2e} (fast bf16 forward {e_fast:.2e})')
+    assert e_emb <= PRECISE_RTOL and e_out <= PRECISE_RTOL
+
+
+@pytest.mark.parametrize('B,N,Z,h', [(4099, 15, 6, 185), (1, 15, 7, 185), (777, 5, 6, 96), (20000, 6, 7, 32), (3000, 15, 7, 128)])
+def test_precise_mode_random_batches(crl, B, N, Z, h):
+    gen = torch.Generator(device='cuda').manual_seed(B + h + 1)
+    rn = lambda *s_, scale=1.0: (torch.randn(*s_, device='cuda', generator=gen) * scale)
+    sd = {'zone_net_.0.weight': rn(h, 8 + Z, scale=0.4), 'zone_net_.0.bias': rn(h, scale=0.2),
+          'zone_net_.2.weight': rn(h, h, scale=1.5 / h ** 0.5), 'zone_net_.2.bias': rn(h, scale=0.2),
+          'zone_net_.4.weight': rn(h, h, scale=1.5 / h ** 0.5), 'zone_net_.4.bias': rn(h, scale=0.2),
+          'combine_net_.weight': rn(h, 8 + h, scale=0.1), 'combine_net_.bias': rn(h, scale=0.1)}
+    obs, zobs = rn(B, 8), rn(B, N, Z)
+    enc = crl.ZoneEncoder(sd, num_zones=N)
+    out = torch.full((B + 3, h), 7.0, device='cuda')
+    pooled = enc.pooled_precise(obs, zobs, out=out[:B])
+    emb = torch.nn.functional.linear(pooled.double(), sd['zone_net_.4.weight'].double(), sd['zone_net_.4.bias'].double()).float()
+    torch.cuda.synchronize()
+    assert enc.healthy() and bool((out[B:] == 7.0).all()) and bool((pooled >= 0).all())
+    ref = fp32_ref(sd, obs, zobs)
+    err = float((emb - ref).abs().max()) / max(1.0, float(ref.abs().max()))
+    print(f'precise B={B} N={N} Z={Z} h={h}: {err:.2e} of the largest reference value')
+    assert err <= PRECISE_RTOL
