@@ -457,6 +457,10 @@ __global__ void __launch_bounds__(kEncThreads, 1) zone_encode_kernel(const EncAr
                  :: "r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // crl_encoder_forward launches the head kernel with programmatic stream serialization: its CTAs may take over an SM the
+  // moment this kernel's CTA there has exited (set up their barriers, TMEM and weights), and wait for the whole grid
+  // -- griddepcontrol.wait -- only before they touch the operand images this kernel writes
+  if (XHEAD) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -767,6 +771,7 @@ __global__ void __launch_bounds__(kGroupThreads * kGroups, 1) encoder_head_kerne
   bool weights_in = false;
   const uint32_t tile_bytes = (uint32_t)(kRows * KH * 2);
   uint32_t xparity = 0u;
+  if (PACKED) asm volatile("griddepcontrol.wait;" ::: "memory");   // the zone kernel's images are complete and visible
   if (PACKED && t == 0) {                                      // the first tile's operand image: one bulk copy
     const int tile0 = kGroups * blockIdx.x + group;
     if (tile0 < a.n_tiles) bulk_load_weights(bar_addr + 8u, smem_u32(xbuf), a.xhead + (size_t)tile0 * tile_bytes, tile_bytes);
@@ -1291,8 +1296,19 @@ static int head_launch(const CrlEncoderShape* s, int32_t num_envs, const float* 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int want = (a.n_tiles + kGroups - 1) / kGroups;
   const int grid = want < sms ? want : sms;
-  if (xhead) encoder_head_kernel<true><<<grid, kGroupThreads * kGroups, o.smem_end, static_cast<cudaStream_t>(stream)>>>(a);
-  else encoder_head_kernel<false><<<grid, kGroupThreads * kGroups, o.smem_end, static_cast<cudaStream_t>(stream)>>>(a);
+  if (xhead) {
+    // programmatic launch behind the zone kernel (see there); without a programmatic predecessor it is an ordinary launch
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(kGroupThreads * kGroups);
+    lc.dynamicSmemBytes = o.smem_end; lc.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    if (cudaLaunchKernelEx(&lc, encoder_head_kernel<true>, a) != cudaSuccess) { (void)cudaGetLastError(); return CRL_ERR_LAUNCH; }
+    return CRL_OK;
+  }
+  encoder_head_kernel<false><<<grid, kGroupThreads * kGroups, o.smem_end, static_cast<cudaStream_t>(stream)>>>(a);
   return cudaGetLastError() == cudaSuccess ? CRL_OK : CRL_ERR_LAUNCH;
 }
 

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, call ai: crl_encoder_forward -- the zone kernel writes the head's bf16 operand image, the head fetches it by bulk copy
+# round 2, call ai: crl_encoder_forward; head kernel launched programmatically behind the zone kernel (prologue under its tail)
 set -u
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_encode.py -m gpu -q > gpurun_out/r02ai_pytest.log 2>&1; echo "pytest rc=$?"; tail -n 12 gpurun_out/r02ai_pytest.log
