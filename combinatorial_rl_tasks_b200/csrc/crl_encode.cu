@@ -308,11 +308,34 @@ __device__ __forceinline__ void relu_to_h1(const uint32_t (&v)[32], uint8_t* h1_
 // 32 consecutive rows m = the zone slots of envs e0 .. e0 + 32 / S - 1: relu, sum in registers, store column j.
 // `col` = out + j (this thread's column of the output); `full`: every env of the tile exists and j < h, so the stores
 // need no predicates (their address chains were a third of epilogue 2's time).
-// bf16 `val` = pooled unit of env e into the head operand image (xh_unit: image base + the unit's offset in a row)
-__device__ __forceinline__ void xhead_store(uint8_t* xh_unit, int KH, int e, float val) {
-  const int m = e & (kRows - 1);
-  *reinterpret_cast<__nv_bfloat16*>(xh_unit + (size_t)(e >> 7) * (size_t)(kRows * KH * 2) + (uint32_t)((m & 7) * 16 + (m >> 3) * (16 * KH))) =
-      __float2bfloat16_rn(val);
+// relu + mean over the 16 zone slots of the two envs whose rows are the 32 columns of v
+__device__ __forceinline__ void relu_pool16(const uint32_t (&v)[32], float inv_n, float& r0, float& r1) {
+  float q[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float s[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      s[i] = fmaxf(__uint_as_float(v[8 * g + 2 * i]), 0.f) + fmaxf(__uint_as_float(v[8 * g + 2 * i + 1]), 0.f);
+    q[g] = (s[0] + s[1]) + (s[2] + s[3]);
+  }
+  r0 = (q[0] + q[1]) * inv_n;
+  r1 = (q[2] + q[3]) * inv_n;
+}
+
+// 8 x 8 transpose inside each group of 8 lanes: element i of lane r <-> element r of lane i (three exchange stages)
+__device__ __forceinline__ void transpose8(float (&a)[8], int lane) {
+#pragma unroll
+  for (int d = 4; d >= 1; d >>= 1) {
+    const bool up = (lane & d) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i & d) continue;                                     // pairs (i, i + d) with bit d of i clear
+      const float send = up ? a[i] : a[i + d];
+      const float got = __shfl_xor_sync(0xffffffffu, send, d);
+      if (up) a[i] = got; else a[i + d] = got;
+    }
+  }
 }
 
 template <bool XHEAD = false>
@@ -328,14 +351,19 @@ __device__ __forceinline__ void relu_pool_store(const uint32_t (&v)[32], float* 
     q[g] = (s[0] + s[1]) + (s[2] + s[3]);
   }
   if (XHEAD) {                                               // crl_encoder_forward: bf16 into the head's operand image
+    // xh_unit: this thread's unit in the image row of the zone tile's FIRST env.  The tile's 8 (S = 16) or 16 (S = 8) envs
+    // are consecutive rows of one or two 8-row groups of the same head tile: env i of the tile at
+    // + (i & 7) * 16 + (i >> 3) * 16 KH -- no per-store index arithmetic
     if (!j_ok) return;
+    const int i0 = e0 & (S == 16 ? 7 : 15);
     if (S == 16) {
-      if (e0 < B) xhead_store(xh_unit, KH, e0, (q[0] + q[1]) * inv_n);
-      if (e0 + 1 < B) xhead_store(xh_unit, KH, e0 + 1, (q[2] + q[3]) * inv_n);
+      if (e0 < B) *reinterpret_cast<__nv_bfloat16*>(xh_unit + i0 * 16) = __float2bfloat16_rn((q[0] + q[1]) * inv_n);
+      if (e0 + 1 < B) *reinterpret_cast<__nv_bfloat16*>(xh_unit + (i0 + 1) * 16) = __float2bfloat16_rn((q[2] + q[3]) * inv_n);
     } else {
 #pragma unroll
       for (int g = 0; g < 4; ++g)
-        if (e0 + g < B) xhead_store(xh_unit, KH, e0 + g, q[g] * inv_n);
+        if (e0 + g < B)
+          *reinterpret_cast<__nv_bfloat16*>(xh_unit + ((i0 + g) & 7) * 16 + ((i0 + g) >> 3) * (16 * KH)) = __float2bfloat16_rn(q[g] * inv_n);
     }
     return;
   }
@@ -587,14 +615,14 @@ __global__ void __launch_bounds__(kEncThreads, 1) zone_encode_kernel(const EncAr
           }
         }
       }
-      if (kK1 == 32)
+      if (!XHEAD && kK1 == 32)                              // (the fused forward exists for one-K-step inputs only)
         *reinterpret_cast<uint4*>(xbuf + x_off + 256) =
             make_uint4(pack_bf16(x2[0], x2[1]), pack_bf16(x2[2], x2[3]), pack_bf16(x2[4], x2[5]), pack_bf16(x2[6], x2[7]));
       fence_async_smem();
     };
     auto fetch_x = [&](int tl) {
       load_half_row<STATE>(a, tl, m, half, x);
-      if (!STATE && kK1 == 32) load_half_row<STATE>(a, tl, m, half + 2, x2);
+      if (!STATE && !XHEAD && kK1 == 32) load_half_row<STATE>(a, tl, m, half + 2, x2);
     };
     fetch_x(tile);
     stage_x(tile);
@@ -639,6 +667,34 @@ __global__ void __launch_bounds__(kEncThreads, 1) zone_encode_kernel(const EncAr
       if (t == 0) CRL_TL(group, k, 6);                         // layer 2 (M-block 0) done, seen by warp 0
       if (drains2) {
         const bool full = j < a.h && ((tile + 1) << (7 - log2_s)) <= a.B;
+        // the image row of the tile's first env (its 8 / 16 envs share a head tile and start an 8-row group)
+        const int et = tile << (7 - log2_s);
+        uint8_t* const xh_tile = XHEAD ? xh_unit + (size_t)(et >> 7) * (size_t)(kRows * a.KH * 2) + (uint32_t)(((et & (kRows - 1)) >> 3) * (16 * a.KH))
+                                       : nullptr;
+        if (XHEAD && a.S == 16) {
+          // 16 zone slots per env: the tile is 8 envs = ONE 8-row group of the head image.  Collect the eight pooled
+          // values of this thread's unit, transpose 8 x 8 inside each group of 8 lanes (lane r then holds units
+          // 8 g .. 8 g + 7 of env r) and write ONE 16-byte piece per lane instead of eight 2-byte ones.
+          float pv[8];
+#pragma unroll
+          for (int c = 0; c < kRows / 32; c += 2) {
+            uint32_t v0[32], v1[32];
+            tmem_ld32(my_acc + (uint32_t)(c * 32), v0);
+            tmem_ld32(my_acc + (uint32_t)(c * 32 + 32), v1);
+            tmem_ld_wait(v0);
+            relu_pool16(v0, inv_n, pv[2 * c], pv[2 * c + 1]);
+            tmem_ld_wait(v1);
+            relu_pool16(v1, inv_n, pv[2 * c + 2], pv[2 * c + 3]);
+          }
+          // units >= h of the image row: the head's ones (h, h + 1), then zeros
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pv[i] = j < a.h ? pv[i] : (j <= a.h + 1 ? 1.f : 0.f);
+          transpose8(pv, lane);
+          const int r = lane & 7;
+          if (et + r < a.B)
+            *reinterpret_cast<uint4*>(xh_tile - (uint32_t)(((8 + j) & 7) * 2) + (uint32_t)(r * 16)) =      // chunk (8 + j) / 8, row r
+                make_uint4(pack_bf16(pv[0], pv[1]), pack_bf16(pv[2], pv[3]), pack_bf16(pv[4], pv[5]), pack_bf16(pv[6], pv[7]));
+        } else
 #pragma unroll 1
         for (int c = 0; c < kRows / 32; c += 2) {             // two TMEM loads in flight
           uint32_t v0[32], v1[32];
@@ -647,9 +703,9 @@ __global__ void __launch_bounds__(kEncThreads, 1) zone_encode_kernel(const EncAr
           tmem_ld_wait(v0);
           if (t == 0) CRL_TL(group, k, 8 + 2 * c);               // 8 / 12: a pair of TMEM loads has arrived
           const int e0 = (tile << (7 - log2_s)) + c * per_chunk;
-          relu_pool_store<XHEAD>(v0, out_col, a.h, a.B, a.S, e0, full, j < a.h, inv_n, xh_unit, a.KH);
+          relu_pool_store<XHEAD>(v0, out_col, a.h, a.B, a.S, e0, full, j < a.h, inv_n, xh_tile, a.KH);
           tmem_ld_wait(v1);
-          relu_pool_store<XHEAD>(v1, out_col, a.h, a.B, a.S, e0 + per_chunk, full, j < a.h, inv_n, xh_unit, a.KH);
+          relu_pool_store<XHEAD>(v1, out_col, a.h, a.B, a.S, e0 + per_chunk, full, j < a.h, inv_n, xh_tile, a.KH);
           if (t == 0) CRL_TL(group, k, 9 + 2 * c);               // 9 / 13: pooled and stored
         }
       }
