@@ -445,7 +445,9 @@ __device__ long long g_timeline[148 * 2 * 64 * 16];
 
 // XHEAD: the output goes into the head kernel's operand image (crl_encoder_forward) instead of `out`; a template
 // parameter so that the plain kernels carry none of it (with a run-time test they lost 8 % to register pressure)
-template <bool STATE, bool XHEAD>
+// WIDE: the layer-1 input takes two K steps (obs_dim + zone_dim + 1 > 16: ZoneEnvGoalModel / ZoneEnvSkillModel); a template
+// parameter because the second prefetched chunk costs the one-step kernels eight registers they do not have (96 per thread)
+template <bool STATE, bool XHEAD, bool WIDE = false>
 __global__ void __launch_bounds__(kEncThreads, 1) zone_encode_kernel(const EncArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const Offsets o = offsets(a.h, a.obs_dim + a.Z);
@@ -615,14 +617,14 @@ __global__ void __launch_bounds__(kEncThreads, 1) zone_encode_kernel(const EncAr
           }
         }
       }
-      if (!XHEAD && kK1 == 32)                              // (the fused forward exists for one-K-step inputs only)
+      if (WIDE)
         *reinterpret_cast<uint4*>(xbuf + x_off + 256) =
             make_uint4(pack_bf16(x2[0], x2[1]), pack_bf16(x2[2], x2[3]), pack_bf16(x2[4], x2[5]), pack_bf16(x2[6], x2[7]));
       fence_async_smem();
     };
     auto fetch_x = [&](int tl) {
       load_half_row<STATE>(a, tl, m, half, x);
-      if (!STATE && !XHEAD && kK1 == 32) load_half_row<STATE>(a, tl, m, half + 2, x2);
+      if (WIDE) load_half_row<STATE>(a, tl, m, half + 2, x2);
     };
     fetch_x(tile);
     stage_x(tile);
@@ -1243,7 +1245,8 @@ static int zone_encode_launch(const CrlEncoderShape* s, int32_t num_envs, const 
   if (cudaGetDevice(&dev) != cudaSuccess) return CRL_ERR_DEVICE;
   static bool attr_set[64] = {false};                       // per device: opt in to > 48 KB of dynamic shared memory
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    if (cudaFuncSetAttribute(zone_encode_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+    if (cudaFuncSetAttribute(zone_encode_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(zone_encode_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(zone_encode_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(zone_encode_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(zone_encode_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
@@ -1291,6 +1294,7 @@ static int zone_encode_launch(const CrlEncoderShape* s, int32_t num_envs, const 
   if (st && xhead) zone_encode_kernel<true, true><<<grid, kEncThreads, o.smem_end, cs>>>(a);
   else if (st) zone_encode_kernel<true, false><<<grid, kEncThreads, o.smem_end, cs>>>(a);
   else if (xhead) zone_encode_kernel<false, true><<<grid, kEncThreads, o.smem_end, cs>>>(a);
+  else if (padded_k1(s->obs_dim + s->zone_dim) == 32) zone_encode_kernel<false, false, true><<<grid, kEncThreads, o.smem_end, cs>>>(a);
   else zone_encode_kernel<false, false><<<grid, kEncThreads, o.smem_end, cs>>>(a);
   return cudaGetLastError() == cudaSuccess ? CRL_OK : CRL_ERR_LAUNCH;
 }
