@@ -398,8 +398,12 @@ __device__ __forceinline__ void relu_pool_store(const uint32_t (&v)[32], float* 
 // of them -- by then that slot's epilogue 2 (which started when ITS L2 completed, i.e. when this one began) has freed
 // its accumulators -- so that slot's epilogue 1 runs under the rest of this L2 and its own L2 is ready to issue the
 // moment this one ends: the pipe always has queued work, and each epilogue has a whole L2 (~1,500 cycles) to hide in.
-constexpr int kIssuerThreads = 32;
-constexpr int kEncThreads = kGroupThreads * kGroups + kIssuerThreads;
+// The issuing warp is warp 4 of group 0: an (M-block 1, lane quadrant 0) warp, which has no accumulator rows to drain
+// (M-block 1's real rows sit in quadrants 2, 3).  Its share of the input staging goes to its neighbour, warp 5, which
+// drains nothing either.  A 17th warp would cap the kernel at 96 registers per thread (five warps on one scheduler);
+// with 16 warps it has 128 and no spills.
+constexpr int kIssuerWarp = 4;
+constexpr int kEncThreads = kGroupThreads * kGroups;
 #ifndef CRL_ENC_INSERT_AFTER
 #define CRL_ENC_INSERT_AFTER 12    // MMAs of an L2 issued before the issuer BLOCKS for the other slot's L1 (earlier if ready)
 #endif
@@ -454,8 +458,8 @@ __global__ void __launch_bounds__(kEncThreads, 1) zone_encode_kernel(const EncAr
   const int KP = padded_k(a.h), MP = padded_m(a.h), kK1 = padded_k1(a.obs_dim + a.Z);
   const int n_mblocks = MP / 128;
   const int warp_idx = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform, and the compiler knows it
-  const bool issuer = warp_idx >= kGroupThreads * kGroups / 32;
-  const int group = issuer ? 0 : warp_idx / (kGroupThreads / 32);   // 0 / 1
+  const bool issuer = warp_idx == kIssuerWarp;
+  const int group = warp_idx / (kGroupThreads / 32);          // 0 / 1 (the issuing warp: 0)
   const int t = threadIdx.x % kGroupThreads;
   const int m = t & (kRows - 1), half = t >> 7;               // input row / half of it this thread stages
   const int warp = t >> 5, lane = t & 31;
@@ -471,8 +475,8 @@ __global__ void __launch_bounds__(kEncThreads, 1) zone_encode_kernel(const EncAr
   if (threadIdx.x == 0) {
     for (int g = 0; g < kGroups; ++g) {
       const uint32_t b = bar0 + (uint32_t)g * o.group_bytes;
-      mbar_init(b + kBarFullX, kGroupThreads / 32);
-      mbar_init(b + kBarFullH1, kGroupThreads / 32);
+      mbar_init(b + kBarFullX, kGroupThreads / 32 - (g == 0 ? 1 : 0));     // group 0 lends a warp to the issue loop
+      mbar_init(b + kBarFullH1, kGroupThreads / 32 - (g == 0 ? 1 : 0));
       mbar_init(b + kBarL1Done, 1);
       mbar_init(b + kBarL2Done, 1);
       mbar_init(b + kBarL2Done + 8, 1);
@@ -598,24 +602,40 @@ __global__ void __launch_bounds__(kEncThreads, 1) zone_encode_kernel(const EncAr
     const int log2_s = a.S == 16 ? 4 : 3, per_chunk = 32 >> log2_s;   // envs per 32 accumulator columns (a runtime
     int tile = kGroups * blockIdx.x + group;                           // division here cost epilogue 2 ~800 cycles per tile)
     float x[8], x2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // 16-byte units `half` and, for 32-wide inputs, `half + 2`
+    // group 0's warp 5 also stages the rows of warp 4 (the issuing warp): rows m - 32, same half
+    const bool dual = group == 0 && warp == kIssuerWarp + 1;
+    float y[8], y2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int md = m - 32;
+    const uint32_t y_off = (uint32_t)((md & 7) * 16 + (md >> 3) * (16 * kK1) + half * 128);
     auto stage_x = [&](int tl) {                               // this thread's part of the slot's layer-1 B operand
       const uint4 xv = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
       *reinterpret_cast<uint4*>(xbuf + x_off) = xv;
-      if (XHEAD && (m & (a.S - 1)) == 0) {
-        // the env's first row: its obs chunk (half 0: the same eight bf16 values) and its ones / zero padding behind
-        // the pooled units (half 1) go into the head operand image
-        const int e = (tl << (7 - (a.S == 16 ? 4 : 3))) + (m >> (a.S == 16 ? 4 : 3));
-        if (tl < a.n_tiles && e < a.B) {
+      if (dual) {
+        *reinterpret_cast<uint4*>(xbuf + y_off) =
+            make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
+        if (WIDE)
+          *reinterpret_cast<uint4*>(xbuf + y_off + 256) =
+              make_uint4(pack_bf16(y2[0], y2[1]), pack_bf16(y2[2], y2[3]), pack_bf16(y2[4], y2[5]), pack_bf16(y2[6], y2[7]));
+      }
+      if (XHEAD) {
+        // an env's first row: its obs chunk (half 0: the same eight bf16 values) and its ones / zero padding behind the
+        // pooled units (half 1) go into the head operand image
+        auto image_row = [&](int mr, const uint4& v) {
+          if ((mr & (a.S - 1)) != 0) return;
+          const int e = (tl << (7 - (a.S == 16 ? 4 : 3))) + (mr >> (a.S == 16 ? 4 : 3));
+          if (tl >= a.n_tiles || e >= a.B) return;
           const int mh = e & (kRows - 1);
           uint8_t* row = a.xhead + (size_t)(e >> 7) * (size_t)(kRows * a.KH * 2) + (uint32_t)((mh & 7) * 16 + (mh >> 3) * (16 * a.KH));
           if (half == 0) {
-            *reinterpret_cast<uint4*>(row) = xv;
+            *reinterpret_cast<uint4*>(row) = v;
           } else {
             for (int k = 8 + a.h; k < a.KH; ++k)
               *reinterpret_cast<__nv_bfloat16*>(row + (uint32_t)((k >> 3) * 128 + (k & 7) * 2)) =
                   __float2bfloat16_rn(k <= 8 + a.h + 1 ? 1.f : 0.f);
           }
-        }
+        };
+        image_row(m, xv);
+        if (dual) image_row(md, xv);                           // (half 1: the value is not used)
       }
       if (WIDE)
         *reinterpret_cast<uint4*>(xbuf + x_off + 256) =
@@ -625,6 +645,10 @@ __global__ void __launch_bounds__(kEncThreads, 1) zone_encode_kernel(const EncAr
     auto fetch_x = [&](int tl) {
       load_half_row<STATE>(a, tl, m, half, x);
       if (WIDE) load_half_row<STATE>(a, tl, m, half + 2, x2);
+      if (dual) {
+        load_half_row<STATE>(a, tl, md, half, y);
+        if (WIDE) load_half_row<STATE>(a, tl, md, half + 2, y2);
+      }
     };
     fetch_x(tile);
     stage_x(tile);
