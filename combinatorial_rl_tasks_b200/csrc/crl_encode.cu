@@ -717,7 +717,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) zone_encode_kernel(const EncAr
           for (int i = 0; i < 8; ++i) pv[i] = j < a.h ? pv[i] : (j <= a.h + 1 ? 1.f : 0.f);
           transpose8(pv, lane);
           const int r = lane & 7;
-          if (et + r < a.B)
+          if (et + r < a.B && ((8 + j) >> 3) < (a.KH >> 3))     // (a warp's last 8-unit groups can lie beyond the image's width)
             *reinterpret_cast<uint4*>(xh_tile - (uint32_t)(((8 + j) & 7) * 2) + (uint32_t)(r * 16)) =      // chunk (8 + j) / 8, row r
                 make_uint4(pack_bf16(pv[0], pv[1]), pack_bf16(pv[2], pv[3]), pack_bf16(pv[4], pv[5]), pack_bf16(pv[6], pv[7]));
         } else

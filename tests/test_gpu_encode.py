@@ -195,12 +195,15 @@ def test_unsupported_shapes_are_refused(crl):
     assert lib.crl_encoder_head_packed_bytes(_lib.CrlEncoderShape(8, 6, 185, 15), ctypes.byref(n)) == 0 and n.value == 256 * 208 * 2
 
 
-@pytest.mark.parametrize('env_id,B', [('PointTSP-v0', 4099), ('ColourMatch-v0', 1000), ('PointTTSP-v0', 129), ('PointTSP-v1', 77)])
-def test_fused_forward_is_the_two_call_forward(crl, env_id, B):
+@pytest.mark.parametrize('env_id,B,h', [('PointTSP-v0', 4099, 185), ('ColourMatch-v0', 1000, 185), ('PointTTSP-v0', 129, 185),
+                                        ('PointTSP-v1', 77, 185), ('PointTSP-v0', 3000, 100), ('PointTTSP-v0', 2000, 64),
+                                        ('ColourMatch-v0', 900, 127), ('PointTSP-v0', 1500, 33)])
+def test_fused_forward_is_the_two_call_forward(crl, env_id, B, h):
     """crl_encoder_forward (the zone kernel writes the head kernel's bf16 operand image, no fp32 pooled in between, one
     bulk copy per 128 envs in the head) gives bit for bit what crl_zone_encode + crl_encoder_head give -- the head rounds
-    pooled to bf16 either way -- from the materialised zone_obs and from the state planes; ragged batches."""
-    N, Z, h = crl.ENV_SPECS[env_id].num_zones, crl.ENV_SPECS[env_id].zone_dim, 185
+    pooled to bf16 either way -- from the materialised zone_obs and from the state planes; ragged batches; hidden widths
+    whose last warp reaches beyond the image's width (100, 33), one M-block (64, 100) and two (127: the ones rows, 185)."""
+    N, Z = crl.ENV_SPECS[env_id].num_zones, crl.ENV_SPECS[env_id].zone_dim
     gen = torch.Generator(device='cuda').manual_seed(B)
     rn = lambda *s_, scale=1.0: (torch.randn(*s_, device='cuda', generator=gen) * scale)
     sd = {'zone_net_.0.weight': rn(h, 8 + Z, scale=0.4), 'zone_net_.0.bias': rn(h, scale=0.2),
