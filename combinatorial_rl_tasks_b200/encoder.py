@@ -117,12 +117,13 @@ class ZoneEncoder:
             self._ws = {B: ws}                      # one batch size at a time
         return ws if ws is not False else None
 
-    def _forward(self, obs, zone_obs=None, env=None, out=None):
+    def _forward(self, obs, zone_obs=None, env=None, out=None, head=None):
         B = obs.shape[0]
+        head = self.packed_head if head is None else head
         ws = self._workspace(B)
         if ws is None:
             pooled = self.pooled(obs, zone_obs) if env is None else self.pooled_from_state(env)
-            return self._head(self.packed_head, obs, pooled, out)
+            return self._head(head, obs, pooled, out)
         if out is None:
             out = torch.empty(B, self.hidden, dtype=torch.float32, device=self.device)
         assert out.shape == (B, self.hidden) and out.dtype == torch.float32 and out.is_contiguous()
@@ -132,7 +133,7 @@ class ZoneEncoder:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.crl_encoder_forward(
                 self.shape, env.cfg if env is not None else None, env.state if env is not None else None, B, obs.data_ptr(),
-                None if env is not None else zone_obs.data_ptr(), self.packed.data_ptr(), self.packed_head.data_ptr(),
+                None if env is not None else zone_obs.data_ptr(), self.packed.data_ptr(), head.data_ptr(),
                 ws.data_ptr(), out.data_ptr(), self._status.data_ptr(), self._stream()))
         return out
 
@@ -152,8 +153,9 @@ class ZoneEncoder:
         return out
 
     def zone_embedding(self, obs, zone_obs, out=None):
-        """mean_z zone_net_([obs, zone_obs[:, z]]) (env_model.py:73) = L3(pooled)."""
-        return self._head(self.packed_l3, obs, self.pooled(obs, zone_obs), out)
+        """mean_z zone_net_([obs, zone_obs[:, z]]) (env_model.py:73) = L3(pooled): the fused two-launch forward with the
+        head weights [0 | W3]."""
+        return self._forward(obs, zone_obs, out=out, head=self.packed_l3)
 
     # ---- precise mode: split-bf16 operands (three MMAs per product), fp32 biases; like for like with the fp32 module ----
     def _precise_image(self):
