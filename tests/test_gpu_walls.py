@@ -195,3 +195,27 @@ def test_walled_flag_is_validated(crl):
     env.cfg.walled = 2
     with pytest.raises(Exception):
         env.step(torch.zeros(64, 2, device='cuda'))
+
+
+@pytest.mark.parametrize('env_id', ['walled/PointTSP-v0', 'walled/PointTTSP-v0'])
+def test_walled_host_step_equals_the_device_step(crl, env_id):
+    """A walled env steps through the EXT kernels on every path: the host-facing call (one kernel writing into the caller's
+    pinned buffers) returns byte for byte what the device step returns, while half the batch is pressed against the walls."""
+    B = 512
+    a_dev, a_host = crl.ZoneVecEnv(env_id, B), crl.ZoneVecEnv(env_id, B)
+    for e in (a_dev, a_host):
+        e.seed(77)
+        e.reset()
+    rs = np.random.RandomState(2)
+    hold = np.zeros((B, 2), dtype=np.float32)
+    touched = 0
+    for t in range(400):
+        if t % 50 == 0:
+            hold = np.stack([rs.uniform(0.3, 1.0, B), rs.uniform(-0.2, 0.2, B)], 1).astype(np.float32)
+        o_d, r_d, d_d, _ = a_dev.step(torch.from_numpy(hold).cuda())
+        o_h, r_h, d_h, _ = a_host.step_host(hold)
+        assert np.array_equal(o_d['obs'].cpu().numpy(), o_h['obs']), t
+        assert np.array_equal(o_d['zone_obs'].cpu().numpy(), np.asarray(o_h['zone_obs'])), t
+        assert np.array_equal(r_d.cpu().numpy(), r_h) and np.array_equal(d_d.cpu().numpy().astype(bool), np.asarray(d_h).astype(bool)), t
+        touched = max(touched, int((a_dev.pose[:, :2].abs().max(dim=1).values > 2.8).sum()))
+    assert touched > B // 8
