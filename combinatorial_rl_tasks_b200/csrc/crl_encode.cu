@@ -601,10 +601,10 @@ __global__ void __launch_bounds__(kEncThreads, 1) zone_encode_kernel(const EncAr
     uint8_t* const xh_unit = XHEAD ? a.xhead + (uint32_t)(((8 + j) >> 3) * 128 + ((8 + j) & 7) * 2) : nullptr;
     const int log2_s = a.S == 16 ? 4 : 3, per_chunk = 32 >> log2_s;   // envs per 32 accumulator columns (a runtime
     int tile = kGroups * blockIdx.x + group;                           // division here cost epilogue 2 ~800 cycles per tile)
-    float x[8], x2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // 16-byte units `half` and, for 32-wide inputs, `half + 2`
+    float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, x2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // 16-byte units `half` and, for 32-wide inputs, `half + 2`
     // group 0's warp 5 also stages the rows of warp 4 (the issuing warp): rows m - 32, same half
     const bool dual = group == 0 && warp == kIssuerWarp + 1;
-    float y[8], y2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float y[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, y2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const int md = m - 32;
     const uint32_t y_off = (uint32_t)((md & 7) * 16 + (md >> 3) * (16 * kK1) + half * 128);
     auto stage_x = [&](int tl) {                               // this thread's part of the slot's layer-1 B operand
