@@ -593,12 +593,8 @@ __global__ void __launch_bounds__(kEncThreads, 1) zone_encode_kernel(const EncAr
     const uint32_t x_off = (uint32_t)((m & 7) * 16 + (m >> 3) * (16 * kK1) + half * 128);
     const uint32_t h1_off = (uint32_t)((j & 7) * 16 + (j >> 3) * 2048);
     const bool drains1 = mblock < n_mblocks && j0 < KP;       // layer 2 reads hidden rows < KP
-    const bool drains2 = mblock < n_mblocks && j0 < a.h;      // the output has h columns
     const uint32_t l2_bar = bars + kBarL2Done + 8u * (uint32_t)(mblock < n_mblocks ? mblock : n_mblocks - 1);
     const float inv_n = 1.0f / (float)a.N;
-    float* const out_col = a.out + j;
-    // this thread's unit in a row of the head operand image: column obs_dim + j = 8 + j (the fused path needs obs_dim 8)
-    uint8_t* const xh_unit = XHEAD ? a.xhead + (uint32_t)(((8 + j) >> 3) * 128 + ((8 + j) & 7) * 2) : nullptr;
     const int log2_s = a.S == 16 ? 4 : 3, per_chunk = 32 >> log2_s;   // envs per 32 accumulator columns (a runtime
     int tile = kGroups * blockIdx.x + group;                           // division here cost epilogue 2 ~800 cycles per tile)
     float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, x2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // 16-byte units `half` and, for 32-wide inputs, `half + 2`
@@ -688,6 +684,12 @@ __global__ void __launch_bounds__(kEncThreads, 1) zone_encode_kernel(const EncAr
       fetch_x(tile + 2 * tile_stride);
       // ---- epilogue 2: ReLU, mean over each env's zone slots (register adds), coalesced stores ----
       if (t == 0) CRL_TL(group, k, 5);                         // next rows staged (warp 0)
+      if (XHEAD) {
+      // (the image-writing variants keep one warp per (M-block, quadrant): their 16-byte stores want all 8 envs of a unit
+      // group in one warp; with the column split below they measured 16 % slower)
+      const bool drains2 = mblock < n_mblocks && j0 < a.h;      // the output has h columns
+      float* const out_col = a.out + j;
+      uint8_t* const xh_unit = a.xhead + (uint32_t)(((8 + j) >> 3) * 128 + ((8 + j) & 7) * 2);   // column 8 + j of an image row
       healthy = mbar_wait(l2_bar, parity) && healthy;
       tc_fence_after();
       if (t == 0) CRL_TL(group, k, 6);                         // layer 2 (M-block 0) done, seen by warp 0
@@ -734,6 +736,77 @@ __global__ void __launch_bounds__(kEncThreads, 1) zone_encode_kernel(const EncAr
           relu_pool_store<XHEAD>(v1, out_col, a.h, a.B, a.S, e0 + per_chunk, full, j < a.h, inv_n, xh_tile, a.KH);
           if (t == 0) CRL_TL(group, k, 9 + 2 * c);               // 9 / 13: pooled and stored
         }
+      }
+      } else {
+      // Who drains what: in lane quadrants 0, 1 only M-block 0 has rows, and its warp takes all 128 columns; in quadrants
+      // 2, 3 BOTH M-blocks have rows and the quadrant's two warps split the COLUMNS of both (warp w / 4 takes half w / 4):
+      // M-block 0 completes 12 MMAs before M-block 1, so this way both warps work on it at once and the tail after the
+      // last MMA is half of M-block 1, not all of it.
+      bool waited = false;
+#pragma unroll 1
+      for (int b = 0; b < n_mblocks; ++b) {
+        const bool split = quad >= 2;
+        const bool mine = split ? true : (mblock == 0 && b == 0);
+        const int jb0 = b == 0 ? quad * 32 : 128 + (quad - 2) * 32, jb = jb0 + lane;   // this thread's unit in M-block b
+        if (!mine || jb0 >= a.h) continue;                     // the output has h columns
+        healthy = mbar_wait(bars + kBarL2Done + 8u * (uint32_t)b, parity) && healthy;
+        tc_fence_after();
+        waited = true;
+        if (t == 0 && b == 0) CRL_TL(group, k, 6);             // layer 2 (M-block 0) done, seen by warp 0
+        const int c_lo = split ? 2 * mblock : 0, c_hi = split ? c_lo + 2 : kRows / 32;   // 32-column chunks
+        const uint32_t acc_b = tmem_base + (uint32_t)group * 256u + (uint32_t)(b * 128) + ((uint32_t)(quad * 32) << 16);
+        const bool full = jb < a.h && ((tile + 1) << (7 - log2_s)) <= a.B;
+        // the image row of the tile's first env (its 8 / 16 envs share a head tile and start an 8-row group)
+        const int et = tile << (7 - log2_s);
+        uint8_t* const xh_tile = XHEAD ? a.xhead + (uint32_t)(((8 + jb) >> 3) * 128 + ((8 + jb) & 7) * 2) +
+                                             (size_t)(et >> 7) * (size_t)(kRows * a.KH * 2) + (uint32_t)(((et & (kRows - 1)) >> 3) * (16 * a.KH))
+                                       : nullptr;
+        float* const out_b = a.out + jb;
+        if (XHEAD && a.S == 16) {
+          // 16 zone slots per env: the tile is 8 envs = ONE 8-row group of the head image.  Collect the pooled values of
+          // this thread's unit (envs 2 c, 2 c + 1 from chunk c; zeros for the chunks of the other warp), transpose 8 x 8
+          // inside each group of 8 lanes (lane r then holds units 8 g .. 8 g + 7 of env r) and write ONE 16-byte piece per
+          // lane and env of this warp's columns instead of eight 2-byte ones.
+          float pv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int c = 0; c < kRows / 32; c += 2) {
+            if (c < c_lo || c >= c_hi) continue;
+            uint32_t v0[32], v1[32];
+            tmem_ld32(acc_b + (uint32_t)(c * 32), v0);
+            tmem_ld32(acc_b + (uint32_t)(c * 32 + 32), v1);
+            tmem_ld_wait(v0);
+            relu_pool16(v0, inv_n, pv[2 * c], pv[2 * c + 1]);
+            tmem_ld_wait(v1);
+            relu_pool16(v1, inv_n, pv[2 * c + 2], pv[2 * c + 3]);
+          }
+          // units >= h of the image row: the head's ones (h, h + 1), then zeros
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pv[i] = jb < a.h ? pv[i] : (jb <= a.h + 1 ? 1.f : 0.f);
+          transpose8(pv, lane);
+          const int r = lane & 7;                              // the env of the tile this lane now holds
+          if (r >= 2 * c_lo && r < 2 * c_hi && et + r < a.B && ((8 + jb) >> 3) < (a.KH >> 3))
+            *reinterpret_cast<uint4*>(xh_tile - (uint32_t)(((8 + jb) & 7) * 2) + (uint32_t)(r * 16)) =      // chunk (8 + jb) / 8, row r
+                make_uint4(pack_bf16(pv[0], pv[1]), pack_bf16(pv[2], pv[3]), pack_bf16(pv[4], pv[5]), pack_bf16(pv[6], pv[7]));
+        } else {
+#pragma unroll 1
+          for (int c = c_lo; c < c_hi; c += 2) {               // two TMEM loads in flight
+            uint32_t v0[32], v1[32];
+            tmem_ld32(acc_b + (uint32_t)(c * 32), v0);
+            tmem_ld32(acc_b + (uint32_t)(c * 32 + 32), v1);
+            tmem_ld_wait(v0);
+            if (t == 0) CRL_TL(group, k, 8 + 2 * c);             // 8 / 12: a pair of TMEM loads has arrived
+            const int e0 = (tile << (7 - log2_s)) + c * per_chunk;
+            relu_pool_store<XHEAD>(v0, out_b, a.h, a.B, a.S, e0, full, jb < a.h, inv_n, xh_tile, a.KH);
+            tmem_ld_wait(v1);
+            relu_pool_store<XHEAD>(v1, out_b, a.h, a.B, a.S, e0 + per_chunk, full, jb < a.h, inv_n, xh_tile, a.KH);
+            if (t == 0) CRL_TL(group, k, 9 + 2 * c);             // 9 / 13: pooled and stored
+          }
+        }
+      }
+      if (!waited) {                                           // a warp without rows still orders itself behind layer 2
+        healthy = mbar_wait(l2_bar, parity) && healthy;
+        tc_fence_after();
+      }
       }
       // accumulators drained + next rows staged: the issuer may overwrite both with the slot's next layer 1
       tc_fence_before();
