@@ -68,6 +68,7 @@ class ZoneEncoder:
                                                       self.packed_l3.data_ptr(), self._stream()))
         self._keep = (w1, b1, w2, b2, l3_w)         # alive until the pack kernels have run
         self._packed_precise = None                 # packed on first use (pooled_precise)
+        self._precise_heads = {}
 
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -185,16 +186,41 @@ class ZoneEncoder:
                                                         out.data_ptr(), self._status.data_ptr(), self._stream()))
         return out
 
+    def _head_precise(self, key, w, b, obs, pooled):
+        """An affine map of [obs, pooled] to fp32-level accuracy on the SAME tensor-core head kernel: it multiplies
+        bf16(W) bf16(X), so three launches -- (W, X), (W - bf16 W, X), (W, X - bf16 X) -- add up to the split product
+        W_hi X_hi + W_lo X_hi + W_hi X_lo; the bias rides in the first one (as its bf16 hi + lo pair).  No library GEMM."""
+        imgs = self._precise_heads.get(key)
+        if imgs is None:
+            n = ctypes.c_int64()
+            _lib.check(self.lib.crl_encoder_head_packed_bytes(self.shape, ctypes.byref(n)))
+            r = lambda t: t.to(torch.bfloat16).to(torch.float32)
+            zero = torch.zeros_like(b)
+            imgs, keep = [], []
+            for wi, bi in ((w, b), ((w - r(w)).contiguous(), zero), (w, zero)):
+                buf = torch.zeros(n.value, dtype=torch.uint8, device=self.device)
+                with torch.cuda.device(self.device):
+                    _lib.check(self.lib.crl_encoder_pack_head(self.shape, wi.data_ptr(), bi.data_ptr(), buf.data_ptr(), self._stream()))
+                imgs.append(buf)
+                keep.append((wi, bi))
+            torch.cuda.current_stream(self.device).synchronize()       # the temporaries may go
+            self._precise_heads[key] = imgs
+        r = lambda t: t.to(torch.bfloat16).to(torch.float32)
+        out = self._head(imgs[0], obs, pooled)
+        out += self._head(imgs[1], obs, pooled)
+        out += self._head(imgs[2], (obs - r(obs)).contiguous(), (pooled - r(pooled)).contiguous())
+        return out
+
     def zone_embedding_precise(self, obs, zone_obs):
-        """L3(pooled) with the precise kernel; the (B, h) affine map itself is an fp32 library GEMM (1 % of the flops)."""
-        return torch.addmm(self.b3, self.pooled_precise(obs, zone_obs), self.w3.t())
+        """L3(pooled) to fp32-level accuracy: precise zone kernel + the split head (three launches of the head kernel)."""
+        l3_w = torch.cat([torch.zeros(self.hidden, self.obs_dim, device=self.device), self.w3], dim=1).contiguous()
+        return self._head_precise('l3', l3_w, self.b3, obs, self.pooled_precise(obs, zone_obs))
 
     def forward_precise(self, obs, zone_obs=None):
-        """ZoneEnvModel.forward to fp32-level accuracy: precise kernel + the folded fp32 affine map of [obs, pooled]."""
+        """ZoneEnvModel.forward to fp32-level accuracy: precise zone kernel + the split head on the folded affine map."""
         if zone_obs is None:
             obs, zone_obs = obs['obs'], obs['zone_obs']
-        x = torch.cat([obs, self.pooled_precise(obs, zone_obs)], dim=1)
-        return torch.addmm(self.fold_b, x, self.fold_w.t())
+        return self._head_precise('fold', self.fold_w, self.fold_b, obs, self.pooled_precise(obs, zone_obs))
 
     def healthy(self):
         """False if a tensor-core completion wait ever expired (synchronises)."""

@@ -443,8 +443,8 @@ int crl_encoder_forward(const CrlEncoderShape* shape, const CrlConfig* cfg, cons
  * tensor-core MMAs (hi hi + lo hi + hi lo), fp32 accumulation, fp32 biases in the epilogues -- `pooled` agrees with the
  * fp32 reference module (env_model.py:56-78) to ~1e-5 of its largest value instead of the fast kernel's 3-5e-3, at about
  * 7x its time (one tile in flight per CTA): the like-for-like / validation mode.  Own packed image (hi and lo of both layers + fp32 biases);
- * needs obs_dim + zone_dim <= 16.  The remaining (B, h) affine map of the forward is then an fp32 GEMM on the
- * caller's side. */
+ * needs obs_dim + zone_dim <= 16.  The remaining (B, h) affine map of the forward reaches the same accuracy with
+ * three launches of crl_encoder_head: (W, X), (W - bf16 W, X), (W, X - bf16 X) (encoder.py does that). */
 int crl_encoder_precise_packed_bytes(const CrlEncoderShape* shape, int64_t* bytes);
 int crl_encoder_pack_precise(const CrlEncoderShape* shape, const float* w1, const float* b1, const float* w2,
                              const float* b2, void* packed, void* stream);
