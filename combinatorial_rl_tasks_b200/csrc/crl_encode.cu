@@ -1071,7 +1071,7 @@ __global__ void __launch_bounds__(kGroupThreads * kGroups, 1) encoder_head_kerne
 // Twice the operand bytes do not fit an SM beside a tile's activations, so a CTA holds ONE M-block of W2 (hi + lo,
 // 96 KB) and computes that block's 128 output units for its tiles; layer 1 (all hidden units: they are layer 2's K)
 // is computed by both CTAs of a pair -- it is 6 of 42 MMAs.  One tile in flight per CTA: this is the validation /
-// like-for-like mode, ~7x the fast kernel's time (686 us at 65,536 PointTSP envs; torch fp32 eager: 7.3 ms).
+// like-for-like mode, ~7x the fast kernel's time (620 us at 65,536 PointTSP envs; torch fp32 eager: 7.3 ms).
 __host__ __device__ inline int precise_k(int h) { return (h + 15) & ~15; }
 
 struct PreciseOffsets {      // bytes; `g_*` in the packed global buffer, `s_*` in shared memory
@@ -1139,7 +1139,9 @@ __global__ void __launch_bounds__(kGroupThreads, 1) zone_encode_precise_kernel(c
   extern __shared__ __align__(128) uint8_t smem[];
   const PreciseOffsets o = precise_offsets(a.h);
   const int KP = precise_k(a.h), MP = (KP + 127) & ~127, n_mblocks = MP / 128;
-  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int t = threadIdx.x, lane = t & 31;
+  const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);       // warp-uniform, and the compiler knows it
+  const bool leader = elect_one();                            // of each warp; warp 0's issues the MMAs
   const int m = t & (kRows - 1), half = t >> 7;
   const int my_block = (int)blockIdx.x % n_mblocks;            // the M-block of layer 2 this CTA owns
   const uint32_t bar = smem_u32(smem + o.s_bar), wbar = smem_u32(smem + o.s_wbar);
@@ -1182,10 +1184,11 @@ __global__ void __launch_bounds__(kGroupThreads, 1) zone_encode_precise_kernel(c
   const int log2_s = a.S == 16 ? 4 : 3;
   uint32_t parity = 0u;
   bool healthy = true, weights_in = false;
+  float x[8];
+  load_half_row<false>(a, (int)blockIdx.x / n_mblocks, m, half, x);
   for (int tile = (int)blockIdx.x / n_mblocks; tile < a.n_tiles; tile += (int)gridDim.x / n_mblocks) {
-    // ---- the tile's input rows, split ----
-    float x[8], xh[8], xl[8];
-    load_half_row<false>(a, tile, m, half, x);
+    // ---- the tile's input rows (prefetched a tile ago), split ----
+    float xh[8], xl[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) split_bf16(x[i], xh[i], xl[i]);
     const uint32_t x_off = (uint32_t)((m & 7) * 16 + (m >> 3) * 256 + half * 128);
@@ -1196,18 +1199,25 @@ __global__ void __launch_bounds__(kGroupThreads, 1) zone_encode_precise_kernel(c
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
-    if (t == 0) {
+    load_half_row<false>(a, tile + (int)gridDim.x / n_mblocks, m, half, x);   // the next tile's rows travel under this tile
+    // MMAs are issued by warp 0 with all its lanes CONVERGED (uniform descriptors; one elected lane executes the
+    // tcgen05 instructions): from a single-thread branch every MMA costs ~300 cycles of issue (see zone_encode_kernel)
+    if (warp == 0) {
       if (!weights_in) healthy = mbar_wait(wbar, 0u) && healthy;
+      __syncwarp();
       tc_fence_after();
+      const uint32_t tmu = __shfl_sync(0xffffffffu, acc1, 0);
       const uint32_t w1hi = smem_u32(smem + o.s_w1), w1lo = w1hi + (uint32_t)MP * 32u;
       const uint32_t xhi = smem_u32(smem + o.s_xhi), xlo = smem_u32(smem + o.s_xlo);
       for (int b = 0; b < n_mblocks; ++b) {
-        const uint32_t d = acc1 + (uint32_t)(b * 128), wo = (uint32_t)(b * 128 * 32);
-        mma_bf16(d, smem_desc(w1hi + wo, 128u, 256u), smem_desc(xhi, 128u, 256u), idesc1, 0u);
-        mma_bf16(d, smem_desc(w1lo + wo, 128u, 256u), smem_desc(xhi, 128u, 256u), idesc1, 1u);
-        mma_bf16(d, smem_desc(w1hi + wo, 128u, 256u), smem_desc(xlo, 128u, 256u), idesc1, 1u);
+        const uint32_t d = tmu + (uint32_t)(b * 128), wo = (uint32_t)(b * 128 * 32);
+        const uint64_t ahi = smem_desc(w1hi + wo, 128u, 256u), alo = smem_desc(w1lo + wo, 128u, 256u);
+        const uint64_t bhi = smem_desc(xhi, 128u, 256u), blo = smem_desc(xlo, 128u, 256u);
+        if (leader) mma_bf16(d, ahi, bhi, idesc1, 0u);
+        if (leader) mma_bf16(d, alo, bhi, idesc1, 1u);
+        if (leader) mma_bf16(d, ahi, blo, idesc1, 1u);
       }
-      mma_commit(bar);
+      if (leader) mma_commit(bar);
     }
     weights_in = true;
     healthy = mbar_wait(bar, parity) && healthy;
@@ -1241,18 +1251,20 @@ __global__ void __launch_bounds__(kGroupThreads, 1) zone_encode_precise_kernel(c
     tc_fence_before();
     __syncthreads();
     // ---- layer 2, this CTA's M-block: three MMAs per K step ----
-    if (t == 0) {
+    if (warp == 0) {
       tc_fence_after();
+      const uint32_t d2 = __shfl_sync(0xffffffffu, acc2, 0);
       const uint32_t w2hi = smem_u32(smem + o.s_w2), w2lo = w2hi + 128u * (uint32_t)KP * 2u;
       const uint32_t hhi = smem_u32(smem + o.s_h1hi), hlo = smem_u32(smem + o.s_h1lo);
-      for (int s2 = 0; s2 < KP / 16; ++s2) {
-        const uint64_t ahi = smem_desc(w2hi + 256u * s2, 128u, 16 * KP), alo = smem_desc(w2lo + 256u * s2, 128u, 16 * KP);
-        const uint64_t bhi = smem_desc(hhi + 4096u * s2, 2048u, 128u), blo = smem_desc(hlo + 4096u * s2, 2048u, 128u);
-        mma_bf16(acc2, ahi, bhi, idesc2, s2 > 0);
-        mma_bf16(acc2, alo, bhi, idesc2, 1u);
-        mma_bf16(acc2, ahi, blo, idesc2, 1u);
+      uint64_t ahi = smem_desc(w2hi, 128u, 16 * KP), alo = smem_desc(w2lo, 128u, 16 * KP);
+      uint64_t bhi = smem_desc(hhi, 2048u, 128u), blo = smem_desc(hlo, 2048u, 128u);
+#pragma unroll 2
+      for (int s2 = 0; s2 < KP / 16; ++s2, ahi += 16u, alo += 16u, bhi += 256u, blo += 256u) {
+        if (leader) mma_bf16(d2, ahi, bhi, idesc2, s2 > 0);
+        if (leader) mma_bf16(d2, alo, bhi, idesc2, 1u);
+        if (leader) mma_bf16(d2, ahi, blo, idesc2, 1u);
       }
-      mma_commit(bar);
+      if (leader) mma_commit(bar);
     }
     healthy = mbar_wait(bar, parity) && healthy;
     parity ^= 1u;

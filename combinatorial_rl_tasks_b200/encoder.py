@@ -173,7 +173,7 @@ class ZoneEncoder:
 
     def pooled_precise(self, obs, zone_obs, out=None):
         """``pooled`` to fp32-level accuracy (crl_zone_encode_precise): ~1e-5 of the largest value against the fp32
-        module instead of 3-5e-3, at ~7x the fast kernel's time (686 us at 65,536 PointTSP envs)."""
+        module instead of 3-5e-3, at ~7x the fast kernel's time (620 us at 65,536 PointTSP envs)."""
         B = obs.shape[0]
         assert obs.shape == (B, self.obs_dim) and zone_obs.shape == (B, self.num_zones, self.zone_dim)
         assert obs.dtype == zone_obs.dtype == torch.float32 and obs.is_contiguous() and zone_obs.is_contiguous()
