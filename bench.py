@@ -456,6 +456,32 @@ def run_ours(args):
     pageable_rate, _, _, _ = timed_host_steps(True, args.e2e_seconds / 3, pageable)
     rate, rows_per_step, e2e_calls, best_rate = timed_host_steps(True, args.e2e_seconds)
     is_delta = rows_per_step < B
+
+    def copy_engine_floor(seconds=0.2):
+        """The copy engine alone moving one call's obs + result (no kernel, no actions) with every rank active: what
+        the box's host path allows for these bytes at this N (eight ranks of one VM share it, profiles/r02_notes.md)."""
+        hb, s_ = env._host_buffers(), torch.cuda.current_stream(dev)
+        def one():
+            hb['obs'].copy_(env.obs, non_blocking=True)
+            hb['result'].copy_(env.result, non_blocking=True)
+            s_.synchronize()
+        for _ in range(3):
+            one()
+        if world > 1:
+            dist.barrier()
+        per, t_start = [], time.perf_counter()
+        while True:
+            t0 = time.perf_counter()
+            for _ in range(10):
+                one()
+            t1 = time.perf_counter()
+            per.append((t1 - t0) / 10)
+            if t1 - t_start >= seconds:
+                break
+        per.sort()
+        return world * B / rank_max(per[len(per) // 2])
+
+    floor_rate = copy_engine_floor()
     e2e = {'value': rate, 'unit': UNIT, 'h2d_bytes_per_step': 8 * B,
            'd2h_bytes_per_step': int((32 + 8) * B + rows_per_step * 4 * N * Z),
            'calls': e2e_calls, 'timing': 'median over groups of 25 calls (host clock, synchronize on both sides)',
@@ -470,6 +496,10 @@ def run_ours(args):
                      else '; crl_step_host: everything copied whole'),
            'host_placement': numa,
            'full_copy_value': full_rate,
+           'copy_engine_floor_value': floor_rate,
+           'copy_engine_floor_note': 'obs + result of one call (%d bytes) moved by the copy engine alone + a stream sync, every '
+                                     'rank at once, same max-over-ranks median: the ceiling the host path of this box sets for '
+                                     'these bytes at this N; no kernel, no action upload' % ((32 + 8) * B),
            'full_copy_d2h_bytes_per_step': (32 + 4 * N * Z + 8) * B}
     del ring, env
     torch.cuda.empty_cache()
