@@ -66,7 +66,7 @@ def test_closed_forms():
 
 @pytest.mark.parametrize('path', EPISODES, ids=os.path.basename)
 def test_c_oracle_matches_reference_fixture(path):
-    g = np.load(path)
+    g = dict(np.load(path))
     env = co.CEnv(str(g['env_id']))
     env.seed(int(g['env_seed']))
     obs = env.reset()

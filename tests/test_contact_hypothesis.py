@@ -106,7 +106,7 @@ def test_fixture_action_sequences_under_the_alternative_reading():
     """How far the trajectories of the recorded episodes move between the two readings."""
     report = {}
     for path in sorted(glob.glob(os.path.join(GOLDEN, 'PointTSP_10000*_*.npz')))[:3]:
-        g = np.load(path)
+        g = dict(np.load(path))
         acts = g['actions'][:400]
         p_free, _ = rollout(acts, 'excluded')
         p_drag, _ = rollout(acts, 'active')

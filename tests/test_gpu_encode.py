@@ -62,8 +62,8 @@ def fp32_ref(sd, obs, zone_obs):
 
 @pytest.mark.parametrize('tag,n', [('tsp', 15), ('cm', 6)])
 def test_fixture_of_the_real_module(crl, tag, n):
-    g = np.load(GOLDEN)
-    sd = {k[len(tag) + 4:]: torch.from_numpy(g[k]).cuda() for k in g.files if k.startswith(tag + '_sd_')}
+    g = dict(np.load(GOLDEN))
+    sd = {k[len(tag) + 4:]: torch.from_numpy(g[k]).cuda() for k in g if k.startswith(tag + '_sd_')}
     enc = crl.ZoneEncoder(sd, num_zones=n)
     obs, zobs = torch.from_numpy(g[f'{tag}_obs']).cuda(), torch.from_numpy(g[f'{tag}_zone_obs']).cuda()
     emb = enc.zone_embedding(obs, zobs)
@@ -125,8 +125,8 @@ def test_random_batches_against_torch(crl, B, N, Z, h, D):
 
 def test_encoder_on_the_env_outputs(crl):
     """The fused step's outputs feed the encoder directly (obs (B,8), zone_obs (B,N,Z) as CrlOut lays them out)."""
-    g = np.load(GOLDEN)
-    sd = {k[7:]: torch.from_numpy(g[k]).cuda() for k in g.files if k.startswith('tsp_sd_')}
+    g = dict(np.load(GOLDEN))
+    sd = {k[7:]: torch.from_numpy(g[k]).cuda() for k in g if k.startswith('tsp_sd_')}
     env = crl.ZoneVecEnv('PointTSP-v0', 4096)
     env.seed(3)
     obs = env.reset()
@@ -233,8 +233,8 @@ PRECISE_RTOL = 1e-4       # the like-for-like bar against the fp32 module (VERDI
 def test_precise_mode_against_the_real_modules_fp32_output(crl, tag, n):
     """crl_zone_encode_precise (split-bf16 operands, three MMAs per product, fp32 biases) against the fixture recorded
     from the REAL ZoneEnvModel in fp32: zone_emb and forward within 1e-4 of the largest value."""
-    g = np.load(GOLDEN)
-    sd = {k[len(tag) + 4:]: torch.from_numpy(g[k]).cuda() for k in g.files if k.startswith(tag + '_sd_')}
+    g = dict(np.load(GOLDEN))
+    sd = {k[len(tag) + 4:]: torch.from_numpy(g[k]).cuda() for k in g if k.startswith(tag + '_sd_')}
     enc = crl.ZoneEncoder(sd, num_zones=n)
     torch.backends.cuda.matmul.allow_tf32 = False
     obs, zobs = torch.from_numpy(g[f'{tag}_obs']).cuda(), torch.from_numpy(g[f'{tag}_zone_obs']).cuda()

@@ -38,7 +38,7 @@ def test_goal_fixture_teacher_forced(crl, path):
     """What the real TSPNextCityEnv / TimedTSPNextCityEnv / ColourMatchNextCityEnv returned,
     replayed on the GPU with the physics state forced to the recorded qpos/qvel before every
     step and the recorded goal choices made through the batched RPCs."""
-    g = np.load(path)
+    g = dict(np.load(path))
     env_id = str(g['env_id'])
     task = ze.TASK_OF_ENV_ID[env_id]
     env = crl.ZoneVecEnv(env_id, 1)

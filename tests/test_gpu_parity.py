@@ -52,7 +52,7 @@ def ang_diff(a, b):
 
 
 def load_layout(g):
-    return {k[len('layout_'):]: g[k] for k in g.files if k.startswith('layout_')}
+    return {k[len('layout_'):]: g[k] for k in g if k.startswith('layout_')}
 
 
 def batched(lay):
@@ -147,7 +147,7 @@ def test_physics_ten_substeps_fused(crl):
 def test_fixture_episode_teacher_forced(crl, path):
     """CUDA path vs what the REAL reference task code returned (fixtures), with the
     physics state forced to the recorded qpos/qvel before every step."""
-    g = np.load(path)
+    g = dict(np.load(path))
     env_id = str(g['env_id'])
     env = crl.ZoneVecEnv(env_id, 1)
     obs = env.reset(layout=batched(load_layout(g)))
@@ -294,7 +294,7 @@ def test_vector_fixture_with_in_kernel_auto_reset(crl, path):
     the reference's own layouts, the physics state is forced to the recorded qpos/qvel before
     every step.  reward / done / goal_met of the finished episode and the FIRST observation of
     the next one must come out of the same call, exactly as penv.py:7-11 returns them."""
-    g = np.load(path)
+    g = dict(np.load(path))
     env_id = str(g['env_id'])
     task = ze.TASK_OF_ENV_ID[env_id]
     n = g['actions'].shape[1]
@@ -306,7 +306,7 @@ def test_vector_fixture_with_in_kernel_auto_reset(crl, path):
     for i in range(n):
         for j in range(int(g['n_layouts'][i])):
             for k in bank:
-                if f'layout_{i}_{j}_{k}' in g.files:
+                if f'layout_{i}_{j}_{k}' in g:
                     bank[k][stride * i + j] = g[f'layout_{i}_{j}_{k}']
     env = crl.ZoneVecEnv(env_id, n, seed_mode='increment', min_seed=0, max_seed=K - 1, layout_bank=bank)
     env.seed(torch.arange(n, dtype=torch.int64) * stride)

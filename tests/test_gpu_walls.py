@@ -134,10 +134,10 @@ def test_wall_fixture_teacher_forced(crl, name):
     forced to the recorded one before every step: task logic and observations as in test_gpu_parity, the post-physics
     state with the grazing allowance above."""
     import os
-    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', name))
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', name)))
     env_id = str(g['env_id'])
     env = crl.ZoneVecEnv(env_id, 1)
-    lay = {k[len('layout_'):]: np.asarray(g[k])[None] for k in g.files if k.startswith('layout_')}
+    lay = {k[len('layout_'):]: np.asarray(g[k])[None] for k in g if k.startswith('layout_')}
     env.reset(layout=lay)
     T = len(g['actions'])
     acts = torch.from_numpy(g['actions']).cuda()

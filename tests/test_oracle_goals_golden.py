@@ -22,7 +22,7 @@ def test_fixtures_present():
 
 @pytest.mark.parametrize('path', EPISODES, ids=os.path.basename)
 def test_goal_episode_matches_reference(path):
-    g = np.load(path)
+    g = dict(np.load(path))
     env_id = str(g['env_id'])
     env = ze.make_fixed_env(env_id, seed=7, env_seed=int(g['env_seed']))
     obs = env.reset()
@@ -52,7 +52,7 @@ def test_goal_episode_matches_reference(path):
 
 
 def test_wait_wrapper_matches_reference():
-    g = np.load(os.path.join(GOLDEN, 'goals_wait_PointTSP.npz'))
+    g = dict(np.load(os.path.join(GOLDEN, 'goals_wait_PointTSP.npz')))
     env = ze.make_train_env(str(g['env_id']), hier=True, num_training_tasks=3, rng_seed=11)
     rs = np.random.RandomState(3)
     obs = env.reset()

@@ -22,7 +22,7 @@ def test_fixtures_present():
 
 @pytest.mark.parametrize('path', EPISODES, ids=os.path.basename)
 def test_seeded_episode_matches_reference(path):
-    g = np.load(path)
+    g = dict(np.load(path))
     env = ze.make_fixed_env(str(g['env_id']), seed=7, env_seed=int(g['env_seed']))
     obs = env.reset()
     e = env.env
@@ -54,9 +54,9 @@ HOST_LAYOUT_EPISODES = [f for f in EPISODES if os.path.basename(f) in (
 @pytest.mark.parametrize('path', HOST_LAYOUT_EPISODES, ids=os.path.basename)
 def test_host_supplied_layout_matches_reference(path):
     """Same episode, but the layout is handed in instead of sampled."""
-    g = np.load(path)
+    g = dict(np.load(path))
     env = ze.ZoneTaskEnv(ze.TASK_OF_ENV_ID[str(g['env_id'])])
-    lay = {k[len('layout_'):]: g[k] for k in g.files if k.startswith('layout_')}
+    lay = {k[len('layout_'):]: g[k] for k in g if k.startswith('layout_')}
     obs = env.reset(layout=lay)
     assert np.array_equal(obs['zone_obs'], g['zone_obs'][0])
     stride = 1 if len(g['actions']) < 800 else 3   # keep the CPU suite short: check every 3rd obs
@@ -72,7 +72,7 @@ def test_hard_instance_vector_trace_matches_reference():
     """Three make_test_env('PointTSP-v5') envs (seeded once, Engine.reset increments the seed) under the vector-env
     protocol, recorded from the REAL TSPHardEnv: two auto-resets each, the distractors re-sampled around the fixed
     cities every time."""
-    g = np.load(os.path.join(GOLDEN, 'hardvec_PointTSP-v5.npz'))
+    g = dict(np.load(os.path.join(GOLDEN, 'hardvec_PointTSP-v5.npz')))
     envs = [ze.make_task_env('PointTSP-v5') for _ in range(3)]
     for i, e in enumerate(envs):
         e.seed(1000 + 50 * i)
@@ -89,7 +89,7 @@ def test_hard_instance_vector_trace_matches_reference():
 
 @pytest.mark.parametrize('path', VECTORS, ids=os.path.basename)
 def test_vector_env_autoreset_matches_reference(path):
-    g = np.load(path)
+    g = dict(np.load(path))
     env_id = str(g['env_id'])
     n = g['actions'].shape[1]
     vec = ze.SerialVecEnv([ze.make_train_env(env_id, num_training_tasks=2, rng_seed=1 + 10000 * i)

@@ -11,8 +11,8 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'mod
 
 
 def load(tag):
-    g = np.load(GOLDEN)
-    sd = {k[len(tag) + 4:]: g[k] for k in g.files if k.startswith(tag + '_sd_')}
+    g = dict(np.load(GOLDEN))
+    sd = {k[len(tag) + 4:]: g[k] for k in g if k.startswith(tag + '_sd_')}
     return g, sd
 
 

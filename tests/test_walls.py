@@ -22,7 +22,7 @@ WALL_RTOL = 2e-5        # per substep in contact, fp32 closed form vs fp64 gener
 def test_wall_list_of_the_real_class():
     assert len(WALLS) == 3
     for path in WALLS:
-        g = np.load(path)
+        g = dict(np.load(path))
         w = g['walls_locations']
         assert w.shape == (244, 2) and float(g['walls_size']) == ze.WALLS_SIZE == 0.1
         assert np.array_equal(w, np.array(ze.wall_locations(3), dtype=np.float64))        # the oracle's restatement
