@@ -490,7 +490,7 @@ def run_ours(args):
            'api': 'ZoneVecEnv.step_host: host numpy actions in (page-locked arrays from env.pinned_actions(), one of 8 per call; '
                   '`pageable_actions_value` = the same with ordinary numpy arrays, staged through a pinned buffer inside the '
                   'call), host numpy obs/zone_obs/reward/done out, transfers + stream sync inside every call'
-                  + ('; crl_step_host_delta, zero-copy: ONE kernel per call -- the step kernel reads the actions from, and writes '
+                  + ('; crl_host_call_step (the prepared form of crl_step_host_delta, zero-copy): ONE kernel per call -- the step kernel reads the actions from, and writes '
                      'obs, result and the zone_obs rows that changed (mean %.1f of %d rows per step) to, the pinned host '
                      'buffers itself; host buffers byte-identical to a full copy' % (rows_per_step, B) if is_delta
                      else '; crl_step_host: everything copied whole'),

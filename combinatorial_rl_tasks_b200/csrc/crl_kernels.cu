@@ -1984,6 +1984,74 @@ int crl_step_host(const CrlConfig* c, const CrlState* st, const float* actions_h
   return CRL_OK;
 }
 
+// device-side alias of a page-locked, device-mapped host pointer (NULL if it is not one); a small per-thread cache:
+// a caller rotating a few action buffers must not evict the fixed ones
+static void* mapped_alias(const void* h) {
+  struct Mapped { const void* host; void* dev; };
+  static thread_local Mapped cache[64] = {};
+  static thread_local int next = 0;
+  if (!h) return nullptr;
+  for (auto& m : cache) if (m.host == h) return m.dev;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, h) != cudaSuccess || a.type != cudaMemoryTypeHost || !a.devicePointer) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  cache[next] = Mapped{h, a.devicePointer};
+  next = (next + 1) % 64;
+  return a.devicePointer;
+}
+
+// crl_host_call_*: the zero-copy host step with everything but the actions resolved once
+struct CrlHostCall {
+  const CrlConfig* cfg;
+  const CrlState* st;
+  CrlOut direct;               // obs / result / shaped_reward: device aliases of the caller's host buffers
+  float* zone_obs_host;        // device alias of the caller's host zone_obs
+  uint32_t flags;
+  const void* act_host[8];     // the caller's action buffers seen so far
+  const float* act_dev[8];
+  int act_next;
+};
+
+int crl_host_call_create(const CrlConfig* c, const CrlState* st, const CrlOut* out, const CrlOut* host_out, uint32_t flags,
+                         CrlHostCall** call) {
+  if (!c || !st || !out || !host_out || !host_out->obs || !host_out->zone_obs || !host_out->result || !st->row_list || !call)
+    return CRL_ERR_NULL;
+  int rc = check_config(c);
+  if (rc) return rc;
+  flags &= ~CRL_STEP_HOST_ZERO_COPY;
+  CrlHostCall h{};
+  h.cfg = c; h.st = st; h.direct = *out; h.flags = flags | CRL_STEP_TRACK_ROWS;
+  h.direct.obs = static_cast<float*>(mapped_alias(host_out->obs));
+  h.direct.result = static_cast<CrlResult*>(mapped_alias(host_out->result));
+  h.zone_obs_host = static_cast<float*>(mapped_alias(host_out->zone_obs));
+  if ((flags & CRL_STEP_GOALS) && host_out->shaped_reward)
+    h.direct.shaped_reward = static_cast<float*>(mapped_alias(host_out->shaped_reward));
+  if (!h.direct.obs || !h.direct.result || !h.zone_obs_host || ((flags & CRL_STEP_GOALS) && !h.direct.shaped_reward))
+    return CRL_ERR_CONFIG;
+  *call = new CrlHostCall(h);
+  return CRL_OK;
+}
+
+int crl_host_call_step(CrlHostCall* h, const float* actions_host, void* stream) {
+  if (!h || !actions_host) return CRL_ERR_NULL;
+  const float* act = nullptr;
+  for (int i = 0; i < 8; ++i) if (h->act_host[i] == actions_host) { act = h->act_dev[i]; break; }
+  if (!act) {
+    act = static_cast<const float*>(mapped_alias(actions_host));
+    if (!act) return CRL_ERR_CONFIG;
+    h->act_host[h->act_next] = actions_host; h->act_dev[h->act_next] = act;
+    h->act_next = (h->act_next + 1) % 8;
+  }
+  int rc = step_launch(h->cfg, h->st, act, &h->direct, h->flags, 0, 0, h->zone_obs_host, stream);
+  if (rc) return rc;
+  if (cudaStreamSynchronize(static_cast<cudaStream_t>(stream)) != cudaSuccess) return CRL_ERR_DEVICE;
+  return CRL_OK;
+}
+
+void crl_host_call_destroy(CrlHostCall* h) { delete h; }
+
 int crl_step_host_delta(const CrlConfig* c, const CrlState* st, const float* actions_host, float* actions_dev,
                         const CrlOut* out, const CrlOut* host_out, void* host_delta, int64_t host_delta_bytes,
                         uint32_t flags, int32_t* delta_rows, void* stream) {
@@ -2000,21 +2068,7 @@ int crl_step_host_delta(const CrlConfig* c, const CrlState* st, const float* act
     // obs / result (/ shaped_reward) and every zone_obs row it changed to, the caller's pinned device-mapped
     // host buffers: no copy-engine transfers, no staging, no row list, no gather, no host-side scatter
     // (host_delta and actions_dev are not used).  row_list[0] counts the rows (cumulative).
-    struct Mapped { const void* host; void* dev; };
-    static thread_local Mapped cache[64] = {};   // a caller rotating a few action buffers must not evict the fixed ones
-    static thread_local int next = 0;
-    auto mapped = [&](const void* h) -> void* {
-      if (!h) return nullptr;
-      for (auto& m : cache) if (m.host == h) return m.dev;
-      cudaPointerAttributes a;
-      if (cudaPointerGetAttributes(&a, h) != cudaSuccess || a.type != cudaMemoryTypeHost || !a.devicePointer) {
-        (void)cudaGetLastError();
-        return nullptr;
-      }
-      cache[next] = Mapped{h, a.devicePointer};
-      next = (next + 1) % 64;
-      return a.devicePointer;
-    };
+    auto mapped = [](const void* h) { return mapped_alias(h); };
     CrlOut direct = *out;
     direct.obs = static_cast<float*>(mapped(host_out->obs));
     direct.result = static_cast<CrlResult*>(mapped(host_out->result));

@@ -164,6 +164,8 @@ class ZoneVecEnv:
         self.bind_outputs(z(B, 8), z(B, N, Z), z(B, 8, dtype=torch.uint8), z(B))
         self._actions_dev = z(B, 2)
         self._host = None
+        self._host_calls = {}                     # (auto_reset, wait) -> CrlHostCall*, see step_host
+        self._host_call_step = self.lib.crl_host_call_step
         self._pinned = {}                         # id(numpy array) -> (pinned tensor, pointer, array): pinned_actions()
         self._step_index = 0
         self.gpu_launches = 0
@@ -482,7 +484,7 @@ class ZoneVecEnv:
         flags = (_lib.STEP_AUTO_RESET if auto_reset else 0) | (_lib.STEP_ACTION_COUNTER if replayable else 0)
         return self._step(None, flags, action_seed, chained=chained)
 
-    def step_host(self, actions, auto_reset=True, delta=True, wait=False, zero_copy=True):
+    def step_host(self, actions, auto_reset=True, delta=True, wait=False, zero_copy=True, prepared=True):
         """The reference-facing call with HOST buffers: numpy actions in, numpy obs /
         reward / done out (pinned staging; host<->device copies inside the call).  The returned
         arrays are persistent host buffers overwritten by the next call, as the device ones are.
@@ -495,8 +497,36 @@ class ZoneVecEnv:
         kernel reads the actions from, and writes obs / result / shaped_reward and the changed zone_obs
         rows to, the pinned host buffers itself; the DEVICE tensors ``env.obs`` / ``env.result`` are then
         not updated by the call (``env.zone_obs`` is).  ``env.delta_rows`` = rows the call moved (B = all;
-        -1 = counted on the device only, see ``host_rows_moved()``)."""
+        -1 = counted on the device only, see ``host_rows_moved()``).  ``prepared=True``: the zero-copy call goes through
+        a prepared call object (``crl_host_call_step``: three arguments per frame, buffers and flags resolved once) instead
+        of ``crl_step_host_delta`` with its eleven; same kernel, same bytes."""
         h = self._host or self._host_buffers()
+        if prepared and delta and zero_copy and self._mirror_ok:
+            # the prepared call (crl_host_call_*): buffers and flags resolved once, three arguments per frame
+            call = self._host_calls.get((auto_reset, wait))
+            if call is None:
+                call = self._host_call(auto_reset, wait)
+            pin = self._pinned.get(id(actions))
+            if pin is not None:                       # one of pinned_actions(): read where it lies
+                aptr = pin[1]
+            else:
+                aptr = h['actions_ptr']
+                if actions is not h['np']['actions']:
+                    np.copyto(h['np']['actions'], np.asarray(actions, dtype=np.float32).reshape(self.num_envs, 2))
+            if torch.cuda.current_device() == self._dev_index:
+                rc = self._host_call_step(call, aptr, _raw_stream(self._dev_index))
+            else:
+                with torch.cuda.device(self.device):
+                    rc = self._host_call_step(call, aptr, _raw_stream(self._dev_index))
+            if rc:
+                _lib.check(rc)
+            self.delta_rows = -1
+            self._step_index += 1
+            self.gpu_launches += 1
+            self._chain_ok = False
+            if self.prefetch_every:
+                self.tick()
+            return h['ret']
         hn = h['np']
         aptr = h['actions_ptr']
         if actions is not hn['actions']:
@@ -555,6 +585,30 @@ class ZoneVecEnv:
         if self.prefetch_every:
             self.tick()                           # the background sampler's cadence, as in _step
         return h['ret']
+
+    def _host_call(self, auto_reset, wait):
+        """crl_host_call_create for one (auto_reset, wait) combination of step_host; kept until close()."""
+        h = self._host
+        flags = (_lib.STEP_AUTO_RESET if auto_reset else 0) | (_lib.STEP_WAIT if wait else 0) | self._mode_flags
+        if self.spec.task == _lib.TASK_TTSP:
+            flags |= _lib.STEP_HOST_PLANES            # plane-major host mirror, see _host_buffers
+        call = ctypes.c_void_p()
+        with self._guard():
+            _lib.check(self.lib.crl_host_call_create(self.cfg, self.state, self.out, h['out'], flags, ctypes.byref(call)))
+        self._host_calls[(auto_reset, wait)] = call
+        return call
+
+    def close(self):
+        """Free the prepared host calls (the tensors go with the object)."""
+        calls, self._host_calls = self._host_calls, {}
+        for call in calls.values():
+            self.lib.crl_host_call_destroy(call)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def host_rows_moved(self, reset=False):
         """zone_obs rows the zero-copy step_host calls have written to the host mirror since the count was last

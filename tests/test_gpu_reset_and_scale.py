@@ -190,14 +190,38 @@ def test_step_host_equals_device_step(crl):
         assert np.array_equal(rew_h, rew_d.cpu().numpy()) and np.array_equal(done_h, done_d.cpu().numpy())
 
 
-@pytest.mark.parametrize('zero_copy', [True, False], ids=['zero_copy', 'staged'])
+def test_step_host_no_reset_wait_equals_device_step_no_reset(crl):
+    """step_host(auto_reset=False, wait=True) -- its own prepared call object -- against step_no_reset of a WaitWrapper
+    env on the device: parked envs (zero observation, reward 0, done) included; then an auto-reset host step."""
+    B = 256
+    env_a = crl.ZoneVecEnv('PointTSP-v0', B, wait=True); env_a.seed(5); env_a.cfg.num_steps = 12; env_a.reset()
+    env_b = crl.ZoneVecEnv('PointTSP-v0', B, wait=True); env_b.seed(5); env_b.cfg.num_steps = 12; env_b.reset()
+    rs = np.random.RandomState(1)
+    for t in range(30):
+        a = rs.uniform(-1, 1, (B, 2)).astype(np.float32)
+        last = t % 15 == 14                               # hier_base.py:180-183: skill_len - 1 step_no_reset, then step
+        obs_h, rew_h, done_h, _ = env_a.step_host(a, auto_reset=last, wait=True)
+        obs_d, rew_d, done_d, _ = (env_b.step if last else env_b.step_no_reset)(torch.from_numpy(a).cuda())
+        assert np.array_equal(obs_h['obs'], obs_d['obs'].cpu().numpy()), t
+        assert np.array_equal(obs_h['zone_obs'], obs_d['zone_obs'].cpu().numpy()), t
+        assert np.array_equal(rew_h, rew_d.cpu().numpy()) and np.array_equal(done_h, done_d.cpu().numpy()), t
+        if t == 13:
+            assert done_h.all() and not obs_h['obs'].any()     # everyone parked after the 12-step episodes
+    assert len(env_a._host_calls) == 2
+    env_a.close()
+    assert not env_a._host_calls
+
+
+@pytest.mark.parametrize('zero_copy', [True, 'unprepared', False], ids=['zero_copy', 'zero_copy_unprepared', 'staged'])
 @pytest.mark.parametrize('env_id', TASKS + ['PointTTSP-v3', 'ColourMatch-v3'])     # -v3: the EXT kernels (shaped_reward too)
 def test_step_host_delta_is_byte_identical_to_full_copy(crl, env_id, zero_copy):
     """crl_step_host_delta moves only the zone_obs rows that changed; what the caller sees in its
     host buffers must be byte for byte what crl_step_host (full copy) delivers -- across zone
     events, cooldown ticks, timeouts and auto-resets (episodes cut short to force many).  Both flavours:
     zero-copy (one kernel; the step writes obs / result / changed rows into the pinned host buffers itself)
-    and staged (row list + gather kernel + copy-engine transfers)."""
+    and staged (row list + gather kernel + copy-engine transfers); zero-copy through the prepared call object
+    (crl_host_call_step, the default) and through crl_step_host_delta itself."""
+    prepared, zero_copy = zero_copy is True, bool(zero_copy)
     B = 1000
     envs = []
     for _ in range(2):
@@ -215,7 +239,7 @@ def test_step_host_delta_is_byte_identical_to_full_copy(crl, env_id, zero_copy):
             for e in envs:
                 e.pose[:200, :2] = e.zone_xy[3, :200, :]
         of, rf, df, inf_ = full.step_host(a, delta=False)
-        od, rd, dd, ind = delta.step_host(a, delta=True, zero_copy=zero_copy)
+        od, rd, dd, ind = delta.step_host(a, delta=True, zero_copy=zero_copy, prepared=prepared)
         rows = delta.delta_rows if delta.delta_rows >= 0 else delta.host_rows_moved(reset=True)   # -1: counted on the device
         if t == 20:
             assert rows >= 200 and (env_id.startswith('ColourMatch') or int((ind['event'] != 0).sum()) >= 200)

@@ -48,7 +48,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.crl_abi_version() == 7
+    assert lib.crl_abi_version() == 8
     assert b'NULL' in lib.crl_strerror(-1)
 
 
@@ -77,6 +77,10 @@ def test_argument_errors_are_detected_on_the_host():
     assert lib.crl_step(cfg, st, None, out, _lib.STEP_CHAINED, 0, 0, None) == -1   # chained needs CrlState.stamp
     assert lib.crl_step(cfg, st, None, out, _lib.STEP_TRACK_ROWS, 0, 0, None) == -1  # needs CrlState.row_list
     assert lib.crl_step_host_delta(cfg, st, a16, a16, out, out, a16, 4096, 0, None, None) == -1  # no row_list
+    call = ctypes.c_void_p()
+    assert lib.crl_host_call_create(cfg, st, out, out, 0, ctypes.byref(call)) == -1   # no row_list
+    assert lib.crl_host_call_step(None, a16, None) == -1 and not call.value
+    lib.crl_host_call_destroy(None)                                        # a no-op
     st.pose = a16 + 4
     assert lib.crl_step(cfg, st, None, out, 0, 0, 0, None) == -3          # misaligned plane
 

@@ -34,6 +34,11 @@ print('empty sync                  %.1f us' % t(lambda: s.synchronize()))
 env.step_host(a)
 print('step_host(delta, zero-copy)           %.1f us' % t(lambda: env.step_host(a, zero_copy=True)))
 print('step_host(delta, zero-copy, pinned in)%.1f us' % t(lambda: env.step_host(h['np']['actions'], zero_copy=True)))
+print('  ... unprepared (crl_step_host_delta)%.1f us' % t(lambda: env.step_host(h['np']['actions'], zero_copy=True, prepared=False)))
+pa = env.pinned_actions(1)[0]; np.copyto(pa, a)
+print('  ... prepared, pinned_actions() array %.1f us' % t(lambda: env.step_host(pa)))
+print('  ... unprepared, same array           %.1f us' % t(lambda: env.step_host(pa, prepared=False)))
+print('  ... prepared again                   %.1f us' % t(lambda: env.step_host(pa)))
 ref = crl.ZoneVecEnv('PointTSP-v0', B); ref.seed(1); ref.reset()
 env2 = crl.ZoneVecEnv('PointTSP-v0', B); env2.seed(1); env2.reset()
 rs = np.random.RandomState(3)
