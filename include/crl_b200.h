@@ -341,7 +341,8 @@ int crl_step_host_delta(const CrlConfig* cfg, const CrlState* st, const float* a
  * alive and may change their fields between steps, as with crl_step_host_delta); `out` and `host_out` are read now; `flags`
  * as for crl_step_host_delta (CRL_STEP_HOST_ZERO_COPY implied).  crl_host_call_step: one step; `actions_host` float[B][2],
  * page-locked and device-mapped (CRL_ERR_CONFIG otherwise); result byte-identical to crl_step_host_delta's; the stream is
- * synchronised before it returns.  Same precondition on host_out->zone_obs.  A call object is used by one thread at a time. */
+ * synchronised before it returns.  Same precondition on host_out->zone_obs.  A call object is used by one thread at a time;
+ * the host buffers it was created with (and the action buffers it has seen) stay allocated and page-locked while it lives. */
 typedef struct CrlHostCall CrlHostCall;
 int crl_host_call_create(const CrlConfig* cfg, const CrlState* st, const CrlOut* out, const CrlOut* host_out,
                          uint32_t flags, CrlHostCall** call);
