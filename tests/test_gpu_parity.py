@@ -276,11 +276,16 @@ def test_integration_md_ctypes_stub_runs(crl):
     finally:
         os.chdir(cwd)
     torch.cuda.synchronize()
+    # three steps in all: crl_step, crl_step_host (device and host copies written), crl_host_call_step (host copies only)
     obs = ns['mem']['obs'].view(torch.float32).reshape(B, 8).cpu().numpy()
     res = ns['mem']['result'].reshape(B, 8).cpu().numpy()
-    assert np.all(obs[:, 0] == np.float32(1999 / 2000)) and not res[:, 4].any()
+    assert np.all(obs[:, 0] == np.float32(1998 / 2000)) and not res[:, 4].any()
     zo = ns['mem']['zone_obs'].view(torch.float32).reshape(B, 15, 6).cpu().numpy()
     assert np.all(zo[:, :, 5] == 0.25) and np.all(np.abs(zo[:, :, :2]) <= 2.45 / 3 + 1e-6)
+    h_obs = ns['host']['obs'].view(torch.float32).reshape(B, 8).numpy()
+    h_zo = ns['host']['zone_obs'].view(torch.float32).reshape(B, 15, 6).numpy()
+    assert np.all(h_obs[:, 0] == np.float32(1997 / 2000)) and np.array_equal(h_zo, zo)
+    assert not ns['host']['result'].reshape(B, 8).numpy()[:, 4].any()
 
 
 VECTORS = sorted(glob.glob(os.path.join(GOLDEN, '*_vector.npz')))
