@@ -410,6 +410,7 @@ def run_ours(args):
         rows = calls = 0
         per_call = []
         env.host_rows_moved(reset=True)
+        env.host_results_moved(reset=True)
         t_start = time.perf_counter()
         while True:
             t0 = time.perf_counter()
@@ -423,6 +424,7 @@ def run_ours(args):
             if t1 - t_start >= seconds or calls >= args.e2e_max_calls:
                 break
         rows += env.host_rows_moved(reset=True)                      # the zero-copy path counts its rows on the device
+        timed_host_steps.results_per_step = env.host_results_moved(reset=True) / calls if delta else float(B)
         per_call.sort()
         med = rank_max(per_call[len(per_call) // 2])
         return world * B / med, rows / calls, calls, world * B / rank_max(per_call[0])
@@ -456,6 +458,7 @@ def run_ours(args):
     pageable_rate, _, _, _ = timed_host_steps(True, args.e2e_seconds / 3, pageable)
     rate, rows_per_step, e2e_calls, best_rate = timed_host_steps(True, args.e2e_seconds)
     is_delta = rows_per_step < B
+    results_per_step = timed_host_steps.results_per_step if is_delta else float(B)
 
     def copy_engine_floor(seconds=0.2):
         """The copy engine alone moving one call's obs + result (no kernel, no actions) with every rank active: what
@@ -483,7 +486,7 @@ def run_ours(args):
 
     floor_rate = copy_engine_floor()
     e2e = {'value': rate, 'unit': UNIT, 'h2d_bytes_per_step': 8 * B,
-           'd2h_bytes_per_step': int((32 + 8) * B + rows_per_step * 4 * N * Z),
+           'd2h_bytes_per_step': int(32 * B + 8 * results_per_step + rows_per_step * 4 * N * Z),
            'calls': e2e_calls, 'timing': 'median over groups of 25 calls (host clock, synchronize on both sides)',
            'best_group_value': best_rate,
            'pageable_actions_value': pageable_rate,
@@ -491,8 +494,9 @@ def run_ours(args):
                   '`pageable_actions_value` = the same with ordinary numpy arrays, staged through a pinned buffer inside the '
                   'call), host numpy obs/zone_obs/reward/done out, transfers + stream sync inside every call'
                   + ('; crl_host_call_step (the prepared form of crl_step_host_delta, zero-copy): ONE kernel per call -- the step kernel reads the actions from, and writes '
-                     'obs, result and the zone_obs rows that changed (mean %.1f of %d rows per step) to, the pinned host '
-                     'buffers itself; host buffers byte-identical to a full copy' % (rows_per_step, B) if is_delta
+                     'obs, and the zone_obs rows and result records that changed (mean %.1f rows and %.1f records of %d per step: a '
+                     'record is all zeros except on an event) to, the pinned host buffers itself; host buffers byte-identical to '
+                     'a full copy' % (rows_per_step, results_per_step, B) if is_delta
                      else '; crl_step_host: everything copied whole'),
            'host_placement': numa,
            'full_copy_value': full_rate,

@@ -70,6 +70,7 @@ struct KParams {
   uint32_t round;               // crl_prefetch_layouts: the round being run
   uint32_t* row_list;
   float* zone_obs_host;         // CRL_STEP_HOST_ZERO_COPY: the caller's host zone_obs (device-mapped); changed rows go there
+  unsigned long long* result_dev;   // CRL_STEP_HOST_ZERO_COPY: the DEVICE copy of the result records (`result` is then the host's)
   int32_t* goal;
   const float2* bank_zone_xy;
   const float4* bank_origin;
@@ -1206,6 +1207,7 @@ __global__ void __maxnreg__(MaxRegs<N>::v) step_kernel(const __grid_constant__ K
       }
     }
     // (4) result word and episode statistics
+    bool res_moved = false;
     if (valid) {
       // need_next_goal (TSP_next_city_env.py:69-75, TTSP_next_city_env.py:49-53): the goal zone
       // was reached, or the episode ended (timeouts included), or there is no goal to pursue
@@ -1213,8 +1215,21 @@ __global__ void __maxnreg__(MaxRegs<N>::v) step_kernel(const __grid_constant__ K
       const unsigned long long word = (unsigned long long)__float_as_uint(reward) |
           ((unsigned long long)((done || parked) ? 1u : 0u) << 32) | ((unsigned long long)(goal ? 1u : 0u) << 40) |
           ((unsigned long long)(uint8_t)(int8_t)event << 48) | ((unsigned long long)(need_next ? 1u : 0u) << 56);
-      p.result[e] = word;
+      if (p.result_dev) {
+        // host-direct step: `result` is the caller's host array, which holds what the device copy holds.  A record is
+        // all zeros except on an event, a done or a goal change, so it crosses the link only when it differs from the
+        // one already there (0.5 of the 2.6 MB a 65,536-env call wrote; the link is what bounds that call)
+        const unsigned long long prev = p.result_dev[e];
+        p.result_dev[e] = word;
+        if (prev != word) { p.result[e] = word; res_moved = true; }
+      } else {
+        p.result[e] = word;
+      }
       if (EXT && goals && live && need_next && goal_zone >= 0) p.goal[e] = -1;
+    }
+    if (p.result_dev) {                            // records moved, cumulative: row_list[1]
+      const unsigned mm = __ballot_sync(kFull, res_moved);
+      if (mm && lane == 0) atomicAdd(p.row_list + 1, (uint32_t)__popc(mm));
     }
     const unsigned dm = __ballot_sync(kFull, done);
     const unsigned rm = EXT ? __ballot_sync(kFull, done || revive) : dm;   // envs to rebuild
@@ -1777,12 +1792,15 @@ int crl_step_bytes(const CrlConfig* c, int64_t* rd, int64_t* wr) {
 }
 
 static int step_launch(const CrlConfig* c, const CrlState* st, const float* actions, const CrlOut* out,
-                       uint32_t flags, uint64_t action_seed, uint64_t step_index, float* zone_obs_host, void* stream) {
+                       uint32_t flags, uint64_t action_seed, uint64_t step_index, float* zone_obs_host, void* stream,
+                       CrlResult* result_dev = nullptr) {
   KParams p;
   if (!out) return CRL_ERR_NULL;
   int rc = fill_params(c, st, out, p);
   if (rc) return rc;
   p.zone_obs_host = zone_obs_host;
+  p.result_dev = reinterpret_cast<unsigned long long*>(result_dev);
+  if (result_dev && (!zone_obs_host || !p.row_list)) return CRL_ERR_CONFIG;
   if (actions && (reinterpret_cast<uintptr_t>(actions) & 7u)) return CRL_ERR_ALIGN;
   p.actions = reinterpret_cast<const float2*>(actions);
   p.flags = flags; p.action_seed = action_seed; p.step_index = step_index;
@@ -2008,6 +2026,7 @@ struct CrlHostCall {
   const CrlState* st;
   CrlOut direct;               // obs / result / shaped_reward: device aliases of the caller's host buffers
   float* zone_obs_host;        // device alias of the caller's host zone_obs
+  CrlResult* result_dev;       // the device copy of the result records
   uint32_t flags;
   const void* act_host[8];     // the caller's action buffers seen so far
   const float* act_dev[8];
@@ -2022,7 +2041,8 @@ int crl_host_call_create(const CrlConfig* c, const CrlState* st, const CrlOut* o
   if (rc) return rc;
   flags &= ~CRL_STEP_HOST_ZERO_COPY;
   CrlHostCall h{};
-  h.cfg = c; h.st = st; h.direct = *out; h.flags = flags | CRL_STEP_TRACK_ROWS;
+  if (!out->result) return CRL_ERR_NULL;
+  h.cfg = c; h.st = st; h.direct = *out; h.flags = flags | CRL_STEP_TRACK_ROWS; h.result_dev = out->result;
   h.direct.obs = static_cast<float*>(mapped_alias(host_out->obs));
   h.direct.result = static_cast<CrlResult*>(mapped_alias(host_out->result));
   h.zone_obs_host = static_cast<float*>(mapped_alias(host_out->zone_obs));
@@ -2044,7 +2064,7 @@ int crl_host_call_step(CrlHostCall* h, const float* actions_host, void* stream) 
     h->act_host[h->act_next] = actions_host; h->act_dev[h->act_next] = act;
     h->act_next = (h->act_next + 1) % 8;
   }
-  int rc = step_launch(h->cfg, h->st, act, &h->direct, h->flags, 0, 0, h->zone_obs_host, stream);
+  int rc = step_launch(h->cfg, h->st, act, &h->direct, h->flags, 0, 0, h->zone_obs_host, stream, h->result_dev);
   if (rc) return rc;
   if (cudaStreamSynchronize(static_cast<cudaStream_t>(stream)) != cudaSuccess) return CRL_ERR_DEVICE;
   return CRL_OK;
@@ -2077,7 +2097,8 @@ int crl_step_host_delta(const CrlConfig* c, const CrlState* st, const float* act
     if ((flags & CRL_STEP_GOALS) && host_out->shaped_reward)
       direct.shaped_reward = static_cast<float*>(mapped(host_out->shaped_reward));
     if (!direct.obs || !direct.result || !act || !zhost || ((flags & CRL_STEP_GOALS) && !direct.shaped_reward)) return CRL_ERR_CONFIG;
-    rc = step_launch(c, st, act, &direct, flags | CRL_STEP_TRACK_ROWS, 0, 0, zhost, stream);
+    if (!out->result) return CRL_ERR_NULL;
+    rc = step_launch(c, st, act, &direct, flags | CRL_STEP_TRACK_ROWS, 0, 0, zhost, stream, out->result);
     if (rc) return rc;
     if (cudaStreamSynchronize(s) != cudaSuccess) return CRL_ERR_DEVICE;
     if (delta_rows) *delta_rows = -1;              // not known to the host: row_list[0] counts them on the device

@@ -495,9 +495,10 @@ class ZoneVecEnv:
         (B, N, Z) strided view of a [Z][B][N] buffer) and that column crosses as one contiguous plane.
         ``zero_copy=True`` (with the delta path): ONE kernel and a stream synchronisation -- the step
         kernel reads the actions from, and writes obs / result / shaped_reward and the changed zone_obs
-        rows to, the pinned host buffers itself; the DEVICE tensors ``env.obs`` / ``env.result`` are then
-        not updated by the call (``env.zone_obs`` is).  ``env.delta_rows`` = rows the call moved (B = all;
-        -1 = counted on the device only, see ``host_rows_moved()``).  ``prepared=True``: the zero-copy call goes through
+        rows to, the pinned host buffers itself; a result record (reward, done, goal_met, event, need_next_goal: all
+        zeros except on an event) crosses only when it differs from the one the host array already holds.  The DEVICE
+        tensor ``env.obs`` is then not updated by the call (``env.zone_obs`` and ``env.result`` are).  ``env.delta_rows`` =
+        rows the call moved (B = all; -1 = counted on the device only, see ``host_rows_moved()`` / ``host_results_moved()``).  ``prepared=True``: the zero-copy call goes through
         a prepared call object (``crl_host_call_step``: three arguments per frame, buffers and flags resolved once) instead
         of ``crl_step_host_delta`` with its eleven; same kernel, same bytes."""
         h = self._host or self._host_buffers()
@@ -616,6 +617,14 @@ class ZoneVecEnv:
         n = int(self._row_list[0].item())
         if reset:
             self._row_list[:1].zero_()
+        return n
+
+    def host_results_moved(self, reset=False):
+        """Result records the zero-copy step_host calls have written to the host array since the count was last reset
+        (CrlState.row_list[1]); the others were equal to what the host already held."""
+        n = int(self._row_list[1].item())
+        if reset:
+            self._row_list[1:2].zero_()
         return n
 
     def _host_buffers(self):

@@ -130,7 +130,11 @@ enum CrlError {
  * to, the caller's host buffers (actions_host and all of host_out), which must be page-locked and
  * device-mapped (cudaHostAlloc; CRL_ERR_CONFIG otherwise).  host_delta and actions_dev are not used
  * (may be NULL); *delta_rows is set to -1 and CrlState.row_list[0] counts the rows moved, cumulatively.
- * The device copies CrlOut.obs / result / shaped_reward are NOT updated by such a call (zone_obs is). */
+ * Result records are treated like zone_obs rows: a record (all zeros except on an event, a done or a goal change) is
+ * written to host_out->result only when it differs from the one there, which the kernel knows from the device copy
+ * out->result (updated by every step) -- PRECONDITION: host_out->result holds out->result as of the previous step, as
+ * crl_step_host leaves it.  CrlState.row_list[1] counts the records moved.
+ * The device copies CrlOut.obs / shaped_reward are NOT updated by such a call (zone_obs and result are). */
 #define CRL_STEP_HOST_ZERO_COPY 256u
 /* The step does not build or write zone_obs (CrlOut.zone_obs may be NULL): for a consumer that derives the zone
  * rows from the state planes itself -- crl_zone_encode_state, the fused ZoneEnvModel encoder -- a rollout that only
