@@ -487,7 +487,9 @@ class ZoneVecEnv:
     def step_host(self, actions, auto_reset=True, delta=True, wait=False, zero_copy=True, prepared=True):
         """The reference-facing call with HOST buffers: numpy actions in, numpy obs /
         reward / done out (pinned staging; host<->device copies inside the call).  The returned
-        arrays are persistent host buffers overwritten by the next call, as the device ones are.
+        arrays are persistent host buffers overwritten by the next call, as the device ones are --
+        READ-ONLY for the caller: on the delta paths a zone_obs row or a result record is rewritten only
+        when it changes, so an in-place edit (``reward *= scale``) would stay there; copy first.
 
         ``delta=True``: once the host zone_obs buffer mirrors the device one, later calls move only
         the rows that changed; the arrays returned are byte-identical to a full copy.  TimedTSP's
