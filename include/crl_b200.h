@@ -53,7 +53,8 @@
  *    sampler round r)
  *  optional stamp uint32[2][ceil(B/32)]: steps started / finished per group of 32 envs,
  *  see CRL_STEP_CHAINED
- *  optional row_list uint32[4 + B] (CRL_STEP_TRACK_ROWS, crl_step_host_delta) and goal int32[B]
+ *  optional row_list uint32[4 + B] (CRL_STEP_TRACK_ROWS, crl_step_host_delta; header word 0 = zone_obs rows listed or
+ *  moved, word 1 = result records moved by the host-direct step, words 2-3 unused, then the env ids) and goal int32[B]
  *  (goal-conditioned variants, CRL_STEP_GOALS): see CrlState
  *  outputs, the layout the reference's consumer builds (main/src/utils/format.py:27-28):
  *    obs       float[B][8]      remaining, pos/3 (2), dir (2), vel/1.5 (2), yaw rate/3
