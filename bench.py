@@ -501,9 +501,10 @@ def run_ours(args):
            'host_placement': numa,
            'full_copy_value': full_rate,
            'copy_engine_floor_value': floor_rate,
-           'copy_engine_floor_note': 'obs + result of one call (%d bytes) moved by the copy engine alone + a stream sync, every '
-                                     'rank at once, same max-over-ranks median: the ceiling the host path of this box sets for '
-                                     'these bytes at this N; no kernel, no action upload' % ((32 + 8) * B),
+           'copy_engine_floor_note': 'obs + result of one call moved WHOLE (%d bytes) by the copy engine alone + a stream sync, every '
+                                     'rank at once, same max-over-ranks median; no kernel, no action upload: what the host path of '
+                                     'this box gives a plain copy of the outputs at this N (the zero-copy call moves fewer bytes: '
+                                     'result records cross only when they change, see d2h_bytes_per_step)' % ((32 + 8) * B),
            'full_copy_d2h_bytes_per_step': (32 + 4 * N * Z + 8) * B}
     del ring, env
     torch.cuda.empty_cache()
